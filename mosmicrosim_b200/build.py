@@ -1,0 +1,70 @@
+"""Builds libmmsgpu.so in-tree for sm_100a with nvcc (cross-compiles without a GPU).
+
+    python -m mosmicrosim_b200.build [--force]
+
+The kernel translation unit csrc/chain_tu.cu is compiled twice: "fast"
+(FMA contraction on) and "strict" (-fmad=false, literal operation order).
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+BUILD = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libmmsgpu.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"] + ARCH
+
+UNITS = [
+    # (source, object, extra flags)
+    ("chain_tu.cu", "chain_fast.o", ["-DMMS_STRICT=0"]),
+    ("chain_tu.cu", "chain_strict.o", ["-DMMS_STRICT=1", "-fmad=false"]),
+    ("mmsgpu_api.cu", "mmsgpu_api.o", []),
+    ("measure.cu", "measure.o", []),
+]
+
+
+def _sources():
+    out = [os.path.join(HERE, "..", "include", "mmsgpu.h")]
+    for f in os.listdir(CSRC):
+        out.append(os.path.join(CSRC, f))
+    return out
+
+
+def is_stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(s) > t for s in _sources())
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not is_stale():
+        return LIB
+    os.makedirs(BUILD, exist_ok=True)
+    procs = []
+    for src, obj, extra in UNITS:
+        cmd = [NVCC] + COMMON + extra + ["-c", os.path.join(CSRC, src), "-o", os.path.join(BUILD, obj)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd), flush=True)
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose and out:
+            print(out)
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + out)
+    link = [NVCC, "-shared", "-o", LIB] + ARCH + [os.path.join(BUILD, o) for _, o, _ in UNITS] + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"]
+    r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

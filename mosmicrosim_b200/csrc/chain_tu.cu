@@ -1,0 +1,92 @@
+// chain_tu.cu -- kernel translation unit, compiled twice by build.py:
+//   -DMMS_STRICT=0              -> chain_fast.o   (launch_*_fast)
+//   -DMMS_STRICT=1 -fmad=false  -> chain_strict.o (launch_*_strict)
+#include "chain_kernel.cuh"
+#include "stage_kernels.cuh"
+
+namespace mms {
+
+#if MMS_STRICT
+#define MMS_LAUNCH(name) name##_strict
+#else
+#define MMS_LAUNCH(name) name##_fast
+#endif
+
+using namespace MMS_MODE;
+
+namespace {
+
+template <int kNS, bool kFull, bool kHourly>
+cudaError_t launch_one(const ChainParams &p, cudaStream_t stream)
+{
+    auto kern = chain_kernel<kNS, kFull, kHourly>;
+    const size_t smem = sizeof(double) * (size_t)(((p.spline.n + 1) & ~1) + p.spline.n * 12);
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    dim3 grid((unsigned)(p.c_stride / kBlock), (unsigned)(p.S / kNS));
+    kern<<<grid, kBlock, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <int kNS>
+cudaError_t launch_ns(const ChainParams &p, bool full, bool hourly, cudaStream_t stream)
+{
+    if (full) return hourly ? launch_one<kNS, true, true>(p, stream) : launch_one<kNS, true, false>(p, stream);
+    return hourly ? launch_one<kNS, false, true>(p, stream) : launch_one<kNS, false, false>(p, stream);
+}
+
+__global__ void log1p_rows_kernel(double *rows, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rows[i] = log1p(rows[i]);                  // R/sim_microclimate.R:33
+}
+
+}  // namespace
+
+cudaError_t MMS_LAUNCH(launch_chain)(const ChainParams &p, cudaStream_t stream)
+{
+    const uint32_t all = p.mean_mask | p.hourly_mask;
+    const bool full = (all & ~MMS_PIPELINE_VAR_MASK) != 0;
+    const bool hourly = p.hourly_mask != 0 || p.wet_flags != nullptr;
+    // settings per thread: the largest of 4, 2, 1 that divides S
+    if (p.S % 4 == 0) return launch_ns<4>(p, full, hourly, stream);
+    if (p.S % 2 == 0) return launch_ns<2>(p, full, hourly, stream);
+    return launch_ns<1>(p, full, hourly, stream);
+}
+
+cudaError_t MMS_LAUNCH(launch_log1p_rows)(double *rows, int64_t n, cudaStream_t stream)
+{
+    if (n <= 0) return cudaSuccess;
+    log1p_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(rows, n);
+    return cudaGetLastError();
+}
+
+cudaError_t MMS_LAUNCH(launch_water_stage)(const WaterStageParams &p, cudaStream_t stream)
+{
+    const bool vec2 = (p.H % 2 == 0) &&
+                      ((((uintptr_t)p.rainfall | (uintptr_t)p.air_temperature | (uintptr_t)p.humidity |
+                         (uintptr_t)p.windspeed | (uintptr_t)p.water_surface_area |
+                         (uintptr_t)p.water_volume) & 15) == 0);
+    const unsigned grid = (unsigned)((p.C + kStageCells - 1) / kStageCells);
+    auto kern = vec2 ? water_stage_kernel<2> : water_stage_kernel<1>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWaterStageSmem);
+    if (err != cudaSuccess) return err;
+    kern<<<grid, kStageCells, kWaterStageSmem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t MMS_LAUNCH(launch_pop_stage)(const PopStageParams &p, cudaStream_t stream)
+{
+    const bool vec2 = (p.H % 2 == 0) &&
+                      ((((uintptr_t)p.larval_habitat_area | (uintptr_t)p.mdr | (uintptr_t)p.efd |
+                         (uintptr_t)p.das_zerodensity | (uintptr_t)p.ds | (uintptr_t)p.aquatic |
+                         (uintptr_t)p.adult) & 15) == 0);
+    const unsigned grid = (unsigned)((p.C + kStageCells - 1) / kStageCells);
+    auto kern = vec2 ? pop_stage_kernel<2> : pop_stage_kernel<1>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPopStageSmem);
+    if (err != cudaSuccess) return err;
+    kern<<<grid, kStageCells, kPopStageSmem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace mms

@@ -1,0 +1,120 @@
+// mms_common.cuh -- structures shared by the host side of libmmsgpu and its
+// sm_100a kernels.  All citations are relative to the reference root.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/mmsgpu.h"
+
+namespace mms {
+
+constexpr int kBlock = 128;          // threads (= cells) per CTA of the fused kernel
+constexpr int kHoursPerYear = 8760;  // n_times_year <- 365 * 24, R/sim_water.R:229, R/sim_pop_dynamics.R:222
+constexpr int kDaysPerYear = 365;
+
+// Hour-of-day constants of the SINEC / VSINE curves.  They depend only on the
+// hour index, so they are evaluated once on the host with the host libm (the
+// same one R uses) and handed to the kernel in parameter (constant) space.
+struct HourTables {
+    double z_light[24];    // sin((360*(t-950)/1400)/57.29577), R/sim_microclimate.R:255
+    double exp_e[24];      // exp(tau * time_since_ss), :260-262
+    double predawn[24];    // 1 - t/600, :275
+    double w_vsine[24];    // vsine_weights(), :431-454
+    double w_vsine_inv[24];// 1 - weight, :498-500
+    double z_night;        // :210
+};
+
+// Per-setting water-body constants, derived on the host exactly as
+// simulate_ephemeral_habitat_vectorised() derives them (R/sim_water.R:257-261).
+struct HabitatDev {
+    double max_volume;     // max_cone_volume
+    double catchment_area; // inflow_multiplier * surface(max_volume)
+    double leak_per_hour;  // EXTENSION
+    double initial_volume;
+    double cyl_area;       // pi r^2 (cylinder, EXTENSION)
+    int32_t shape;
+    int32_t pad;
+};
+
+struct DayEntry {          // approx1() interval of one prediction day (same for all cells)
+    int32_t idx;           // i: knots i, i+1
+    int32_t flag;          // 0 = interpolate, 1 = v == x[j] -> y[j], 2 = v == x[i] -> y[i]
+    double  w;             // (v - x[i]) / (x[j] - x[i]), R approx1()
+};
+
+// Device-resident spline tables: one knot vector shared by the three
+// positive_spline() closures, coefficients interleaved [knot][function][y,b,c,d].
+struct SplineDev {
+    const double *x;       // [n]
+    const double *coef;    // [n][3][4]  function order: mdr, efd, das
+    int32_t n;
+    int32_t uniform;       // 1: x[i] == x0 + i*step bit for bit (then x is not read)
+    double x0, step, inv_step;
+};
+
+// Device-resident ds(T, RH) surface: quad table, one 32-byte record per
+// bilinear cell (z00, z10, z01, z11), record (i, j) at [i + (nx-1)*j].
+struct SurfaceDev {
+    const double *x, *y;   // [nx], [ny]
+    const double *quad;    // [(nx-1)*(ny-1)][4]
+    int32_t nx, ny;
+    double x0, inv_dx, y0, inv_dy;   // index guess only; intervals are verified against x, y
+};
+
+struct ChainParams {
+    // per-cell inputs (device), cell index fastest, row stride = c_stride
+    const double *monthly;     // [9][M][c_stride]; rainfall row holds log1p(rainfall_daily)
+    const double *altitude;    // [c_stride]
+    const DayEntry *days;      // [D]
+    const int32_t *period_of_day; // [D] or nullptr
+    int64_t c_stride;          // padded number of cells of this shard
+    int64_t n_cells;           // real cells of this shard
+    int32_t M, D, S, P;
+    int32_t burnin_years_water, burnin_years_pop;
+    double initial_adult, initial_aquatic;
+    // density dependence
+    int32_t densmod_type; int32_t pad0;
+    double dd_effect, surface_area_cm2;
+    SplineDev spline;
+    SurfaceDev ds;
+    // outputs (device) -- same layouts as the host ones with C -> c_stride
+    double *mean_state, *mean_forcing, *hourly_state, *hourly_forcing;
+    int32_t *wet_hours;
+    uint8_t *wet_flags;
+    uint32_t mean_mask, hourly_mask;
+    int32_t *error_flag;       // set non-zero by the kernel on non-finite forcing
+    HourTables hr;
+    HabitatDev hab[MMS_MAX_SETTINGS];
+};
+
+// launchers, one translation unit per math mode (chain_fast.cu / chain_strict.cu)
+cudaError_t launch_chain_fast(const ChainParams &p, cudaStream_t stream);
+cudaError_t launch_chain_strict(const ChainParams &p, cudaStream_t stream);
+// monthly rainfall -> log1p(rainfall) in place (R/sim_microclimate.R:33)
+cudaError_t launch_log1p_rows_fast(double *rows, int64_t n, cudaStream_t stream);
+cudaError_t launch_log1p_rows_strict(double *rows, int64_t n, cudaStream_t stream);
+
+struct WaterStageParams {
+    const double *rainfall, *air_temperature, *humidity, *windspeed; // [C][H] (R column-major)
+    const double *altitude;   // [C]
+    double *water_surface_area, *water_volume;  // [C][H]
+    uint8_t *wet;             // [C][H]
+    int64_t H, C;
+    int32_t burnin_years;
+    HabitatDev hab;
+};
+struct PopStageParams {
+    const double *larval_habitat_area, *mdr, *efd, *das_zerodensity, *ds; // [C][H]
+    double *aquatic, *adult;
+    int64_t H, C;
+    int32_t burnin_years;
+    int32_t densmod_type;
+    double dd_effect, surface_area_cm2, initial_adult, initial_aquatic;
+};
+cudaError_t launch_water_stage_fast(const WaterStageParams &p, cudaStream_t stream);
+cudaError_t launch_water_stage_strict(const WaterStageParams &p, cudaStream_t stream);
+cudaError_t launch_pop_stage_fast(const PopStageParams &p, cudaStream_t stream);
+cudaError_t launch_pop_stage_strict(const PopStageParams &p, cudaStream_t stream);
+
+}  // namespace mms

@@ -1,0 +1,186 @@
+// mms_math.cuh -- per-step device arithmetic of the mosmicrosim chain.
+//
+// Compiled twice (see build.py): MMS_STRICT=1 with -fmad=false keeps the
+// reference's literal operation order and CUDA's IEEE-accurate libm, so that the
+// only differences from the CPU oracle are libm last-bit differences;
+// MMS_STRICT=0 ("fast", the default at run time) allows FMA contraction and
+// replaces pow() by exp(y*log(x)) compositions and divisions by literals with
+// multiplications.  Cheap, badly conditioned operations (1 - (1 - p), 1 - exp(-x),
+// lx - floor(lx), the clamps) are kept literal in both modes: the target is
+// the reference's floating-point arithmetic, not the exact mathematics.
+//
+// Citations are relative to the reference root.
+#pragma once
+
+#include "mms_common.cuh"
+
+#ifndef MMS_STRICT
+#define MMS_STRICT 0
+#endif
+
+#if MMS_STRICT
+#define MMS_MODE strict
+#else
+#define MMS_MODE fast
+#endif
+
+namespace mms {
+namespace MMS_MODE {
+
+constexpr double kEps = 1.4901161193847656e-08;   // sqrt(.Machine$double.eps), R/sim_pop_dynamics.R:26
+constexpr double kTimestep = 1.0 / 24.0;          // timestep = 1 / 24, R/sim_pop_dynamics.R:23
+
+// x / c for a literal c of the R source
+#if MMS_STRICT
+#define MMS_DIVC(x, c) ((x) / (c))
+#else
+#define MMS_DIVC(x, c) ((x) * (1.0 / (c)))
+#endif
+
+// R's `^` (arithmetic.c R_pow) for a positive, non-integer literal exponent y.
+__device__ __forceinline__ double r_pow_pos(double x, double y)
+{
+#if MMS_STRICT
+    if (x == 1.0) return 1.0;
+    if (x == 0.0) return 0.0;           // also -0.0 -> +0.0, like R_pow
+    return pow(x, y);
+#else
+    // exp(y log x): log(+-0) = -inf -> 0, x < 0 -> NaN, NaN -> NaN, like pow
+    return exp(y * log(x));
+#endif
+}
+
+// saturation_vapour_pressure_kpa(), R/sim_water.R:36-38 (Buck)
+__device__ __forceinline__ double svp_kpa(double t)
+{
+    return 0.61121 * exp((18.678 - MMS_DIVC(t, 234.5)) * (t / (257.14 + t)));
+}
+
+// evaporation_rate_kg_h() with surface_area_m2 = 1, R/sim_water.R:50-90,264-270.
+// p_a = air_pressure_kpa(altitude) (R/sim_water.R:41-46) is per cell.
+__device__ __forceinline__ double evaporation_rate(double t, double rh, double p_a, double wind)
+{
+    const double theta = 25.0 + 19.0 * wind;                   // :67
+    const double p_ws = svp_kpa(t);                            // :73
+    const double xs = 0.62198 * p_ws / (p_a - p_ws);           // :75
+    const double p_w = p_ws * MMS_DIVC(rh, 100.0);             // :84
+    const double x = 0.62198 * p_w / (p_a - p_w);              // :85
+    return theta * (xs - x);                                   // :88 (A = 1: theta * 1 == theta)
+}
+
+__device__ __forceinline__ double air_pressure_kpa(double altitude)
+{
+    return 101.325 - MMS_DIVC(1.2 * altitude, 100.0);          // R/sim_water.R:44-45
+}
+
+// ensure_positive(), R/utils.R:159-161: x * as.numeric(x > 0).  x > 0 -> x; +-0 -> +-0;
+// x < 0 -> -0.0; NaN -> NaN.  Also used by positive_spline(),
+// R/lifehistory_estimation_functions.R:236-250.
+__device__ __forceinline__ double ensure_positive(double v)
+{
+    return (v > 0.0) ? v : ((v != v) ? v : ((v == 0.0) ? v : -0.0));
+}
+
+// cone_volume_to_surface(), R/sim_water.R:24-31; cylinder is an EXTENSION
+__device__ __forceinline__ double habitat_surface(const HabitatDev &hb, double volume)
+{
+    if (hb.shape == 0) return 3.046474 * r_pow_pos(volume, 0.666667);
+    return (volume != volume) ? volume : ((volume > 0.0) ? hb.cyl_area : 0.0);
+}
+
+// iterate_cone_volume(), R/sim_water.R:94-132; `surface` is
+// habitat_surface(volume) (already known from the previous step's output).
+// gain = catchment_area * (rainfall / 1000), :122-123, is constant over a day.
+__device__ __forceinline__ double iterate_volume(const HabitatDev &hb, double volume, double surface,
+                                                 double evap_rate, double gain)
+{
+    const double loss = MMS_DIVC(evap_rate * surface, 1000.0); // :107,:113
+    double x = volume - loss;                                  // :116
+    x = x - hb.leak_per_hour * volume;                         // EXTENSION (leak = 0: x - 0 == x)
+    x = ensure_positive(x);                                    // R/utils.R:159-161
+    double y = x + gain;                                       // :126
+    if (y > hb.max_volume) y = hb.max_volume;                  // enforce_max(), R/utils.R:164-168
+    return y;
+}
+
+// State-independent part of iterate_state() for one hour.
+struct PopHour {
+    double surv_ad;     // ds ^ timestep                          R/sim_pop_dynamics.R:50
+    double emf;         // 1 - exp(-timestep * mdr)               :58-59
+    double one_m_emf;   // 1 - emergence_fraction                 :74
+    double egg;         // efd * timestep                         :62
+    double link0;       // logit(das0) or log(-log(1 - (1 - das0)))  densmod, state independent
+};
+
+__device__ __forceinline__ PopHour pop_hour(int densmod_type, double mdr, double efd, double das0, double ds)
+{
+    PopHour ph;
+    ph.surv_ad = r_pow_pos(ds, kTimestep);
+    const double e = exp(-(kTimestep * mdr));
+    ph.emf = 1.0 - e;
+#if MMS_STRICT
+    ph.one_m_emf = 1.0 - ph.emf;
+#else
+    ph.one_m_emf = e;
+#endif
+    ph.egg = efd * kTimestep;
+    if (densmod_type == 1) {
+        // cox_ph, R/lifehistory_estimation_functions.R:551-553
+        const double daily_mortality_zero_density = 1.0 - das0;
+#if MMS_STRICT
+        ph.link0 = log(-log(1.0 - daily_mortality_zero_density));
+#else
+        ph.link0 = log(1.0 - daily_mortality_zero_density);      // log p'; exp(loghaz) = -log p' * exp(dd*D)
+#endif
+    } else {
+        ph.link0 = log(das0 / (1.0 - das0));                     // logit(), :533,:571
+    }
+    return ph;
+}
+
+// iterate_state(), R/sim_pop_dynamics.R:14-96 (state dependent part)
+__device__ __forceinline__ void iterate_state(double &aquatic, double &adult, const PopHour &ph,
+                                              int densmod_type, double dd_effect, double area_cm2,
+                                              double larval_habitat_area)
+{
+    double aq = (aquatic != aquatic) ? 0.0 : aquatic;           // :33
+    double ad = (adult != adult) ? 0.0 : adult;                 // :34
+    const double density = aq / (larval_habitat_area + kEps);   // :42
+    const double density_dish = density * area_cm2;             // densmod :549 / :569
+    double surv_aq;
+#if MMS_STRICT
+    double das_t;
+    if (densmod_type == 1) {
+        const double loghaz = ph.link0 + dd_effect * density_dish;          // :556-557
+        const double daily_mortality = 1.0 - exp(-exp(loghaz));             // :560
+        das_t = 1.0 - daily_mortality;                                      // :562
+    } else {
+        const double lg = ph.link0 + dd_effect * density_dish;              // :574-575
+        das_t = 1.0 / (1.0 + exp(-lg));                                     // :537,:578
+    }
+    surv_aq = r_pow_pos(das_t, kTimestep);                                  // :49
+#else
+    if (densmod_type == 1) {
+        // exp(-exp(log(-log p') + dd*D)) = exp(log p' * exp(dd*D)); the reference's
+        // 1 - (1 - z) rounding (z < 1.1e-16 -> 0) is kept literally
+        const double z = exp(ph.link0 * exp(dd_effect * density_dish));
+        const double das_t = 1.0 - (1.0 - z);
+        surv_aq = r_pow_pos(das_t, kTimestep);
+    } else {
+        // das_t = 1 / (1 + e), e = exp(-lg);  das_t ^ (1/24) = exp(-log(1 + e) / 24)
+        const double lg = ph.link0 + dd_effect * density_dish;
+        const double e = exp(-lg);
+        surv_aq = exp(-kTimestep * log(1.0 + e));
+    }
+#endif
+    const double surviving_adult = ad * ph.surv_ad;             // :67
+    const double surviving_aquatic = aq * surv_aq;              // :68
+    const double new_aquatic = surviving_adult * ph.egg;        // :71
+    const double remaining_aquatic = surviving_aquatic * ph.one_m_emf;   // :74
+    const double new_adult = surviving_aquatic * ph.emf;        // :77
+    aquatic = remaining_aquatic + new_aquatic;                  // :92
+    adult = surviving_adult + new_adult + kEps;                 // :93
+}
+
+}  // namespace MMS_MODE
+}  // namespace mms

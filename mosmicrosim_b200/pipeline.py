@@ -1,0 +1,138 @@
+"""Host-side mirror of the reference's interface for the hot path: the same
+function names, argument names, defaults, error behaviour and output schema as
+R/sim_water.R, R/sim_pop_dynamics.R and R/pipeline_functions.R, with the
+arithmetic done by libmmsgpu on the GPU.  (R is not installed in this image,
+so this Python layer stands where the R functions of r-binding/R/gpu_backend.R
+stand in a real installation; both sit on the same C ABI.)
+
+R tibbles become plain dicts of numpy arrays; R matrices are numpy [n_times,
+n_pixels] arrays (stored column-major before they cross the ABI, like R).
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+from . import backend, dates
+from .lifehistory import Lifehistory, SurvDensmod
+
+SPECIES = ("An. gambiae", "An. stephensi")
+FORCING_VARS = ("tmin", "tmax", "rhmin", "rhmax", "wsmin", "wsmax", "ccmin", "ccmax", "rainfall_daily")
+VECTOR_VARIABLES = ("adult", "aquatic", "mdr", "efd", "das_zerodensity", "ds")   # R/pipeline_functions.R:1041-1048
+
+
+def _match_arg(value, choices, name):
+    if isinstance(value, (tuple, list)):
+        value = value[0]
+    if value not in choices:
+        raise ValueError(f"'{name}' should be one of " + ", ".join(repr(c) for c in choices))
+    return value
+
+
+# ---------------------------------------------------------------------------
+# numeric cores (matrix in / matrix out)
+# ---------------------------------------------------------------------------
+
+def simulate_ephemeral_habitat_vectorised(rainfall_matrix, air_temperature_matrix, humidity_matrix,
+                                          windspeed_matrix, altitude_vector=None, initial_volume=0,
+                                          burnin_years=0, max_cone_depth=1, inflow_multiplier=1, *,
+                                          shape="cone", radius=1.0, leak_per_hour=0.0,
+                                          math_mode="fast", device=0):
+    """simulate_ephemeral_habitat_vectorised(), R/sim_water.R:216-301.  Returns
+    {"water_surface_area": [n_times, n_pixels]}.  The keyword-only arguments are
+    extensions (cylinder / leakage; math mode; device)."""
+    rainfall_matrix = np.asarray(rainfall_matrix, dtype=np.float64)
+    if altitude_vector is None:
+        altitude_vector = np.zeros(rainfall_matrix.shape[1])
+    hb = backend.make_habitat(shape={"cone": 0, "cylinder": 1}[shape], max_depth=max_cone_depth, radius=radius,
+                              inflow_multiplier=inflow_multiplier, leak_per_hour=leak_per_hour,
+                              initial_volume=initial_volume)
+    res = backend.water_vectorised(rainfall_matrix, air_temperature_matrix, humidity_matrix, windspeed_matrix,
+                                   altitude_vector, hb, burnin_years=burnin_years, math_mode=math_mode,
+                                   device=device)
+    return {"water_surface_area": res["water_surface_area"]}
+
+
+def simulate_population_vectorised(larval_habitat_area_matrix, mdr_matrix, efd_matrix, das_zerodensity_matrix,
+                                   ds_matrix, das_densmod_function: SurvDensmod, initial_adult=100,
+                                   initial_aquatic=100, burnin_years=1, *, math_mode="fast", device=0):
+    """simulate_population_vectorised(), R/sim_pop_dynamics.R:208-284.  Returns
+    {"aquatic": ..., "adult": ...} as [n_times, n_pixels] matrices."""
+    dm = backend.make_densmod(das_densmod_function.type, das_densmod_function.dd_effect,
+                              das_densmod_function.surface_area_cm2)
+    return backend.population_vectorised(larval_habitat_area_matrix, mdr_matrix, efd_matrix,
+                                         das_zerodensity_matrix, ds_matrix, dm, initial_adult=initial_adult,
+                                         initial_aquatic=initial_aquatic, burnin_years=burnin_years,
+                                         math_mode=math_mode, device=device)
+
+
+# ---------------------------------------------------------------------------
+# the pipeline (tc_to_vectors() after terraclimate_to_monthly_climate())
+# ---------------------------------------------------------------------------
+
+def _monthly_array(pixel_monthly_climate):
+    m = pixel_monthly_climate
+    start, end = np.asarray(m["start"], "datetime64[D]"), np.asarray(m["end"], "datetime64[D]")
+    M = len(start)
+    cols = []
+    for v in FORCING_VARS:
+        a = np.asarray(m[v], dtype=np.float64)
+        if a.ndim == 1:
+            a = a[:, None]
+        if a.shape[0] != M:
+            raise ValueError(f"monthly variable {v} must have one row per month")
+        cols.append(a)
+    monthly = np.ascontiguousarray(np.stack(cols, axis=0))            # [9][M][C]
+    altitude = np.atleast_1d(np.asarray(m["altitude"], dtype=np.float64))
+    return start, end, monthly, altitude
+
+
+def monthly_climate_to_vectors(pixel_monthly_climate, lifehistory_functions, species=SPECIES,
+                               included_dates=None, aggregate_by="month", dates_predict=None, *,
+                               habitats=None, model_water_temperature=False, water_shade_proportion=1,
+                               burnin_years_pop=1, extra_variables=(), math_mode="fast", devices=None):
+    """tc_to_vectors() (R/pipeline_functions.R:1099-1130) from
+    interpolate_daily_climate() to summarise_vectors(), for a whole tile in one
+    fused kernel launch per device.
+
+    pixel_monthly_climate: dict with start[M], end[M] (dates), altitude[C],
+      longitude[C], latitude[C] (carried through) and the nine monthly
+      variables as [M, C] arrays (the `monthly_climate` tibbles of
+      terraclimate_to_monthly_climate(), side by side).
+    lifehistory_functions: {"An_gambiae": Lifehistory, "An_stephensi": Lifehistory}
+      (the reference's sysdata object of the same name).
+    Returns a dict: longitude, latitude, species, start[P], end[P] and one
+    [P, C] array per vector variable -- the `pixel_vectors` tibbles side by side.
+    """
+    species = _match_arg(species, SPECIES, "species")
+    aggregate_by = _match_arg(aggregate_by, ("month", "day"), "aggregate_by")
+    # simulate_hourly_conditions() argument handling, R/pipeline_functions.R:324-338
+    if water_shade_proportion != 1 and not model_water_temperature:
+        warnings.warn("water temperature is not being modelled, so water_shade_proportion argument is ignored")
+    if model_water_temperature:
+        raise NotImplementedError("model of water temperature not yet implemented, "
+                                  "model_water_temperature must be set to FALSE")
+    lh: Lifehistory = lifehistory_functions[{"An. gambiae": "An_gambiae", "An. stephensi": "An_stephensi"}[species]]
+    start, end, monthly, altitude = _monthly_array(pixel_monthly_climate)
+    if dates_predict is None:
+        dates_predict = dates.default_dates_predict(start, end)
+    mid_day, day_predict = dates.datenums(start, end, dates_predict)
+    period_of_day, p_start, p_end = dates.period_index(dates_predict, aggregate_by, included_dates)
+    if habitats is None:      # R/pipeline_functions.R:431-441
+        habitats = [dict(shape=0, max_depth=1.0, radius=1.0, inflow_multiplier=1.0, leak_per_hour=0.0,
+                         initial_volume=0.0)]
+    names = list(VECTOR_VARIABLES) + [v for v in extra_variables if v not in VECTOR_VARIABLES]
+    out = backend.run_chain(
+        monthly, altitude, mid_day=mid_day, day_predict=day_predict, habitats=habitats,
+        densmod=backend.make_densmod(lh.das_densmod.type, lh.das_densmod.dd_effect, lh.das_densmod.surface_area_cm2),
+        tables=lh.tables(), period_of_day=period_of_day, n_periods=len(p_start), burnin_years_water=0,
+        burnin_years_pop=burnin_years_pop, mean_vars=names, want_wet_hours=True, math_mode=math_mode,
+        devices=devices)
+    res = {"longitude": pixel_monthly_climate.get("longitude"), "latitude": pixel_monthly_climate.get("latitude"),
+           "species": species, "start": p_start, "end": p_end, "wet_hours": out["wet_hours"]}
+    for k, v in enumerate(out["mean_state_vars"]):
+        res[v] = out["mean_state"][:, k] if len(habitats) > 1 else out["mean_state"][0, k]
+    for k, v in enumerate(out["mean_forcing_vars"]):
+        res[v] = out["mean_forcing"][k]
+    return res

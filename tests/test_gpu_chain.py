@@ -1,0 +1,141 @@
+"""GPU parity: the fused sm_100a chain (through the C ABI) against the CPU oracle."""
+import numpy as np
+import pytest
+
+from helpers import ABS_FLOOR, ORACLE_VAR, REL_TOL_FAST, REL_TOL_STRICT, Case, rel_err
+from mosmicrosim_b200 import backend, synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+ALL_VARS = [v for v in backend.VAR_NAMES if v != "cloudcover"]
+
+
+def compare(case, out, ref, tol, what=("mean", "hourly")):
+    worst = {}
+    flips = 0
+    if "hourly" in what and "hourly_state" in out:
+        for k, v in enumerate(out["hourly_state_vars"]):
+            e = rel_err(out["hourly_state"][:, k], ref["hourly"][:, ORACLE_VAR[v]])
+            worst["hourly " + v] = e
+        for k, v in enumerate(out["hourly_forcing_vars"]):
+            if v == "cloudcover":
+                continue
+            e = rel_err(out["hourly_forcing"][k], ref["hourly"][0, ORACLE_VAR[v]])
+            worst["hourly " + v] = e
+        if "wet_flags" in out:
+            flips = int((out["wet_flags"] != ref["wet"]).sum())
+    if "mean" in what and "mean_state" in out:
+        for k, v in enumerate(out["mean_state_vars"]):
+            worst["mean " + v] = rel_err(out["mean_state"][:, k], ref["mean"][:, ORACLE_VAR[v]])
+        for k, v in enumerate(out["mean_forcing_vars"]):
+            if v == "cloudcover":
+                continue
+            worst["mean " + v] = rel_err(out["mean_forcing"][k], ref["mean"][0, ORACLE_VAR[v]])
+        if "wet_hours" in out:
+            flips += int((out["wet_hours"] != ref["wet_hours"]).sum())
+    bad = {k: v for k, v in worst.items() if not v <= tol}
+    assert not bad, f"parity beyond {tol}: {bad} (all: {worst})"
+    assert flips == 0, f"{flips} wet/dry flag or wet-hour-count mismatches"
+    return worst
+
+
+@pytest.mark.parametrize("mode,tol", [("strict", REL_TOL_STRICT), ("fast", REL_TOL_FAST)])
+def test_chain_hourly_and_monthly_cone(gpu, mode, tol):
+    """cfg1-like: cone/no-leak (the reference's water body), 1 year, full series + monthly means."""
+    case = Case(n_cells=70)
+    ref = case.oracle()
+    out = backend.run_chain(case.monthly, case.altitude, **case.gpu_kwargs(
+        mean_vars=ALL_VARS, hourly_vars=ALL_VARS, want_wet_hours=True, want_wet_flags=True, math_mode=mode))
+    worst = compare(case, out, ref, tol)
+    print(mode, worst)
+
+
+@pytest.mark.parametrize("mode,tol", [("strict", REL_TOL_STRICT), ("fast", REL_TOL_FAST)])
+def test_chain_two_habitats_pipeline_vars(gpu, mode, tol):
+    """cfg2-like: cone + cylinder with leakage, the six reference variables, monthly means only."""
+    case = Case(n_cells=300, habitats=[syn.habitat_cone(), syn.habitat_cylinder(leak_per_hour=0.002)])
+    ref = case.oracle(want_hourly=False)
+    out = backend.run_chain(case.monthly, case.altitude, **case.gpu_kwargs(
+        mean_vars=list(backend.VAR_NAMES[:6]), want_wet_hours=True, math_mode=mode))
+    compare(case, out, ref, tol, what=("mean",))
+
+
+def test_chain_cox_ph_species(gpu):
+    case = Case(n_cells=64, species="An. stephensi")
+    ref = case.oracle()
+    for mode, tol in (("strict", REL_TOL_STRICT), ("fast", REL_TOL_FAST)):
+        out = backend.run_chain(case.monthly, case.altitude, **case.gpu_kwargs(
+            mean_vars=ALL_VARS, hourly_vars=["adult", "aquatic"], want_wet_flags=True, math_mode=mode))
+        compare(case, out, ref, tol)
+
+
+def test_chain_four_settings_and_daily_periods(gpu):
+    habs = syn.habitat_ensemble(4)
+    case = Case(n_cells=40, habitats=habs, aggregate_by="day")
+    ref = case.oracle(want_hourly=False)
+    out = backend.run_chain(case.monthly, case.altitude, **case.gpu_kwargs(
+        mean_vars=ALL_VARS, want_wet_hours=True, math_mode="fast"))
+    compare(case, out, ref, REL_TOL_FAST, what=("mean",))
+
+
+def test_chain_default_dates_included_dates_and_water_burnin(gpu):
+    """dates_predict = mid-first-month .. mid-last-month (the reference default), summaries only
+    over included_dates, water burn-in year on."""
+    case0 = Case(n_cells=33, default_dates=True)
+    included = syn.year_dates(2001, 1)[40:300]
+    case = Case(n_cells=33, default_dates=True, included=included)
+    assert case.D == case0.D and case.P < case0.P
+    ref = case.oracle(want_hourly=False, burnin_years_water=1, burnin_years_pop=2)
+    out = backend.run_chain(case.monthly, case.altitude, **case.gpu_kwargs(
+        mean_vars=ALL_VARS, want_wet_hours=True, math_mode="strict", burnin_years_water=1, burnin_years_pop=2))
+    compare(case, out, ref, REL_TOL_STRICT, what=("mean",))
+
+
+def test_chain_three_settings_odd(gpu):
+    """S = 3 exercises the one-setting-per-thread kernel with grid.y = 3."""
+    case = Case(n_cells=20, habitats=syn.habitat_ensemble(3))
+    ref = case.oracle(want_hourly=False)
+    out = backend.run_chain(case.monthly, case.altitude, **case.gpu_kwargs(
+        mean_vars=list(backend.VAR_NAMES[:8]), math_mode="fast"))
+    compare(case, out, ref, REL_TOL_FAST, what=("mean",))
+
+
+def test_plan_matches_one_shot_and_is_repeatable(gpu):
+    case = Case(n_cells=200)
+    kw = case.gpu_kwargs(mean_vars=list(backend.VAR_NAMES[:6]), want_wet_hours=True)
+    one = backend.run_chain(case.monthly, case.altitude, **kw)
+    with backend.ChainPlan(case.C, **kw) as plan:
+        plan.upload(case.monthly, case.altitude)
+        plan.launch()
+        a = plan.download(plan.allocate_outputs())
+        plan.launch()                       # relaunch on resident inputs: identical bits
+        b = plan.download(plan.allocate_outputs())
+        assert plan.kernel_ms() > 0
+        assert plan.launch_count() >= 3
+    for k in ("mean_state", "mean_forcing", "wet_hours"):
+        assert np.array_equal(one[k], a[k], equal_nan=True)
+        assert np.array_equal(a[k], b[k], equal_nan=True)
+
+
+def test_errors(gpu):
+    case = Case(n_cells=8)
+    kw = case.gpu_kwargs(mean_vars=["adult"])
+    # extrapolation: a prediction day before the first knot
+    bad = dict(kw, day_predict=case.day_predict - 400.0)
+    with pytest.raises(backend.MmsError) as e:
+        backend.run_chain(case.monthly, case.altitude, **bad)
+    assert e.value.code == "MMS_ERR_EXTRAPOLATION"
+    # burn-in longer than the series
+    short = Case(n_cells=8)
+    kw2 = dict(short.gpu_kwargs(mean_vars=["adult"]))
+    kw2["day_predict"] = short.day_predict[:100]
+    kw2["period_of_day"] = short.period_of_day[:100]
+    with pytest.raises(backend.MmsError) as e:
+        backend.run_chain(short.monthly, short.altitude, **kw2)
+    assert e.value.code == "MMS_ERR_BURNIN"
+    # NA in the forcing
+    m = case.monthly.copy()
+    m[1, 3, 5] = np.nan
+    with pytest.raises(backend.MmsError) as e:
+        backend.run_chain(m, case.altitude, **kw)
+    assert e.value.code == "MMS_ERR_NONFINITE"
