@@ -1,10 +1,20 @@
 // chain_kernel.cuh -- the fused per-cell chain: monthly forcing -> daily
 // (approx) -> hourly (SINEC / VSINE) -> evaporation -> water body ->
-// life-history parameters -> population -> period summaries, one thread per
+// life-history parameters -> population -> period summaries.  One thread per
 // cell, the whole hourly time loop inside the kernel, state in registers.
 //
-// Included by chain_fast.cu (MMS_STRICT=0) and chain_strict.cu (MMS_STRICT=1).
-// Citations are relative to the reference root.
+// Execution shape (B200: 148 SMs, FP64 pipe = 1 warp instruction / 2 cycles / SMSP):
+//   * one persistent CTA per SM; the three spline tables (96 KB) and the ds grid
+//     axes are staged in shared memory ONCE per SM,
+//   * work unit = 32 adjacent cells x one group of kNS habitat settings; warps
+//     fetch units from a global counter, so the number of warps per CTA can be
+//     chosen on the host to make the rounds come out even,
+//   * the hour loop is software pipelined: the state-independent half of hour
+//     h+1 (microclimate, evaporation rate, life-history tables, ds^(1/24), ...)
+//     is issued next to the state-dependent half of hour h (water body and
+//     population recursions), giving every warp two independent FP64 chains.
+//
+// Included by chain_tu.cu for MMS_STRICT=0 and 1.  Citations: reference root.
 #pragma once
 
 #include "mms_math.cuh"
@@ -33,7 +43,7 @@ __device__ __forceinline__ double knot_interp(const double *__restrict__ col, in
 template <bool kCloud>
 __device__ __forceinline__ Daily load_daily(const ChainParams &p, int64_t cell, int day, int &bad)
 {
-    const DayEntry de = p.days[day];                     // uniform across the block
+    const DayEntry de = p.days[day];                     // uniform across the warp
     const int64_t cs = p.c_stride;
     const double *base = p.monthly + cell;
     const int64_t vs = (int64_t)p.M * cs;                // variable stride
@@ -57,18 +67,33 @@ __device__ __forceinline__ Daily load_daily(const ChainParams &p, int64_t cell, 
     return d;
 }
 
-// ---- life-history tables ------------------------------------------------
+// ---- life-history tables (shared memory) -------------------------------------
+struct SmemTables {
+    const double *sx;      // [n] spline knots
+    const double *coef;    // [n][3][4]
+    const double *gx, *gy; // ds grid axes
+};
+
 // spline_eval() (base R splines.c) interval: largest i with x[i] <= u, 0 below the
 // first knot, n-1 at or beyond the last one.
 __device__ __forceinline__ int spline_interval(const SplineDev &sp, const double *__restrict__ xs, double u)
 {
     const int n = sp.n;
+#if MMS_STRICT
     double g = (u - sp.x0) * sp.inv_step;
     g = fmin(fmax(g, 0.0), (double)(n - 1));             // NaN -> 0
     int i = (int)g;
     while (i > 0 && u < xs[i]) --i;
     while (i < n - 1 && !(u < xs[i + 1])) ++i;
     return i;
+#else
+    // fast mode runs only on knots the host verified to be equally spaced: direct index,
+    // no search.  A last-bit slip to the neighbouring interval changes the value by
+    // O(dx^3 * 1e-16) because the spline is C2.
+    (void)xs;
+    const int i = __double2int_rd((u - sp.x0) * sp.inv_step);   // NaN -> 0
+    return min(max(i, 0), n - 1);
+#endif
 }
 
 // fields::interp.surface() on the ds(T, RH) grid, R/lifehistory_estimation_functions.R:1144-1190
@@ -87,10 +112,11 @@ __device__ __forceinline__ double approx_index(const double *__restrict__ x, int
     return (double)(i + 1) + 1.0 * ((v - xi) / (xj - xi));
 }
 
-__device__ __forceinline__ double ds_surface(const SurfaceDev &g, double temperature, double humidity)
+__device__ __forceinline__ double ds_surface(const SurfaceDev &g, const SmemTables &tb, double temperature, double humidity)
 {
-    double lx = approx_index(g.x, g.nx, g.x0, g.inv_dx, temperature);
-    double ly = approx_index(g.y, g.ny, g.y0, g.inv_dy, humidity);
+#if MMS_STRICT
+    double lx = approx_index(tb.gx, g.nx, g.x0, g.inv_dx, temperature);
+    double ly = approx_index(tb.gy, g.ny, g.y0, g.inv_dy, humidity);
     if (lx != lx || ly != ly) return __longlong_as_double(0x7ff8000000000000LL);   // NA outside the grid
     double lx1 = floor(lx), ly1 = floor(ly);
     double ex = lx - lx1, ey = ly - ly1;
@@ -101,29 +127,107 @@ __device__ __forceinline__ double ds_surface(const SurfaceDev &g, double tempera
     const double2 a = __ldg(q), b = __ldg(q + 1);        // (z00, z10), (z01, z11)
     return a.x * (1.0 - ex) * (1.0 - ey) + a.y * ex * (1.0 - ey) +
            b.x * (1.0 - ex) * ey + b.y * ex * ey;
+#else
+    // fast mode runs only on axes the host verified to be equally spaced: the fractional
+    // index is (v - x0) / dx directly, no search and no axis loads; branch free, NaN
+    // (the reference's NA) outside the grid is selected at the end.
+    (void)tb;
+    const bool inside = temperature >= g.x0 && temperature <= g.x1 && humidity >= g.y0 && humidity <= g.y1;
+    const double fx = (temperature - g.x0) * g.inv_dx, fy = (humidity - g.y0) * g.inv_dy;
+    int i = __double2int_rd(fx), j = __double2int_rd(fy);     // NaN -> 0
+    i = min(max(i, 0), g.nx - 2);
+    j = min(max(j, 0), g.ny - 2);
+    const double ex = fx - (double)i, ey = fy - (double)j;    // == 1 on the last grid line
+    const double2 *q = reinterpret_cast<const double2 *>(g.quad) + (i + (g.nx - 1) * j) * 2;
+    const double2 a = __ldg(q), b = __ldg(q + 1);             // (z00, z10), (z01, z11)
+    const double mx = 1.0 - ex, my = 1.0 - ey;
+    const double v = (a.x * mx + a.y * ex) * my + (b.x * mx + b.y * ex) * ey;
+    return inside ? v : __longlong_as_double(0x7ff8000000000000LL);
+#endif
 }
 
-// ---- the kernel -----------------------------------------------------------
-// kNS     : habitat settings integrated per thread (they share all forcing-derived work)
-// kFull   : false = only the reference's six vector_variables can be summarised / written;
-//           true  = all MMS_NVARS (adds water body and microclimate variables, cloud cover)
-// kHourly : write full hourly series
-template <int kNS, bool kFull, bool kHourly>
-__global__ void __launch_bounds__(kBlock)
-chain_kernel(const __grid_constant__ ChainParams p)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *s_x = reinterpret_cast<double *>(smem_raw);                 // [n]
-    double *s_coef = s_x + ((p.spline.n + 1) & ~1);                     // [n][3][4]
-    for (int k = threadIdx.x; k < p.spline.n; k += blockDim.x) s_x[k] = p.spline.x[k];
-    for (int k = threadIdx.x; k < p.spline.n * 12; k += blockDim.x) s_coef[k] = p.spline.coef[k];
-    __syncthreads();
+// ---- state-independent half of one hour ---------------------------------------
+struct DayCtx {          // everything the hourly curves need about yesterday / today / tomorrow
+    Daily cur, nxt;
+    double A, t_sunset, t_midnight_prev, rhmin_prev, wsmax_prev, ccmin_prev;
+};
 
-    const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // < c_stride (padded)
-    const int set0 = blockIdx.y * kNS;
+struct HourF {
+    double air_t, rh, wind, cloud;     // hourly microclimate
+    double evap;                       // evaporation rate per unit area
+    double mdr, efd, das0, ds;         // life-history parameters
+    PopHour ph;
+};
+
+template <bool kFull>
+__device__ __forceinline__ HourF hour_forcing(const ChainParams &p, const SmemTables &tb, const DayCtx &dc,
+                                              double p_a, int h, bool water_only)
+{
+    HourF f;
+    // ---- SINEC air temperature, R/sim_microclimate.R:185-285 (hour = h + 1, times = 100 * hour)
+#if !MMS_STRICT
+    {   // the three segments as one fma with warp-uniform selects (no branch in the hour loop):
+        // pre-dawn  tmin + (Tmidnight_yesterday - tmin) * (1 - t/600)            :275-277
+        // daylight  A * Z(t) + tmin + A                                          :255-256
+        // night     (Tsunset - tmin_tomorrow) * (1 / exp(tau * tss)) + tmin_tomorrow   :260-262
+        const bool pre = h < 5, night = h > 17;
+        const double base = night ? dc.nxt.tmin : dc.cur.tmin;
+        const double amp = pre ? (dc.t_midnight_prev - dc.cur.tmin) : (night ? (dc.t_sunset - dc.nxt.tmin) : dc.A);
+        const double add = (pre || night) ? 0.0 : dc.A;
+        f.air_t = fma(amp, p.hr.air_coef[h], base) + add;
+    }
+#else
+    if (h < 5) {                     // times < time_sunrise: pre-dawn ramp, :275-277
+        f.air_t = dc.cur.tmin + (dc.t_midnight_prev - dc.cur.tmin) * p.hr.predawn[h];
+    } else if (h <= 17) {            // 600 <= times <= 1800: sine, :255-256
+        f.air_t = dc.A * p.hr.z_light[h] + dc.cur.tmin + dc.A;
+    } else {                         // night: exponential decay, :260-262
+        f.air_t = (dc.t_sunset - dc.nxt.tmin) / p.hr.exp_e[h] + dc.nxt.tmin;
+    }
+#endif
+    // ---- VSINE humidity / wind speed [/ cloud cover], :466-566
+    const bool before_sunrise = h < 5;          // times < 6
+    const bool after_inflection = h > 12;       // times > 13
+    double inf_last = before_sunrise ? dc.rhmin_prev : dc.cur.rhmin;       // :529-530
+    double sun_next = after_inflection ? dc.nxt.rhmax : dc.cur.rhmax;      // :548-549
+    f.rh = inf_last + p.hr.w_vsine[h] * (sun_next - inf_last);             // :556-557
+    inf_last = before_sunrise ? dc.wsmax_prev : dc.cur.wsmax;
+    sun_next = after_inflection ? dc.nxt.wsmin : dc.cur.wsmin;
+    f.wind = sun_next + p.hr.w_vsine_inv[h] * (inf_last - sun_next);       // :553-554
+    f.cloud = 0.0;
+    if (kFull) {
+        inf_last = before_sunrise ? dc.ccmin_prev : dc.cur.ccmin;
+        sun_next = after_inflection ? dc.nxt.ccmax : dc.cur.ccmax;
+        f.cloud = inf_last + p.hr.w_vsine[h] * (sun_next - inf_last);
+    }
+    // ---- evaporation rate per unit area, R/sim_water.R:264-270 (air temperature)
+    f.evap = evaporation_rate(f.air_t, f.rh, p_a, f.wind);
+    // ---- life-history parameters, R/sim_pop_dynamics.R:100-135
+    // water_temperature = air_temperature, R/sim_microclimate.R:163
+    f.mdr = f.efd = f.das0 = f.ds = 0.0;
+    if (!water_only) {
+        const int i = spline_interval(p.spline, tb.sx, f.air_t);
+        const double dx = f.air_t - tb.sx[i];
+        const double4 *cf = reinterpret_cast<const double4 *>(tb.coef + (size_t)i * 12);
+        const double4 c0 = cf[0], c1 = cf[1], c2 = cf[2];
+        f.mdr = ensure_positive(c0.x + dx * (c0.y + dx * (c0.z + dx * c0.w)));
+        f.efd = ensure_positive(c1.x + dx * (c1.y + dx * (c1.z + dx * c1.w)));
+        f.das0 = ensure_positive(c2.x + dx * (c2.y + dx * (c2.z + dx * c2.w)));
+        f.ds = ds_surface(p.ds, tb, f.air_t, f.rh);
+        f.ph = pop_hour(p.densmod_type, f.mdr, f.efd, f.das0, f.ds);
+    }
+    return f;
+}
+
+// ---- one work unit: 32 cells x kNS settings, all passes, all hours ------------
+template <int kNS, bool kFull, bool kHourly>
+__device__ __forceinline__ void simulate_unit(const ChainParams &p, const SmemTables &tb, int64_t cell, int set0,
+                                              bool write_forcing)
+{
     const bool live = cell < p.n_cells;
     const int64_t cs = p.c_stride;
     const int H = 24 * p.D;
+    constexpr int kNF = kFull ? 9 : 4;
 
     const double p_a = air_pressure_kpa(__ldg(p.altitude + cell));
     int bad = 0;
@@ -136,21 +240,18 @@ chain_kernel(const __grid_constant__ ChainParams p)
     const int n_mean_state = __popc(p.mean_mask & kState);
     const int n_hourly_state = __popc(p.hourly_mask & kState);
 
-    double volume[kNS], surface[kNS], aquatic[kNS], adult[kNS];
+    double volume[kNS], surface[kNS], aquatic[kNS], adult[kNS], vol_after_water_burnin[kNS];
 #pragma unroll
     for (int s = 0; s < kNS; ++s) {
         aquatic[s] = p.initial_aquatic;                  // R/sim_pop_dynamics.R:249-252
         adult[s] = p.initial_adult;
         volume[s] = p.hab[set0 + s].initial_volume;      // R/sim_water.R:277
+        vol_after_water_burnin[s] = volume[s];
     }
 
-    // passes: water burn-in years (water only), population burn-in years (first
-    // 8760 steps, R/sim_pop_dynamics.R:221-226), then the full series
+    // passes: water burn-in years (water only, R/sim_water.R:228-233), population
+    // burn-in years (first 8760 steps, R/sim_pop_dynamics.R:221-226), then the full series
     const int n_pass = p.burnin_years_water + p.burnin_years_pop + 1;
-    double vol_after_water_burnin[kNS];
-#pragma unroll
-    for (int s = 0; s < kNS; ++s) vol_after_water_burnin[s] = volume[s];
-
     for (int pass = 0; pass < n_pass; ++pass) {
         const bool water_only = pass < p.burnin_years_water;
         const bool final_pass = pass == n_pass - 1;
@@ -168,25 +269,28 @@ chain_kernel(const __grid_constant__ ChainParams p)
 #pragma unroll
         for (int s = 0; s < kNS; ++s) surface[s] = habitat_surface(p.hab[set0 + s], volume[s]);
 
-        // period accumulators
+        // period accumulators (aggregate_vectors(), R/pipeline_functions.R:1030-1091)
         double acc_state[kNS][4];      // adult, aquatic, area, volume
-        double acc_forc[kFull ? 9 : 4];// mdr, efd, das0, ds [, airT, RH, wind, rain, cloud]
+        double acc_forc[kNF];          // mdr, efd, das0, ds [, airT, RH, wind, rain, cloud]
         int acc_wet[kNS];
         int acc_n = 0, cur_period = -1;
+        auto reset_acc = [&]() {
 #pragma unroll
-        for (int s = 0; s < kNS; ++s) {
-            acc_wet[s] = 0;
+            for (int s = 0; s < kNS; ++s) {
+                acc_wet[s] = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) acc_state[s][k] = 0.0;
-        }
+                for (int k = 0; k < 4; ++k) acc_state[s][k] = 0.0;
+            }
 #pragma unroll
-        for (int k = 0; k < (kFull ? 9 : 4); ++k) acc_forc[k] = 0.0;
+            for (int k = 0; k < kNF; ++k) acc_forc[k] = 0.0;
+            acc_n = 0;
+        };
+        reset_acc();
 
         auto flush = [&](int period) {
             if (!live) return;
-            const double inv_n = 1.0 / (double)acc_n;
-            (void)inv_n;
             const int64_t pc = (int64_t)period * cs + cell;
+            const double n = (double)acc_n;
 #pragma unroll
             for (int s = 0; s < kNS; ++s) {
                 const int vid[4] = {MMS_V_ADULT, MMS_V_AQUATIC, MMS_V_LARVAL_HABITAT_AREA, MMS_V_WATER_VOLUME};
@@ -195,33 +299,33 @@ chain_kernel(const __grid_constant__ ChainParams p)
                     if (!kFull && k >= 2) continue;
                     if (p.mean_mask & (1u << vid[k])) {
                         const int64_t row = (int64_t)(set0 + s) * n_mean_state + slot(p.mean_mask, kState, vid[k]);
-                        p.mean_state[row * p.P * cs + pc] = acc_state[s][k] / (double)acc_n;
+                        p.mean_state[row * p.P * cs + pc] = acc_state[s][k] / n;
                     }
                 }
                 if (p.wet_hours) p.wet_hours[(int64_t)(set0 + s) * p.P * cs + pc] = acc_wet[s];
             }
-            if (blockIdx.y == 0) {
+            if (write_forcing) {
                 const int vid[9] = {MMS_V_MDR, MMS_V_EFD, MMS_V_DAS_ZERODENSITY, MMS_V_DS, MMS_V_AIR_TEMPERATURE,
                                     MMS_V_HUMIDITY, MMS_V_WINDSPEED, MMS_V_RAINFALL, MMS_V_CLOUDCOVER};
 #pragma unroll
-                for (int k = 0; k < (kFull ? 9 : 4); ++k) {
+                for (int k = 0; k < kNF; ++k) {
                     if (p.mean_mask & (1u << vid[k])) {
                         const int64_t row = slot(p.mean_mask, ~kState, vid[k]);
-                        p.mean_forcing[row * p.P * cs + pc] = acc_forc[k] / (double)acc_n;
+                        p.mean_forcing[row * p.P * cs + pc] = acc_forc[k] / n;
                     }
                 }
             }
         };
 
         // day window: today, tomorrow; carried values of yesterday
-        Daily cur = load_daily<kFull>(p, cell, 0, bad);
-        Daily nxt = load_daily<kFull>(p, cell, (p.D > 1) ? 1 : 0, bad);
-        double A = MMS_DIVC(cur.tmax - cur.tmin, 2.0);                        // R/sim_microclimate.R:217
-        double t_sunset = A * p.hr.z_night + cur.tmin + A;                    // :220
-        double t_sunset_prev = t_sunset;                                      // :223 (first day: its own)
+        DayCtx dc;
+        dc.cur = load_daily<kFull>(p, cell, 0, bad);
+        dc.nxt = load_daily<kFull>(p, cell, (p.D > 1) ? 1 : 0, bad);
+        dc.A = MMS_DIVC(dc.cur.tmax - dc.cur.tmin, 2.0);                       // R/sim_microclimate.R:217
+        dc.t_sunset = dc.A * p.hr.z_night + dc.cur.tmin + dc.A;                // :220
         // :271-272 (first day: its own midnight = night curve at t = 2400)
-        double t_midnight_prev = (t_sunset - nxt.tmin) / p.hr.exp_e[23] + nxt.tmin;
-        double rhmin_prev = cur.rhmin, wsmax_prev = cur.wsmax, ccmin_prev = cur.ccmin;   // :522
+        dc.t_midnight_prev = (dc.t_sunset - dc.nxt.tmin) / p.hr.exp_e[23] + dc.nxt.tmin;
+        dc.rhmin_prev = dc.cur.rhmin; dc.wsmax_prev = dc.cur.wsmax; dc.ccmin_prev = dc.cur.ccmin;   // :522
 
         for (int day = 0; day < n_days; ++day) {
             const bool record = final_pass;
@@ -230,80 +334,33 @@ chain_kernel(const __grid_constant__ ChainParams p)
                 period = p.period_of_day[day];
                 if (period >= 0 && period != cur_period) {
                     if (cur_period >= 0) flush(cur_period);
-#pragma unroll
-                    for (int s = 0; s < kNS; ++s) {
-                        acc_wet[s] = 0;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) acc_state[s][k] = 0.0;
-                    }
-#pragma unroll
-                    for (int k = 0; k < (kFull ? 9 : 4); ++k) acc_forc[k] = 0.0;
-                    acc_n = 0;
+                    reset_acc();
                     cur_period = period;
                 }
             }
             const bool accumulate = period >= 0;
 
-            const double rain_h = MMS_DIVC(cur.rain, 24.0);                   // R/sim_microclimate.R:132
+            const double rain_h = MMS_DIVC(dc.cur.rain, 24.0);                // R/sim_microclimate.R:132
             const double gain_m_h = MMS_DIVC(rain_h, 1000.0);                 // R/sim_water.R:122
             double gain[kNS];
 #pragma unroll
             for (int s = 0; s < kNS; ++s) gain[s] = p.hab[set0 + s].catchment_area * gain_m_h;   // :123
 
-            double air_t = 0.0;
+            HourF f = hour_forcing<kFull>(p, tb, dc, p_a, 0, water_only);
 #pragma unroll 1
-            for (int h = 0; h < 24; ++h) {       // hour = h + 1, times = 100 * (h + 1)
-                // ---- SINEC air temperature, R/sim_microclimate.R:185-285
-                if (h < 5) {                     // times < time_sunrise: pre-dawn ramp, :275-277
-                    air_t = cur.tmin + (t_midnight_prev - cur.tmin) * p.hr.predawn[h];
-                } else if (h <= 17) {            // 600 <= times <= 1800: sine, :255-256
-                    air_t = A * p.hr.z_light[h] + cur.tmin + A;
-                } else {                         // night: exponential decay, :260-262
-                    air_t = (t_sunset - nxt.tmin) / p.hr.exp_e[h] + nxt.tmin;
-                }
-                // ---- VSINE humidity / wind speed [/ cloud cover], :466-566
-                const bool before_sunrise = h < 5;          // times < 6
-                const bool after_inflection = h > 12;       // times > 13
-                double inf_last = before_sunrise ? rhmin_prev : cur.rhmin;       // :529-530
-                double sun_next = after_inflection ? nxt.rhmax : cur.rhmax;      // :548-549
-                const double rh = inf_last + p.hr.w_vsine[h] * (sun_next - inf_last);       // :556-557
-                inf_last = before_sunrise ? wsmax_prev : cur.wsmax;
-                sun_next = after_inflection ? nxt.wsmin : cur.wsmin;
-                const double wind = sun_next + p.hr.w_vsine_inv[h] * (inf_last - sun_next); // :553-554
-                double cloud = 0.0;
-                if (kFull) {
-                    inf_last = before_sunrise ? ccmin_prev : cur.ccmin;
-                    sun_next = after_inflection ? nxt.ccmax : cur.ccmax;
-                    cloud = inf_last + p.hr.w_vsine[h] * (sun_next - inf_last);
-                }
+            for (int h = 0; h < 24; ++h) {
+                // software pipeline: state-independent half of hour h + 1 ...
+                HourF fn = f;
+                if (h < 23) fn = hour_forcing<kFull>(p, tb, dc, p_a, h + 1, water_only);
 
-                // ---- evaporation rate per unit area, R/sim_water.R:264-270 (air temperature)
-                const double evap = evaporation_rate(air_t, rh, p_a, wind);
-
-                // ---- life-history parameters, R/sim_pop_dynamics.R:100-135
-                // water_temperature = air_temperature, R/sim_microclimate.R:163
-                double mdr = 0.0, efd = 0.0, das0 = 0.0, ds = 0.0;
-                PopHour ph;
-                if (!water_only) {
-                    const int i = spline_interval(p.spline, s_x, air_t);
-                    const double dx = air_t - s_x[i];
-                    const double4 *cf = reinterpret_cast<const double4 *>(s_coef + (size_t)i * 12);
-                    const double4 c0 = cf[0], c1 = cf[1], c2 = cf[2];
-                    mdr = ensure_positive(c0.x + dx * (c0.y + dx * (c0.z + dx * c0.w)));
-                    efd = ensure_positive(c1.x + dx * (c1.y + dx * (c1.z + dx * c1.w)));
-                    das0 = ensure_positive(c2.x + dx * (c2.y + dx * (c2.z + dx * c2.w)));
-                    ds = ds_surface(p.ds, air_t, rh);
-                    ph = pop_hour(p.densmod_type, mdr, efd, das0, ds);
-                }
-
-                // ---- water body and population, per habitat setting
+                // ... next to the state-dependent half of hour h
 #pragma unroll
                 for (int s = 0; s < kNS; ++s) {
                     const HabitatDev &hb = p.hab[set0 + s];
-                    volume[s] = iterate_volume(hb, volume[s], surface[s], evap, gain[s]);   // R/sim_water.R:279-287
-                    surface[s] = habitat_surface(hb, volume[s]);                            // :294
+                    volume[s] = iterate_volume(hb, volume[s], surface[s], f.evap, gain[s]);   // R/sim_water.R:279-287
+                    surface[s] = habitat_surface(hb, volume[s]);                              // :294
                     if (!water_only)   // larval_habitat_area = water_surface_area, R/sim_pop_dynamics.R:123
-                        iterate_state(aquatic[s], adult[s], ph, p.densmod_type, p.dd_effect,
+                        iterate_state(aquatic[s], adult[s], f.ph, p.densmod_type, p.dd_effect,
                                       p.surface_area_cm2, surface[s]);
                 }
 
@@ -320,10 +377,10 @@ chain_kernel(const __grid_constant__ ChainParams p)
                             }
                             acc_wet[s] += (volume[s] > 0.0) ? 1 : 0;
                         }
-                        acc_forc[0] += mdr; acc_forc[1] += efd; acc_forc[2] += das0; acc_forc[3] += ds;
+                        acc_forc[0] += f.mdr; acc_forc[1] += f.efd; acc_forc[2] += f.das0; acc_forc[3] += f.ds;
                         if (kFull) {
-                            acc_forc[4] += air_t; acc_forc[5] += rh; acc_forc[6] += wind;
-                            acc_forc[7] += rain_h; acc_forc[8] += cloud;
+                            acc_forc[4] += f.air_t; acc_forc[5] += f.rh; acc_forc[6] += f.wind;
+                            acc_forc[7] += rain_h; acc_forc[8] += f.cloud;
                         }
                         ++acc_n;
                     }
@@ -344,12 +401,12 @@ chain_kernel(const __grid_constant__ ChainParams p)
                             if (p.wet_flags)
                                 p.wet_flags[(int64_t)(set0 + s) * H * cs + tc] = (volume[s] > 0.0) ? 1 : 0;
                         }
-                        if (blockIdx.y == 0) {
-                            const double val[9] = {mdr, efd, das0, ds, air_t, rh, wind, rain_h, cloud};
+                        if (write_forcing) {
+                            const double val[9] = {f.mdr, f.efd, f.das0, f.ds, f.air_t, f.rh, f.wind, rain_h, f.cloud};
                             const int vid[9] = {MMS_V_MDR, MMS_V_EFD, MMS_V_DAS_ZERODENSITY, MMS_V_DS, MMS_V_AIR_TEMPERATURE,
                                                 MMS_V_HUMIDITY, MMS_V_WINDSPEED, MMS_V_RAINFALL, MMS_V_CLOUDCOVER};
 #pragma unroll
-                            for (int k = 0; k < (kFull ? 9 : 4); ++k) {
+                            for (int k = 0; k < kNF; ++k) {
                                 if (p.hourly_mask & (1u << vid[k])) {
                                     const int64_t row = slot(p.hourly_mask, ~kState, vid[k]);
                                     p.hourly_forcing[row * H * cs + tc] = val[k];
@@ -358,23 +415,55 @@ chain_kernel(const __grid_constant__ ChainParams p)
                         }
                     }
                 }
+                f = fn;
             }   // hours
 
             // ---- roll the day window
-            t_midnight_prev = air_t;                     // hour-24 value, R/sim_microclimate.R:271
-            t_sunset_prev = t_sunset;
-            rhmin_prev = cur.rhmin; wsmax_prev = cur.wsmax; ccmin_prev = cur.ccmin;
-            cur = nxt;
+            dc.t_midnight_prev = f.air_t;                // hour-24 value, R/sim_microclimate.R:271
+            dc.rhmin_prev = dc.cur.rhmin; dc.wsmax_prev = dc.cur.wsmax; dc.ccmin_prev = dc.cur.ccmin;
+            dc.cur = dc.nxt;
             const int d2 = day + 2;
-            nxt = load_daily<kFull>(p, cell, d2 < p.D ? d2 : p.D - 1, bad);
-            A = MMS_DIVC(cur.tmax - cur.tmin, 2.0);
-            t_sunset = A * p.hr.z_night + cur.tmin + A;
+            dc.nxt = load_daily<kFull>(p, cell, d2 < p.D ? d2 : p.D - 1, bad);
+            dc.A = MMS_DIVC(dc.cur.tmax - dc.cur.tmin, 2.0);
+            dc.t_sunset = dc.A * p.hr.z_night + dc.cur.tmin + dc.A;
         }   // days
-        (void)t_sunset_prev;
         if (final_pass && cur_period >= 0) flush(cur_period);
     }   // passes
 
     if (bad && live) atomicOr(p.error_flag, 1);
+}
+
+// ---- the kernel -----------------------------------------------------------
+// kNS     : habitat settings integrated per thread (they share all forcing-derived work)
+// kFull   : false = only the reference's six vector_variables can be summarised / written;
+//           true  = all MMS_NVARS (adds water body and microclimate variables, cloud cover)
+// kHourly : write full hourly series
+// kMaxWarps: largest CTA this instantiation may be launched with (register budget = 64K / threads)
+template <int kNS, bool kFull, bool kHourly, int kMaxWarps>
+__global__ void __launch_bounds__(kMaxWarps * 32, 1)
+chain_kernel(const __grid_constant__ ChainParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_coef = reinterpret_cast<double *>(smem_raw);              // [n][3][4]
+    double *s_x = s_coef + (size_t)p.spline.n * 12;                     // [n]
+    double *s_gx = s_x + p.spline.n;                                    // [nx]
+    double *s_gy = s_gx + p.ds.nx;                                      // [ny]
+    for (int k = threadIdx.x; k < p.spline.n * 12; k += blockDim.x) s_coef[k] = p.spline.coef[k];
+    for (int k = threadIdx.x; k < p.spline.n; k += blockDim.x) s_x[k] = p.spline.x[k];
+    for (int k = threadIdx.x; k < p.ds.nx; k += blockDim.x) s_gx[k] = p.ds.x[k];
+    for (int k = threadIdx.x; k < p.ds.ny; k += blockDim.x) s_gy[k] = p.ds.y[k];
+    __syncthreads();
+    SmemTables tb{s_x, s_coef, s_gx, s_gy};
+
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int unit = 0;
+        if (lane == 0) unit = atomicAdd(p.unit_counter, 1);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= p.n_units) break;
+        const int cb = unit % p.n_cell_blocks, g = unit / p.n_cell_blocks;
+        simulate_unit<kNS, kFull, kHourly>(p, tb, (int64_t)cb * 32 + lane, g * kNS, g == 0);
+    }
 }
 
 }  // namespace MMS_MODE

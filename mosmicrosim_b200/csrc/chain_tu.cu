@@ -16,23 +16,42 @@ using namespace MMS_MODE;
 
 namespace {
 
-template <int kNS, bool kFull, bool kHourly>
-cudaError_t launch_one(const ChainParams &p, cudaStream_t stream)
+template <int kNS, bool kFull, bool kHourly, int kMaxWarps>
+cudaError_t launch_kernel(const ChainParams &p, int grid, int warps, cudaStream_t stream)
 {
-    auto kern = chain_kernel<kNS, kFull, kHourly>;
-    const size_t smem = sizeof(double) * (size_t)(((p.spline.n + 1) & ~1) + p.spline.n * 12);
+    auto kern = chain_kernel<kNS, kFull, kHourly, kMaxWarps>;
+    const size_t smem = sizeof(double) * ((size_t)p.spline.n * 13 + p.ds.nx + p.ds.ny);
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    dim3 grid((unsigned)(p.c_stride / kBlock), (unsigned)(p.S / kNS));
-    kern<<<grid, kBlock, smem, stream>>>(p);
+    kern<<<grid, warps * 32, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
-template <int kNS>
-cudaError_t launch_ns(const ChainParams &p, bool full, bool hourly, cudaStream_t stream)
+template <int kNS, bool kFull, bool kHourly>
+cudaError_t launch_one(ChainParams &p, int n_sm, cudaStream_t stream)
 {
-    if (full) return hourly ? launch_one<kNS, true, true>(p, stream) : launch_one<kNS, true, false>(p, stream);
-    return hourly ? launch_one<kNS, false, true>(p, stream) : launch_one<kNS, false, false>(p, stream);
+    // work units: 32 cells x one group of kNS settings.  Pick the number of warps
+    // per persistent CTA so that the rounds come out even: the fewest rounds that
+    // fit the largest CTA, then the fewest warps that still need only that many.
+    p.n_cell_blocks = (int32_t)(p.c_stride / 32);
+    p.n_units = p.n_cell_blocks * (p.S / kNS);
+    const int w_max = p.force_warps > 0 ? p.force_warps : kChainMaxWarps;
+    const int64_t per_round = (int64_t)n_sm * w_max;
+    const int64_t rounds = (p.n_units + per_round - 1) / per_round;
+    int warps = (int)((p.n_units + (int64_t)n_sm * rounds - 1) / ((int64_t)n_sm * rounds));
+    warps = warps < 1 ? 1 : (warps > w_max ? w_max : warps);
+    const int64_t ctas = (p.n_units + warps - 1) / warps;
+    const int grid = (int)(ctas < n_sm ? ctas : n_sm);
+    // fewer warps -> the instantiation with the larger register budget
+    if (warps <= kChainFewWarps) return launch_kernel<kNS, kFull, kHourly, kChainFewWarps>(p, grid, warps, stream);
+    return launch_kernel<kNS, kFull, kHourly, kChainMaxWarps>(p, grid, warps, stream);
+}
+
+template <int kNS>
+cudaError_t launch_ns(ChainParams &p, int n_sm, bool full, bool hourly, cudaStream_t stream)
+{
+    if (full) return hourly ? launch_one<kNS, true, true>(p, n_sm, stream) : launch_one<kNS, true, false>(p, n_sm, stream);
+    return hourly ? launch_one<kNS, false, true>(p, n_sm, stream) : launch_one<kNS, false, false>(p, n_sm, stream);
 }
 
 __global__ void log1p_rows_kernel(double *rows, int64_t n)
@@ -43,15 +62,15 @@ __global__ void log1p_rows_kernel(double *rows, int64_t n)
 
 }  // namespace
 
-cudaError_t MMS_LAUNCH(launch_chain)(const ChainParams &p, cudaStream_t stream)
+cudaError_t MMS_LAUNCH(launch_chain)(ChainParams &p, int n_sm, cudaStream_t stream)
 {
     const uint32_t all = p.mean_mask | p.hourly_mask;
     const bool full = (all & ~MMS_PIPELINE_VAR_MASK) != 0;
     const bool hourly = p.hourly_mask != 0 || p.wet_flags != nullptr;
     // settings per thread: the largest of 4, 2, 1 that divides S
-    if (p.S % 4 == 0) return launch_ns<4>(p, full, hourly, stream);
-    if (p.S % 2 == 0) return launch_ns<2>(p, full, hourly, stream);
-    return launch_ns<1>(p, full, hourly, stream);
+    if (p.S % 4 == 0) return launch_ns<4>(p, n_sm, full, hourly, stream);
+    if (p.S % 2 == 0) return launch_ns<2>(p, n_sm, full, hourly, stream);
+    return launch_ns<1>(p, n_sm, full, hourly, stream);
 }
 
 cudaError_t MMS_LAUNCH(launch_log1p_rows)(double *rows, int64_t n, cudaStream_t stream)

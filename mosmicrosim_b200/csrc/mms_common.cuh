@@ -9,7 +9,9 @@
 
 namespace mms {
 
-constexpr int kBlock = 128;          // threads (= cells) per CTA of the fused kernel
+constexpr int kBlock = 128;          // cell padding granule of a shard (keeps [period][cell] rows 1 KB aligned)
+constexpr int kChainMaxWarps = 16;   // largest persistent CTA of the fused kernel: 512 threads, <= 128 registers / thread
+constexpr int kChainFewWarps = 12;   // second instantiation: <= 384 threads, <= 168 registers / thread
 constexpr int kHoursPerYear = 8760;  // n_times_year <- 365 * 24, R/sim_water.R:229, R/sim_pop_dynamics.R:222
 constexpr int kDaysPerYear = 365;
 
@@ -22,6 +24,7 @@ struct HourTables {
     double predawn[24];    // 1 - t/600, :275
     double w_vsine[24];    // vsine_weights(), :431-454
     double w_vsine_inv[24];// 1 - weight, :498-500
+    double air_coef[24];   // fast mode: predawn[h] | z_light[h] | 1 / exp_e[h] by segment
     double z_night;        // :210
 };
 
@@ -59,7 +62,9 @@ struct SurfaceDev {
     const double *x, *y;   // [nx], [ny]
     const double *quad;    // [(nx-1)*(ny-1)][4]
     int32_t nx, ny;
-    double x0, inv_dx, y0, inv_dy;   // index guess only; intervals are verified against x, y
+    double x0, inv_dx, y0, inv_dy;   // strict: index guess only (intervals are verified against x, y);
+                                     // fast: the index itself (host verified the axes are equally spaced)
+    double x1, y1;                   // last grid values
 };
 
 struct ChainParams {
@@ -84,13 +89,18 @@ struct ChainParams {
     uint8_t *wet_flags;
     uint32_t mean_mask, hourly_mask;
     int32_t *error_flag;       // set non-zero by the kernel on non-finite forcing
+    int32_t *unit_counter;     // work-unit dispenser, zeroed before every launch
+    int32_t n_units;           // n_cell_blocks * (S / settings per thread)
+    int32_t n_cell_blocks;     // c_stride / 32
+    int32_t force_warps;       // > 0: cap on warps per CTA (tuning aid, env MMS_CHAIN_WARPS)
     HourTables hr;
     HabitatDev hab[MMS_MAX_SETTINGS];
 };
 
 // launchers, one translation unit per math mode (chain_fast.cu / chain_strict.cu)
-cudaError_t launch_chain_fast(const ChainParams &p, cudaStream_t stream);
-cudaError_t launch_chain_strict(const ChainParams &p, cudaStream_t stream);
+// (p.unit_counter must be zero when the kernel starts; n_units / n_cell_blocks are filled in here)
+cudaError_t launch_chain_fast(ChainParams &p, int n_sm, cudaStream_t stream);
+cudaError_t launch_chain_strict(ChainParams &p, int n_sm, cudaStream_t stream);
 // monthly rainfall -> log1p(rainfall) in place (R/sim_microclimate.R:33)
 cudaError_t launch_log1p_rows_fast(double *rows, int64_t n, cudaStream_t stream);
 cudaError_t launch_log1p_rows_strict(double *rows, int64_t n, cudaStream_t stream);

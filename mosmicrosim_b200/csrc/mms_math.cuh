@@ -3,16 +3,18 @@
 // Compiled twice (see build.py): MMS_STRICT=1 with -fmad=false keeps the
 // reference's literal operation order and CUDA's IEEE-accurate libm, so that the
 // only differences from the CPU oracle are libm last-bit differences;
-// MMS_STRICT=0 ("fast", the default at run time) allows FMA contraction and
-// replaces pow() by exp(y*log(x)) compositions and divisions by literals with
-// multiplications.  Cheap, badly conditioned operations (1 - (1 - p), 1 - exp(-x),
-// lx - floor(lx), the clamps) are kept literal in both modes: the target is
-// the reference's floating-point arithmetic, not the exact mathematics.
+// MMS_STRICT=0 ("fast", the default at run time) allows FMA contraction, turns
+// pow() into exp(y*log(x)) compositions and divisions by literals into
+// multiplications, and uses the branch-free exp/log of mms_fastmath.cuh.
+// Cheap, badly conditioned operations (1 - (1 - p), 1 - exp(-x), lx - floor(lx),
+// the clamps) are kept literal in both modes: the target is the reference's
+// floating-point arithmetic, not the exact mathematics.
 //
 // Citations are relative to the reference root.
 #pragma once
 
 #include "mms_common.cuh"
+#include "mms_fastmath.cuh"
 
 #ifndef MMS_STRICT
 #define MMS_STRICT 0
@@ -30,11 +32,17 @@ namespace MMS_MODE {
 constexpr double kEps = 1.4901161193847656e-08;   // sqrt(.Machine$double.eps), R/sim_pop_dynamics.R:26
 constexpr double kTimestep = 1.0 / 24.0;          // timestep = 1 / 24, R/sim_pop_dynamics.R:23
 
-// x / c for a literal c of the R source
+// x / c for a literal c of the R source; exp / log / division flavour
 #if MMS_STRICT
 #define MMS_DIVC(x, c) ((x) / (c))
+#define MMS_EXP(x) exp(x)
+#define MMS_LOG(x) log(x)
+#define MMS_DIV(a, b) ((a) / (b))
 #else
 #define MMS_DIVC(x, c) ((x) * (1.0 / (c)))
+#define MMS_EXP(x) ::mms::fm::exp_sat(x)
+#define MMS_LOG(x) ::mms::fm::log_sat(x)
+#define MMS_DIV(a, b) ((a) / (b))
 #endif
 
 // R's `^` (arithmetic.c R_pow) for a positive, non-integer literal exponent y.
@@ -45,15 +53,14 @@ __device__ __forceinline__ double r_pow_pos(double x, double y)
     if (x == 0.0) return 0.0;           // also -0.0 -> +0.0, like R_pow
     return pow(x, y);
 #else
-    // exp(y log x): log(+-0) = -inf -> 0, x < 0 -> NaN, NaN -> NaN, like pow
-    return exp(y * log(x));
+    return ::mms::fm::pow_pos(x, y);
 #endif
 }
 
 // saturation_vapour_pressure_kpa(), R/sim_water.R:36-38 (Buck)
 __device__ __forceinline__ double svp_kpa(double t)
 {
-    return 0.61121 * exp((18.678 - MMS_DIVC(t, 234.5)) * (t / (257.14 + t)));
+    return 0.61121 * MMS_EXP((18.678 - MMS_DIVC(t, 234.5)) * MMS_DIV(t, 257.14 + t));
 }
 
 // evaporation_rate_kg_h() with surface_area_m2 = 1, R/sim_water.R:50-90,264-270.
@@ -62,9 +69,9 @@ __device__ __forceinline__ double evaporation_rate(double t, double rh, double p
 {
     const double theta = 25.0 + 19.0 * wind;                   // :67
     const double p_ws = svp_kpa(t);                            // :73
-    const double xs = 0.62198 * p_ws / (p_a - p_ws);           // :75
+    const double xs = MMS_DIV(0.62198 * p_ws, p_a - p_ws);     // :75
     const double p_w = p_ws * MMS_DIVC(rh, 100.0);             // :84
-    const double x = 0.62198 * p_w / (p_a - p_w);              // :85
+    const double x = MMS_DIV(0.62198 * p_w, p_a - p_w);        // :85
     return theta * (xs - x);                                   // :88 (A = 1: theta * 1 == theta)
 }
 
@@ -78,7 +85,12 @@ __device__ __forceinline__ double air_pressure_kpa(double altitude)
 // R/lifehistory_estimation_functions.R:236-250.
 __device__ __forceinline__ double ensure_positive(double v)
 {
+#if MMS_STRICT
     return (v > 0.0) ? v : ((v != v) ? v : ((v == 0.0) ? v : -0.0));
+#else
+    // same values (a zero of either sign behaves identically downstream), one compare
+    return (v < 0.0) ? 0.0 : v;
+#endif
 }
 
 // cone_volume_to_surface(), R/sim_water.R:24-31; cylinder is an EXTENSION
@@ -99,7 +111,7 @@ __device__ __forceinline__ double iterate_volume(const HabitatDev &hb, double vo
     x = x - hb.leak_per_hour * volume;                         // EXTENSION (leak = 0: x - 0 == x)
     x = ensure_positive(x);                                    // R/utils.R:159-161
     double y = x + gain;                                       // :126
-    if (y > hb.max_volume) y = hb.max_volume;                  // enforce_max(), R/utils.R:164-168
+    y = (y > hb.max_volume) ? hb.max_volume : y;               // enforce_max(), R/utils.R:164-168
     return y;
 }
 
@@ -109,14 +121,14 @@ struct PopHour {
     double emf;         // 1 - exp(-timestep * mdr)               :58-59
     double one_m_emf;   // 1 - emergence_fraction                 :74
     double egg;         // efd * timestep                         :62
-    double link0;       // logit(das0) or log(-log(1 - (1 - das0)))  densmod, state independent
+    double link0;       // logit(das0) / cox_ph link of das0: the state independent part of densmod
 };
 
 __device__ __forceinline__ PopHour pop_hour(int densmod_type, double mdr, double efd, double das0, double ds)
 {
     PopHour ph;
     ph.surv_ad = r_pow_pos(ds, kTimestep);
-    const double e = exp(-(kTimestep * mdr));
+    const double e = MMS_EXP(-(kTimestep * mdr));
     ph.emf = 1.0 - e;
 #if MMS_STRICT
     ph.one_m_emf = 1.0 - ph.emf;
@@ -130,10 +142,10 @@ __device__ __forceinline__ PopHour pop_hour(int densmod_type, double mdr, double
 #if MMS_STRICT
         ph.link0 = log(-log(1.0 - daily_mortality_zero_density));
 #else
-        ph.link0 = log(1.0 - daily_mortality_zero_density);      // log p'; exp(loghaz) = -log p' * exp(dd*D)
+        ph.link0 = MMS_LOG(1.0 - daily_mortality_zero_density);      // log p'; exp(loghaz) = -log p' * exp(dd*D)
 #endif
     } else {
-        ph.link0 = log(das0 / (1.0 - das0));                     // logit(), :533,:571
+        ph.link0 = MMS_LOG(MMS_DIV(das0, 1.0 - das0));               // logit(), :533,:571
     }
     return ph;
 }
@@ -143,9 +155,9 @@ __device__ __forceinline__ void iterate_state(double &aquatic, double &adult, co
                                               int densmod_type, double dd_effect, double area_cm2,
                                               double larval_habitat_area)
 {
-    double aq = (aquatic != aquatic) ? 0.0 : aquatic;           // :33
-    double ad = (adult != adult) ? 0.0 : adult;                 // :34
-    const double density = aq / (larval_habitat_area + kEps);   // :42
+    const double aq = (aquatic != aquatic) ? 0.0 : aquatic;     // :33
+    const double ad = (adult != adult) ? 0.0 : adult;           // :34
+    const double density = MMS_DIV(aq, larval_habitat_area + kEps);   // :42
     const double density_dish = density * area_cm2;             // densmod :549 / :569
     double surv_aq;
 #if MMS_STRICT
@@ -162,15 +174,32 @@ __device__ __forceinline__ void iterate_state(double &aquatic, double &adult, co
 #else
     if (densmod_type == 1) {
         // exp(-exp(log(-log p') + dd*D)) = exp(log p' * exp(dd*D)); the reference's
-        // 1 - (1 - z) rounding (z < 1.1e-16 -> 0) is kept literally
-        const double z = exp(ph.link0 * exp(dd_effect * density_dish));
+        // 1 - (1 - z) rounding (z < 1.1e-16 -> 0) is kept literally.  dd*D is clamped to
+        // +-700 before exp (beyond that z is 0 or 1 either way) so that 0 * Inf cannot arise.
+        const double u = dd_effect * density_dish;
+        const int uhi = __double2hiint(u);
+        const bool ubig = ((unsigned)uhi & 0x7fffffffu) >= 0x4085e000u;      // |u| >= 700, Inf, NaN
+        const double e1 = ::mms::fm::exp_core(ubig ? ((uhi < 0) ? -700.0 : 700.0) : u);
+        double z = ::mms::fm::exp_sat(ph.link0 * e1);
+        z = ::mms::fm::is_nan_bits(u) ? u : z;
         const double das_t = 1.0 - (1.0 - z);
-        surv_aq = r_pow_pos(das_t, kTimestep);
+        surv_aq = ::mms::fm::pow_pos(das_t, kTimestep);
     } else {
-        // das_t = 1 / (1 + e), e = exp(-lg);  das_t ^ (1/24) = exp(-log(1 + e) / 24)
-        const double lg = ph.link0 + dd_effect * density_dish;
-        const double e = exp(-lg);
-        surv_aq = exp(-kTimestep * log(1.0 + e));
+        // das_t = 1 / (1 + e), e = exp(a), a = -lg;  das_t ^ (1/24) = exp(-log(1 + e) / 24).
+        // a is clamped to [-50, 40] for e: below, 1 + e == 1 exactly; above, log(1 + e) == a
+        // to double precision, and e = Inf (a > 709.78...) makes the reference's das_t 0.
+        const double a = -(ph.link0 + dd_effect * density_dish);
+        const int ahi = __double2hiint(a);
+        const unsigned aabs = (unsigned)ahi & 0x7fffffffu;
+        const bool hi_side = ahi >= 0x40440000;                               // a >= 40 (or +Inf, +NaN)
+        const bool lo_side = ahi < 0 && aabs >= 0x40490000u;                  // a <= -50 (or -Inf, -NaN)
+        const double ac = hi_side ? 40.0 : (lo_side ? -50.0 : a);
+        double L = ::mms::fm::log_core(1.0 + ::mms::fm::exp_core(ac));
+        L = hi_side ? a : L;
+        surv_aq = ::mms::fm::exp_sat(-kTimestep * L);
+        const bool overflow = ahi > 0x40862e42 || (ahi == 0x40862e42 && (unsigned)__double2loint(a) > 0xfefa39efu);
+        surv_aq = overflow ? 0.0 : surv_aq;                                   // exp(a) = Inf -> das_t = 0
+        surv_aq = ::mms::fm::is_nan_bits(a) ? a : surv_aq;
     }
 #endif
     const double surviving_adult = ad * ph.surv_ad;             // :67

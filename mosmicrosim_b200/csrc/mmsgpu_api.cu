@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -73,6 +74,7 @@ void fill_hour_tables(mms::HourTables &hr)
         const double w3 = 0.5 * std::min(1.0, std::max(0.0, (t - inf) / (24 - inf))) * m3;
         hr.w_vsine[h] = w1 + w2 + w3;                                                            // :451
         hr.w_vsine_inv[h] = 1 - hr.w_vsine[h];                                                   // :498-500
+        hr.air_coef[h] = (h < 5) ? hr.predawn[h] : ((h <= 17) ? hr.z_light[h] : 1.0 / hr.exp_e[h]);
     }
 }
 
@@ -171,9 +173,17 @@ int pack_tables(const mms_lifehistory &lh, HostTables &t)
     t.x0 = t.sx[0];
     t.step = (t.sx[n - 1] - t.sx[0]) / (n - 1);
     t.inv_step = 1.0 / t.step;
-    t.uniform = 0;
+    // equally spaced to within 1e-9 of a step?  (the reference's knots are seq(-20, 80, by = 0.1))
+    t.uniform = 1;
+    for (int k = 0; k < n; ++k)
+        if (std::fabs(t.sx[k] - (t.x0 + k * t.step)) > 1e-9 * t.step) t.uniform = 0;
     const mms_surface &g = lh.ds_temp_humid;
     if (g.nx < 2 || g.ny < 2 || !g.x || !g.y || !g.z) return fail(MMS_ERR_INVALID_ARG, "ds surface needs a grid of at least 2 x 2");
+    {
+        const double dx = (g.x[g.nx - 1] - g.x[0]) / (g.nx - 1), dy = (g.y[g.ny - 1] - g.y[0]) / (g.ny - 1);
+        for (int k = 0; k < g.nx; ++k) if (std::fabs(g.x[k] - (g.x[0] + k * dx)) > 1e-9 * dx) t.uniform = 0;
+        for (int k = 0; k < g.ny; ++k) if (std::fabs(g.y[k] - (g.y[0] + k * dy)) > 1e-9 * dy) t.uniform = 0;
+    }
     for (int k = 1; k < g.nx; ++k) if (!(g.x[k] > g.x[k - 1])) return fail(MMS_ERR_INVALID_ARG, "ds surface x must be strictly increasing");
     for (int k = 1; k < g.ny; ++k) if (!(g.y[k] > g.y[k - 1])) return fail(MMS_ERR_INVALID_ARG, "ds surface y must be strictly increasing");
     t.quad.resize((size_t)(g.nx - 1) * (g.ny - 1) * 4);
@@ -202,7 +212,8 @@ struct Shard {
     double *d_mean_state = nullptr, *d_mean_forcing = nullptr, *d_hourly_state = nullptr, *d_hourly_forcing = nullptr;
     int32_t *d_wet_hours = nullptr;
     uint8_t *d_wet_flags = nullptr;
-    int32_t *d_error = nullptr;
+    int32_t *d_error = nullptr;    // [0] error flag, [1] work-unit counter
+    int n_sm = 0;
     bool launched = false;
 };
 
@@ -289,8 +300,9 @@ int setup_shard(mms_chain_plan *pl, Shard &s)
     if ((rc = dev_alloc(&s.d_hourly_forcing, (size_t)pl->n_hourly_forcing * H * cs))) return rc;
     if (pl->want_wet_hours && (rc = dev_alloc(&s.d_wet_hours, (size_t)pl->S * pl->P * cs))) return rc;
     if (pl->want_wet_flags && (rc = dev_alloc(&s.d_wet_flags, (size_t)pl->S * H * cs))) return rc;
-    if ((rc = dev_alloc(&s.d_error, 1))) return rc;
-    MMS_CUDA(cudaMemsetAsync(s.d_error, 0, sizeof(int32_t), s.stream));
+    if ((rc = dev_alloc(&s.d_error, 2))) return rc;
+    MMS_CUDA(cudaMemsetAsync(s.d_error, 0, 2 * sizeof(int32_t), s.stream));
+    MMS_CUDA(cudaDeviceGetAttribute(&s.n_sm, cudaDevAttrMultiProcessorCount, s.device));
     return MMS_OK;
 }
 
@@ -452,11 +464,15 @@ int mms_chain_launch(mms_chain_plan *pl)
         p.ds.x = s.d_gx; p.ds.y = s.d_gy; p.ds.quad = s.d_quad; p.ds.nx = pl->ds_nx; p.ds.ny = pl->ds_ny;
         p.ds.x0 = pl->gx[0]; p.ds.inv_dx = (pl->ds_nx - 1) / (pl->gx[pl->ds_nx - 1] - pl->gx[0]);
         p.ds.y0 = pl->gy[0]; p.ds.inv_dy = (pl->ds_ny - 1) / (pl->gy[pl->ds_ny - 1] - pl->gy[0]);
+        p.ds.x1 = pl->gx[pl->ds_nx - 1]; p.ds.y1 = pl->gy[pl->ds_ny - 1];
         p.mean_state = s.d_mean_state; p.mean_forcing = s.d_mean_forcing;
         p.hourly_state = s.d_hourly_state; p.hourly_forcing = s.d_hourly_forcing;
         p.wet_hours = s.d_wet_hours; p.wet_flags = s.d_wet_flags;
         p.mean_mask = pl->mean_mask; p.hourly_mask = pl->hourly_mask;
         p.error_flag = s.d_error;
+        p.unit_counter = s.d_error + 1;
+        if (const char *fw = std::getenv("MMS_CHAIN_WARPS")) p.force_warps = std::atoi(fw);
+        MMS_CUDA(cudaMemsetAsync(s.d_error + 1, 0, sizeof(int32_t), s.stream));
         p.hr = pl->hr;
         for (int k = 0; k < pl->S; ++k) p.hab[k] = pl->hab[k];
         // periods that never occur stay NaN (all-ones bit pattern) / 0
@@ -465,7 +481,11 @@ int mms_chain_launch(mms_chain_plan *pl)
         if (s.d_mean_forcing) MMS_CUDA(cudaMemsetAsync(s.d_mean_forcing, 0xFF, sizeof(double) * pl->n_mean_forcing * pl->P * cs, s.stream));
         if (s.d_wet_hours) MMS_CUDA(cudaMemsetAsync(s.d_wet_hours, 0, sizeof(int32_t) * pl->S * pl->P * cs, s.stream));
         MMS_CUDA(cudaEventRecord(s.ev0, s.stream));
-        MMS_CUDA(pl->math_mode ? mms::launch_chain_strict(p, s.stream) : mms::launch_chain_fast(p, s.stream));
+        // the fast kernels index the tables arithmetically, which needs equally spaced knots /
+        // axes (true for every table the reference builds); anything else runs the strict
+        // kernels, which search the stored knots like R does
+        const bool strict = pl->math_mode != 0 || !pl->tab.uniform;
+        MMS_CUDA(strict ? mms::launch_chain_strict(p, s.n_sm, s.stream) : mms::launch_chain_fast(p, s.n_sm, s.stream));
         MMS_CUDA(cudaEventRecord(s.ev1, s.stream));
         s.launched = true;
         pl->launches += 1;

@@ -1,7 +1,7 @@
 """Ad-hoc timing of the fused kernel (development aid; bench.py is the contract)."""
 import sys, time
 import numpy as np
-sys.path.insert(0, ".")
+sys.path.insert(0, ".."); sys.path.insert(0, ".")
 from helpers import Case
 from mosmicrosim_b200 import backend, synthetic as syn
 
