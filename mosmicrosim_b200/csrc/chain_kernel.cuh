@@ -159,9 +159,9 @@ struct HourF {
     PopHour ph;
 };
 
-template <bool kFull>
+template <bool kFull, bool kWaterOnly>
 __device__ __forceinline__ HourF hour_forcing(const ChainParams &p, const SmemTables &tb, const DayCtx &dc,
-                                              double p_a, int h, bool water_only)
+                                              double p_a, int h)
 {
     HourF f;
     // ---- SINEC air temperature, R/sim_microclimate.R:185-285 (hour = h + 1, times = 100 * hour)
@@ -205,7 +205,7 @@ __device__ __forceinline__ HourF hour_forcing(const ChainParams &p, const SmemTa
     // ---- life-history parameters, R/sim_pop_dynamics.R:100-135
     // water_temperature = air_temperature, R/sim_microclimate.R:163
     f.mdr = f.efd = f.das0 = f.ds = 0.0;
-    if (!water_only) {
+    if (!kWaterOnly) {
         const int i = spline_interval(p.spline, tb.sx, f.air_t);
         const double dx = f.air_t - tb.sx[i];
         const double4 *cf = reinterpret_cast<const double4 *>(tb.coef + (size_t)i * 12);
@@ -219,218 +219,243 @@ __device__ __forceinline__ HourF hour_forcing(const ChainParams &p, const SmemTa
     return f;
 }
 
-// ---- one work unit: 32 cells x kNS settings, all passes, all hours ------------
+// ---- per-unit state carried across passes ---------------------------------------
+template <int kNS>
+struct UnitState {
+    double volume[kNS], surface[kNS], aquatic[kNS], adult[kNS];
+};
+
+struct UnitCtx {
+    int64_t cell, cs;
+    int set0, H;
+    bool live, write_forcing;
+    double p_a;
+    int n_mean_state, n_hourly_state;
+};
+
+__device__ __forceinline__ int out_slot(uint32_t mask, uint32_t class_mask, int v)
+{
+    return __popc(mask & class_mask & ((1u << v) - 1u));   // position among the selected variables
+}
+
+// ---- one pass over n_days days ----------------------------------------------------
+// kWaterOnly : water burn-in year (R/sim_water.R:228-233): no life history, no population
+// kRecord    : the final pass over the full series: period summaries / hourly series
+template <int kNS, bool kFull, bool kHourly, bool kWaterOnly, bool kRecord>
+__device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables &tb, const UnitCtx &u,
+                                         UnitState<kNS> &st, int n_days, int &bad)
+{
+    constexpr int kNF = kFull ? 9 : 4;
+    constexpr uint32_t kState = MMS_STATE_VAR_MASK;
+    const int64_t cs = u.cs, cell = u.cell;
+    const int set0 = u.set0;
+
+    // period accumulators (aggregate_vectors(), R/pipeline_functions.R:1030-1091)
+    double acc_state[kNS][4];      // adult, aquatic, area, volume
+    double acc_forc[kNF];          // mdr, efd, das0, ds [, airT, RH, wind, rain, cloud]
+    int acc_wet[kNS];
+    int acc_n = 0, cur_period = -1;
+    auto reset_acc = [&]() {
+#pragma unroll
+        for (int s = 0; s < kNS; ++s) {
+            acc_wet[s] = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc_state[s][k] = 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < kNF; ++k) acc_forc[k] = 0.0;
+        acc_n = 0;
+    };
+    reset_acc();
+
+    auto flush = [&](int period) {
+        if (!u.live) return;
+        const int64_t pc = (int64_t)period * cs + cell;
+        const double n = (double)acc_n;
+#pragma unroll
+        for (int s = 0; s < kNS; ++s) {
+            const int vid[4] = {MMS_V_ADULT, MMS_V_AQUATIC, MMS_V_LARVAL_HABITAT_AREA, MMS_V_WATER_VOLUME};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!kFull && k >= 2) continue;
+                if (p.mean_mask & (1u << vid[k])) {
+                    const int64_t row = (int64_t)(set0 + s) * u.n_mean_state + out_slot(p.mean_mask, kState, vid[k]);
+                    p.mean_state[row * p.P * cs + pc] = acc_state[s][k] / n;
+                }
+            }
+            if (p.wet_hours) p.wet_hours[(int64_t)(set0 + s) * p.P * cs + pc] = acc_wet[s];
+        }
+        if (u.write_forcing) {
+            const int vid[9] = {MMS_V_MDR, MMS_V_EFD, MMS_V_DAS_ZERODENSITY, MMS_V_DS, MMS_V_AIR_TEMPERATURE,
+                                MMS_V_HUMIDITY, MMS_V_WINDSPEED, MMS_V_RAINFALL, MMS_V_CLOUDCOVER};
+#pragma unroll
+            for (int k = 0; k < kNF; ++k) {
+                if (p.mean_mask & (1u << vid[k])) {
+                    const int64_t row = out_slot(p.mean_mask, ~kState, vid[k]);
+                    p.mean_forcing[row * p.P * cs + pc] = acc_forc[k] / n;
+                }
+            }
+        }
+    };
+
+    // day window: today, tomorrow; carried values of yesterday
+    DayCtx dc;
+    dc.cur = load_daily<kFull>(p, cell, 0, bad);
+    dc.nxt = load_daily<kFull>(p, cell, (p.D > 1) ? 1 : 0, bad);
+    dc.A = MMS_DIVC(dc.cur.tmax - dc.cur.tmin, 2.0);                       // R/sim_microclimate.R:217
+    dc.t_sunset = dc.A * p.hr.z_night + dc.cur.tmin + dc.A;                // :220
+    // :271-272 (first day: its own midnight = night curve at t = 2400)
+    dc.t_midnight_prev = (dc.t_sunset - dc.nxt.tmin) / p.hr.exp_e[23] + dc.nxt.tmin;
+    dc.rhmin_prev = dc.cur.rhmin; dc.wsmax_prev = dc.cur.wsmax; dc.ccmin_prev = dc.cur.ccmin;   // :522
+
+    for (int day = 0; day < n_days; ++day) {
+        bool acc_on = false;               // true while this day's hours go into the current period
+        int acc_inc = 0;
+        if (kRecord && p.period_of_day) {
+            const int period = p.period_of_day[day];
+            if (period >= 0 && period != cur_period) {
+                if (cur_period >= 0) flush(cur_period);
+                reset_acc();
+                cur_period = period;
+            }
+            acc_on = period >= 0;
+            acc_inc = (period >= 0) ? 1 : 0;
+        }
+
+        const double rain_h = MMS_DIVC(dc.cur.rain, 24.0);                // R/sim_microclimate.R:132
+        const double gain_m_h = MMS_DIVC(rain_h, 1000.0);                 // R/sim_water.R:122
+        double gain[kNS];
+#pragma unroll
+        for (int s = 0; s < kNS; ++s) gain[s] = p.hab[set0 + s].catchment_area * gain_m_h;   // :123
+
+        // state-dependent half of one hour + its outputs
+        auto state_half = [&](const HourF &f, int h) {
+#pragma unroll
+            for (int s = 0; s < kNS; ++s) {
+                const HabitatDev &hb = p.hab[set0 + s];
+                st.volume[s] = iterate_volume(hb, st.volume[s], st.surface[s], f.evap, gain[s]);   // R/sim_water.R:279-287
+                st.surface[s] = habitat_surface(hb, st.volume[s]);                                 // :294
+                if (!kWaterOnly)   // larval_habitat_area = water_surface_area, R/sim_pop_dynamics.R:123
+                    iterate_state(st.aquatic[s], st.adult[s], f.ph, p.densmod_type, p.dd_effect,
+                                  p.surface_area_cm2, st.surface[s]);
+            }
+            if (kRecord) {
+                // branch free: days outside included_dates add 0 (their sums are never written)
+#pragma unroll
+                for (int s = 0; s < kNS; ++s) {
+                    acc_state[s][0] += (acc_on ? st.adult[s] : 0.0);
+                    acc_state[s][1] += (acc_on ? st.aquatic[s] : 0.0);
+                    if (kFull) {
+                        acc_state[s][2] += (acc_on ? st.surface[s] : 0.0);
+                        acc_state[s][3] += (acc_on ? st.volume[s] : 0.0);
+                    }
+                    acc_wet[s] += (st.volume[s] > 0.0) ? acc_inc : 0;
+                }
+                acc_forc[0] += (acc_on ? f.mdr : 0.0); acc_forc[1] += (acc_on ? f.efd : 0.0);
+                acc_forc[2] += (acc_on ? f.das0 : 0.0); acc_forc[3] += (acc_on ? f.ds : 0.0);
+                if (kFull) {
+                    acc_forc[4] += (acc_on ? f.air_t : 0.0); acc_forc[5] += (acc_on ? f.rh : 0.0); acc_forc[6] += (acc_on ? f.wind : 0.0);
+                    acc_forc[7] += (acc_on ? rain_h : 0.0); acc_forc[8] += (acc_on ? f.cloud : 0.0);
+                }
+                acc_n += acc_inc;
+                if (kHourly && u.live) {
+                    const int64_t tc = (int64_t)(day * 24 + h) * cs + cell;
+#pragma unroll
+                    for (int s = 0; s < kNS; ++s) {
+                        const double val[4] = {st.adult[s], st.aquatic[s], st.surface[s], st.volume[s]};
+                        const int vid[4] = {MMS_V_ADULT, MMS_V_AQUATIC, MMS_V_LARVAL_HABITAT_AREA, MMS_V_WATER_VOLUME};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (!kFull && k >= 2) continue;
+                            if (p.hourly_mask & (1u << vid[k])) {
+                                const int64_t row = (int64_t)(set0 + s) * u.n_hourly_state + out_slot(p.hourly_mask, kState, vid[k]);
+                                p.hourly_state[row * u.H * cs + tc] = val[k];
+                            }
+                        }
+                        if (p.wet_flags)
+                            p.wet_flags[(int64_t)(set0 + s) * u.H * cs + tc] = (st.volume[s] > 0.0) ? 1 : 0;
+                    }
+                    if (u.write_forcing) {
+                        const double val[9] = {f.mdr, f.efd, f.das0, f.ds, f.air_t, f.rh, f.wind, rain_h, f.cloud};
+                        const int vid[9] = {MMS_V_MDR, MMS_V_EFD, MMS_V_DAS_ZERODENSITY, MMS_V_DS, MMS_V_AIR_TEMPERATURE,
+                                            MMS_V_HUMIDITY, MMS_V_WINDSPEED, MMS_V_RAINFALL, MMS_V_CLOUDCOVER};
+#pragma unroll
+                        for (int k = 0; k < kNF; ++k) {
+                            if (p.hourly_mask & (1u << vid[k])) {
+                                const int64_t row = out_slot(p.hourly_mask, ~kState, vid[k]);
+                                p.hourly_forcing[row * u.H * cs + tc] = val[k];
+                            }
+                        }
+                    }
+                }
+            }
+        };
+
+        // software pipeline over the 24 hours: the state-independent half of hour h + 1 sits in
+        // the same basic block as the state-dependent half of hour h (two independent chains)
+        HourF f = hour_forcing<kFull, kWaterOnly>(p, tb, dc, u.p_a, 0);
+#pragma unroll 1
+        for (int h = 0; h < 23; ++h) {
+            const HourF fn = hour_forcing<kFull, kWaterOnly>(p, tb, dc, u.p_a, h + 1);
+            state_half(f, h);
+            f = fn;
+        }
+        state_half(f, 23);
+
+        // ---- roll the day window
+        dc.t_midnight_prev = f.air_t;                // hour-24 value, R/sim_microclimate.R:271
+        dc.rhmin_prev = dc.cur.rhmin; dc.wsmax_prev = dc.cur.wsmax; dc.ccmin_prev = dc.cur.ccmin;
+        dc.cur = dc.nxt;
+        const int d2 = day + 2;
+        dc.nxt = load_daily<kFull>(p, cell, d2 < p.D ? d2 : p.D - 1, bad);
+        dc.A = MMS_DIVC(dc.cur.tmax - dc.cur.tmin, 2.0);
+        dc.t_sunset = dc.A * p.hr.z_night + dc.cur.tmin + dc.A;
+    }   // days
+    if (kRecord && cur_period >= 0) flush(cur_period);
+}
+
+// ---- one work unit: 32 cells x kNS settings, all passes ---------------------------
 template <int kNS, bool kFull, bool kHourly>
 __device__ __forceinline__ void simulate_unit(const ChainParams &p, const SmemTables &tb, int64_t cell, int set0,
                                               bool write_forcing)
 {
-    const bool live = cell < p.n_cells;
-    const int64_t cs = p.c_stride;
-    const int H = 24 * p.D;
-    constexpr int kNF = kFull ? 9 : 4;
-
-    const double p_a = air_pressure_kpa(__ldg(p.altitude + cell));
+    UnitCtx u;
+    u.cell = cell; u.cs = p.c_stride; u.set0 = set0; u.H = 24 * p.D;
+    u.live = cell < p.n_cells; u.write_forcing = write_forcing;
+    u.p_a = air_pressure_kpa(__ldg(p.altitude + cell));
+    u.n_mean_state = __popc(p.mean_mask & MMS_STATE_VAR_MASK);
+    u.n_hourly_state = __popc(p.hourly_mask & MMS_STATE_VAR_MASK);
     int bad = 0;
 
-    // output slot of each variable (position among the selected ones)
-    auto slot = [](uint32_t mask, uint32_t class_mask, int v) {
-        return __popc(mask & class_mask & ((1u << v) - 1u));
-    };
-    const uint32_t kState = MMS_STATE_VAR_MASK;
-    const int n_mean_state = __popc(p.mean_mask & kState);
-    const int n_hourly_state = __popc(p.hourly_mask & kState);
-
-    double volume[kNS], surface[kNS], aquatic[kNS], adult[kNS], vol_after_water_burnin[kNS];
+    UnitState<kNS> st;
 #pragma unroll
     for (int s = 0; s < kNS; ++s) {
-        aquatic[s] = p.initial_aquatic;                  // R/sim_pop_dynamics.R:249-252
-        adult[s] = p.initial_adult;
-        volume[s] = p.hab[set0 + s].initial_volume;      // R/sim_water.R:277
-        vol_after_water_burnin[s] = volume[s];
+        st.aquatic[s] = p.initial_aquatic;               // R/sim_pop_dynamics.R:249-252
+        st.adult[s] = p.initial_adult;
+        st.volume[s] = p.hab[set0 + s].initial_volume;   // R/sim_water.R:277
+        st.surface[s] = habitat_surface(p.hab[set0 + s], st.volume[s]);
     }
-
-    // passes: water burn-in years (water only, R/sim_water.R:228-233), population
-    // burn-in years (first 8760 steps, R/sim_pop_dynamics.R:221-226), then the full series
-    const int n_pass = p.burnin_years_water + p.burnin_years_pop + 1;
-    for (int pass = 0; pass < n_pass; ++pass) {
-        const bool water_only = pass < p.burnin_years_water;
-        const bool final_pass = pass == n_pass - 1;
-        const int n_days = final_pass ? p.D : kDaysPerYear;
-        if (pass == p.burnin_years_water) {
+    // water burn-in years: first 8760 steps, water only (R/sim_water.R:228-233)
+    for (int y = 0; y < p.burnin_years_water; ++y)
+        run_pass<kNS, kFull, kHourly, true, false>(p, tb, u, st, kDaysPerYear, bad);
+    // every later pass re-runs the water model from this volume: the reference computes the
+    // water series once and the population burn-in re-indexes its first year
+    double vol0[kNS];
 #pragma unroll
-            for (int s = 0; s < kNS; ++s) vol_after_water_burnin[s] = volume[s];
+    for (int s = 0; s < kNS; ++s) vol0[s] = st.volume[s];
+    // population burn-in years: first 8760 steps (R/sim_pop_dynamics.R:221-226)
+    for (int y = 0; y < p.burnin_years_pop; ++y) {
+        run_pass<kNS, kFull, kHourly, false, false>(p, tb, u, st, kDaysPerYear, bad);
+#pragma unroll
+        for (int s = 0; s < kNS; ++s) {
+            st.volume[s] = vol0[s];
+            st.surface[s] = habitat_surface(p.hab[set0 + s], vol0[s]);
         }
-        if (!water_only) {
-            // each population pass re-runs the water model from its post-burn-in volume:
-            // the reference computes the water series once and re-indexes its first year
-#pragma unroll
-            for (int s = 0; s < kNS; ++s) volume[s] = vol_after_water_burnin[s];
-        }
-#pragma unroll
-        for (int s = 0; s < kNS; ++s) surface[s] = habitat_surface(p.hab[set0 + s], volume[s]);
+    }
+    // the full series, recorded
+    run_pass<kNS, kFull, kHourly, false, true>(p, tb, u, st, p.D, bad);
 
-        // period accumulators (aggregate_vectors(), R/pipeline_functions.R:1030-1091)
-        double acc_state[kNS][4];      // adult, aquatic, area, volume
-        double acc_forc[kNF];          // mdr, efd, das0, ds [, airT, RH, wind, rain, cloud]
-        int acc_wet[kNS];
-        int acc_n = 0, cur_period = -1;
-        auto reset_acc = [&]() {
-#pragma unroll
-            for (int s = 0; s < kNS; ++s) {
-                acc_wet[s] = 0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) acc_state[s][k] = 0.0;
-            }
-#pragma unroll
-            for (int k = 0; k < kNF; ++k) acc_forc[k] = 0.0;
-            acc_n = 0;
-        };
-        reset_acc();
-
-        auto flush = [&](int period) {
-            if (!live) return;
-            const int64_t pc = (int64_t)period * cs + cell;
-            const double n = (double)acc_n;
-#pragma unroll
-            for (int s = 0; s < kNS; ++s) {
-                const int vid[4] = {MMS_V_ADULT, MMS_V_AQUATIC, MMS_V_LARVAL_HABITAT_AREA, MMS_V_WATER_VOLUME};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (!kFull && k >= 2) continue;
-                    if (p.mean_mask & (1u << vid[k])) {
-                        const int64_t row = (int64_t)(set0 + s) * n_mean_state + slot(p.mean_mask, kState, vid[k]);
-                        p.mean_state[row * p.P * cs + pc] = acc_state[s][k] / n;
-                    }
-                }
-                if (p.wet_hours) p.wet_hours[(int64_t)(set0 + s) * p.P * cs + pc] = acc_wet[s];
-            }
-            if (write_forcing) {
-                const int vid[9] = {MMS_V_MDR, MMS_V_EFD, MMS_V_DAS_ZERODENSITY, MMS_V_DS, MMS_V_AIR_TEMPERATURE,
-                                    MMS_V_HUMIDITY, MMS_V_WINDSPEED, MMS_V_RAINFALL, MMS_V_CLOUDCOVER};
-#pragma unroll
-                for (int k = 0; k < kNF; ++k) {
-                    if (p.mean_mask & (1u << vid[k])) {
-                        const int64_t row = slot(p.mean_mask, ~kState, vid[k]);
-                        p.mean_forcing[row * p.P * cs + pc] = acc_forc[k] / n;
-                    }
-                }
-            }
-        };
-
-        // day window: today, tomorrow; carried values of yesterday
-        DayCtx dc;
-        dc.cur = load_daily<kFull>(p, cell, 0, bad);
-        dc.nxt = load_daily<kFull>(p, cell, (p.D > 1) ? 1 : 0, bad);
-        dc.A = MMS_DIVC(dc.cur.tmax - dc.cur.tmin, 2.0);                       // R/sim_microclimate.R:217
-        dc.t_sunset = dc.A * p.hr.z_night + dc.cur.tmin + dc.A;                // :220
-        // :271-272 (first day: its own midnight = night curve at t = 2400)
-        dc.t_midnight_prev = (dc.t_sunset - dc.nxt.tmin) / p.hr.exp_e[23] + dc.nxt.tmin;
-        dc.rhmin_prev = dc.cur.rhmin; dc.wsmax_prev = dc.cur.wsmax; dc.ccmin_prev = dc.cur.ccmin;   // :522
-
-        for (int day = 0; day < n_days; ++day) {
-            const bool record = final_pass;
-            int period = -1;
-            if (record && p.period_of_day) {
-                period = p.period_of_day[day];
-                if (period >= 0 && period != cur_period) {
-                    if (cur_period >= 0) flush(cur_period);
-                    reset_acc();
-                    cur_period = period;
-                }
-            }
-            const bool accumulate = period >= 0;
-
-            const double rain_h = MMS_DIVC(dc.cur.rain, 24.0);                // R/sim_microclimate.R:132
-            const double gain_m_h = MMS_DIVC(rain_h, 1000.0);                 // R/sim_water.R:122
-            double gain[kNS];
-#pragma unroll
-            for (int s = 0; s < kNS; ++s) gain[s] = p.hab[set0 + s].catchment_area * gain_m_h;   // :123
-
-            HourF f = hour_forcing<kFull>(p, tb, dc, p_a, 0, water_only);
-#pragma unroll 1
-            for (int h = 0; h < 24; ++h) {
-                // software pipeline: state-independent half of hour h + 1 ...
-                HourF fn = f;
-                if (h < 23) fn = hour_forcing<kFull>(p, tb, dc, p_a, h + 1, water_only);
-
-                // ... next to the state-dependent half of hour h
-#pragma unroll
-                for (int s = 0; s < kNS; ++s) {
-                    const HabitatDev &hb = p.hab[set0 + s];
-                    volume[s] = iterate_volume(hb, volume[s], surface[s], f.evap, gain[s]);   // R/sim_water.R:279-287
-                    surface[s] = habitat_surface(hb, volume[s]);                              // :294
-                    if (!water_only)   // larval_habitat_area = water_surface_area, R/sim_pop_dynamics.R:123
-                        iterate_state(aquatic[s], adult[s], f.ph, p.densmod_type, p.dd_effect,
-                                      p.surface_area_cm2, surface[s]);
-                }
-
-                // ---- outputs
-                if (record) {
-                    if (accumulate) {
-#pragma unroll
-                        for (int s = 0; s < kNS; ++s) {
-                            acc_state[s][0] += adult[s];
-                            acc_state[s][1] += aquatic[s];
-                            if (kFull) {
-                                acc_state[s][2] += surface[s];
-                                acc_state[s][3] += volume[s];
-                            }
-                            acc_wet[s] += (volume[s] > 0.0) ? 1 : 0;
-                        }
-                        acc_forc[0] += f.mdr; acc_forc[1] += f.efd; acc_forc[2] += f.das0; acc_forc[3] += f.ds;
-                        if (kFull) {
-                            acc_forc[4] += f.air_t; acc_forc[5] += f.rh; acc_forc[6] += f.wind;
-                            acc_forc[7] += rain_h; acc_forc[8] += f.cloud;
-                        }
-                        ++acc_n;
-                    }
-                    if (kHourly && live) {
-                        const int64_t tc = (int64_t)(day * 24 + h) * cs + cell;
-#pragma unroll
-                        for (int s = 0; s < kNS; ++s) {
-                            const double val[4] = {adult[s], aquatic[s], surface[s], volume[s]};
-                            const int vid[4] = {MMS_V_ADULT, MMS_V_AQUATIC, MMS_V_LARVAL_HABITAT_AREA, MMS_V_WATER_VOLUME};
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                if (!kFull && k >= 2) continue;
-                                if (p.hourly_mask & (1u << vid[k])) {
-                                    const int64_t row = (int64_t)(set0 + s) * n_hourly_state + slot(p.hourly_mask, kState, vid[k]);
-                                    p.hourly_state[row * H * cs + tc] = val[k];
-                                }
-                            }
-                            if (p.wet_flags)
-                                p.wet_flags[(int64_t)(set0 + s) * H * cs + tc] = (volume[s] > 0.0) ? 1 : 0;
-                        }
-                        if (write_forcing) {
-                            const double val[9] = {f.mdr, f.efd, f.das0, f.ds, f.air_t, f.rh, f.wind, rain_h, f.cloud};
-                            const int vid[9] = {MMS_V_MDR, MMS_V_EFD, MMS_V_DAS_ZERODENSITY, MMS_V_DS, MMS_V_AIR_TEMPERATURE,
-                                                MMS_V_HUMIDITY, MMS_V_WINDSPEED, MMS_V_RAINFALL, MMS_V_CLOUDCOVER};
-#pragma unroll
-                            for (int k = 0; k < kNF; ++k) {
-                                if (p.hourly_mask & (1u << vid[k])) {
-                                    const int64_t row = slot(p.hourly_mask, ~kState, vid[k]);
-                                    p.hourly_forcing[row * H * cs + tc] = val[k];
-                                }
-                            }
-                        }
-                    }
-                }
-                f = fn;
-            }   // hours
-
-            // ---- roll the day window
-            dc.t_midnight_prev = f.air_t;                // hour-24 value, R/sim_microclimate.R:271
-            dc.rhmin_prev = dc.cur.rhmin; dc.wsmax_prev = dc.cur.wsmax; dc.ccmin_prev = dc.cur.ccmin;
-            dc.cur = dc.nxt;
-            const int d2 = day + 2;
-            dc.nxt = load_daily<kFull>(p, cell, d2 < p.D ? d2 : p.D - 1, bad);
-            dc.A = MMS_DIVC(dc.cur.tmax - dc.cur.tmin, 2.0);
-            dc.t_sunset = dc.A * p.hr.z_night + dc.cur.tmin + dc.A;
-        }   // days
-        if (final_pass && cur_period >= 0) flush(cur_period);
-    }   // passes
-
-    if (bad && live) atomicOr(p.error_flag, 1);
+    if (bad && u.live) atomicOr(p.error_flag, 1);
 }
 
 // ---- the kernel -----------------------------------------------------------

@@ -42,7 +42,9 @@ constexpr double kTimestep = 1.0 / 24.0;          // timestep = 1 / 24, R/sim_po
 #define MMS_DIVC(x, c) ((x) * (1.0 / (c)))
 #define MMS_EXP(x) ::mms::fm::exp_sat(x)
 #define MMS_LOG(x) ::mms::fm::log_sat(x)
-#define MMS_DIV(a, b) ((a) / (b))
+// branch-free division (MUFU.RCP64H + Newton): operands here are normal, finite numbers
+// (pressures, densities); CUDA's IEEE division would put a slow-path branch in the hour loop
+#define MMS_DIV(a, b) ::mms::fm::div_core(a, b)
 #endif
 
 // R's `^` (arithmetic.c R_pow) for a positive, non-integer literal exponent y.
@@ -145,7 +147,13 @@ __device__ __forceinline__ PopHour pop_hour(int densmod_type, double mdr, double
         ph.link0 = MMS_LOG(1.0 - daily_mortality_zero_density);      // log p'; exp(loghaz) = -log p' * exp(dd*D)
 #endif
     } else {
-        ph.link0 = MMS_LOG(MMS_DIV(das0, 1.0 - das0));               // logit(), :533,:571
+#if MMS_STRICT
+        ph.link0 = log(das0 / (1.0 - das0));                         // logit(), :533,:571
+#else
+        const double om = 1.0 - das0;                                // das0 == 1 -> p / 0 = +Inf like R
+        const double odds = (om == 0.0) ? ::mms::fm::make_inf() : ::mms::fm::div_core(das0, om);
+        ph.link0 = MMS_LOG(odds);
+#endif
     }
     return ph;
 }
