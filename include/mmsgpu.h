@@ -201,6 +201,10 @@ MMS_API int  mms_chain_download(mms_chain_plan *plan, const mms_chain_outputs *o
 MMS_API int  mms_chain_kernel_ms(mms_chain_plan *plan, float *ms);   /* max over shards, last launch */
 MMS_API int  mms_chain_launch_count(mms_chain_plan *plan, int64_t *n);/* kernels launched so far */
 MMS_API void mms_chain_destroy(mms_chain_plan *plan);
+/* the contiguous cell range [cell0, cell0 + count) that shard `index` of `n_shards` owns
+ * (pure host logic; what mms_chain_create uses, and what a one-process-per-GPU caller
+ * uses to cut its own tile out of a raster) */
+MMS_API int  mms_shard_range(int64_t n_cells, int32_t n_shards, int32_t index, int64_t *cell0, int64_t *count);
 
 /* ---- stage-level twins (R matrices in, R matrices out) -------------------
  * simulate_ephemeral_habitat_vectorised(), R/sim_water.R:216-301.

@@ -86,6 +86,7 @@ class ChainOutputs(ct.Structure):
 EXPORTS = ("mms_abi_version", "mms_device_count", "mms_last_error", "mms_run_chain",
            "mms_chain_create", "mms_chain_upload", "mms_chain_launch", "mms_chain_sync",
            "mms_chain_download", "mms_chain_kernel_ms", "mms_chain_launch_count", "mms_chain_destroy",
+           "mms_shard_range",
            "mms_water_vectorised", "mms_population_vectorised", "mms_host_alloc", "mms_host_free",
            "mms_measure_fp64_peak", "mms_measure_hbm_copy", "mms_flush_l2")
 
@@ -112,6 +113,8 @@ def lib() -> ct.CDLL:
         L.mms_chain_launch_count.argtypes = [vp, ct.POINTER(ct.c_int64)]
         L.mms_chain_destroy.argtypes = [vp]
         L.mms_chain_destroy.restype = None
+        L.mms_shard_range.argtypes = [ct.c_int64, ct.c_int32, ct.c_int32, ct.POINTER(ct.c_int64),
+                                      ct.POINTER(ct.c_int64)]
         L.mms_water_vectorised.argtypes = [_dp, _dp, _dp, _dp, _dp, ct.c_int64, ct.c_int64,
                                            ct.POINTER(Habitat), ct.c_int32, ct.c_int32, ct.c_int32,
                                            _dp, _dp, _bp]
@@ -130,6 +133,13 @@ def lib() -> ct.CDLL:
 def check(status: int) -> None:
     if status != 0:
         raise MmsError(status, lib().mms_last_error().decode("utf-8", "replace"))
+
+
+def shard_range(n_cells: int, n_shards: int, index: int):
+    """(cell0, count) of shard `index` of `n_shards` (mms_shard_range; pure host logic)."""
+    c0, n = ct.c_int64(), ct.c_int64()
+    check(lib().mms_shard_range(int(n_cells), int(n_shards), int(index), ct.byref(c0), ct.byref(n)))
+    return int(c0.value), int(n.value)
 
 
 def device_count() -> int:

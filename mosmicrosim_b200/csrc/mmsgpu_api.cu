@@ -337,6 +337,23 @@ void mms_chain_destroy(mms_chain_plan *plan)
     delete plan;
 }
 
+// Contiguous cell range of shard `index` out of `n_shards`: whole 128-cell blocks, the
+// remainder blocks going to the first shards, the last shard taking the ragged tail.
+int mms_shard_range(int64_t n_cells, int32_t n_shards, int32_t index, int64_t *cell0, int64_t *count)
+{
+    if (n_cells < 0 || n_shards < 1 || index < 0 || index >= n_shards || !cell0 || !count)
+        return fail(MMS_ERR_INVALID_ARG, "bad shard request");
+    const int64_t blocks_total = (n_cells + mms::kBlock - 1) / mms::kBlock;
+    const int64_t base = blocks_total / n_shards, extra = blocks_total % n_shards;
+    const int64_t b0 = base * index + std::min<int64_t>(index, extra);
+    const int64_t nb = base + (index < extra ? 1 : 0);
+    const int64_t first = std::min<int64_t>(b0 * mms::kBlock, n_cells);
+    const int64_t last = std::min<int64_t>((b0 + nb) * mms::kBlock, n_cells);
+    *cell0 = first;
+    *count = last - first;
+    return MMS_OK;
+}
+
 int mms_chain_create(const mms_chain_config *cfg, mms_chain_plan **out)
 {
     if (!cfg || !out) return fail(MMS_ERR_INVALID_ARG, "NULL config or plan pointer");
@@ -404,19 +421,16 @@ int mms_chain_create(const mms_chain_config *cfg, mms_chain_plan **out)
 
     // contiguous cell ranges, one per device; each shard padded to whole CTAs
     const int G = (int)devs.size();
-    const int64_t blocks_total = (pl->C + mms::kBlock - 1) / mms::kBlock;
-    int64_t cell = 0;
     for (int g = 0; g < G; ++g) {
-        const int64_t blocks = blocks_total / G + (g < blocks_total % G ? 1 : 0);
-        const int64_t n = std::min<int64_t>(blocks * mms::kBlock, pl->C - cell);
+        int64_t cell0 = 0, n = 0;
+        mms_shard_range(pl->C, G, g, &cell0, &n);
         if (n <= 0) continue;
         Shard s;
         s.device = devs[g];
-        s.cell0 = cell;
+        s.cell0 = cell0;
         s.n_cells = n;
         s.c_stride = ((n + mms::kBlock - 1) / mms::kBlock) * mms::kBlock;
         pl->shards.push_back(s);
-        cell += n;
     }
     for (Shard &s : pl->shards) {
         rc = setup_shard(pl, s);

@@ -1,0 +1,210 @@
+"""CPU-only tests: host-side mirror of the reference interface (dates, tables,
+argument handling), the C-ABI library loads and exports every symbol that
+include/mmsgpu.h declares, there is no CPU fallback, and the one-process-per-GPU
+sharding logic is equivalent to a single run (gloo, world size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+from helpers import Case
+from mosmicrosim_b200 import backend, dates, lifehistory as lh, pipeline, synthetic as syn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- the C ABI ---------------------------------------------------------------------
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "mmsgpu.h")).read()
+    declared = set(re.findall(r"MMS_API\s+[\w\s\*]*?\b(mms_\w+)\s*\(", hdr))
+    assert len(declared) >= 18
+    L = ctypes.CDLL(backend.LIB_PATH)
+    missing = [n for n in sorted(declared) if not hasattr(L, n)]
+    assert not missing, missing
+    assert declared == set(backend.EXPORTS), declared ^ set(backend.EXPORTS)
+    assert L.mms_abi_version() == 1
+
+
+def test_struct_layouts_match_the_header():
+    # sizes the C compiler gives the structs in include/mmsgpu.h
+    src = '#include <stdio.h>\n#include "mmsgpu.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu",' \
+          "sizeof(mms_habitat),sizeof(mms_densmod),sizeof(mms_spline),sizeof(mms_surface)," \
+          "sizeof(mms_lifehistory),sizeof(mms_chain_config),sizeof(mms_chain_outputs));return 0;}"
+    exe = "/tmp/mms_sizes"
+    subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src.encode(),
+                   check=True)
+    sizes = [int(x) for x in subprocess.run([exe], capture_output=True, check=True).stdout.split()]
+    got = [ctypes.sizeof(t) for t in (backend.Habitat, backend.Densmod, backend.Spline, backend.Surface,
+                                      backend.LifehistoryC, backend.ChainConfig, backend.ChainOutputs)]
+    assert got == sizes
+
+
+def test_no_cpu_fallback_without_a_device():
+    if backend.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    case = Case(n_cells=4)
+    with pytest.raises(backend.MmsError) as e:
+        backend.run_chain(case.monthly, case.altitude, **case.gpu_kwargs(mean_vars=["adult"]))
+    assert e.value.code == "MMS_ERR_NO_DEVICE"
+    z = np.zeros((24, 2))
+    with pytest.raises(backend.MmsError) as e:
+        backend.water_vectorised(z, z, z, z, np.zeros(2), backend.make_habitat())
+    assert e.value.code == "MMS_ERR_NO_DEVICE"
+    with pytest.raises(backend.MmsError) as e:
+        pipeline.simulate_population_vectorised(z, z, z, z, z, lh.make_surv_densmod_function(-0.004, 900.0, "logit"),
+                                                burnin_years=0)
+    assert e.value.code == "MMS_ERR_NO_DEVICE"
+
+
+def test_argument_validation_happens_before_any_device_work():
+    case = Case(n_cells=4)
+    bad = dict(case.gpu_kwargs(mean_vars=["adult"]))
+    bad["habitats"] = []                                        # n_settings = 0
+    with pytest.raises(backend.MmsError) as e:
+        backend.run_chain(case.monthly, case.altitude, **bad)
+    assert e.value.code == "MMS_ERR_INVALID_ARG"
+    z = np.zeros((100, 2))
+    with pytest.raises(backend.MmsError) as e:                  # R: subscript out of bounds
+        backend.population_vectorised(z, z, z, z, z, backend.make_densmod("logit", -0.004, 900.0), burnin_years=1)
+    assert e.value.code == "MMS_ERR_BURNIN"
+
+
+def test_shard_ranges_cover_the_raster():
+    for n, g in ((100_000, 8), (1_500_000, 8), (1000, 3), (127, 4), (129, 2), (5, 8)):
+        ranges = [backend.shard_range(n, g, i) for i in range(g)]
+        pos = 0
+        for c0, cnt in ranges:
+            assert c0 == pos and cnt >= 0
+            pos += cnt
+            assert c0 % 128 == 0 or cnt == 0
+        assert pos == n
+        assert max(c for _, c in ranges) - min(c for _, c in ranges) <= 256      # balanced to 2 blocks
+
+
+# ---- dates ---------------------------------------------------------------------------
+
+def test_mid_dates_and_default_dates_predict():
+    start, end = syn.month_table(2001, 1)
+    assert len(start) == 14 and str(start[0]) == "2000-12-01" and str(end[-1]) == "2002-01-31"
+    mid = dates.month_mid_days(start, end)
+    d0 = np.datetime64("2000-12-01").astype("datetime64[D]").astype(np.int64)
+    assert mid[0] == d0 + 15.0                                   # 31-day month: start + 15
+    assert mid[2] - (d0 + 31 + 31) == 13.5                       # Feb 2001 (28 days): start + 13.5
+    dp = dates.default_dates_predict(start, end)
+    assert str(dp[0]) == "2000-12-16" and str(dp[-1]) == "2002-01-16"
+    mid_day, day_predict = dates.datenums(start, end, dp)
+    assert mid_day[0] == 0.0 and day_predict[0] == 0.0 and not dates.needs_extrapolation(mid_day, day_predict)
+    # a 30-day first month (mid = start + 14.5, rounded limit start + 14) triggers the GAM branch in R
+    s2 = np.array(["2001-04-01", "2001-05-01", "2001-06-01"], "datetime64[D]")
+    e2 = np.array(["2001-04-30", "2001-05-31", "2001-06-30"], "datetime64[D]")
+    md2, dp2 = dates.datenums(s2, e2, dates.default_dates_predict(s2, e2))
+    assert dates.needs_extrapolation(md2, dp2)
+
+
+def test_period_index_month_day_included():
+    dp = syn.year_dates(2001, 1)
+    pod, ps, pe = dates.period_index(dp, "month")
+    assert len(ps) == 12 and str(ps[1]) == "2001-02-01" and str(pe[1]) == "2001-02-28"
+    assert np.bincount(pod).tolist() == [31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31]
+    inc = dp[40:100]
+    pod2, ps2, _ = dates.period_index(dp, "month", inc)
+    assert (pod2 >= 0).sum() == 60 and len(ps2) == 3 and pod2[39] == -1 and pod2[40] == 0
+    pod3, ps3, pe3 = dates.period_index(dp, "day", inc)
+    assert len(ps3) == 60 and np.array_equal(ps3, pe3)
+    with pytest.raises(ValueError):
+        dates.period_index(dp, "week")
+
+
+# ---- life-history table carriers --------------------------------------------------------
+
+def test_lifehistory_tables_follow_the_reference_shapes():
+    L = syn.synthetic_lifehistory("An. gambiae")
+    t = L.tables()
+    assert len(t["mdr"]["x"]) == 1001 and t["mdr"]["x"][0] == -20.0 and t["mdr"]["x"][-1] == 80.0
+    assert np.array_equal(t["mdr"]["x"], t["efd"]["x"]) and np.array_equal(t["mdr"]["x"], t["das"]["x"])
+    g = t["ds"]
+    assert len(g["x"]) == 250 and len(g["y"]) == 250 and g["z"].shape == (62500,)
+    assert g["x"][0] == 0.0 and g["x"][-1] == 45.0 and g["y"][-1] == 100.0
+    assert g["x"][1] == 45.0 / 249                              # seq(0, 45, length.out = 250)
+    assert L.das_densmod.type == "logit" and syn.synthetic_lifehistory("An. stephensi").das_densmod.type == "cox_ph"
+    with pytest.raises(ValueError):
+        lh.make_surv_densmod_function(1.0, 1.0, "probit")
+    assert not callable(L.mdr_temp)                             # table carriers, no CPU evaluation path
+
+
+def test_pipeline_argument_handling_mirrors_the_reference():
+    case = Case(n_cells=3)
+    pmc = {"start": case.start, "end": case.end, "altitude": case.altitude,
+           "longitude": np.arange(3.0), "latitude": np.arange(3.0)}
+    for v, name in enumerate(pipeline.FORCING_VARS):
+        pmc[name] = case.monthly[v]
+    lhf = {"An_gambiae": case.lh, "An_stephensi": syn.synthetic_lifehistory("An. stephensi")}
+    with pytest.raises(ValueError):
+        pipeline.monthly_climate_to_vectors(pmc, lhf, species="An. funestus")
+    with pytest.raises(NotImplementedError):                     # R/pipeline_functions.R:334-338
+        pipeline.monthly_climate_to_vectors(pmc, lhf, model_water_temperature=True)
+    if backend.device_count() == 0:
+        with warnings.catch_warnings(record=True) as wlist:      # R/pipeline_functions.R:327-332
+            warnings.simplefilter("always")
+            with pytest.raises(backend.MmsError):
+                pipeline.monthly_climate_to_vectors(pmc, lhf, water_shade_proportion=0.5)
+            assert any("water_shade_proportion" in str(x.message) for x in wlist)
+
+
+# ---- one process per GPU: shards == whole (gloo, world size 2, CPU) --------------------------
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch, torch.distributed as dist
+import oracle
+from helpers import Case
+from mosmicrosim_b200 import backend
+dist.init_process_group(backend="gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+case = Case(n_cells=300)                       # the same raster on every rank
+c0, n = backend.shard_range(case.C, world, rank)
+sub = oracle.run_chain(np.ascontiguousarray(case.monthly[:, :, c0:c0 + n]), case.mid_day, case.day_predict,
+                       case.altitude[c0:c0 + n], [oracle.habitat(**h) for h in case.habitats],
+                       oracle.densmod(case.densmod["type_"], case.densmod["dd_effect"], case.densmod["surface_area_cm2"]),
+                       case.tables, case.period_of_day, case.P, want_hourly=False, n_threads=2)
+mine = torch.zeros((1, 12, case.P, 256), dtype=torch.float64)
+mine[..., :n] = torch.from_numpy(sub["mean"])
+parts = [torch.zeros_like(mine) for _ in range(world)]
+dist.all_gather(parts, mine)                   # the gather at the end: the only communication
+t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+dist.all_reduce(t, op=dist.ReduceOp.MAX)       # bench.py's max-over-ranks timing reduction
+if rank == 0:
+    whole = oracle.run_chain(case.monthly, case.mid_day, case.day_predict, case.altitude,
+                             [oracle.habitat(**h) for h in case.habitats],
+                             oracle.densmod(case.densmod["type_"], case.densmod["dd_effect"], case.densmod["surface_area_cm2"]),
+                             case.tables, case.period_of_day, case.P, want_hourly=False, n_threads=2)["mean"]
+    cat = []
+    for r in range(world):
+        _, nr = backend.shard_range(case.C, world, r)
+        cat.append(parts[r][..., :nr].numpy())
+    cat = np.concatenate(cat, axis=-1)
+    assert cat.shape == whole.shape, (cat.shape, whole.shape)
+    assert np.array_equal(cat, whole, equal_nan=True), "concatenated shards differ from the single run"
+    assert float(t.item()) == world
+    print("SHARDS_OK")
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_sharding_equals_single_run(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "SHARDS_OK" in r.stdout

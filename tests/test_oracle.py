@@ -1,0 +1,203 @@
+"""The CPU oracle against (i) the known-answer constants derivable from the R
+source, (ii) the properties of the reference's commented
+demos, (iii) the independently written numpy restatement, (iv) scipy/numpy for the
+third-party algorithms it restates, and (v) the committed golden vectors."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import restate_numpy as rn
+from helpers import Case
+from mosmicrosim_b200 import synthetic as syn
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "chain_small.npz")
+
+
+# ---- known-answer constants ---------------------------------------------------
+
+def test_kat_constants():
+    L = oracle.lib()
+    assert np.sqrt(np.finfo(float).eps) == 1.4901161193847656e-08
+    assert L.mmso_cone_depth_to_volume(1.0) == 1.0471975511965976
+    assert 3.046474 * L.mmso_R_pow(1.0471975511965976, 0.666667) == 3.141592812544754
+    hb = oracle.habitat()
+    assert L.mmso_habitat_catchment(hb) == 3.141592812544754          # "pi", but not exactly
+    assert L.mmso_evaporation_rate_kg_h(25.0, 60.0, 500.0, 2.0, 1.0) == pytest.approx(0.5498675133833498, rel=1e-15)
+    assert L.mmso_R_pow(2.0 / 10.0, 0.15) == pytest.approx(0.7855150302317644, rel=1e-15)
+    assert L.mmso_R_pow(3.0, 2.0) == 9.0 and L.mmso_R_pow(0.0, 0.5) == 0.0 and L.mmso_R_pow(-0.0, 0.666667) == 0.0
+    assert L.mmso_cone_volume_to_surface(0.0) == 0.0
+
+
+def test_kat_sinec_constants():
+    # a day with tmin = 0, tmax = 2 (A = 1) exposes the hour-of-day constants directly
+    air = oracle.interpolate_daily_air_temp([2.0, 2.0, 2.0], [0.0, 0.0, 0.0])[24:48]
+    light = np.array([-0.999999999999966, -0.9009689487307901, -0.6234898892473616, -0.2225209702802615,
+                      0.2225209702802615, 0.6234898892473616, 0.9009689487307901, 0.999999999999966,
+                      0.9009687224112726, 0.6234894814336972, 0.2225204617449742, -0.22252147881548834,
+                      -0.6234902970608567])
+    np.testing.assert_allclose(air[5:18], light + 1.0, rtol=0, atol=2e-16)
+    z_night = -0.6234902970608567
+    e = np.array([1.2840254166877414, 1.6487212707001282, 2.117000016612675, 2.718281828459045,
+                  3.4903429574618414, 4.4816890703380645])
+    np.testing.assert_allclose(air[18:24], (z_night + 1.0) / e, rtol=1e-15)
+
+
+def test_kat_vsine_weights():
+    w = oracle.vsine_weights(np.arange(1.0, 25.0))
+    expect = [7 / 12, 8 / 12, 9 / 12, 10 / 12, 11 / 12, 1, 6 / 7, 5 / 7, 4 / 7, 3 / 7, 2 / 7, 1 / 7, 0] + \
+             [k / 22 for k in range(1, 12)]
+    np.testing.assert_allclose(w, expect, rtol=0, atol=1.2e-16)
+
+
+def test_densmod_forms():
+    lg = oracle.densmod("logit", syn.DD_EFFECT_AG, syn.MURIU_AREA_CM2)
+    cx = oracle.densmod("cox_ph", 0.002, syn.EVANS_AREA_CM2)
+    L = oracle.lib()
+    assert L.mmso_densmod_apply(lg, 0.9, 0.0) == pytest.approx(0.9, rel=1e-15)
+    assert L.mmso_densmod_apply(cx, 0.9, 0.0) == pytest.approx(0.9, rel=1e-15)
+    assert L.mmso_densmod_apply(lg, 0.9, 10.0) < 0.9 and L.mmso_densmod_apply(cx, 0.9, 10.0) < 0.9
+    assert L.mmso_densmod_apply(lg, 0.9, 1e12) == 0.0          # dry habitat: density / eps -> survival 0
+    assert L.mmso_densmod_apply(lg, 0.0, 1.0) == 0.0           # logit(0) = -Inf
+
+
+# ---- properties from the reference's commented demos ----------------------------
+
+def test_hourly_curve_anchor_properties():
+    rng = np.random.default_rng(1)
+    n = 12
+    tmax, tmin = rng.uniform(25, 32, n), rng.uniform(11, 15, n)
+    air = oracle.interpolate_daily_air_temp(tmax, tmin).reshape(n, 24)
+    np.testing.assert_allclose(air[:, 12], tmax, rtol=1e-12)      # hour 13 = daily max (R/sim_microclimate.R:300-301)
+    np.testing.assert_allclose(air[:, 5], tmin, rtol=1e-12)       # hour 6 = daily min (:302-303)
+    hmax, hmin = rng.uniform(85, 92, n), rng.uniform(51, 55, n)
+    rh = oracle.vsine_interpolate_daily(hmax, hmin, "max").reshape(n, 24)
+    np.testing.assert_allclose(rh[:, 5], hmax, rtol=1e-15)        # max at 6 (:343-344)
+    np.testing.assert_allclose(rh[:, 12], hmin, rtol=1e-15)       # min at 13 (:345-346)
+    wmax, wmin = rng.uniform(3, 5, n), rng.uniform(1, 1.5, n)
+    ws = oracle.vsine_interpolate_daily(wmax, wmin, "min").reshape(n, 24)
+    np.testing.assert_allclose(ws[:, 5], wmin, rtol=1e-15)        # min at 6 (:385-386)
+    np.testing.assert_allclose(ws[:, 12], wmax, rtol=1e-15)       # max at 13 (:383-384)
+
+
+def test_water_and_population_invariants():
+    case = Case(n_cells=24, habitats=[syn.habitat_cone(), syn.habitat_cylinder(leak_per_hour=0.01)])
+    ref = case.oracle()
+    for s, hb in enumerate(case.habitats):
+        h = oracle.habitat(**hb)
+        vmax = oracle.lib().mmso_habitat_max_volume(h)
+        vol = ref["hourly"][s, 7]
+        area = ref["hourly"][s, 6]
+        assert np.nanmin(vol) >= 0.0 and np.nanmax(vol) <= vmax
+        assert np.all(area[vol == 0.0] == 0.0)
+        assert np.array_equal(ref["wet"][s].astype(bool), vol > 0)
+        adult = ref["hourly"][s, 0]
+        assert np.nanmin(adult) >= np.sqrt(np.finfo(float).eps)   # imported adults keep it positive
+    # leak = 0 cylinder equals ... itself with leak 0.0 bit for bit through the extension term
+    a = Case(n_cells=8, habitats=[syn.habitat_cone(leak_per_hour=0.0)]).oracle()
+    b = Case(n_cells=8, habitats=[syn.habitat_cone()]).oracle()
+    assert np.array_equal(a["hourly"], b["hourly"], equal_nan=True)
+
+
+def test_na_outside_ds_grid_is_reset_next_step():
+    case = Case(n_cells=40, out_of_range_fraction=0.5)
+    ref = case.oracle()
+    ds, adult = ref["hourly"][0, 5], ref["hourly"][0, 0]
+    assert np.isnan(ds).any()
+    assert np.array_equal(np.isnan(adult), np.isnan(ds))          # NA that hour only (R/sim_pop_dynamics.R:33-34)
+    t, c = np.argwhere(np.isnan(ds[:-1]) & ~np.isnan(ds[1:]))[0]
+    assert adult[t + 1, c] >= np.sqrt(np.finfo(float).eps)
+
+
+def test_extrapolation_and_burnin_errors():
+    case = Case(n_cells=2)
+    with pytest.raises(ValueError):
+        oracle.spline_seasonal(case.monthly[0, :, 0], case.mid_day, case.day_predict - 400.0)
+    with pytest.raises(ValueError):
+        oracle.run_chain(case.monthly, case.mid_day, case.day_predict[:100], case.altitude,
+                         [oracle.habitat()], oracle.densmod("logit", -0.004, 900.0), case.tables,
+                         case.period_of_day[:100], case.P)      # burn-in needs >= 8760 steps
+
+
+# ---- third-party algorithms the oracle restates -----------------------------------
+
+def test_approx_matches_numpy_interp():
+    rng = np.random.default_rng(3)
+    x = np.cumsum(rng.uniform(0.5, 2.0, 30))
+    y = rng.normal(size=30)
+    v = rng.uniform(x[0], x[-1], 200)
+    got = np.array([oracle.approx1(t, x, y) for t in v])
+    np.testing.assert_allclose(got, np.interp(v, x, y), rtol=1e-13, atol=1e-15)
+    assert oracle.approx1(x[7], x, y) == y[7] and oracle.approx1(x[-1], x, y) == y[-1]
+    assert np.isnan(oracle.approx1(x[0] - 1, x, y)) and np.isnan(oracle.approx1(x[-1] + 1, x, y))
+
+
+def test_fmm_spline_reproduces_cubics_and_matches_host_builder():
+    from mosmicrosim_b200.lifehistory import splinefun_fmm
+    x = np.linspace(-3, 5, 41)
+    y = 0.3 * x ** 3 - 1.1 * x ** 2 + 0.2 * x + 4.0       # fmm end conditions make cubics exact
+    b, c, d = oracle.fmm_spline(x, y)
+    tab = {"x": x, "y": y, "b": b, "c": c, "d": d}
+    u = np.linspace(-3, 5, 333)
+    np.testing.assert_allclose(oracle.spline_eval(tab, u), 0.3 * u ** 3 - 1.1 * u ** 2 + 0.2 * u + 4.0, rtol=1e-11)
+    host = splinefun_fmm(x, y)
+    assert np.array_equal(host.b, b) and np.array_equal(host.c, c) and np.array_equal(host.d, d)
+    # extrapolation uses the end cubics, like R's splinefun
+    assert oracle.spline_eval(tab, [6.0])[0] == pytest.approx(0.3 * 216 - 1.1 * 36 + 1.2 + 4.0, rel=1e-9)
+
+
+def test_interp_surface_matches_scipy_bilinear():
+    from scipy.interpolate import RegularGridInterpolator
+    tabs = syn.synthetic_lifehistory().tables()["ds"]
+    z2 = tabs["z"].reshape(len(tabs["y"]), len(tabs["x"])).T
+    rgi = RegularGridInterpolator((tabs["x"], tabs["y"]), z2, method="linear")
+    rng = np.random.default_rng(5)
+    t, h = rng.uniform(0, 45, 500), rng.uniform(0, 100, 500)
+    np.testing.assert_allclose(oracle.interp_surface(tabs, t, h), rgi(np.stack([t, h], 1)), rtol=1e-12)
+    out = oracle.interp_surface(tabs, [-0.1, 45.0001, 20.0, 45.0], [50.0, 50.0, 100.5, 100.0])
+    assert np.isnan(out[:3]).all() and out[3] == z2[-1, -1]        # NA outside, exact on the last grid line
+
+
+def test_r_mean_is_long_double_two_pass():
+    x = np.array([1e16, 1.0, -1e16, 1.0])
+    assert oracle.R_mean(x) == 0.5 and rn.r_mean(x) == 0.5
+    assert np.isnan(oracle.R_mean(np.array([1.0, np.nan])))
+
+
+# ---- double-entry: C restatement vs numpy restatement --------------------------------
+
+@pytest.mark.parametrize("species", ["An. gambiae", "An. stephensi"])
+def test_c_oracle_matches_numpy_restatement(species):
+    case = Case(n_cells=5, species=species,
+                habitats=[syn.habitat_cone(), syn.habitat_cylinder(leak_per_hour=0.002)])
+    ref = case.oracle()
+    dm = dict(type=case.densmod["type_"], dd_effect=case.densmod["dd_effect"],
+              surface_area_cm2=case.densmod["surface_area_cm2"])
+    alt = rn.run_chain(case.monthly, case.mid_day, case.day_predict, case.altitude, case.habitats, dm,
+                       case.tables, case.period_of_day, case.P)
+    for v, name in enumerate(oracle.VAR_NAMES):
+        a, b = ref["hourly"][:, v], alt["hourly"][:, v]
+        assert np.array_equal(np.isnan(a), np.isnan(b)), name
+        ok = ~np.isnan(a)
+        rel = np.max(np.abs(a[ok] - b[ok]) / np.maximum(np.abs(a[ok]), 1e-300) * (np.abs(a[ok] - b[ok]) > 1e-15))
+        assert rel < 1e-11, (name, rel)        # glibc scalar vs numpy SIMD exp/log/pow last bits
+    # the state-independent stages are bit identical
+    for name in ("mdr", "efd", "das_zerodensity", "ds", "air_temperature", "humidity", "windspeed"):
+        v = oracle.VAR_NAMES.index(name)
+        assert np.array_equal(ref["hourly"][0, v], alt["hourly"][0, v], equal_nan=True), name
+    assert np.array_equal(ref["wet"], alt["wet"]) and np.array_equal(ref["wet_hours"], alt["wet_hours"])
+    np.testing.assert_allclose(ref["mean"], alt["mean"], rtol=1e-11, atol=1e-15)
+
+
+# ---- golden vectors ----------------------------------------------------------------------
+
+def test_golden_vectors():
+    g = np.load(GOLDEN)
+    case = Case(n_cells=int(g["n_cells"]), habitats=[syn.habitat_cone(), syn.habitat_cylinder(leak_per_hour=0.002)])
+    assert np.array_equal(case.monthly, g["monthly"]) and np.array_equal(case.altitude, g["altitude"])
+    ref = case.oracle(want_hourly=True)
+    np.testing.assert_allclose(ref["mean"], g["mean"], rtol=1e-11, atol=1e-15)
+    assert np.array_equal(ref["wet_hours"], g["wet_hours"])
+    sel = g["hourly_steps"]
+    np.testing.assert_allclose(ref["hourly"][:, :, sel, :], g["hourly_sample"], rtol=1e-11, atol=1e-15)
