@@ -55,6 +55,15 @@ __device__ __forceinline__ double div_core(double a, double b)
     return fma(fma(-b, q, a), r, q);
 }
 
+// c ? a : b as a real SELP: written in PTX so that the compiler cannot turn the select back
+// into a branch around the (expensive) computation of one operand
+__device__ __forceinline__ double sel(bool c, double a, double b)
+{
+    double r;
+    asm("{ .reg .pred p; setp.ne.s32 p, %3, 0; selp.f64 %0, %1, %2, p; }" : "=d"(r) : "d"(a), "d"(b), "r"((int)c));
+    return r;
+}
+
 __device__ __forceinline__ double make_nan() { return __longlong_as_double(0x7ff8000000000000LL); }
 __device__ __forceinline__ double make_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
 
@@ -93,9 +102,9 @@ __device__ __forceinline__ double exp_sat(double x)
 {
     const int hi = __double2hiint(x);
     const bool big = ((unsigned)hi & 0x7fffffffu) >= 0x40862000u;   // |x| >= 708, Inf, NaN
-    const double r = exp_core(big ? 0.0 : x);
+    const double r = exp_core(sel(big, 0.0, x));
     const double special = is_nan_bits(x) ? make_nan() : ((hi < 0) ? 0.0 : make_inf());
-    return big ? special : r;
+    return sel(big, special, r);
 }
 
 // log(x) for normal, positive, finite x (caller guarantees it)
@@ -130,13 +139,13 @@ __device__ __forceinline__ double log_sat(double x)
 {
     const int hi = __double2hiint(x);
     const bool ok = (unsigned)(hi - 0x00100000) < 0x7fe00000u;      // normal, positive, finite
-    const double r = log_core(ok ? x : 1.0);
+    const double r = log_core(sel(ok, x, 1.0));
     const bool zero = (((unsigned)hi & 0x7fffffffu) | (unsigned)__double2loint(x)) == 0u;
     const bool pinf = hi == 0x7ff00000 && __double2loint(x) == 0;
     double special = (hi < 0 || is_nan_bits(x)) ? make_nan() : -708.3964185322641;   // negative / NaN, else denormal
     special = pinf ? make_inf() : special;
     special = zero ? -make_inf() : special;
-    return ok ? r : special;
+    return sel(ok, r, special);
 }
 
 // R's x ^ y for a positive, non-integer literal y: 0 -> 0, x < 0 / NaN -> NaN (x < Inf assumed)

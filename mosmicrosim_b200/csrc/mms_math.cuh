@@ -151,7 +151,8 @@ __device__ __forceinline__ PopHour pop_hour(int densmod_type, double mdr, double
         ph.link0 = log(das0 / (1.0 - das0));                         // logit(), :533,:571
 #else
         const double om = 1.0 - das0;                                // das0 == 1 -> p / 0 = +Inf like R
-        const double odds = (om == 0.0) ? ::mms::fm::make_inf() : ::mms::fm::div_core(das0, om);
+        const double odds = ::mms::fm::sel(om == 0.0, ::mms::fm::make_inf(),
+                                           ::mms::fm::div_core(das0, ::mms::fm::sel(om == 0.0, 1.0, om)));
         ph.link0 = MMS_LOG(odds);
 #endif
     }
@@ -187,9 +188,9 @@ __device__ __forceinline__ void iterate_state(double &aquatic, double &adult, co
         const double u = dd_effect * density_dish;
         const int uhi = __double2hiint(u);
         const bool ubig = ((unsigned)uhi & 0x7fffffffu) >= 0x4085e000u;      // |u| >= 700, Inf, NaN
-        const double e1 = ::mms::fm::exp_core(ubig ? ((uhi < 0) ? -700.0 : 700.0) : u);
+        const double e1 = ::mms::fm::exp_core(::mms::fm::sel(ubig, (uhi < 0) ? -700.0 : 700.0, u));
         double z = ::mms::fm::exp_sat(ph.link0 * e1);
-        z = ::mms::fm::is_nan_bits(u) ? u : z;
+        z = ::mms::fm::sel(::mms::fm::is_nan_bits(u), u, z);
         const double das_t = 1.0 - (1.0 - z);
         surv_aq = ::mms::fm::pow_pos(das_t, kTimestep);
     } else {
@@ -201,13 +202,13 @@ __device__ __forceinline__ void iterate_state(double &aquatic, double &adult, co
         const unsigned aabs = (unsigned)ahi & 0x7fffffffu;
         const bool hi_side = ahi >= 0x40440000;                               // a >= 40 (or +Inf, +NaN)
         const bool lo_side = ahi < 0 && aabs >= 0x40490000u;                  // a <= -50 (or -Inf, -NaN)
-        const double ac = hi_side ? 40.0 : (lo_side ? -50.0 : a);
+        const double ac = ::mms::fm::sel(hi_side || lo_side, hi_side ? 40.0 : -50.0, a);
         double L = ::mms::fm::log_core(1.0 + ::mms::fm::exp_core(ac));
-        L = hi_side ? a : L;
+        L = ::mms::fm::sel(hi_side, a, L);
         surv_aq = ::mms::fm::exp_sat(-kTimestep * L);
         const bool overflow = ahi > 0x40862e42 || (ahi == 0x40862e42 && (unsigned)__double2loint(a) > 0xfefa39efu);
-        surv_aq = overflow ? 0.0 : surv_aq;                                   // exp(a) = Inf -> das_t = 0
-        surv_aq = ::mms::fm::is_nan_bits(a) ? a : surv_aq;
+        surv_aq = ::mms::fm::sel(overflow, 0.0, surv_aq);                     // exp(a) = Inf -> das_t = 0
+        surv_aq = ::mms::fm::sel(::mms::fm::is_nan_bits(a), a, surv_aq);
     }
 #endif
     const double surviving_adult = ad * ph.surv_ad;             // :67
