@@ -35,16 +35,8 @@ constexpr double kTimestep = 1.0 / 24.0;          // timestep = 1 / 24, R/sim_po
 // x / c for a literal c of the R source; exp / log / division flavour
 #if MMS_STRICT
 #define MMS_DIVC(x, c) ((x) / (c))
-#define MMS_EXP(x) exp(x)
-#define MMS_LOG(x) log(x)
-#define MMS_DIV(a, b) ((a) / (b))
 #else
 #define MMS_DIVC(x, c) ((x) * (1.0 / (c)))
-#define MMS_EXP(x) ::mms::fm::exp_sat(x)
-#define MMS_LOG(x) ::mms::fm::log_sat(x)
-// branch-free division (MUFU.RCP64H + Newton): operands here are normal, finite numbers
-// (pressures, densities); CUDA's IEEE division would put a slow-path branch in the hour loop
-#define MMS_DIV(a, b) ::mms::fm::div_core(a, b)
 #endif
 
 // R's `^` (arithmetic.c R_pow) for a positive, non-integer literal exponent y.
@@ -55,14 +47,19 @@ __device__ __forceinline__ double r_pow_pos(double x, double y)
     if (x == 0.0) return 0.0;           // also -0.0 -> +0.0, like R_pow
     return pow(x, y);
 #else
-    return ::mms::fm::pow_pos(x, y);
+    return ::mms::fm::pow_unit(x, y);    // callers: water volume, survival probabilities (0 <= x, or NaN)
 #endif
 }
 
 // saturation_vapour_pressure_kpa(), R/sim_water.R:36-38 (Buck)
 __device__ __forceinline__ double svp_kpa(double t)
 {
-    return 0.61121 * MMS_EXP((18.678 - MMS_DIVC(t, 234.5)) * MMS_DIV(t, 257.14 + t));
+#if MMS_STRICT
+    return 0.61121 * exp((18.678 - t / 234.5) * (t / (257.14 + t)));
+#else
+    // the exponent is within +-20 for any temperature between -100 and +1000 C: no range guard
+    return 0.61121 * ::mms::fm::exp_core((18.678 - t * (1.0 / 234.5)) * ::mms::fm::div_fast(t, 257.14 + t));
+#endif
 }
 
 // evaporation_rate_kg_h() with surface_area_m2 = 1, R/sim_water.R:50-90,264-270.
@@ -71,10 +68,19 @@ __device__ __forceinline__ double evaporation_rate(double t, double rh, double p
 {
     const double theta = 25.0 + 19.0 * wind;                   // :67
     const double p_ws = svp_kpa(t);                            // :73
-    const double xs = MMS_DIV(0.62198 * p_ws, p_a - p_ws);     // :75
-    const double p_w = p_ws * MMS_DIVC(rh, 100.0);             // :84
-    const double x = MMS_DIV(0.62198 * p_w, p_a - p_w);        // :85
+#if MMS_STRICT
+    const double xs = 0.62198 * p_ws / (p_a - p_ws);           // :75
+    const double p_w = p_ws * (rh / 100.0);                    // :84
+    const double x = 0.62198 * p_w / (p_a - p_w);              // :85
     return theta * (xs - x);                                   // :88 (A = 1: theta * 1 == theta)
+#else
+    // xs - x over one denominator (one division instead of two; no cancellation of two
+    // rounded quotients): 0.62198 p_a (p_ws - p_w) / ((p_a - p_ws)(p_a - p_w))
+    const double p_w = p_ws * (rh * (1.0 / 100.0));
+    const double num = (0.62198 * p_a) * (p_ws - p_w);
+    const double den = (p_a - p_ws) * (p_a - p_w);
+    return theta * ::mms::fm::div_fast(num, den);
+#endif
 }
 
 __device__ __forceinline__ double air_pressure_kpa(double altitude)
@@ -130,7 +136,11 @@ __device__ __forceinline__ PopHour pop_hour(int densmod_type, double mdr, double
 {
     PopHour ph;
     ph.surv_ad = r_pow_pos(ds, kTimestep);
-    const double e = MMS_EXP(-(kTimestep * mdr));
+#if MMS_STRICT
+    const double e = exp(-(kTimestep * mdr));
+#else
+    const double e = ::mms::fm::exp_core(-(kTimestep * mdr));   // mdr is a clamped spline value: 0 <= mdr << 708 * 24
+#endif
     ph.emf = 1.0 - e;
 #if MMS_STRICT
     ph.one_m_emf = 1.0 - ph.emf;
@@ -144,7 +154,7 @@ __device__ __forceinline__ PopHour pop_hour(int densmod_type, double mdr, double
 #if MMS_STRICT
         ph.link0 = log(-log(1.0 - daily_mortality_zero_density));
 #else
-        ph.link0 = MMS_LOG(1.0 - daily_mortality_zero_density);      // log p'; exp(loghaz) = -log p' * exp(dd*D)
+        ph.link0 = ::mms::fm::log_nonneg(1.0 - daily_mortality_zero_density);   // log p'; exp(loghaz) = -log p' * exp(dd*D)
 #endif
     } else {
 #if MMS_STRICT
@@ -152,8 +162,8 @@ __device__ __forceinline__ PopHour pop_hour(int densmod_type, double mdr, double
 #else
         const double om = 1.0 - das0;                                // das0 == 1 -> p / 0 = +Inf like R
         const double odds = ::mms::fm::sel(om == 0.0, ::mms::fm::make_inf(),
-                                           ::mms::fm::div_core(das0, ::mms::fm::sel(om == 0.0, 1.0, om)));
-        ph.link0 = MMS_LOG(odds);
+                                           ::mms::fm::div_fast(das0, ::mms::fm::sel(om == 0.0, 1.0, om)));
+        ph.link0 = ::mms::fm::log_nonneg(odds);
 #endif
     }
     return ph;
@@ -166,7 +176,11 @@ __device__ __forceinline__ void iterate_state(double &aquatic, double &adult, co
 {
     const double aq = (aquatic != aquatic) ? 0.0 : aquatic;     // :33
     const double ad = (adult != adult) ? 0.0 : adult;           // :34
-    const double density = MMS_DIV(aq, larval_habitat_area + kEps);   // :42
+#if MMS_STRICT
+    const double density = aq / (larval_habitat_area + kEps);   // :42
+#else
+    const double density = ::mms::fm::div_fast(aq, larval_habitat_area + kEps);
+#endif
     const double density_dish = density * area_cm2;             // densmod :549 / :569
     double surv_aq;
 #if MMS_STRICT
@@ -203,11 +217,13 @@ __device__ __forceinline__ void iterate_state(double &aquatic, double &adult, co
         const bool hi_side = ahi >= 0x40440000;                               // a >= 40 (or +Inf, +NaN)
         const bool lo_side = ahi < 0 && aabs >= 0x40490000u;                  // a <= -50 (or -Inf, -NaN)
         const double ac = ::mms::fm::sel(hi_side || lo_side, hi_side ? 40.0 : -50.0, a);
-        double L = ::mms::fm::log_core(1.0 + ::mms::fm::exp_core(ac));
+        double L = ::mms::fm::log_fastdiv(1.0 + ::mms::fm::exp_core(ac));
         L = ::mms::fm::sel(hi_side, a, L);
-        surv_aq = ::mms::fm::exp_sat(-kTimestep * L);
+        // -L / 24 is within [-29.6, 0] whenever the result is used: beyond a = 709.78 the select
+        // below wins (exp(a) = Inf -> das_t = 0); a NaN a propagates through exp_core
         const bool overflow = ahi > 0x40862e42 || (ahi == 0x40862e42 && (unsigned)__double2loint(a) > 0xfefa39efu);
-        surv_aq = ::mms::fm::sel(overflow, 0.0, surv_aq);                     // exp(a) = Inf -> das_t = 0
+        surv_aq = ::mms::fm::exp_core(-kTimestep * ::mms::fm::sel(overflow, 0.0, L));
+        surv_aq = ::mms::fm::sel(overflow, 0.0, surv_aq);
         surv_aq = ::mms::fm::sel(::mms::fm::is_nan_bits(a), a, surv_aq);
     }
 #endif
