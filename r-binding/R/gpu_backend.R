@@ -1,0 +1,170 @@
+# gpu_backend.R -- R side of the GPU backend: what a maintainer adds to the
+# reference's R/ directory next to src/mmsgpu_shim.c.  Signatures of the
+# reference functions are unchanged; the backend is selected with
+#   options(mosmicrosim.backend = "gpu")      # default "r": the existing R code
+# There is no arithmetic here beyond date bookkeeping the reference already
+# does in R, and no CPU fallback: with the GPU backend selected and no CUDA
+# device the .Call errors.
+#
+# NOT EXECUTED in the development image of the B200 backend (no R there); the
+# Python package mosmicrosim_b200/ mirrors these wrappers on the same C ABI and
+# is what the test-suite drives.
+
+mms_backend <- function() {
+  getOption("mosmicrosim.backend", "r")
+}
+
+mms_math_mode <- function() {
+  # 0 = fast (default), 1 = strict (literal operation order, for debugging parity)
+  as.integer(identical(getOption("mosmicrosim.gpu_math", "fast"), "strict"))
+}
+
+mms_devices <- function() {
+  # integer(0) = all visible devices; a furrr/future worker should set this to
+  # its own device, e.g. options(mosmicrosim.gpu_devices = 3L)
+  as.integer(getOption("mosmicrosim.gpu_devices", integer(0)))
+}
+
+# habitat list for the shim; shape / radius / leak_per_hour are extensions of
+# the reference's 90-degree cone (R/sim_water.R:12-31)
+mms_habitat <- function(initial_volume = 0, max_cone_depth = 1, inflow_multiplier = 1,
+                        shape = c("cone", "cylinder"), radius = 1, leak_per_hour = 0) {
+  shape <- match.arg(shape)
+  list(shape = if (shape == "cone") 0L else 1L,
+       max_depth = as.numeric(max_cone_depth),
+       radius = as.numeric(radius),
+       inflow_multiplier = as.numeric(inflow_multiplier),
+       leak_per_hour = as.numeric(leak_per_hour),
+       initial_volume = as.numeric(initial_volume))
+}
+
+# plain parameters of a make_surv_densmod_function() closure
+# (R/lifehistory_estimation_functions.R:525-587)
+mms_densmod <- function(das_densmod_function) {
+  env <- environment(das_densmod_function)
+  list(type = if (attr(das_densmod_function, "type") == "logit") 0L else 1L,
+       dd_effect = as.numeric(env$dd_effect),
+       surface_area_cm2 = as.numeric(env$surface_area_cm2))
+}
+
+# coefficient table of a positive_spline() closure
+# (R/lifehistory_estimation_functions.R:236-250): splinefun keeps it in `z`
+mms_spline_table <- function(positive_spline_function) {
+  raw <- environment(positive_spline_function)$function_raw
+  z <- environment(raw)$z
+  list(x = as.numeric(z$x), y = as.numeric(z$y), b = as.numeric(z$b),
+       c = as.numeric(z$c), d = as.numeric(z$d))
+}
+
+# tables of one element of lifehistory_functions, with ds_temp_humid replaced by
+# its bilinear emulator exactly as simulate_hourly_lifehistory() does
+# (R/pipeline_functions.R:649-653)
+mms_lifehistory_tables <- function(lifehistory) {
+  ds_fun <- make_temp_humid_interpolator(lifehistory$ds_temp_humid)
+  info <- environment(ds_fun)$interpolation_info
+  list(mdr = mms_spline_table(lifehistory$mdr_temp),
+       efd = mms_spline_table(lifehistory$efd_temp),
+       das = mms_spline_table(lifehistory$das_temp),
+       ds = list(x = as.numeric(info$x), y = as.numeric(info$y),
+                 z = as.numeric(info$z)))
+}
+
+# ---- drop-in numeric cores ---------------------------------------------------
+
+# simulate_ephemeral_habitat_vectorised(), R/sim_water.R:216-301
+simulate_ephemeral_habitat_vectorised_gpu <- function(
+    rainfall_matrix, air_temperature_matrix, humidity_matrix, windspeed_matrix,
+    altitude_vector = rep(0, ncol(rainfall_matrix)),
+    initial_volume = 0, burnin_years = 0, max_cone_depth = 1, inflow_multiplier = 1) {
+  storage.mode(rainfall_matrix) <- "double"
+  storage.mode(air_temperature_matrix) <- "double"
+  storage.mode(humidity_matrix) <- "double"
+  storage.mode(windspeed_matrix) <- "double"
+  .Call("mms_R_water_vectorised", rainfall_matrix, air_temperature_matrix,
+        humidity_matrix, windspeed_matrix, as.numeric(altitude_vector),
+        mms_habitat(initial_volume, max_cone_depth, inflow_multiplier),
+        as.integer(burnin_years), mms_math_mode(),
+        if (length(mms_devices())) mms_devices()[1] else 0L,
+        PACKAGE = "mosmicrosim")
+}
+
+# simulate_population_vectorised(), R/sim_pop_dynamics.R:208-284
+simulate_population_vectorised_gpu <- function(
+    larval_habitat_area_matrix, mdr_matrix, efd_matrix, das_zerodensity_matrix,
+    ds_matrix, das_densmod_function, initial_adult = 100, initial_aquatic = 100,
+    burnin_years = 1) {
+  .Call("mms_R_population_vectorised", larval_habitat_area_matrix, mdr_matrix,
+        efd_matrix, das_zerodensity_matrix, ds_matrix,
+        mms_densmod(das_densmod_function), as.numeric(initial_adult),
+        as.numeric(initial_aquatic), as.integer(burnin_years), mms_math_mode(),
+        if (length(mms_devices())) mms_devices()[1] else 0L,
+        PACKAGE = "mosmicrosim")
+}
+
+# ---- the fused pipeline --------------------------------------------------------
+# tc_to_vectors() (R/pipeline_functions.R:1099-1130) from interpolate_daily_climate()
+# on, for the whole tile in one call.  pixel_monthly_climate is the tibble that
+# terraclimate_to_monthly_climate() returns; the result has the schema of
+# summarise_vectors(): longitude, latitude, species, pixel_vectors = list(tibble(
+# start, end, adult, aquatic, mdr, efd, das_zerodensity, ds)).
+monthly_climate_to_vectors_gpu <- function(pixel_monthly_climate,
+                                           species = c("An. gambiae", "An. stephensi"),
+                                           included_dates = NULL,
+                                           aggregate_by = c("month", "day")) {
+  species <- match.arg(species)
+  aggregate_by <- match.arg(aggregate_by)
+  lifehistory <- switch(species,
+                        "An. gambiae" = lifehistory_functions$An_gambiae,
+                        "An. stephensi" = lifehistory_functions$An_stephensi)
+  first <- pixel_monthly_climate$monthly_climate[[1]]
+  n_pixels <- nrow(pixel_monthly_climate)
+  vars <- c("tmin", "tmax", "rhmin", "rhmax", "wsmin", "wsmax", "ccmin", "ccmax",
+            "rainfall_daily")
+  # [cells, months, 9]: the cell index is the fastest one, as the kernel wants it
+  monthly <- array(NA_real_, dim = c(n_pixels, nrow(first), length(vars)))
+  for (i in seq_len(n_pixels)) {
+    monthly[i, , ] <- as.matrix(pixel_monthly_climate$monthly_climate[[i]][, vars])
+  }
+  # dates exactly as daily_from_monthly_climate() derives them (R/sim_microclimate.R:12-31)
+  midpoint <- first$start + round((first$end - first$start) / 2)
+  dates_predict <- seq(from = min(midpoint), to = max(midpoint), by = 1)
+  mid_date <- first$start + (first$end - first$start) / 2
+  mid_day <- as.numeric(mid_date - min(mid_date))
+  day_predict <- as.numeric(dates_predict - min(mid_date))
+  # periods exactly as aggregate_vectors() groups them (R/pipeline_functions.R:1050-1088)
+  if (is.null(included_dates)) included_dates <- dates_predict
+  keep <- dates_predict %in% included_dates
+  key <- if (aggregate_by == "month") lubridate::floor_date(dates_predict, "month") else dates_predict
+  periods <- sort(unique(key[keep]))
+  period_of_day <- ifelse(keep, match(key, periods) - 1L, -1L)
+
+  res <- .Call("mms_R_run_chain", monthly, as.numeric(pixel_monthly_climate$altitude),
+               mid_day, day_predict, as.integer(period_of_day),
+               list(mms_habitat()),                # R/pipeline_functions.R:431-441
+               mms_densmod(lifehistory$das_densmod), mms_lifehistory_tables(lifehistory),
+               63L,                                # the six vector_variables
+               length(periods), 1L, mms_math_mode(), mms_devices(),
+               PACKAGE = "mosmicrosim")
+  n_periods <- length(periods)
+  state <- array(res$mean_state, dim = c(n_pixels, n_periods, 2))      # adult, aquatic
+  forcing <- array(res$mean_forcing, dim = c(n_pixels, n_periods, 4))  # mdr, efd, das_zerodensity, ds
+  end <- if (aggregate_by == "month") lubridate::ceiling_date(periods + 1, "month") - 1 else periods
+  dplyr::tibble(
+    longitude = pixel_monthly_climate$longitude,
+    latitude = pixel_monthly_climate$latitude,
+    species = species,
+    pixel_vectors = lapply(seq_len(n_pixels), function(i) {
+      dplyr::tibble(start = periods, end = end,
+                    adult = state[i, , 1], aquatic = state[i, , 2],
+                    mdr = forcing[i, , 1], efd = forcing[i, , 2],
+                    das_zerodensity = forcing[i, , 3], ds = forcing[i, , 4])
+    })
+  )
+}
+
+# ---- the switch: one line each in the reference's own functions ------------------
+# R/sim_water.R:216     if (mms_backend() == "gpu") return(simulate_ephemeral_habitat_vectorised_gpu(...))
+# R/sim_pop_dynamics.R:208  if (mms_backend() == "gpu") return(simulate_population_vectorised_gpu(...))
+# R/pipeline_functions.R:1099 (tc_to_vectors):
+#   monthly <- terraclimate_to_monthly_climate(pixel_terraclimate_data)
+#   if (mms_backend() == "gpu") return(monthly_climate_to_vectors_gpu(monthly, species, included_dates))

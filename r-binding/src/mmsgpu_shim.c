@@ -1,0 +1,222 @@
+/*
+ * mmsgpu_shim.c -- the `.Call` shim a maintainer adds to the reference's src/
+ * (the reference has no src/ today: NAMESPACE:1-5, no useDynLib).
+ *
+ * Responsibilities, and nothing else:
+ *   - read-only REAL()/INTEGER() views of R-owned inputs (never modified, never
+ *     retained past the call);
+ *   - allocate R outputs with PROTECT(Rf_alloc*);
+ *   - hand plain pointers and sizes to libmmsgpu (include/mmsgpu.h);
+ *   - turn a non-zero status into Rf_error("%s", mms_last_error()), mirroring the
+ *     reference's stop(..., call. = FALSE) convention (R/pipeline_functions.R:335-337).
+ * There is NO arithmetic here, no Rcpp, and no CPU fallback: without a CUDA
+ * device libmmsgpu returns MMS_ERR_NO_DEVICE and the call errors.
+ *
+ * Build (inside the reference package):  PKG_CPPFLAGS = -I<mmsgpu>/include,
+ * PKG_LIBS = -L<mmsgpu> -lmmsgpu  in src/Makevars; add useDynLib(mosmicrosim) to
+ * NAMESPACE.  R is not installed in the development image of this repository,
+ * so this file is compiled there only against tests/r_stub/Rinternals.h (a
+ * syntax / prototype check); see INTEGRATION.md.
+ */
+#include <stdint.h>
+#include <string.h>
+
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+
+#include "mmsgpu.h"
+
+static void check(int status)
+{
+    if (status != MMS_OK) Rf_error("%s", mms_last_error());
+}
+
+/* list element by name (R-exts idiom) */
+static SEXP list_get(SEXP list, const char *name)
+{
+    SEXP names = Rf_getAttrib(list, R_NamesSymbol);
+    for (R_xlen_t i = 0; i < Rf_xlength(list); ++i)
+        if (strcmp(CHAR(STRING_ELT(names, i)), name) == 0) return VECTOR_ELT(list, i);
+    Rf_error("mmsgpu: list element '%s' is missing", name);
+    return R_NilValue;
+}
+
+static mms_spline spline_from(SEXP z)        /* environment(function_raw)$z of a splinefun closure */
+{
+    mms_spline s;
+    s.n = (int32_t)Rf_xlength(list_get(z, "x"));
+    s.reserved = 0;
+    s.x = REAL(list_get(z, "x"));
+    s.y = REAL(list_get(z, "y"));
+    s.b = REAL(list_get(z, "b"));
+    s.c = REAL(list_get(z, "c"));
+    s.d = REAL(list_get(z, "d"));
+    return s;
+}
+
+static mms_habitat habitat_from(SEXP h)      /* list(shape, max_depth, radius, inflow_multiplier, leak_per_hour, initial_volume) */
+{
+    mms_habitat hb;
+    hb.shape = Rf_asInteger(list_get(h, "shape"));
+    hb.reserved = 0;
+    hb.max_depth = Rf_asReal(list_get(h, "max_depth"));
+    hb.radius = Rf_asReal(list_get(h, "radius"));
+    hb.inflow_multiplier = Rf_asReal(list_get(h, "inflow_multiplier"));
+    hb.leak_per_hour = Rf_asReal(list_get(h, "leak_per_hour"));
+    hb.initial_volume = Rf_asReal(list_get(h, "initial_volume"));
+    return hb;
+}
+
+static mms_densmod densmod_from(SEXP d)      /* list(type = 0L/1L, dd_effect, surface_area_cm2) */
+{
+    mms_densmod dm;
+    dm.type = Rf_asInteger(list_get(d, "type"));
+    dm.reserved = 0;
+    dm.dd_effect = Rf_asReal(list_get(d, "dd_effect"));
+    dm.surface_area_cm2 = Rf_asReal(list_get(d, "surface_area_cm2"));
+    return dm;
+}
+
+/* .Call("mms_R_device_count") */
+SEXP mms_R_device_count(void)
+{
+    return Rf_ScalarInteger(mms_device_count());
+}
+
+/* simulate_ephemeral_habitat_vectorised(), R/sim_water.R:216-301.
+ * Matrices are R's own n_times x n_pixels column-major doubles. */
+SEXP mms_R_water_vectorised(SEXP rainfall, SEXP air_temperature, SEXP humidity, SEXP windspeed,
+                            SEXP altitude, SEXP habitat, SEXP burnin_years, SEXP math_mode, SEXP device)
+{
+    const int64_t H = Rf_nrows(rainfall), C = Rf_ncols(rainfall);
+    if (Rf_nrows(air_temperature) != H || Rf_ncols(air_temperature) != C || Rf_nrows(humidity) != H ||
+        Rf_ncols(humidity) != C || Rf_nrows(windspeed) != H || Rf_ncols(windspeed) != C)
+        Rf_error("all microclimate matrices must have the same dimensions");
+    if (Rf_xlength(altitude) != C) Rf_error("altitude_vector must have one element per pixel");
+    mms_habitat hb = habitat_from(habitat);
+    SEXP area = PROTECT(Rf_allocMatrix(REALSXP, (int)H, (int)C));
+    check(mms_water_vectorised(REAL(rainfall), REAL(air_temperature), REAL(humidity), REAL(windspeed),
+                               REAL(altitude), H, C, &hb, Rf_asInteger(burnin_years), Rf_asInteger(math_mode),
+                               Rf_asInteger(device), REAL(area), NULL, NULL));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 1));
+    SEXP names = PROTECT(Rf_allocVector(STRSXP, 1));
+    SET_VECTOR_ELT(out, 0, area);
+    SET_STRING_ELT(names, 0, Rf_mkChar("water_surface_area"));
+    Rf_setAttrib(out, R_NamesSymbol, names);
+    UNPROTECT(3);
+    return out;                         /* list(water_surface_area = ) like R/sim_water.R:297-299 */
+}
+
+/* simulate_population_vectorised(), R/sim_pop_dynamics.R:208-284 */
+SEXP mms_R_population_vectorised(SEXP larval_habitat_area, SEXP mdr, SEXP efd, SEXP das_zerodensity, SEXP ds,
+                                 SEXP densmod, SEXP initial_adult, SEXP initial_aquatic, SEXP burnin_years,
+                                 SEXP math_mode, SEXP device)
+{
+    const int64_t H = Rf_nrows(larval_habitat_area), C = Rf_ncols(larval_habitat_area);
+    mms_densmod dm = densmod_from(densmod);
+    SEXP aquatic = PROTECT(Rf_allocMatrix(REALSXP, (int)H, (int)C));
+    SEXP adult = PROTECT(Rf_allocMatrix(REALSXP, (int)H, (int)C));
+    check(mms_population_vectorised(REAL(larval_habitat_area), REAL(mdr), REAL(efd), REAL(das_zerodensity), REAL(ds),
+                                    H, C, &dm, Rf_asReal(initial_adult), Rf_asReal(initial_aquatic),
+                                    Rf_asInteger(burnin_years), Rf_asInteger(math_mode), Rf_asInteger(device),
+                                    REAL(aquatic), REAL(adult)));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SEXP names = PROTECT(Rf_allocVector(STRSXP, 2));
+    SET_VECTOR_ELT(out, 0, aquatic);
+    SET_VECTOR_ELT(out, 1, adult);
+    SET_STRING_ELT(names, 0, Rf_mkChar("aquatic"));
+    SET_STRING_ELT(names, 1, Rf_mkChar("adult"));
+    Rf_setAttrib(out, R_NamesSymbol, names);
+    UNPROTECT(4);
+    return out;                         /* list(aquatic = , adult = ) like R/sim_pop_dynamics.R:279-282 */
+}
+
+/* The fused chain: interpolate_daily_climate() ... summarise_vectors() for a whole tile,
+ * R/pipeline_functions.R:258-1026.
+ *   monthly        double [C, M, 9] array (R column-major = [9][M][C] with the cell index fastest)
+ *   altitude       double [C]
+ *   mid_day        double [M];  day_predict double [D];  period_of_day integer [D] (-1 = excluded)
+ *   habitats       list of habitat lists;  densmod list;  tables list(mdr=z, efd=z, das=z, ds=list(x,y,z))
+ *   mean_var_mask  integer;  n_periods integer;  burnin_years_pop integer;  math_mode integer
+ *   devices        integer vector of CUDA ordinals (length 0 = all)
+ * Returns list(mean_state = [C, P, ns, S], mean_forcing = [C, P, nf], wet_hours = [C, P, S]). */
+SEXP mms_R_run_chain(SEXP monthly, SEXP altitude, SEXP mid_day, SEXP day_predict, SEXP period_of_day,
+                     SEXP habitats, SEXP densmod, SEXP tables, SEXP mean_var_mask, SEXP n_periods,
+                     SEXP burnin_years_pop, SEXP math_mode, SEXP devices)
+{
+    mms_chain_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.n_cells = Rf_xlength(altitude);
+    cfg.n_months = (int32_t)Rf_xlength(mid_day);
+    cfg.n_days = (int32_t)Rf_xlength(day_predict);
+    cfg.n_settings = (int32_t)Rf_xlength(habitats);
+    cfg.n_periods = Rf_asInteger(n_periods);
+    if (Rf_xlength(monthly) != (R_xlen_t)cfg.n_cells * cfg.n_months * MMS_NFORCING)
+        Rf_error("monthly must be a [cells, months, 9] array");
+    if (cfg.n_settings < 1 || cfg.n_settings > MMS_MAX_SETTINGS) Rf_error("1 to %d habitat settings", MMS_MAX_SETTINGS);
+    cfg.mid_day = REAL(mid_day);
+    cfg.day_predict = REAL(day_predict);
+    cfg.period_of_day = (const int32_t *)INTEGER(period_of_day);
+    mms_habitat hab[MMS_MAX_SETTINGS];
+    for (int s = 0; s < cfg.n_settings; ++s) hab[s] = habitat_from(VECTOR_ELT(habitats, s));
+    cfg.habitats = hab;
+    cfg.burnin_years_water = 0;                               /* R/pipeline_functions.R:438 */
+    cfg.burnin_years_pop = Rf_asInteger(burnin_years_pop);    /* R/sim_pop_dynamics.R:217 */
+    cfg.initial_adult = 100.0;                                /* R/sim_pop_dynamics.R:215-216 */
+    cfg.initial_aquatic = 100.0;
+    cfg.densmod = densmod_from(densmod);
+    cfg.lifehistory.mdr_temp = spline_from(list_get(tables, "mdr"));
+    cfg.lifehistory.efd_temp = spline_from(list_get(tables, "efd"));
+    cfg.lifehistory.das_temp = spline_from(list_get(tables, "das"));
+    SEXP ds = list_get(tables, "ds");
+    cfg.lifehistory.ds_temp_humid.nx = (int32_t)Rf_xlength(list_get(ds, "x"));
+    cfg.lifehistory.ds_temp_humid.ny = (int32_t)Rf_xlength(list_get(ds, "y"));
+    cfg.lifehistory.ds_temp_humid.x = REAL(list_get(ds, "x"));
+    cfg.lifehistory.ds_temp_humid.y = REAL(list_get(ds, "y"));
+    cfg.lifehistory.ds_temp_humid.z = REAL(list_get(ds, "z"));
+    cfg.mean_var_mask = (uint32_t)Rf_asInteger(mean_var_mask);
+    cfg.want_wet_hours = 1;
+    cfg.math_mode = Rf_asInteger(math_mode);
+    cfg.n_devices = (int32_t)Rf_xlength(devices);
+    cfg.devices = cfg.n_devices ? (const int32_t *)INTEGER(devices) : NULL;
+
+    int ns = 0, nf = 0;
+    for (int v = 0; v < MMS_NVARS; ++v)
+        if (cfg.mean_var_mask >> v & 1u) { if (MMS_STATE_VAR_MASK >> v & 1u) ++ns; else ++nf; }
+    const R_xlen_t C = (R_xlen_t)cfg.n_cells, P = cfg.n_periods, S = cfg.n_settings;
+    SEXP mean_state = PROTECT(Rf_allocVector(REALSXP, C * P * ns * S));
+    SEXP mean_forcing = PROTECT(Rf_allocVector(REALSXP, C * P * nf));
+    SEXP wet_hours = PROTECT(Rf_allocVector(INTSXP, C * P * S));
+    mms_chain_outputs out;
+    memset(&out, 0, sizeof out);
+    out.mean_state = REAL(mean_state);
+    out.mean_forcing = REAL(mean_forcing);
+    out.wet_hours = (int32_t *)INTEGER(wet_hours);
+    check(mms_run_chain(&cfg, REAL(monthly), REAL(altitude), &out));
+
+    SEXP res = PROTECT(Rf_allocVector(VECSXP, 3));
+    SEXP names = PROTECT(Rf_allocVector(STRSXP, 3));
+    SET_VECTOR_ELT(res, 0, mean_state);
+    SET_VECTOR_ELT(res, 1, mean_forcing);
+    SET_VECTOR_ELT(res, 2, wet_hours);
+    SET_STRING_ELT(names, 0, Rf_mkChar("mean_state"));
+    SET_STRING_ELT(names, 1, Rf_mkChar("mean_forcing"));
+    SET_STRING_ELT(names, 2, Rf_mkChar("wet_hours"));
+    Rf_setAttrib(res, R_NamesSymbol, names);
+    UNPROTECT(5);
+    return res;
+}
+
+static const R_CallMethodDef call_methods[] = {
+    {"mms_R_device_count", (DL_FUNC)&mms_R_device_count, 0},
+    {"mms_R_water_vectorised", (DL_FUNC)&mms_R_water_vectorised, 9},
+    {"mms_R_population_vectorised", (DL_FUNC)&mms_R_population_vectorised, 11},
+    {"mms_R_run_chain", (DL_FUNC)&mms_R_run_chain, 13},
+    {NULL, NULL, 0}};
+
+void R_init_mosmicrosim(DllInfo *dll)
+{
+    R_registerRoutines(dll, NULL, call_methods, NULL, NULL);
+    R_useDynamicSymbols(dll, FALSE);
+}

@@ -45,6 +45,16 @@ def test_struct_layouts_match_the_header():
     assert got == sizes
 
 
+def test_r_shim_compiles_against_the_abi_header():
+    """r-binding/src/mmsgpu_shim.c (the .Call shim for the reference's src/) against a stub of
+    R's C API: every libmmsgpu call in it must match include/mmsgpu.h."""
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror=implicit-function-declaration",
+                        "-Werror=incompatible-pointer-types", "-Werror=int-conversion", "-fsyntax-only",
+                        "-I", os.path.join(ROOT, "tests", "r_stub"), "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "r-binding", "src", "mmsgpu_shim.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_no_cpu_fallback_without_a_device():
     if backend.device_count() > 0:
         pytest.skip("a GPU is visible")
