@@ -82,17 +82,20 @@ __device__ __forceinline__ double exp_core(double x)
     const double nf = t - magic;
     double r = fma(nf, -kLn2Hi, x);
     r = fma(nf, -kLn2Lo, r);
-    double q = kExpQ[9];
-    q = fma(q, r, kExpQ[8]);
-    q = fma(q, r, kExpQ[7]);
-    q = fma(q, r, kExpQ[6]);
-    q = fma(q, r, kExpQ[5]);
-    q = fma(q, r, kExpQ[4]);
-    q = fma(q, r, kExpQ[3]);
-    q = fma(q, r, kExpQ[2]);
-    q = fma(q, r, kExpQ[1]);
-    q = fma(q, r, kExpQ[0]);
-    const double p = fma(q * r, r, r);                        // exp(r) - 1
+    // even / odd split of the degree-9 polynomial: two independent Horner chains in r^2
+    // (the FP64 pipe needs four independent DFMAs in flight per warp; ptxas interleaves two
+    // call sites at most, so the other factor of two has to come from inside the evaluation)
+    const double r2 = r * r;
+    double qe = fma(kExpQ[8], r2, kExpQ[6]);
+    double qo = fma(kExpQ[9], r2, kExpQ[7]);
+    qe = fma(qe, r2, kExpQ[4]);
+    qo = fma(qo, r2, kExpQ[5]);
+    qe = fma(qe, r2, kExpQ[2]);
+    qo = fma(qo, r2, kExpQ[3]);
+    qe = fma(qe, r2, kExpQ[0]);
+    qo = fma(qo, r2, kExpQ[1]);
+    const double q = fma(qo, r, qe);
+    const double p = fma(q, r2, r);                           // exp(r) - 1
     const double res = 1.0 + p;
     return __hiloint2double(__double2hiint(res) + (n << 20), __double2loint(res));
 }
@@ -190,13 +193,13 @@ __device__ __forceinline__ double log_fastdiv(double x)
     const double m = __hiloint2double(hi, lo);
     const double f = div_fast(m - 1.0, m + 1.0);
     const double s = f * f;
-    double q = kLogQ[6];
-    q = fma(q, s, kLogQ[5]);
-    q = fma(q, s, kLogQ[4]);
-    q = fma(q, s, kLogQ[3]);
-    q = fma(q, s, kLogQ[2]);
-    q = fma(q, s, kLogQ[1]);
-    q = fma(q, s, kLogQ[0]);
+    const double s2 = s * s;                                  // even / odd split, as in exp_core
+    double qe = fma(kLogQ[6], s2, kLogQ[4]);
+    double qo = fma(kLogQ[5], s2, kLogQ[3]);
+    qe = fma(qe, s2, kLogQ[2]);
+    qo = fma(qo, s2, kLogQ[1]);
+    qe = fma(qe, s2, kLogQ[0]);
+    const double q = fma(qo, s, qe);
     const double ef = (double)e;
     const double small = fma(f * s, q, ef * kLn2Lo);
     return fma(ef, kLn2Hi, fma(2.0, f, small));
