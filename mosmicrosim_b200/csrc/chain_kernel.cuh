@@ -477,6 +477,7 @@ chain_kernel(const __grid_constant__ ChainParams p)
     for (int k = threadIdx.x; k < p.spline.n; k += blockDim.x) s_x[k] = p.spline.x[k];
     for (int k = threadIdx.x; k < p.ds.nx; k += blockDim.x) s_gx[k] = p.ds.x[k];
     for (int k = threadIdx.x; k < p.ds.ny; k += blockDim.x) s_gy[k] = p.ds.y[k];
+    ::mms::fm::math_tables_init();                                      // exp / log tables of the fast math
     __syncthreads();
     SmemTables tb{s_x, s_coef, s_gx, s_gy};
 

@@ -217,7 +217,7 @@ __device__ __forceinline__ void iterate_state(double &aquatic, double &adult, co
         const bool hi_side = ahi >= 0x40440000;                               // a >= 40 (or +Inf, +NaN)
         const bool lo_side = ahi < 0 && aabs >= 0x40490000u;                  // a <= -50 (or -Inf, -NaN)
         const double ac = ::mms::fm::sel(hi_side || lo_side, hi_side ? 40.0 : -50.0, a);
-        double L = ::mms::fm::log_fastdiv(1.0 + ::mms::fm::exp_core(ac));
+        double L = ::mms::fm::log_core(1.0 + ::mms::fm::exp_core(ac));
         L = ::mms::fm::sel(hi_side, a, L);
         // -L / 24 is within [-29.6, 0] whenever the result is used: beyond a = 709.78 the select
         // below wins (exp(a) = Inf -> das_t = 0); a NaN a propagates through exp_core

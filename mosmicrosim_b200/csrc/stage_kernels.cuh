@@ -90,6 +90,8 @@ water_stage_kernel(const __grid_constant__ WaterStageParams p)
     const int me = threadIdx.x;
     const bool live = me < nc;
     const double p_a = live ? air_pressure_kpa(p.altitude[cell0 + me]) : 101.325;
+    ::mms::fm::math_tables_init();
+    __syncthreads();
 
     double volume = p.hab.initial_volume;                                  // R/sim_water.R:277
     double surface = habitat_surface(p.hab, volume);
@@ -152,6 +154,8 @@ pop_stage_kernel(const __grid_constant__ PopStageParams p)
     const bool live = me < nc;
 
     double aquatic = p.initial_aquatic, adult = p.initial_adult;           // R/sim_pop_dynamics.R:249-252
+    ::mms::fm::math_tables_init();
+    __syncthreads();
     for (int pass = 0; pass <= p.burnin_years; ++pass) {                   // :225-226
         const bool final_pass = pass == p.burnin_years;
         const int64_t n_steps = final_pass ? p.H : (int64_t)kHoursPerYear;
