@@ -146,6 +146,39 @@ __device__ __forceinline__ double ds_surface(const SurfaceDev &g, const SmemTabl
 #endif
 }
 
+#if !MMS_STRICT
+// the same look-up in two steps, so that the caller can put independent arithmetic between
+// the (L2-latency) loads and their first use
+struct DsFetch {
+    double2 a, b;          // (z00, z10), (z01, z11)
+    double ex, ey;
+    bool inside;
+};
+
+__device__ __forceinline__ DsFetch ds_fetch(const SurfaceDev &g, double temperature, double humidity)
+{
+    DsFetch d;
+    d.inside = temperature >= g.x0 && temperature <= g.x1 && humidity >= g.y0 && humidity <= g.y1;
+    const double fx = (temperature - g.x0) * g.inv_dx, fy = (humidity - g.y0) * g.inv_dy;
+    int i = __double2int_rd(fx), j = __double2int_rd(fy);     // NaN -> 0
+    i = min(max(i, 0), g.nx - 2);
+    j = min(max(j, 0), g.ny - 2);
+    d.ex = fx - (double)i;
+    d.ey = fy - (double)j;                                    // == 1 on the last grid line
+    const double2 *q = reinterpret_cast<const double2 *>(g.quad) + (i + (g.nx - 1) * j) * 2;
+    d.a = __ldg(q);
+    d.b = __ldg(q + 1);
+    return d;
+}
+
+__device__ __forceinline__ double ds_blend(const DsFetch &d)
+{
+    const double mx = 1.0 - d.ex, my = 1.0 - d.ey;
+    const double v = (d.a.x * mx + d.a.y * d.ex) * my + (d.b.x * mx + d.b.y * d.ex) * d.ey;
+    return d.inside ? v : __longlong_as_double(0x7ff8000000000000LL);
+}
+#endif
+
 // ---- state-independent half of one hour ---------------------------------------
 struct DayCtx {          // everything the hourly curves need about yesterday / today / tomorrow
     Daily cur, nxt;
@@ -200,20 +233,36 @@ __device__ __forceinline__ HourF hour_forcing(const ChainParams &p, const SmemTa
         sun_next = after_inflection ? dc.nxt.ccmax : dc.cur.ccmax;
         f.cloud = inf_last + p.hr.w_vsine[h] * (sun_next - inf_last);
     }
+    // ---- life-history parameters, R/sim_pop_dynamics.R:100-135
+    // water_temperature = air_temperature, R/sim_microclimate.R:163.  The table look-ups
+    // (L2-resident ds quad table, shared-memory spline rows) are issued first so that their
+    // latency overlaps the evaporation arithmetic below.
+    f.mdr = f.efd = f.das0 = f.ds = 0.0;
+    double dx = 0.0;
+    double4 c0 = make_double4(0, 0, 0, 0), c1 = c0, c2 = c0;
+#if !MMS_STRICT
+    DsFetch dsf;
+#endif
+    if (!kWaterOnly) {
+#if MMS_STRICT
+        f.ds = ds_surface(p.ds, tb, f.air_t, f.rh);
+#else
+        dsf = ds_fetch(p.ds, f.air_t, f.rh);
+#endif
+        const int i = spline_interval(p.spline, tb.sx, f.air_t);
+        dx = f.air_t - tb.sx[i];
+        const double4 *cf = reinterpret_cast<const double4 *>(tb.coef + (size_t)i * 12);
+        c0 = cf[0]; c1 = cf[1]; c2 = cf[2];
+    }
     // ---- evaporation rate per unit area, R/sim_water.R:264-270 (air temperature)
     f.evap = evaporation_rate(f.air_t, f.rh, p_a, f.wind);
-    // ---- life-history parameters, R/sim_pop_dynamics.R:100-135
-    // water_temperature = air_temperature, R/sim_microclimate.R:163
-    f.mdr = f.efd = f.das0 = f.ds = 0.0;
     if (!kWaterOnly) {
-        const int i = spline_interval(p.spline, tb.sx, f.air_t);
-        const double dx = f.air_t - tb.sx[i];
-        const double4 *cf = reinterpret_cast<const double4 *>(tb.coef + (size_t)i * 12);
-        const double4 c0 = cf[0], c1 = cf[1], c2 = cf[2];
+#if !MMS_STRICT
+        f.ds = ds_blend(dsf);
+#endif
         f.mdr = ensure_positive(c0.x + dx * (c0.y + dx * (c0.z + dx * c0.w)));
         f.efd = ensure_positive(c1.x + dx * (c1.y + dx * (c1.z + dx * c1.w)));
         f.das0 = ensure_positive(c2.x + dx * (c2.y + dx * (c2.z + dx * c2.w)));
-        f.ds = ds_surface(p.ds, tb, f.air_t, f.rh);
         f.ph = pop_hour(p.densmod_type, f.mdr, f.efd, f.das0, f.ds);
     }
     return f;

@@ -2,6 +2,7 @@
 //   -DMMS_STRICT=0              -> chain_fast.o   (launch_*_fast)
 //   -DMMS_STRICT=1 -fmad=false  -> chain_strict.o (launch_*_strict)
 #include "chain_kernel.cuh"
+#include "chain_ws.cuh"
 #include "stage_kernels.cuh"
 
 namespace mms {
@@ -27,6 +28,20 @@ cudaError_t launch_kernel(const ChainParams &p, int grid, int warps, cudaStream_
     return cudaGetLastError();
 }
 
+#if !MMS_STRICT
+template <int kNS, bool kFull, bool kHourly, int kMaxPairs>
+cudaError_t launch_kernel_ws(const ChainParams &p, int grid, int pairs, cudaStream_t stream)
+{
+    auto kern = chain_kernel_ws<kNS, kFull, kHourly, kMaxPairs>;
+    const size_t smem = sizeof(double) * ((size_t)p.spline.n * 13 + p.ds.nx + p.ds.ny + (size_t)pairs * kWsRingDoubles) +
+                        sizeof(int) * (size_t)pairs;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    kern<<<grid, pairs * 64, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+#endif
+
 template <int kNS, bool kFull, bool kHourly>
 cudaError_t launch_one(ChainParams &p, int n_sm, cudaStream_t stream)
 {
@@ -35,6 +50,26 @@ cudaError_t launch_one(ChainParams &p, int n_sm, cudaStream_t stream)
     // fit the largest CTA, then the fewest warps that still need only that many.
     p.n_cell_blocks = (int32_t)(p.c_stride / 32);
     p.n_units = p.n_cell_blocks * (p.S / kNS);
+#if !MMS_STRICT
+    // Which form?  Measured on B200 (profiles/r01_*): the pair form wins when the launch is
+    // short of warps -- several settings per cell and at most two rounds of units per SM (the
+    // 100k-cell tile of BASELINE configs[1]: 61.7 vs 67.4 ms) -- and loses a little when the
+    // monolithic kernel can already fill 16 warps per SM or with one setting per cell.
+    const bool ws = p.warp_specialised >= 0 ? p.warp_specialised != 0
+                                            : (kNS >= 2 && p.n_units <= (int64_t)2 * n_sm * kChainMaxPairs);
+    if (ws) {
+        // warp-specialised form: a pair of warps (forcing + state) per unit, chain_ws.cuh
+        const int pairs_max = p.force_warps > 0 ? p.force_warps : kChainMaxPairs;
+        const int64_t per_round = (int64_t)n_sm * pairs_max;
+        const int64_t rounds = (p.n_units + per_round - 1) / per_round;
+        int pairs = (int)((p.n_units + (int64_t)n_sm * rounds - 1) / ((int64_t)n_sm * rounds));
+        pairs = pairs < 1 ? 1 : (pairs > pairs_max ? pairs_max : pairs);
+        const int64_t ctas = (p.n_units + pairs - 1) / pairs;
+        const int grid = (int)(ctas < n_sm ? ctas : n_sm);
+        if (pairs <= kChainFewPairs) return launch_kernel_ws<kNS, kFull, kHourly, kChainFewPairs>(p, grid, pairs, stream);
+        return launch_kernel_ws<kNS, kFull, kHourly, kChainMaxPairs>(p, grid, pairs, stream);
+    }
+#endif
     const int w_max = p.force_warps > 0 ? p.force_warps : kChainMaxWarps;
     const int64_t per_round = (int64_t)n_sm * w_max;
     const int64_t rounds = (p.n_units + per_round - 1) / per_round;

@@ -1,0 +1,363 @@
+// chain_ws.cuh -- warp-specialised form of the fused chain (fast math mode only).
+//
+// Why: the monolithic kernel (chain_kernel.cuh) is latency bound.  B200's FP64 pipe wants four
+// independent DFMAs in flight per SM sub-partition (8-cycle latency, one issue per 2 cycles),
+// ptxas interleaves at most two independent chains, and ~168 registers per cell limit an SM to
+// 11 warps.  Here every 32-cell work unit is served by a PAIR of warps:
+//   * the forcing warp runs the state-independent half (monthly -> daily -> hourly
+//     microclimate, evaporation rate, life-history tables, ds^(1/24), emergence, logit link)
+//     and hands kWsK hours at a time to
+//   * the state warp, which runs the recursions (water bodies and populations of the kNS
+//     habitat settings) and the summaries of the state variables,
+// through a double-buffered shared-memory ring guarded by one named barrier per pair
+// (bar.sync id, 64).  The hand-off is one-directional, so the forcing warp runs ahead.  Each
+// role needs about half the registers, so twice as many warps -- twice as many independent
+// instruction streams -- fit per SM for the same number of cells in flight.
+//
+// Arithmetic is exactly that of the monolithic fast kernel (same device functions).
+#pragma once
+
+#include "chain_kernel.cuh"
+
+#if !MMS_STRICT
+
+namespace mms {
+namespace MMS_MODE {
+
+constexpr int kWsK = 3;              // hours per hand-off (divides 24)
+constexpr int kWsFields = 6;         // evap, surv_ad, exp(-mdr/24), egg, link0, gain_m_h
+constexpr int kWsRingDoubles = 2 * kWsK * kWsFields * 32;   // per pair
+
+__device__ __forceinline__ void pair_barrier(int pair)
+{
+    asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");   // barrier 0 is __syncthreads()
+}
+
+// period bookkeeping shared by both roles (aggregate_vectors(), R/pipeline_functions.R:1050-1088)
+struct PeriodCursor {
+    int cur_period, acc_n, acc_inc;
+    bool acc_on;
+    __device__ __forceinline__ void init() { cur_period = -1; acc_n = 0; acc_inc = 0; acc_on = false; }
+    // returns the period to flush (or -1) and whether a new period starts on this day
+    __device__ __forceinline__ int begin_day(const ChainParams &p, int day, bool &fresh)
+    {
+        fresh = false;
+        int to_flush = -1;
+        const int period = p.period_of_day ? p.period_of_day[day] : -1;
+        if (period >= 0 && period != cur_period) {
+            to_flush = cur_period;
+            fresh = true;
+            cur_period = period;
+        }
+        acc_on = period >= 0;
+        acc_inc = acc_on ? 1 : 0;
+        return to_flush;
+    }
+};
+
+// ---- forcing warp ---------------------------------------------------------------------------
+template <bool kFull, bool kHourly, bool kWaterOnly, bool kRecord>
+__device__ __forceinline__ void forcing_pass(const ChainParams &p, const SmemTables &tb, const UnitCtx &u,
+                                             double *ring, int pair, int n_days, int &bad)
+{
+    constexpr int kNF = kFull ? 9 : 4;
+    constexpr uint32_t kState = MMS_STATE_VAR_MASK;
+    const int lane = threadIdx.x & 31;
+    double acc[kNF];
+#pragma unroll
+    for (int k = 0; k < kNF; ++k) acc[k] = 0.0;
+    PeriodCursor pc;
+    pc.init();
+
+    auto flush = [&](int period) {
+        if (!u.live || !u.write_forcing) return;
+        const int64_t at = (int64_t)period * u.cs + u.cell;
+        const double n = (double)pc.acc_n;
+        const int vid[9] = {MMS_V_MDR, MMS_V_EFD, MMS_V_DAS_ZERODENSITY, MMS_V_DS, MMS_V_AIR_TEMPERATURE,
+                            MMS_V_HUMIDITY, MMS_V_WINDSPEED, MMS_V_RAINFALL, MMS_V_CLOUDCOVER};
+#pragma unroll
+        for (int k = 0; k < kNF; ++k) {
+            if (p.mean_mask & (1u << vid[k])) {
+                const int64_t row = out_slot(p.mean_mask, ~kState, vid[k]);
+                p.mean_forcing[row * p.P * u.cs + at] = acc[k] / n;
+            }
+        }
+    };
+
+    DayCtx dc;
+    dc.cur = load_daily<kFull>(p, u.cell, 0, bad);
+    dc.nxt = load_daily<kFull>(p, u.cell, (p.D > 1) ? 1 : 0, bad);
+    dc.A = (dc.cur.tmax - dc.cur.tmin) * 0.5;                              // R/sim_microclimate.R:217
+    dc.t_sunset = dc.A * p.hr.z_night + dc.cur.tmin + dc.A;                // :220
+    dc.t_midnight_prev = (dc.t_sunset - dc.nxt.tmin) / p.hr.exp_e[23] + dc.nxt.tmin;   // :271-272
+    dc.rhmin_prev = dc.cur.rhmin; dc.wsmax_prev = dc.cur.wsmax; dc.ccmin_prev = dc.cur.ccmin;
+
+    int buf = 0;
+    for (int day = 0; day < n_days; ++day) {
+        if (kRecord) {
+            bool fresh;
+            const int to_flush = pc.begin_day(p, day, fresh);
+            if (fresh) {
+                if (to_flush >= 0) flush(to_flush);
+#pragma unroll
+                for (int k = 0; k < kNF; ++k) acc[k] = 0.0;
+                pc.acc_n = 0;
+            }
+        }
+        const double rain_h = dc.cur.rain * (1.0 / 24.0);                 // R/sim_microclimate.R:132
+        const double gain_m_h = rain_h * (1.0 / 1000.0);                  // R/sim_water.R:122
+        double air_t_last = 0.0;
+#pragma unroll 1
+        for (int h0 = 0; h0 < 24; h0 += kWsK) {
+            double *slot = ring + (size_t)buf * (kWsK * kWsFields * 32) + lane;
+#pragma unroll
+            for (int k = 0; k < kWsK; ++k) {
+                const int h = h0 + k;
+                const HourF f = hour_forcing<kFull, kWaterOnly>(p, tb, dc, u.p_a, h);
+                double *rec = slot + (size_t)k * (kWsFields * 32);
+                rec[0 * 32] = f.evap;
+                rec[1 * 32] = f.ph.surv_ad;
+                rec[2 * 32] = f.ph.one_m_emf;          // exp(-timestep * mdr); emf = 1 - it
+                rec[3 * 32] = f.ph.egg;
+                rec[4 * 32] = f.ph.link0;
+                rec[5 * 32] = gain_m_h;
+                air_t_last = f.air_t;
+                if (kRecord) {
+                    acc[0] += (pc.acc_on ? f.mdr : 0.0); acc[1] += (pc.acc_on ? f.efd : 0.0);
+                    acc[2] += (pc.acc_on ? f.das0 : 0.0); acc[3] += (pc.acc_on ? f.ds : 0.0);
+                    if (kFull) {
+                        acc[4] += (pc.acc_on ? f.air_t : 0.0); acc[5] += (pc.acc_on ? f.rh : 0.0);
+                        acc[6] += (pc.acc_on ? f.wind : 0.0); acc[7] += (pc.acc_on ? rain_h : 0.0);
+                        acc[8] += (pc.acc_on ? f.cloud : 0.0);
+                    }
+                    pc.acc_n += pc.acc_inc;
+                    if (kHourly && u.live && u.write_forcing) {
+                        const int64_t tc = (int64_t)(day * 24 + h) * u.cs + u.cell;
+                        const double val[9] = {f.mdr, f.efd, f.das0, f.ds, f.air_t, f.rh, f.wind, rain_h, f.cloud};
+                        const int vid[9] = {MMS_V_MDR, MMS_V_EFD, MMS_V_DAS_ZERODENSITY, MMS_V_DS, MMS_V_AIR_TEMPERATURE,
+                                            MMS_V_HUMIDITY, MMS_V_WINDSPEED, MMS_V_RAINFALL, MMS_V_CLOUDCOVER};
+#pragma unroll
+                        for (int q = 0; q < kNF; ++q) {
+                            if (p.hourly_mask & (1u << vid[q])) {
+                                const int64_t row = out_slot(p.hourly_mask, ~kState, vid[q]);
+                                p.hourly_forcing[row * u.H * u.cs + tc] = val[q];
+                            }
+                        }
+                    }
+                }
+            }
+            pair_barrier(pair);                      // the state warp may now read this buffer
+            buf ^= 1;
+        }
+        // ---- roll the day window
+        dc.t_midnight_prev = air_t_last;             // hour-24 value, R/sim_microclimate.R:271
+        dc.rhmin_prev = dc.cur.rhmin; dc.wsmax_prev = dc.cur.wsmax; dc.ccmin_prev = dc.cur.ccmin;
+        dc.cur = dc.nxt;
+        const int d2 = day + 2;
+        dc.nxt = load_daily<kFull>(p, u.cell, d2 < p.D ? d2 : p.D - 1, bad);
+        dc.A = (dc.cur.tmax - dc.cur.tmin) * 0.5;
+        dc.t_sunset = dc.A * p.hr.z_night + dc.cur.tmin + dc.A;
+    }
+    if (kRecord && pc.cur_period >= 0) flush(pc.cur_period);
+}
+
+// ---- state warp ------------------------------------------------------------------------------
+template <int kNS, bool kFull, bool kHourly, bool kWaterOnly, bool kRecord>
+__device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &u, UnitState<kNS> &st,
+                                           const double *ring, int pair, int n_days)
+{
+    constexpr uint32_t kState = MMS_STATE_VAR_MASK;
+    const int lane = threadIdx.x & 31;
+    double acc[kNS][4];
+    int acc_wet[kNS];
+    auto reset = [&]() {
+#pragma unroll
+        for (int s = 0; s < kNS; ++s) {
+            acc_wet[s] = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[s][k] = 0.0;
+        }
+    };
+    reset();
+    PeriodCursor pc;
+    pc.init();
+
+    auto flush = [&](int period) {
+        if (!u.live) return;
+        const int64_t at = (int64_t)period * u.cs + u.cell;
+        const double n = (double)pc.acc_n;
+#pragma unroll
+        for (int s = 0; s < kNS; ++s) {
+            const int vid[4] = {MMS_V_ADULT, MMS_V_AQUATIC, MMS_V_LARVAL_HABITAT_AREA, MMS_V_WATER_VOLUME};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!kFull && k >= 2) continue;
+                if (p.mean_mask & (1u << vid[k])) {
+                    const int64_t row = (int64_t)(u.set0 + s) * u.n_mean_state + out_slot(p.mean_mask, kState, vid[k]);
+                    p.mean_state[row * p.P * u.cs + at] = acc[s][k] / n;
+                }
+            }
+            if (p.wet_hours) p.wet_hours[(int64_t)(u.set0 + s) * p.P * u.cs + at] = acc_wet[s];
+        }
+    };
+
+    int buf = 0;
+    for (int day = 0; day < n_days; ++day) {
+        if (kRecord) {
+            bool fresh;
+            const int to_flush = pc.begin_day(p, day, fresh);
+            if (fresh) {
+                if (to_flush >= 0) flush(to_flush);
+                reset();
+                pc.acc_n = 0;
+            }
+        }
+#pragma unroll 1
+        for (int h0 = 0; h0 < 24; h0 += kWsK) {
+            pair_barrier(pair);                      // the forcing warp has filled this buffer
+            const double *slot = ring + (size_t)buf * (kWsK * kWsFields * 32) + lane;
+#pragma unroll
+            for (int k = 0; k < kWsK; ++k) {
+                const double *rec = slot + (size_t)k * (kWsFields * 32);
+                const double evap = rec[0 * 32];
+                PopHour ph;
+                ph.surv_ad = rec[1 * 32];
+                ph.one_m_emf = rec[2 * 32];
+                ph.emf = 1.0 - ph.one_m_emf;
+                ph.egg = rec[3 * 32];
+                ph.link0 = rec[4 * 32];
+                const double gain_m_h = rec[5 * 32];
+#pragma unroll
+                for (int s = 0; s < kNS; ++s) {
+                    const HabitatDev &hb = p.hab[u.set0 + s];
+                    st.volume[s] = iterate_volume(hb, st.volume[s], st.surface[s], evap,
+                                                  hb.catchment_area * gain_m_h);             // R/sim_water.R:279-287
+                    st.surface[s] = habitat_surface(hb, st.volume[s]);                       // :294
+                    if (!kWaterOnly)
+                        iterate_state(st.aquatic[s], st.adult[s], ph, p.densmod_type, p.dd_effect,
+                                      p.surface_area_cm2, st.surface[s]);
+                }
+                if (kRecord) {
+#pragma unroll
+                    for (int s = 0; s < kNS; ++s) {
+                        acc[s][0] += (pc.acc_on ? st.adult[s] : 0.0);
+                        acc[s][1] += (pc.acc_on ? st.aquatic[s] : 0.0);
+                        if (kFull) {
+                            acc[s][2] += (pc.acc_on ? st.surface[s] : 0.0);
+                            acc[s][3] += (pc.acc_on ? st.volume[s] : 0.0);
+                        }
+                        acc_wet[s] += (st.volume[s] > 0.0) ? pc.acc_inc : 0;
+                    }
+                    pc.acc_n += pc.acc_inc;
+                    if (kHourly && u.live) {
+                        const int64_t tc = (int64_t)(day * 24 + h0 + k) * u.cs + u.cell;
+#pragma unroll
+                        for (int s = 0; s < kNS; ++s) {
+                            const double val[4] = {st.adult[s], st.aquatic[s], st.surface[s], st.volume[s]};
+                            const int vid[4] = {MMS_V_ADULT, MMS_V_AQUATIC, MMS_V_LARVAL_HABITAT_AREA, MMS_V_WATER_VOLUME};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                if (!kFull && q >= 2) continue;
+                                if (p.hourly_mask & (1u << vid[q])) {
+                                    const int64_t row = (int64_t)(u.set0 + s) * u.n_hourly_state + out_slot(p.hourly_mask, kState, vid[q]);
+                                    p.hourly_state[row * u.H * u.cs + tc] = val[q];
+                                }
+                            }
+                            if (p.wet_flags) p.wet_flags[(int64_t)(u.set0 + s) * u.H * u.cs + tc] = (st.volume[s] > 0.0) ? 1 : 0;
+                        }
+                    }
+                }
+            }
+            buf ^= 1;
+        }
+    }
+    if (kRecord && pc.cur_period >= 0) flush(pc.cur_period);
+}
+
+// ---- the kernel: warp 2i = forcing role, warp 2i + 1 = state role of pair i ---------------------
+template <int kNS, bool kFull, bool kHourly, int kMaxPairs>
+__global__ void __launch_bounds__(kMaxPairs * 64, 1)
+chain_kernel_ws(const __grid_constant__ ChainParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_coef = reinterpret_cast<double *>(smem_raw);              // [n][3][4]
+    double *s_x = s_coef + (size_t)p.spline.n * 12;                     // [n]
+    double *s_gx = s_x + p.spline.n;                                    // [nx]
+    double *s_gy = s_gx + p.ds.nx;                                      // [ny]
+    double *s_ring = s_gy + p.ds.ny;                                    // [pairs][kWsRingDoubles]
+    const int n_pairs = blockDim.x >> 6;
+    int *s_unit = reinterpret_cast<int *>(s_ring + (size_t)n_pairs * kWsRingDoubles);   // [pairs]
+    for (int k = threadIdx.x; k < p.spline.n * 12; k += blockDim.x) s_coef[k] = p.spline.coef[k];
+    for (int k = threadIdx.x; k < p.spline.n; k += blockDim.x) s_x[k] = p.spline.x[k];
+    for (int k = threadIdx.x; k < p.ds.nx; k += blockDim.x) s_gx[k] = p.ds.x[k];
+    for (int k = threadIdx.x; k < p.ds.ny; k += blockDim.x) s_gy[k] = p.ds.y[k];
+    ::mms::fm::math_tables_init();
+    __syncthreads();
+    SmemTables tb{s_x, s_coef, s_gx, s_gy};
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // warp w runs on SM sub-partition w % 4: sub-partitions 0, 1 host the forcing warps and 2, 3
+    // the state warps, so that each sub-partition's L0 instruction cache sees one loop only
+    // (an odd last pair takes the two leftover warps)
+    const bool tail = (n_pairs & 1) && warp >= 2 * (n_pairs - 1);
+    const int pair = tail ? n_pairs - 1 : (warp & 1) + ((warp >> 2) << 1);
+    const bool forcing_role = tail ? (warp & 1) == 0 : (warp & 2) == 0;
+    double *ring = s_ring + (size_t)pair * kWsRingDoubles;
+
+    for (;;) {
+        if (forcing_role && lane == 0) s_unit[pair] = atomicAdd(p.unit_counter, 1);
+        pair_barrier(pair);
+        const int unit = s_unit[pair];
+        pair_barrier(pair);                          // both have read it before it is overwritten
+        if (unit >= p.n_units) break;
+        const int cb = unit % p.n_cell_blocks, g = unit / p.n_cell_blocks;
+
+        UnitCtx u;
+        u.cell = (int64_t)cb * 32 + lane; u.cs = p.c_stride; u.set0 = g * kNS; u.H = 24 * p.D;
+        u.live = u.cell < p.n_cells; u.write_forcing = g == 0;
+        u.n_mean_state = __popc(p.mean_mask & MMS_STATE_VAR_MASK);
+        u.n_hourly_state = __popc(p.hourly_mask & MMS_STATE_VAR_MASK);
+        // passes: water burn-in years (R/sim_water.R:228-233), population burn-in years
+        // (R/sim_pop_dynamics.R:221-226), then the full series -- identical loop structure in
+        // both roles, so the two warps meet at every barrier
+        if (forcing_role) {
+            u.p_a = air_pressure_kpa(__ldg(p.altitude + u.cell));
+            int bad = 0;
+            for (int y = 0; y < p.burnin_years_water; ++y)
+                forcing_pass<kFull, kHourly, true, false>(p, tb, u, ring, pair, kDaysPerYear, bad);
+            for (int y = 0; y < p.burnin_years_pop; ++y)
+                forcing_pass<kFull, kHourly, false, false>(p, tb, u, ring, pair, kDaysPerYear, bad);
+            forcing_pass<kFull, kHourly, false, true>(p, tb, u, ring, pair, p.D, bad);
+            if (bad && u.live) atomicOr(p.error_flag, 1);
+        } else {
+            u.p_a = 0.0;
+            UnitState<kNS> st;
+#pragma unroll
+            for (int s = 0; s < kNS; ++s) {
+                st.aquatic[s] = p.initial_aquatic;               // R/sim_pop_dynamics.R:249-252
+                st.adult[s] = p.initial_adult;
+                st.volume[s] = p.hab[u.set0 + s].initial_volume; // R/sim_water.R:277
+                st.surface[s] = habitat_surface(p.hab[u.set0 + s], st.volume[s]);
+            }
+            for (int y = 0; y < p.burnin_years_water; ++y)
+                state_pass<kNS, kFull, kHourly, true, false>(p, u, st, ring, pair, kDaysPerYear);
+            double vol0[kNS];
+#pragma unroll
+            for (int s = 0; s < kNS; ++s) vol0[s] = st.volume[s];
+            for (int y = 0; y < p.burnin_years_pop; ++y) {
+                state_pass<kNS, kFull, kHourly, false, false>(p, u, st, ring, pair, kDaysPerYear);
+#pragma unroll
+                for (int s = 0; s < kNS; ++s) {
+                    st.volume[s] = vol0[s];
+                    st.surface[s] = habitat_surface(p.hab[u.set0 + s], vol0[s]);
+                }
+            }
+            state_pass<kNS, kFull, kHourly, false, true>(p, u, st, ring, pair, p.D);
+        }
+    }
+}
+
+}  // namespace MMS_MODE
+}  // namespace mms
+
+#endif  // !MMS_STRICT

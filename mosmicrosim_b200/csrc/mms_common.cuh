@@ -12,6 +12,8 @@ namespace mms {
 constexpr int kBlock = 128;          // cell padding granule of a shard (keeps [period][cell] rows 1 KB aligned)
 constexpr int kChainMaxWarps = 16;   // largest persistent CTA of the fused kernel: 512 threads, <= 128 registers / thread
 constexpr int kChainFewWarps = 12;   // second instantiation: <= 384 threads, <= 168 registers / thread
+constexpr int kChainMaxPairs = 11;   // warp-specialised kernel: 11 forcing + 11 state warps, <= 88 registers / thread
+constexpr int kChainFewPairs = 10;   // second instantiation: 640 threads, <= 96 registers / thread
 constexpr int kHoursPerYear = 8760;  // n_times_year <- 365 * 24, R/sim_water.R:229, R/sim_pop_dynamics.R:222
 constexpr int kDaysPerYear = 365;
 
@@ -92,7 +94,8 @@ struct ChainParams {
     int32_t *unit_counter;     // work-unit dispenser, zeroed before every launch
     int32_t n_units;           // n_cell_blocks * (S / settings per thread)
     int32_t n_cell_blocks;     // c_stride / 32
-    int32_t force_warps;       // > 0: cap on warps per CTA (tuning aid, env MMS_CHAIN_WARPS)
+    int32_t force_warps;       // > 0: cap on warps (pairs) per CTA (tuning aid, env MMS_CHAIN_WARPS)
+    int32_t warp_specialised;  // fast mode: 1 = chain_ws.cuh (forcing / state warp pairs), 0 = monolithic, -1 = auto
     HourTables hr;
     HabitatDev hab[MMS_MAX_SETTINGS];
 };

@@ -486,6 +486,8 @@ int mms_chain_launch(mms_chain_plan *pl)
         p.error_flag = s.d_error;
         p.unit_counter = s.d_error + 1;
         if (const char *fw = std::getenv("MMS_CHAIN_WARPS")) p.force_warps = std::atoi(fw);
+        p.warp_specialised = -1;   // automatic choice; MMS_CHAIN_WS = 0 / 1 forces one form (tests, tuning)
+        if (const char *ws = std::getenv("MMS_CHAIN_WS")) p.warp_specialised = std::atoi(ws);
         MMS_CUDA(cudaMemsetAsync(s.d_error + 1, 0, sizeof(int32_t), s.stream));
         p.hr = pl->hr;
         for (int k = 0; k < pl->S; ++k) p.hab[k] = pl->hab[k];

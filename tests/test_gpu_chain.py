@@ -100,6 +100,27 @@ def test_chain_three_settings_odd(gpu):
     compare(case, out, ref, REL_TOL_FAST, what=("mean",))
 
 
+@pytest.mark.parametrize("form", ["0", "1"])
+@pytest.mark.parametrize("n_settings", [1, 2, 4])
+def test_both_kernel_forms(gpu, monkeypatch, form, n_settings):
+    """fast mode has two kernel forms (monolithic, and forcing/state warp pairs); the library picks
+    one by problem shape.  Force each and check it: hourly series, means, flags, NA cells, a ragged
+    number of cells, and summaries restricted to included dates."""
+    monkeypatch.setenv("MMS_CHAIN_WS", form)
+    included = syn.year_dates(2001, 1)[20:200]
+    case = Case(n_cells=77, habitats=syn.habitat_ensemble(8)[2:2 + n_settings], included=included,
+                out_of_range_fraction=0.2)
+    ref = case.oracle()
+    out = backend.run_chain(case.monthly, case.altitude, **case.gpu_kwargs(
+        mean_vars=ALL_VARS, hourly_vars=ALL_VARS, want_wet_hours=True, want_wet_flags=True, math_mode="fast"))
+    compare(case, out, ref, REL_TOL_FAST)
+    # the pipeline-variables-only instantiation (kFull = false), water burn-in on
+    ref2 = case.oracle(want_hourly=False, burnin_years_water=1)
+    out2 = backend.run_chain(case.monthly, case.altitude, **case.gpu_kwargs(
+        mean_vars=list(backend.VAR_NAMES[:6]), want_wet_hours=True, math_mode="fast", burnin_years_water=1))
+    compare(case, out2, ref2, REL_TOL_FAST, what=("mean",))
+
+
 def test_plan_matches_one_shot_and_is_repeatable(gpu):
     case = Case(n_cells=200)
     kw = case.gpu_kwargs(mean_vars=list(backend.VAR_NAMES[:6]), want_wet_hours=True)
