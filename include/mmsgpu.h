@@ -226,6 +226,9 @@ MMS_API int mms_population_vectorised(const double *larval_habitat_area, const d
                               int32_t math_mode, int32_t device,
                               double *aquatic, double *adult);
 
+/* device time (CUDA events) of the kernel of the last stage-level twin call on this thread */
+MMS_API int mms_stage_kernel_ms(float *ms);
+
 /* ---- pinned host buffers --------------------------------------------------
  * Optional: host<->device copies of buffers obtained here run asynchronously at
  * full PCIe speed; any other host memory works too (staged by the driver). */

@@ -87,7 +87,7 @@ EXPORTS = ("mms_abi_version", "mms_device_count", "mms_last_error", "mms_run_cha
            "mms_chain_create", "mms_chain_upload", "mms_chain_launch", "mms_chain_sync",
            "mms_chain_download", "mms_chain_kernel_ms", "mms_chain_launch_count", "mms_chain_destroy",
            "mms_shard_range",
-           "mms_water_vectorised", "mms_population_vectorised", "mms_host_alloc", "mms_host_free",
+           "mms_water_vectorised", "mms_population_vectorised", "mms_stage_kernel_ms", "mms_host_alloc", "mms_host_free",
            "mms_measure_fp64_peak", "mms_measure_hbm_copy", "mms_flush_l2")
 
 _lib = None
@@ -121,6 +121,7 @@ def lib() -> ct.CDLL:
         L.mms_population_vectorised.argtypes = [_dp, _dp, _dp, _dp, _dp, ct.c_int64, ct.c_int64,
                                                 ct.POINTER(Densmod), ct.c_double, ct.c_double,
                                                 ct.c_int32, ct.c_int32, ct.c_int32, _dp, _dp]
+        L.mms_stage_kernel_ms.argtypes = [ct.POINTER(ct.c_float)]
         L.mms_host_alloc.argtypes = [ct.POINTER(vp), ct.c_uint64]
         L.mms_host_free.argtypes = [vp]
         L.mms_measure_fp64_peak.argtypes = [ct.c_int32, ct.POINTER(ct.c_double)]
@@ -394,6 +395,13 @@ def population_vectorised(larval_habitat_area, mdr, efd, das_zerodensity, ds, de
                                           {"fast": 0, "strict": 1}.get(math_mode, math_mode), int(device),
                                           aquatic.ctypes.data_as(_dp), adult.ctypes.data_as(_dp)))
     return {"aquatic": aquatic, "adult": adult}
+
+
+def stage_kernel_ms() -> float:
+    """Device time of the kernel of the last stage-level twin call on this thread."""
+    ms = ct.c_float()
+    check(lib().mms_stage_kernel_ms(ct.byref(ms)))
+    return float(ms.value)
 
 
 def measure_fp64_peak(device=0) -> float:

@@ -20,6 +20,31 @@
 namespace {
 
 thread_local std::string g_error;
+thread_local float g_stage_kernel_ms = 0.f;   // device time of the last stage-twin kernel on this thread
+
+// CUDA-event bracket around one kernel launch on a stream
+struct EventTimer {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaStream_t st;
+    explicit EventTimer(cudaStream_t s) : st(s)
+    {
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+    }
+    void stop() { cudaEventRecord(e1, st); }
+    float ms()
+    {
+        float t = 0.f;
+        if (cudaEventSynchronize(e1) == cudaSuccess) cudaEventElapsedTime(&t, e0, e1);
+        return t;
+    }
+    ~EventTimer()
+    {
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    }
+};
 
 int fail(int status, const char *fmt, ...)
 {
@@ -643,11 +668,14 @@ int mms_water_vectorised(const double *rainfall, const double *air_temperature, 
     p.altitude = (const double *)alt.p;
     p.water_surface_area = (double *)area.p; p.water_volume = (double *)vol.p; p.wet = (uint8_t *)wetb.p;
     p.H = n_times; p.C = n_pixels; p.burnin_years = burnin_years;
+    EventTimer timer(st);
     MMS_CUDA(math_mode ? mms::launch_water_stage_strict(p, st) : mms::launch_water_stage_fast(p, st));
+    timer.stop();
     MMS_CUDA(cudaMemcpyAsync(water_surface_area, area.p, bytes, cudaMemcpyDeviceToHost, st));
     if (water_volume) MMS_CUDA(cudaMemcpyAsync(water_volume, vol.p, bytes, cudaMemcpyDeviceToHost, st));
     if (wet) MMS_CUDA(cudaMemcpyAsync(wet, wetb.p, (size_t)n_times * n_pixels, cudaMemcpyDeviceToHost, st));
     MMS_CUDA(cudaStreamSynchronize(st));
+    g_stage_kernel_ms = timer.ms();
     cudaStreamDestroy(st);
     return MMS_OK;
 }
@@ -684,11 +712,21 @@ int mms_population_vectorised(const double *larval_habitat_area, const double *m
     p.H = n_times; p.C = n_pixels; p.burnin_years = burnin_years;
     p.densmod_type = densmod->type; p.dd_effect = densmod->dd_effect; p.surface_area_cm2 = densmod->surface_area_cm2;
     p.initial_adult = initial_adult; p.initial_aquatic = initial_aquatic;
+    EventTimer timer(st);
     MMS_CUDA(math_mode ? mms::launch_pop_stage_strict(p, st) : mms::launch_pop_stage_fast(p, st));
+    timer.stop();
     MMS_CUDA(cudaMemcpyAsync(aquatic, aq.p, bytes, cudaMemcpyDeviceToHost, st));
     MMS_CUDA(cudaMemcpyAsync(adult, ad.p, bytes, cudaMemcpyDeviceToHost, st));
     MMS_CUDA(cudaStreamSynchronize(st));
+    g_stage_kernel_ms = timer.ms();
     cudaStreamDestroy(st);
+    return MMS_OK;
+}
+
+int mms_stage_kernel_ms(float *ms)
+{
+    if (!ms) return fail(MMS_ERR_INVALID_ARG, "NULL ms");
+    *ms = g_stage_kernel_ms;
     return MMS_OK;
 }
 
