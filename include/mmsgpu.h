@@ -226,6 +226,26 @@ MMS_API int mms_population_vectorised(const double *larval_habitat_area, const d
                               int32_t math_mode, int32_t device,
                               double *aquatic, double *adult);
 
+/* ---- state-free verbs, for callers that want the intermediate products ----------------
+ * (layouts with the cell index fastest, like the fused chain)
+ *
+ * interpolate_daily_climate() -> daily_from_monthly_climate(), R/pipeline_functions.R:258-275,
+ * R/sim_microclimate.R:7-64:  monthly [9][M][C] -> daily [9][D][C] */
+MMS_API int mms_daily_from_monthly(const double *monthly, const double *mid_day, const double *day_predict,
+                                   int64_t n_cells, int32_t n_months, int32_t n_days, int32_t math_mode,
+                                   int32_t device, double *daily);
+/* simulate_hourly_microclimate() -> hourly_from_daily_climate_ambient(), R/pipeline_functions.R:284-301,
+ * R/sim_microclimate.R:126-173:  daily [9][D][C] -> hourly [6][24 D][C] = air_temperature, humidity,
+ * cloudcover, windspeed, water_temperature, rainfall */
+MMS_API int mms_hourly_from_daily(const double *daily, int64_t n_cells, int32_t n_days, int32_t math_mode,
+                                  int32_t device, double *hourly);
+/* simulate_hourly_lifehistory() -> simulate_vector_lifehistory(), R/pipeline_functions.R:634-683,
+ * R/sim_pop_dynamics.R:100-135: element-wise over n values (any layout) */
+MMS_API int mms_lifehistory_vectorised(const double *water_temperature, const double *air_temperature,
+                                       const double *humidity, int64_t n, const mms_lifehistory *lifehistory,
+                                       int32_t math_mode, int32_t device, double *mdr, double *efd,
+                                       double *das_zerodensity, double *ds);
+
 /* device time (CUDA events) of the kernel of the last stage-level twin call on this thread */
 MMS_API int mms_stage_kernel_ms(float *ms);
 

@@ -87,7 +87,8 @@ EXPORTS = ("mms_abi_version", "mms_device_count", "mms_last_error", "mms_run_cha
            "mms_chain_create", "mms_chain_upload", "mms_chain_launch", "mms_chain_sync",
            "mms_chain_download", "mms_chain_kernel_ms", "mms_chain_launch_count", "mms_chain_destroy",
            "mms_shard_range",
-           "mms_water_vectorised", "mms_population_vectorised", "mms_stage_kernel_ms", "mms_host_alloc", "mms_host_free",
+           "mms_water_vectorised", "mms_population_vectorised", "mms_stage_kernel_ms",
+           "mms_daily_from_monthly", "mms_hourly_from_daily", "mms_lifehistory_vectorised", "mms_host_alloc", "mms_host_free",
            "mms_measure_fp64_peak", "mms_measure_hbm_copy", "mms_flush_l2")
 
 _lib = None
@@ -122,6 +123,11 @@ def lib() -> ct.CDLL:
                                                 ct.POINTER(Densmod), ct.c_double, ct.c_double,
                                                 ct.c_int32, ct.c_int32, ct.c_int32, _dp, _dp]
         L.mms_stage_kernel_ms.argtypes = [ct.POINTER(ct.c_float)]
+        L.mms_daily_from_monthly.argtypes = [_dp, _dp, _dp, ct.c_int64, ct.c_int32, ct.c_int32, ct.c_int32,
+                                             ct.c_int32, _dp]
+        L.mms_hourly_from_daily.argtypes = [_dp, ct.c_int64, ct.c_int32, ct.c_int32, ct.c_int32, _dp]
+        L.mms_lifehistory_vectorised.argtypes = [_dp, _dp, _dp, ct.c_int64, ct.POINTER(LifehistoryC), ct.c_int32,
+                                                 ct.c_int32, _dp, _dp, _dp, _dp]
         L.mms_host_alloc.argtypes = [ct.POINTER(vp), ct.c_uint64]
         L.mms_host_free.argtypes = [vp]
         L.mms_measure_fp64_peak.argtypes = [ct.c_int32, ct.POINTER(ct.c_double)]
@@ -395,6 +401,54 @@ def population_vectorised(larval_habitat_area, mdr, efd, das_zerodensity, ds, de
                                           {"fast": 0, "strict": 1}.get(math_mode, math_mode), int(device),
                                           aquatic.ctypes.data_as(_dp), adult.ctypes.data_as(_dp)))
     return {"aquatic": aquatic, "adult": adult}
+
+
+def _mode(math_mode) -> int:
+    return {"fast": 0, "strict": 1}.get(math_mode, math_mode)
+
+
+def daily_from_monthly(monthly, mid_day, day_predict, math_mode="fast", device=0):
+    """mms_daily_from_monthly(): monthly [9][M][C] -> daily [9][D][C]."""
+    monthly, mid_day, day_predict = _d(monthly), _d(mid_day), _d(day_predict)
+    _, M, C = monthly.shape
+    D = len(day_predict)
+    if len(mid_day) != M:
+        raise ValueError("mid_day must have one entry per monthly knot")
+    daily = np.empty((NFORCING, D, C))
+    check(lib().mms_daily_from_monthly(_p(monthly), _p(mid_day), _p(day_predict), C, M, D, _mode(math_mode),
+                                       int(device), _p(daily)))
+    return daily
+
+
+def hourly_from_daily(daily, math_mode="fast", device=0):
+    """mms_hourly_from_daily(): daily [9][D][C] -> dict of [24 D][C] arrays."""
+    daily = _d(daily)
+    _, D, C = daily.shape
+    hourly = np.empty((6, 24 * D, C))
+    check(lib().mms_hourly_from_daily(_p(daily), C, D, _mode(math_mode), int(device), _p(hourly)))
+    names = ("air_temperature", "humidity", "cloudcover", "windspeed", "water_temperature", "rainfall")
+    return {n: hourly[k] for k, n in enumerate(names)}
+
+
+def lifehistory_vectorised(water_temperature, air_temperature, humidity, tables, math_mode="fast", device=0):
+    """mms_lifehistory_vectorised(): element-wise mdr, efd, das_zerodensity, ds (any array shape)."""
+    shape = np.shape(water_temperature)
+    tw, ta, rh = (_d(a).ravel() for a in (water_temperature, air_temperature, humidity))
+    if not (tw.size == ta.size == rh.size):
+        raise ValueError("inputs must have the same number of elements")
+    tabs = {k: {kk: _d(vv) for kk, vv in v.items()} for k, v in tables.items()}
+
+    def sp(t):
+        return Spline(len(t["x"]), 0, _p(t["x"]), _p(t["y"]), _p(t["b"]), _p(t["c"]), _p(t["d"]))
+
+    g = tabs["ds"]
+    lh = LifehistoryC(sp(tabs["mdr"]), sp(tabs["efd"]), sp(tabs["das"]),
+                      Surface(len(g["x"]), len(g["y"]), _p(g["x"]), _p(g["y"]), _p(g["z"])))
+    outs = [np.empty(tw.size) for _ in range(4)]
+    check(lib().mms_lifehistory_vectorised(_p(tw), _p(ta), _p(rh), tw.size, ct.byref(lh), _mode(math_mode),
+                                           int(device), *[_p(o) for o in outs]))
+    names = ("mdr", "efd", "das_zerodensity", "ds")
+    return {n: o.reshape(shape) for n, o in zip(names, outs)}
 
 
 def stage_kernel_ms() -> float:

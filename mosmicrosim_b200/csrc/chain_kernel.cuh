@@ -192,11 +192,11 @@ struct HourF {
     PopHour ph;
 };
 
-template <bool kFull, bool kWaterOnly>
-__device__ __forceinline__ HourF hour_forcing(const ChainParams &p, const SmemTables &tb, const DayCtx &dc,
-                                              double p_a, int h)
+// hourly microclimate of hour index h (0..23): SINEC air temperature, VSINE humidity / wind
+// speed [/ cloud cover]; hourly_from_daily_climate_ambient(), R/sim_microclimate.R:126-173
+template <bool kFull>
+__device__ __forceinline__ void hour_microclimate(const HourTables &hr, const DayCtx &dc, int h, HourF &f)
 {
-    HourF f;
     // ---- SINEC air temperature, R/sim_microclimate.R:185-285 (hour = h + 1, times = 100 * hour)
 #if !MMS_STRICT
     {   // the three segments as one fma with warp-uniform selects (no branch in the hour loop):
@@ -207,15 +207,15 @@ __device__ __forceinline__ HourF hour_forcing(const ChainParams &p, const SmemTa
         const double base = night ? dc.nxt.tmin : dc.cur.tmin;
         const double amp = pre ? (dc.t_midnight_prev - dc.cur.tmin) : (night ? (dc.t_sunset - dc.nxt.tmin) : dc.A);
         const double add = (pre || night) ? 0.0 : dc.A;
-        f.air_t = fma(amp, p.hr.air_coef[h], base) + add;
+        f.air_t = fma(amp, hr.air_coef[h], base) + add;
     }
 #else
     if (h < 5) {                     // times < time_sunrise: pre-dawn ramp, :275-277
-        f.air_t = dc.cur.tmin + (dc.t_midnight_prev - dc.cur.tmin) * p.hr.predawn[h];
+        f.air_t = dc.cur.tmin + (dc.t_midnight_prev - dc.cur.tmin) * hr.predawn[h];
     } else if (h <= 17) {            // 600 <= times <= 1800: sine, :255-256
-        f.air_t = dc.A * p.hr.z_light[h] + dc.cur.tmin + dc.A;
+        f.air_t = dc.A * hr.z_light[h] + dc.cur.tmin + dc.A;
     } else {                         // night: exponential decay, :260-262
-        f.air_t = (dc.t_sunset - dc.nxt.tmin) / p.hr.exp_e[h] + dc.nxt.tmin;
+        f.air_t = (dc.t_sunset - dc.nxt.tmin) / hr.exp_e[h] + dc.nxt.tmin;
     }
 #endif
     // ---- VSINE humidity / wind speed [/ cloud cover], :466-566
@@ -223,16 +223,24 @@ __device__ __forceinline__ HourF hour_forcing(const ChainParams &p, const SmemTa
     const bool after_inflection = h > 12;       // times > 13
     double inf_last = before_sunrise ? dc.rhmin_prev : dc.cur.rhmin;       // :529-530
     double sun_next = after_inflection ? dc.nxt.rhmax : dc.cur.rhmax;      // :548-549
-    f.rh = inf_last + p.hr.w_vsine[h] * (sun_next - inf_last);             // :556-557
+    f.rh = inf_last + hr.w_vsine[h] * (sun_next - inf_last);             // :556-557
     inf_last = before_sunrise ? dc.wsmax_prev : dc.cur.wsmax;
     sun_next = after_inflection ? dc.nxt.wsmin : dc.cur.wsmin;
-    f.wind = sun_next + p.hr.w_vsine_inv[h] * (inf_last - sun_next);       // :553-554
+    f.wind = sun_next + hr.w_vsine_inv[h] * (inf_last - sun_next);       // :553-554
     f.cloud = 0.0;
     if (kFull) {
         inf_last = before_sunrise ? dc.ccmin_prev : dc.cur.ccmin;
         sun_next = after_inflection ? dc.nxt.ccmax : dc.cur.ccmax;
-        f.cloud = inf_last + p.hr.w_vsine[h] * (sun_next - inf_last);
+        f.cloud = inf_last + hr.w_vsine[h] * (sun_next - inf_last);
     }
+}
+
+template <bool kFull, bool kWaterOnly>
+__device__ __forceinline__ HourF hour_forcing(const ChainParams &p, const SmemTables &tb, const DayCtx &dc,
+                                              double p_a, int h)
+{
+    HourF f;
+    hour_microclimate<kFull>(p.hr, dc, h, f);
     // ---- life-history parameters, R/sim_pop_dynamics.R:100-135
     // water_temperature = air_temperature, R/sim_microclimate.R:163.  The table look-ups
     // (L2-resident ds quad table, shared-memory spline rows) are issued first so that their

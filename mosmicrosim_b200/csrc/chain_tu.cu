@@ -4,6 +4,7 @@
 #include "chain_kernel.cuh"
 #include "chain_ws.cuh"
 #include "stage_kernels.cuh"
+#include "verb_kernels.cuh"
 
 namespace mms {
 
@@ -112,6 +113,33 @@ cudaError_t MMS_LAUNCH(launch_log1p_rows)(double *rows, int64_t n, cudaStream_t 
 {
     if (n <= 0) return cudaSuccess;
     log1p_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(rows, n);
+    return cudaGetLastError();
+}
+
+cudaError_t MMS_LAUNCH(launch_daily)(const ChainParams &p, double *out_daily, cudaStream_t stream)
+{
+    dim3 grid((unsigned)(p.c_stride / 128), (unsigned)p.D);
+    daily_kernel<<<grid, 128, 0, stream>>>(p, out_daily);
+    return cudaGetLastError();
+}
+
+cudaError_t MMS_LAUNCH(launch_hourly)(const ChainParams &p, const double *daily, double *out_hourly, cudaStream_t stream)
+{
+    dim3 grid((unsigned)(p.c_stride / 128), (unsigned)p.D);
+    hourly_kernel<<<grid, 128, 0, stream>>>(p, daily, out_hourly);
+    return cudaGetLastError();
+}
+
+cudaError_t MMS_LAUNCH(launch_lifehistory)(const ChainParams &p, int64_t n, const double *water_t, const double *air_t,
+                                           const double *humidity, double *mdr, double *efd, double *das0, double *ds,
+                                           int n_sm, cudaStream_t stream)
+{
+    const size_t smem = sizeof(double) * ((size_t)p.spline.n * 13 + p.ds.nx + p.ds.ny);
+    cudaError_t err = cudaFuncSetAttribute(lifehistory_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    const int64_t want = (n + 255) / 256;
+    const int grid = (int)(want < 2 * (int64_t)n_sm ? want : 2 * (int64_t)n_sm);   // 2 CTAs of 256 per SM (smem bound)
+    lifehistory_kernel<<<grid < 1 ? 1 : grid, 256, smem, stream>>>(p, n, water_t, air_t, humidity, mdr, efd, das0, ds);
     return cudaGetLastError();
 }
 

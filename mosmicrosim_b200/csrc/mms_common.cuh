@@ -108,6 +108,18 @@ cudaError_t launch_chain_strict(ChainParams &p, int n_sm, cudaStream_t stream);
 cudaError_t launch_log1p_rows_fast(double *rows, int64_t n, cudaStream_t stream);
 cudaError_t launch_log1p_rows_strict(double *rows, int64_t n, cudaStream_t stream);
 
+// state-free verbs (verb_kernels.cuh); p carries monthly / days / hr / tables as for the chain
+cudaError_t launch_daily_fast(const ChainParams &p, double *out_daily, cudaStream_t stream);
+cudaError_t launch_daily_strict(const ChainParams &p, double *out_daily, cudaStream_t stream);
+cudaError_t launch_hourly_fast(const ChainParams &p, const double *daily, double *out_hourly, cudaStream_t stream);
+cudaError_t launch_hourly_strict(const ChainParams &p, const double *daily, double *out_hourly, cudaStream_t stream);
+cudaError_t launch_lifehistory_fast(const ChainParams &p, int64_t n, const double *water_t, const double *air_t,
+                                    const double *humidity, double *mdr, double *efd, double *das0, double *ds,
+                                    int n_sm, cudaStream_t stream);
+cudaError_t launch_lifehistory_strict(const ChainParams &p, int64_t n, const double *water_t, const double *air_t,
+                                      const double *humidity, double *mdr, double *efd, double *das0, double *ds,
+                                      int n_sm, cudaStream_t stream);
+
 struct WaterStageParams {
     const double *rainfall, *air_temperature, *humidity, *windspeed; // [C][H] (R column-major)
     const double *altitude;   // [C]

@@ -723,6 +723,134 @@ int mms_population_vectorised(const double *larval_habitat_area, const double *m
     return MMS_OK;
 }
 
+// ---- state-free verbs ----------------------------------------------------------
+
+// interpolate_daily_climate() / daily_from_monthly_climate(), R/sim_microclimate.R:7-64
+int mms_daily_from_monthly(const double *monthly, const double *mid_day, const double *day_predict,
+                           int64_t n_cells, int32_t n_months, int32_t n_days, int32_t math_mode, int32_t device,
+                           double *daily)
+{
+    if (!monthly || !mid_day || !day_predict || !daily) return fail(MMS_ERR_INVALID_ARG, "NULL argument");
+    if (n_cells < 1 || n_months < 2 || n_days < 1) return fail(MMS_ERR_INVALID_ARG, "need cells >= 1, months >= 2, days >= 1");
+    int rc = pick_device(device);
+    if (rc) return rc;
+    std::vector<mms::DayEntry> days;
+    if ((rc = build_day_table(mid_day, n_months, day_predict, n_days, days))) return rc;
+    const int64_t cs = ((n_cells + mms::kBlock - 1) / mms::kBlock) * mms::kBlock;
+    DevBuf d_monthly, d_days, d_out, d_err;
+    cudaStream_t st;
+    MMS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    if ((rc = d_monthly.alloc(sizeof(double) * MMS_NFORCING * n_months * cs)) || (rc = d_days.alloc(sizeof(mms::DayEntry) * n_days)) ||
+        (rc = d_out.alloc(sizeof(double) * MMS_NFORCING * n_days * cs)) || (rc = d_err.alloc(2 * sizeof(int32_t)))) {
+        cudaStreamDestroy(st);
+        return rc;
+    }
+    MMS_CUDA(cudaMemsetAsync(d_monthly.p, 0, sizeof(double) * MMS_NFORCING * n_months * cs, st));
+    MMS_CUDA(cudaMemsetAsync(d_err.p, 0, 2 * sizeof(int32_t), st));
+    if ((rc = copy_in_2d(d_monthly.p, 8 * cs, monthly, 8 * n_cells, 8 * n_cells, (size_t)MMS_NFORCING * n_months, st))) return rc;
+    MMS_CUDA(cudaMemcpyAsync(d_days.p, days.data(), sizeof(mms::DayEntry) * n_days, cudaMemcpyHostToDevice, st));
+    double *rain = (double *)d_monthly.p + (size_t)MMS_F_RAINFALL_DAILY * n_months * cs;
+    MMS_CUDA(math_mode ? mms::launch_log1p_rows_strict(rain, (int64_t)n_months * cs, st)
+                       : mms::launch_log1p_rows_fast(rain, (int64_t)n_months * cs, st));
+    mms::ChainParams p{};
+    p.monthly = (const double *)d_monthly.p; p.days = (const mms::DayEntry *)d_days.p;
+    p.c_stride = cs; p.n_cells = n_cells; p.M = n_months; p.D = n_days;
+    p.error_flag = (int32_t *)d_err.p;
+    MMS_CUDA(math_mode ? mms::launch_daily_strict(p, (double *)d_out.p, st) : mms::launch_daily_fast(p, (double *)d_out.p, st));
+    if ((rc = copy_out_2d(daily, 8 * n_cells, d_out.p, 8 * cs, 8 * n_cells, (size_t)MMS_NFORCING * n_days, st))) return rc;
+    int32_t flag = 0;
+    MMS_CUDA(cudaMemcpyAsync(&flag, d_err.p, sizeof flag, cudaMemcpyDeviceToHost, st));
+    MMS_CUDA(cudaStreamSynchronize(st));
+    cudaStreamDestroy(st);
+    if (flag) return fail(MMS_ERR_NONFINITE, "non-finite (NA/NaN/Inf) monthly forcing; R's approx() would drop those knots, "
+                          "the GPU backend refuses them");
+    return MMS_OK;
+}
+
+// simulate_hourly_microclimate() / hourly_from_daily_climate_ambient(), R/sim_microclimate.R:126-173
+int mms_hourly_from_daily(const double *daily, int64_t n_cells, int32_t n_days, int32_t math_mode, int32_t device,
+                          double *hourly)
+{
+    if (!daily || !hourly) return fail(MMS_ERR_INVALID_ARG, "NULL argument");
+    if (n_cells < 1 || n_days < 1) return fail(MMS_ERR_INVALID_ARG, "need cells >= 1 and days >= 1");
+    int rc = pick_device(device);
+    if (rc) return rc;
+    const int64_t cs = ((n_cells + mms::kBlock - 1) / mms::kBlock) * mms::kBlock;
+    DevBuf d_in, d_out;
+    cudaStream_t st;
+    MMS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    if ((rc = d_in.alloc(sizeof(double) * MMS_NFORCING * n_days * cs)) || (rc = d_out.alloc(sizeof(double) * 6 * 24 * n_days * cs))) {
+        cudaStreamDestroy(st);
+        return rc;
+    }
+    MMS_CUDA(cudaMemsetAsync(d_in.p, 0, sizeof(double) * MMS_NFORCING * n_days * cs, st));
+    if ((rc = copy_in_2d(d_in.p, 8 * cs, daily, 8 * n_cells, 8 * n_cells, (size_t)MMS_NFORCING * n_days, st))) return rc;
+    mms::ChainParams p{};
+    p.c_stride = cs; p.n_cells = n_cells; p.D = n_days;
+    fill_hour_tables(p.hr);
+    MMS_CUDA(math_mode ? mms::launch_hourly_strict(p, (const double *)d_in.p, (double *)d_out.p, st)
+                       : mms::launch_hourly_fast(p, (const double *)d_in.p, (double *)d_out.p, st));
+    if ((rc = copy_out_2d(hourly, 8 * n_cells, d_out.p, 8 * cs, 8 * n_cells, (size_t)6 * 24 * n_days, st))) return rc;
+    MMS_CUDA(cudaStreamSynchronize(st));
+    cudaStreamDestroy(st);
+    return MMS_OK;
+}
+
+// simulate_hourly_lifehistory() / simulate_vector_lifehistory(), R/sim_pop_dynamics.R:100-135
+int mms_lifehistory_vectorised(const double *water_temperature, const double *air_temperature, const double *humidity,
+                               int64_t n, const mms_lifehistory *lh, int32_t math_mode, int32_t device,
+                               double *mdr, double *efd, double *das_zerodensity, double *ds)
+{
+    if (!water_temperature || !air_temperature || !humidity || !lh || !mdr || !efd || !das_zerodensity || !ds)
+        return fail(MMS_ERR_INVALID_ARG, "NULL argument");
+    if (n < 1) return fail(MMS_ERR_INVALID_ARG, "need at least one value");
+    int rc = pick_device(device);
+    if (rc) return rc;
+    HostTables tab;
+    if ((rc = pack_tables(*lh, tab))) return rc;
+    const mms_surface &g = lh->ds_temp_humid;
+    DevBuf in[3], out[4], d_sx, d_scoef, d_gx, d_gy, d_quad;
+    const double *src[3] = {water_temperature, air_temperature, humidity};
+    double *dst[4] = {mdr, efd, das_zerodensity, ds};
+    cudaStream_t st;
+    MMS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    const size_t bytes = sizeof(double) * (size_t)n;
+    for (int k = 0; k < 3; ++k) {
+        if ((rc = in[k].alloc(bytes))) { cudaStreamDestroy(st); return rc; }
+        MMS_CUDA(cudaMemcpyAsync(in[k].p, src[k], bytes, cudaMemcpyHostToDevice, st));
+    }
+    for (int k = 0; k < 4; ++k)
+        if ((rc = out[k].alloc(bytes))) { cudaStreamDestroy(st); return rc; }
+    if ((rc = d_sx.alloc(8 * tab.sx.size())) || (rc = d_scoef.alloc(8 * tab.scoef.size())) || (rc = d_gx.alloc(8 * (size_t)g.nx)) ||
+        (rc = d_gy.alloc(8 * (size_t)g.ny)) || (rc = d_quad.alloc(8 * tab.quad.size()))) {
+        cudaStreamDestroy(st);
+        return rc;
+    }
+    MMS_CUDA(cudaMemcpyAsync(d_sx.p, tab.sx.data(), 8 * tab.sx.size(), cudaMemcpyHostToDevice, st));
+    MMS_CUDA(cudaMemcpyAsync(d_scoef.p, tab.scoef.data(), 8 * tab.scoef.size(), cudaMemcpyHostToDevice, st));
+    MMS_CUDA(cudaMemcpyAsync(d_gx.p, g.x, 8 * (size_t)g.nx, cudaMemcpyHostToDevice, st));
+    MMS_CUDA(cudaMemcpyAsync(d_gy.p, g.y, 8 * (size_t)g.ny, cudaMemcpyHostToDevice, st));
+    MMS_CUDA(cudaMemcpyAsync(d_quad.p, tab.quad.data(), 8 * tab.quad.size(), cudaMemcpyHostToDevice, st));
+    mms::ChainParams p{};
+    p.spline.x = (const double *)d_sx.p; p.spline.coef = (const double *)d_scoef.p; p.spline.n = (int)tab.sx.size();
+    p.spline.uniform = tab.uniform; p.spline.x0 = tab.x0; p.spline.step = tab.step; p.spline.inv_step = tab.inv_step;
+    p.ds.x = (const double *)d_gx.p; p.ds.y = (const double *)d_gy.p; p.ds.quad = (const double *)d_quad.p;
+    p.ds.nx = g.nx; p.ds.ny = g.ny;
+    p.ds.x0 = g.x[0]; p.ds.inv_dx = (g.nx - 1) / (g.x[g.nx - 1] - g.x[0]); p.ds.x1 = g.x[g.nx - 1];
+    p.ds.y0 = g.y[0]; p.ds.inv_dy = (g.ny - 1) / (g.y[g.ny - 1] - g.y[0]); p.ds.y1 = g.y[g.ny - 1];
+    int n_sm = 0;
+    MMS_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    const bool strict = math_mode != 0 || !tab.uniform;
+    MMS_CUDA(strict ? mms::launch_lifehistory_strict(p, n, (const double *)in[0].p, (const double *)in[1].p, (const double *)in[2].p,
+                                                     (double *)out[0].p, (double *)out[1].p, (double *)out[2].p, (double *)out[3].p, n_sm, st)
+                    : mms::launch_lifehistory_fast(p, n, (const double *)in[0].p, (const double *)in[1].p, (const double *)in[2].p,
+                                                   (double *)out[0].p, (double *)out[1].p, (double *)out[2].p, (double *)out[3].p, n_sm, st));
+    for (int k = 0; k < 4; ++k) MMS_CUDA(cudaMemcpyAsync(dst[k], out[k].p, bytes, cudaMemcpyDeviceToHost, st));
+    MMS_CUDA(cudaStreamSynchronize(st));
+    cudaStreamDestroy(st);
+    return MMS_OK;
+}
+
 int mms_stage_kernel_ms(float *ms)
 {
     if (!ms) return fail(MMS_ERR_INVALID_ARG, "NULL ms");

@@ -1,0 +1,129 @@
+// verb_kernels.cuh -- stage-level twins of the three state-free pipeline verbs, for callers that
+// want the intermediate products the reference materialises between its verbs:
+//   interpolate_daily_climate()     R/pipeline_functions.R:258-275  -> daily_kernel
+//   simulate_hourly_microclimate()  R/pipeline_functions.R:284-301  -> hourly_kernel
+//   simulate_hourly_lifehistory()   R/pipeline_functions.R:634-683  -> lifehistory_kernel
+// (the fused chain computes the same quantities on the fly and never stores them).
+// All three are element-wise in the cell index: HBM-bound streaming kernels, layout
+// [variable][time][cell] with the cell index fastest (coalesced loads and stores).
+// They share the device functions of the fused kernel, so the arithmetic is identical.
+#pragma once
+
+#include "chain_kernel.cuh"
+
+namespace mms {
+namespace MMS_MODE {
+
+// daily_from_monthly_climate(), R/sim_microclimate.R:7-64: out[9][D][cs]
+// grid (cells / 128, D); p.monthly rows hold log1p(rainfall) already
+__global__ void __launch_bounds__(128) daily_kernel(const __grid_constant__ ChainParams p, double *__restrict__ out)
+{
+    const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int day = blockIdx.y;
+    if (cell >= p.c_stride) return;
+    int bad = 0;
+    const Daily d = load_daily<true>(p, cell, day, bad);
+    const int64_t plane = (int64_t)p.D * p.c_stride, at = (int64_t)day * p.c_stride + cell;
+    out[MMS_F_TMIN * plane + at] = d.tmin;
+    out[MMS_F_TMAX * plane + at] = d.tmax;
+    out[MMS_F_RHMIN * plane + at] = d.rhmin;
+    out[MMS_F_RHMAX * plane + at] = d.rhmax;
+    out[MMS_F_WSMIN * plane + at] = d.wsmin;
+    out[MMS_F_WSMAX * plane + at] = d.wsmax;
+    out[MMS_F_CCMIN * plane + at] = d.ccmin;
+    out[MMS_F_CCMAX * plane + at] = d.ccmax;
+    out[MMS_F_RAINFALL_DAILY * plane + at] = d.rain;
+    if (bad && cell < p.n_cells) atomicOr(p.error_flag, 1);
+}
+
+__device__ __forceinline__ Daily read_daily(const double *__restrict__ daily, int64_t plane, int64_t at)
+{
+    Daily d;
+    d.tmin = daily[MMS_F_TMIN * plane + at];
+    d.tmax = daily[MMS_F_TMAX * plane + at];
+    d.rhmin = daily[MMS_F_RHMIN * plane + at];
+    d.rhmax = daily[MMS_F_RHMAX * plane + at];
+    d.wsmin = daily[MMS_F_WSMIN * plane + at];
+    d.wsmax = daily[MMS_F_WSMAX * plane + at];
+    d.ccmin = daily[MMS_F_CCMIN * plane + at];
+    d.ccmax = daily[MMS_F_CCMAX * plane + at];
+    d.rain = daily[MMS_F_RAINFALL_DAILY * plane + at];
+    return d;
+}
+
+// hourly_from_daily_climate_ambient(), R/sim_microclimate.R:126-173: daily[9][D][cs] ->
+// out[6][24 D][cs] = air_temperature, humidity, cloudcover, windspeed, water_temperature, rainfall.
+// Every (cell, day) is independent: yesterday's midnight temperature only needs yesterday's and
+// today's daily values (R/sim_microclimate.R:271-275).  grid (cells / 128, D).
+__global__ void __launch_bounds__(128) hourly_kernel(const __grid_constant__ ChainParams p,
+                                                     const double *__restrict__ daily, double *__restrict__ out)
+{
+    const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int day = blockIdx.y;
+    if (cell >= p.c_stride) return;
+    const int64_t cs = p.c_stride, plane = (int64_t)p.D * cs;
+    const int dprev = day > 0 ? day - 1 : 0, dnext = day + 1 < p.D ? day + 1 : p.D - 1;
+    const Daily prv = read_daily(daily, plane, (int64_t)dprev * cs + cell);
+    DayCtx dc;
+    dc.cur = read_daily(daily, plane, (int64_t)day * cs + cell);
+    dc.nxt = read_daily(daily, plane, (int64_t)dnext * cs + cell);
+    dc.A = MMS_DIVC(dc.cur.tmax - dc.cur.tmin, 2.0);                       // R/sim_microclimate.R:217
+    dc.t_sunset = dc.A * p.hr.z_night + dc.cur.tmin + dc.A;                // :220
+    // yesterday's hour-24 value: night curve from yesterday's sunset towards today's minimum;
+    // the first day repeats its own (:271-272), i.e. towards tomorrow's minimum
+    const double a_prev = MMS_DIVC(prv.tmax - prv.tmin, 2.0);
+    const double sunset_prev = a_prev * p.hr.z_night + prv.tmin + a_prev;
+    const double tmin_after_prev = day > 0 ? dc.cur.tmin : dc.nxt.tmin;
+    dc.t_midnight_prev = (sunset_prev - tmin_after_prev) / p.hr.exp_e[23] + tmin_after_prev;
+    dc.rhmin_prev = prv.rhmin; dc.wsmax_prev = prv.wsmax; dc.ccmin_prev = prv.ccmin;   // :522
+    const double rain_h = MMS_DIVC(dc.cur.rain, 24.0);                     // :132
+    const int64_t hplane = (int64_t)24 * p.D * cs;
+#pragma unroll 4
+    for (int h = 0; h < 24; ++h) {
+        HourF f;
+        hour_microclimate<true>(p.hr, dc, h, f);
+        const int64_t at = ((int64_t)day * 24 + h) * cs + cell;
+        out[0 * hplane + at] = f.air_t;
+        out[1 * hplane + at] = f.rh;
+        out[2 * hplane + at] = f.cloud;
+        out[3 * hplane + at] = f.wind;
+        out[4 * hplane + at] = f.air_t;                                    // water_temperature = air_temperature, :163
+        out[5 * hplane + at] = rain_h;
+    }
+}
+
+// simulate_vector_lifehistory(), R/sim_pop_dynamics.R:100-135: element-wise over n values;
+// out mdr, efd, das_zerodensity, ds.  Spline rows and ds axes in shared memory like the fused kernel.
+__global__ void __launch_bounds__(256) lifehistory_kernel(const __grid_constant__ ChainParams p, int64_t n,
+                                                          const double *__restrict__ water_t,
+                                                          const double *__restrict__ air_t,
+                                                          const double *__restrict__ humidity,
+                                                          double *__restrict__ mdr, double *__restrict__ efd,
+                                                          double *__restrict__ das0, double *__restrict__ ds)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_coef = reinterpret_cast<double *>(smem_raw);              // [n][3][4]
+    double *s_x = s_coef + (size_t)p.spline.n * 12;
+    double *s_gx = s_x + p.spline.n;
+    double *s_gy = s_gx + p.ds.nx;
+    for (int k = threadIdx.x; k < p.spline.n * 12; k += blockDim.x) s_coef[k] = p.spline.coef[k];
+    for (int k = threadIdx.x; k < p.spline.n; k += blockDim.x) s_x[k] = p.spline.x[k];
+    for (int k = threadIdx.x; k < p.ds.nx; k += blockDim.x) s_gx[k] = p.ds.x[k];
+    for (int k = threadIdx.x; k < p.ds.ny; k += blockDim.x) s_gy[k] = p.ds.y[k];
+    __syncthreads();
+    const SmemTables tb{s_x, s_coef, s_gx, s_gy};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double tw = water_t[i], ta = air_t[i];
+        // mdr and das take the water temperature, efd the air temperature (R/sim_pop_dynamics.R:108-114)
+        const int iw = spline_interval(p.spline, tb.sx, tw), ia = spline_interval(p.spline, tb.sx, ta);
+        const double dw = tw - tb.sx[iw], da = ta - tb.sx[ia];
+        const double *cw = tb.coef + (size_t)iw * 12, *ca = tb.coef + (size_t)ia * 12;
+        mdr[i] = ensure_positive(cw[0] + dw * (cw[1] + dw * (cw[2] + dw * cw[3])));
+        efd[i] = ensure_positive(ca[4] + da * (ca[5] + da * (ca[6] + da * ca[7])));
+        das0[i] = ensure_positive(cw[8] + dw * (cw[9] + dw * (cw[10] + dw * cw[11])));
+        ds[i] = ds_surface(p.ds, tb, ta, humidity[i]);
+    }
+}
+
+}  // namespace MMS_MODE
+}  // namespace mms

@@ -88,6 +88,57 @@ def _monthly_array(pixel_monthly_climate):
     return start, end, monthly, altitude
 
 
+def interpolate_daily_climate(pixel_monthly_climate, dates_predict=None, *, math_mode="fast", device=0):
+    """interpolate_daily_climate() (R/pipeline_functions.R:258-275): monthly -> daily for every
+    pixel of the tile.  Returns the tile's `daily_climate` tibbles side by side: a dict with
+    `date` [D], the pixel columns carried through, and one [D, C] array per daily variable."""
+    start, end, monthly, altitude = _monthly_array(pixel_monthly_climate)
+    if dates_predict is None:
+        dates_predict = dates.default_dates_predict(start, end)
+    mid_day, day_predict = dates.datenums(start, end, dates_predict)
+    daily = backend.daily_from_monthly(monthly, mid_day, day_predict, math_mode=math_mode, device=device)
+    out = {"date": np.asarray(dates_predict, "datetime64[D]"), "altitude": altitude,
+           "longitude": pixel_monthly_climate.get("longitude"), "latitude": pixel_monthly_climate.get("latitude")}
+    for v, name in enumerate(FORCING_VARS):
+        out[name] = daily[v]
+    return out
+
+
+def simulate_hourly_microclimate(pixel_daily_climate, *, math_mode="fast", device=0):
+    """simulate_hourly_microclimate() (R/pipeline_functions.R:284-301): daily -> hourly ambient
+    microclimate.  Returns `date` [H], `hour` [H] (1..24) and one [H, C] array per hourly variable
+    (air_temperature, humidity, cloudcover, windspeed, water_temperature, rainfall)."""
+    daily = np.stack([np.asarray(pixel_daily_climate[name], dtype=np.float64) for name in FORCING_VARS], axis=0)
+    hourly = backend.hourly_from_daily(daily, math_mode=math_mode, device=device)
+    date = np.asarray(pixel_daily_climate["date"], "datetime64[D]")
+    out = {"date": np.repeat(date, 24), "hour": np.tile(np.arange(1, 25), len(date)),
+           "altitude": pixel_daily_climate.get("altitude"), "longitude": pixel_daily_climate.get("longitude"),
+           "latitude": pixel_daily_climate.get("latitude")}
+    out.update(hourly)
+    return out
+
+
+def simulate_hourly_lifehistory(pixel_hourly_conditions, lifehistory_functions, species=SPECIES,
+                                fast_ds_temp_humid=True, *, math_mode="fast", device=0):
+    """simulate_hourly_lifehistory() (R/pipeline_functions.R:634-683): mdr, efd, das_zerodensity, ds
+    from the hourly conditions (water_temperature, air_temperature, humidity, water_surface_area).
+    Only the bilinear ds emulator (fast_ds_temp_humid = TRUE, the reference default) exists here."""
+    species = _match_arg(species, SPECIES, "species")
+    if not fast_ds_temp_humid:
+        raise NotImplementedError("the GAM-predict form of ds_temp_humid is not available on the GPU; "
+                                  "fast_ds_temp_humid must be TRUE (the reference default)")
+    lh: Lifehistory = lifehistory_functions[{"An. gambiae": "An_gambiae", "An. stephensi": "An_stephensi"}[species]]
+    c = pixel_hourly_conditions
+    res = backend.lifehistory_vectorised(c["water_temperature"], c["air_temperature"], c["humidity"], lh.tables(),
+                                         math_mode=math_mode, device=device)
+    out = {k: c.get(k) for k in ("date", "hour", "longitude", "latitude")}
+    out.update(res)
+    out["larval_habitat_area"] = c.get("water_surface_area")      # R/sim_pop_dynamics.R:123
+    out["species"] = species
+    out["das_densmod_function"] = lh.das_densmod
+    return out
+
+
 def monthly_climate_to_vectors(pixel_monthly_climate, lifehistory_functions, species=SPECIES,
                                included_dates=None, aggregate_by="month", dates_predict=None, *,
                                habitats=None, model_water_temperature=False, water_shade_proportion=1,

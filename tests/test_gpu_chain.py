@@ -121,6 +121,18 @@ def test_both_kernel_forms(gpu, monkeypatch, form, n_settings):
     compare(case, out2, ref2, REL_TOL_FAST, what=("mean",))
 
 
+@pytest.mark.parametrize("mode,tol", [("strict", REL_TOL_STRICT), ("fast", REL_TOL_FAST)])
+def test_chain_two_years_with_leap_day(gpu, mode, tol):
+    """2004-2005: 731 days, M = 26 knots; the burn-in still repeats the first 8760 steps
+    (365 * 24 is hard-coded in the reference, R/sim_pop_dynamics.R:222), annual periods."""
+    case = Case(n_cells=24, years=2, first_year=2004, aggregate_by="year")
+    assert case.D == 731 and case.P == 2
+    ref = case.oracle(want_hourly=False)
+    out = backend.run_chain(case.monthly, case.altitude, **case.gpu_kwargs(
+        mean_vars=ALL_VARS, want_wet_hours=True, math_mode=mode))
+    compare(case, out, ref, tol, what=("mean",))
+
+
 def test_plan_matches_one_shot_and_is_repeatable(gpu):
     case = Case(n_cells=200)
     kw = case.gpu_kwargs(mean_vars=list(backend.VAR_NAMES[:6]), want_wet_hours=True)

@@ -1,0 +1,113 @@
+"""GPU parity of the state-free pipeline verbs (daily, hourly microclimate, life history) and of the
+verb-by-verb pipeline against the fused chain."""
+import numpy as np
+import pytest
+
+import oracle
+from helpers import ORACLE_VAR, REL_TOL_FAST, REL_TOL_STRICT, Case, rel_err
+from mosmicrosim_b200 import backend, pipeline, synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_daily(case):
+    return np.stack([oracle.daily_from_monthly(case.monthly[:, :, c], case.mid_day, case.day_predict)
+                     for c in range(case.C)], axis=2)                     # [9][D][C]
+
+
+@pytest.mark.parametrize("mode,tol", [("strict", REL_TOL_STRICT), ("fast", REL_TOL_FAST)])
+def test_daily_from_monthly(gpu, mode, tol):
+    for kw in (dict(n_cells=37), dict(n_cells=130, default_dates=True), dict(n_cells=5, years=2, first_year=2004)):
+        case = Case(**kw)
+        ref = oracle_daily(case)
+        got = backend.daily_from_monthly(case.monthly, case.mid_day, case.day_predict, math_mode=mode)
+        assert got.shape == ref.shape
+        assert rel_err(got, ref) <= tol
+    # the linear branch reproduces the knots exactly on knot days (approx1: v == x[j] -> y[j])
+    case = Case(n_cells=4, default_dates=True)
+    got = backend.daily_from_monthly(case.monthly, case.mid_day, case.day_predict, math_mode="strict")
+    on_knot = np.isin(case.day_predict, case.mid_day)
+    idx = np.searchsorted(case.mid_day, case.day_predict[on_knot])
+    assert on_knot.sum() >= 8             # the 31-day months have integral mid-dates
+    assert np.array_equal(got[:8][:, on_knot, :], case.monthly[:8][:, idx, :])
+    with pytest.raises(backend.MmsError) as e:
+        backend.daily_from_monthly(case.monthly, case.mid_day, case.day_predict + 40.0)
+    assert e.value.code == "MMS_ERR_EXTRAPOLATION"
+
+
+@pytest.mark.parametrize("mode,tol", [("strict", REL_TOL_STRICT), ("fast", REL_TOL_FAST)])
+def test_hourly_from_daily(gpu, mode, tol):
+    for n_cells, days in ((33, None), (3, 1), (2, 2)):
+        case = Case(n_cells=n_cells)
+        daily = oracle_daily(case)
+        if days:
+            daily = np.ascontiguousarray(daily[:, :days, :])
+        got = backend.hourly_from_daily(daily, math_mode=mode)
+        for c in range(n_cells):
+            ref = oracle.hourly_from_daily_ambient(daily[:, :, c])
+            for name in ("air_temperature", "humidity", "cloudcover", "windspeed", "water_temperature", "rainfall"):
+                assert rel_err(got[name][:, c], ref[name]) <= tol, (name, c, days)
+    # anchors of the reference's demos: max T at 13 h, min at 6 h; humidity max at 6 h, min at 13 h
+    case = Case(n_cells=8)
+    daily = oracle_daily(case)
+    got = backend.hourly_from_daily(daily, math_mode="strict")
+    air = got["air_temperature"].reshape(case.D, 24, 8)
+    np.testing.assert_allclose(air[:, 12, :], daily[1], rtol=1e-12)
+    np.testing.assert_allclose(air[:, 5, :], daily[0], rtol=1e-12)
+    rh = got["humidity"].reshape(case.D, 24, 8)
+    np.testing.assert_allclose(rh[:, 5, :], daily[3], rtol=1e-14)
+    np.testing.assert_allclose(rh[:, 12, :], daily[2], rtol=1e-14)
+
+
+@pytest.mark.parametrize("mode,tol", [("strict", REL_TOL_STRICT), ("fast", REL_TOL_FAST)])
+def test_lifehistory_vectorised(gpu, mode, tol):
+    rng = np.random.default_rng(7)
+    n = 20_000
+    tw = rng.uniform(-25, 85, n)          # beyond the knots on both sides: end-cubic extrapolation
+    ta = rng.uniform(-5, 50, n)           # partly outside the ds grid -> NA
+    rh = rng.uniform(-2, 103, n)
+    ta[:4] = [0.0, 45.0, 45.0, 22.5]      # exactly on the grid edges
+    rh[:4] = [0.0, 100.0, 50.0, 100.0]
+    for species in ("An. gambiae", "An. stephensi"):
+        tabs = syn.synthetic_lifehistory(species).tables()
+        got = backend.lifehistory_vectorised(tw, ta, rh, tabs, math_mode=mode)
+        assert rel_err(got["mdr"], oracle.spline_eval(tabs["mdr"], tw, positive=True)) <= tol
+        assert rel_err(got["efd"], oracle.spline_eval(tabs["efd"], ta, positive=True)) <= tol
+        assert rel_err(got["das_zerodensity"], oracle.spline_eval(tabs["das"], tw, positive=True)) <= tol
+        ref_ds = oracle.interp_surface(tabs["ds"], ta, rh)
+        assert np.isnan(ref_ds).sum() > 100 and not np.isnan(ref_ds[:4]).any()
+        assert rel_err(got["ds"], ref_ds) <= tol
+
+
+def test_verb_by_verb_pipeline_equals_fused_chain(gpu):
+    """interpolate_daily_climate |> simulate_hourly_microclimate |> water |> lifehistory |> population,
+    one GPU call per verb like the reference pipeline, against the fused kernel's hourly series."""
+    case = Case(n_cells=40)
+    pmc = {"start": case.start, "end": case.end, "altitude": case.altitude,
+           "longitude": np.arange(40.0), "latitude": np.arange(40.0)}
+    for v, name in enumerate(pipeline.FORCING_VARS):
+        pmc[name] = case.monthly[v]
+    lhf = {"An_gambiae": case.lh, "An_stephensi": syn.synthetic_lifehistory("An. stephensi")}
+    daily = pipeline.interpolate_daily_climate(pmc, dates_predict=case.dates_predict, math_mode="strict")
+    hourly = pipeline.simulate_hourly_microclimate(daily, math_mode="strict")
+    assert hourly["hour"][:25].tolist() == list(range(1, 25)) + [1]
+    water = pipeline.simulate_ephemeral_habitat_vectorised(hourly["rainfall"], hourly["air_temperature"],
+                                                           hourly["humidity"], hourly["windspeed"], case.altitude,
+                                                           math_mode="strict")
+    cond = dict(hourly, water_surface_area=water["water_surface_area"])
+    life = pipeline.simulate_hourly_lifehistory(cond, lhf, species="An. gambiae", math_mode="strict")
+    pop = pipeline.simulate_population_vectorised(life["larval_habitat_area"], life["mdr"], life["efd"],
+                                                  life["das_zerodensity"], life["ds"], life["das_densmod_function"],
+                                                  math_mode="strict")
+    fused = backend.run_chain(case.monthly, case.altitude, **case.gpu_kwargs(
+        hourly_vars=["adult", "aquatic", "larval_habitat_area", "mdr", "ds", "air_temperature"], math_mode="strict"))
+    st = {v: fused["hourly_state"][0, k] for k, v in enumerate(fused["hourly_state_vars"])}
+    fo = {v: fused["hourly_forcing"][k] for k, v in enumerate(fused["hourly_forcing_vars"])}
+    # same device functions, same order of operations: bit-identical
+    assert np.array_equal(hourly["air_temperature"], fo["air_temperature"])
+    assert np.array_equal(water["water_surface_area"], st["larval_habitat_area"])
+    assert np.array_equal(life["mdr"], fo["mdr"]) and np.array_equal(life["ds"], fo["ds"], equal_nan=True)
+    assert np.array_equal(pop["adult"], st["adult"], equal_nan=True)
+    assert np.array_equal(pop["aquatic"], st["aquatic"], equal_nan=True)
+    ref = case.oracle()
+    assert rel_err(pop["adult"], ref["hourly"][0, ORACLE_VAR["adult"]]) <= REL_TOL_STRICT
