@@ -101,6 +101,37 @@ simulate_population_vectorised_gpu <- function(
         PACKAGE = "mosmicrosim")
 }
 
+# ---- state-free verbs (for callers that want the intermediate tibbles) -------------
+
+# daily_from_monthly_climate() for a whole tile, R/sim_microclimate.R:7-64.
+# monthly: [cells, months, 9] array; returns a [cells, days, 9] array
+daily_from_monthly_gpu <- function(monthly, mid_day, day_predict) {
+  d <- .Call("mms_R_daily_from_monthly", monthly, as.numeric(mid_day), as.numeric(day_predict),
+             as.numeric(dim(monthly)[1]), mms_math_mode(),
+             if (length(mms_devices())) mms_devices()[1] else 0L, PACKAGE = "mosmicrosim")
+  array(d, dim = c(dim(monthly)[1], length(day_predict), 9))
+}
+
+# hourly_from_daily_climate_ambient() for a whole tile, R/sim_microclimate.R:126-173.
+# daily: [cells, days, 9]; returns [cells, 24 * days, 6] = air_temperature, humidity,
+# cloudcover, windspeed, water_temperature, rainfall
+hourly_from_daily_gpu <- function(daily) {
+  h <- .Call("mms_R_hourly_from_daily", daily, as.numeric(dim(daily)[1]), as.integer(dim(daily)[2]),
+             mms_math_mode(), if (length(mms_devices())) mms_devices()[1] else 0L, PACKAGE = "mosmicrosim")
+  array(h, dim = c(dim(daily)[1], 24 * dim(daily)[2], 6))
+}
+
+# simulate_vector_lifehistory(), R/sim_pop_dynamics.R:100-135, on plain vectors
+simulate_vector_lifehistory_gpu <- function(hourly_conditions, lifehistory) {
+  res <- .Call("mms_R_lifehistory_vectorised", as.numeric(hourly_conditions$water_temperature),
+               as.numeric(hourly_conditions$air_temperature), as.numeric(hourly_conditions$humidity),
+               mms_lifehistory_tables(lifehistory), mms_math_mode(),
+               if (length(mms_devices())) mms_devices()[1] else 0L, PACKAGE = "mosmicrosim")
+  dplyr::tibble(date = hourly_conditions$date, hour = hourly_conditions$hour,
+                mdr = res$mdr, efd = res$efd, das_zerodensity = res$das_zerodensity, ds = res$ds,
+                larval_habitat_area = hourly_conditions$water_surface_area)
+}
+
 # ---- the fused pipeline --------------------------------------------------------
 # tc_to_vectors() (R/pipeline_functions.R:1099-1130) from interpolate_daily_climate()
 # on, for the whole tile in one call.  pixel_monthly_climate is the tibble that

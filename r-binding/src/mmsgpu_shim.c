@@ -208,7 +208,69 @@ SEXP mms_R_run_chain(SEXP monthly, SEXP altitude, SEXP mid_day, SEXP day_predict
     return res;
 }
 
+/* interpolate_daily_climate(), R/pipeline_functions.R:258-275: monthly [C, M, 9] -> daily [C, D, 9] */
+SEXP mms_R_daily_from_monthly(SEXP monthly, SEXP mid_day, SEXP day_predict, SEXP n_cells, SEXP math_mode, SEXP device)
+{
+    const int64_t C = (int64_t)Rf_asReal(n_cells);
+    const int M = (int)Rf_xlength(mid_day), D = (int)Rf_xlength(day_predict);
+    if (Rf_xlength(monthly) != (R_xlen_t)C * M * MMS_NFORCING) Rf_error("monthly must be a [cells, months, 9] array");
+    SEXP daily = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)C * D * MMS_NFORCING));
+    check(mms_daily_from_monthly(REAL(monthly), REAL(mid_day), REAL(day_predict), C, M, D, Rf_asInteger(math_mode),
+                                 Rf_asInteger(device), REAL(daily)));
+    UNPROTECT(1);
+    return daily;
+}
+
+/* simulate_hourly_microclimate(), R/pipeline_functions.R:284-301: daily [C, D, 9] -> hourly [C, 24 D, 6] */
+SEXP mms_R_hourly_from_daily(SEXP daily, SEXP n_cells, SEXP n_days, SEXP math_mode, SEXP device)
+{
+    const int64_t C = (int64_t)Rf_asReal(n_cells);
+    const int D = Rf_asInteger(n_days);
+    if (Rf_xlength(daily) != (R_xlen_t)C * D * MMS_NFORCING) Rf_error("daily must be a [cells, days, 9] array");
+    SEXP hourly = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)C * 24 * D * 6));
+    check(mms_hourly_from_daily(REAL(daily), C, D, Rf_asInteger(math_mode), Rf_asInteger(device), REAL(hourly)));
+    UNPROTECT(1);
+    return hourly;
+}
+
+/* simulate_hourly_lifehistory(), R/pipeline_functions.R:634-683: element-wise over the hourly vectors */
+SEXP mms_R_lifehistory_vectorised(SEXP water_temperature, SEXP air_temperature, SEXP humidity, SEXP tables,
+                                  SEXP math_mode, SEXP device)
+{
+    const R_xlen_t n = Rf_xlength(water_temperature);
+    if (Rf_xlength(air_temperature) != n || Rf_xlength(humidity) != n) Rf_error("inputs must have the same length");
+    mms_lifehistory lh;
+    lh.mdr_temp = spline_from(list_get(tables, "mdr"));
+    lh.efd_temp = spline_from(list_get(tables, "efd"));
+    lh.das_temp = spline_from(list_get(tables, "das"));
+    SEXP ds = list_get(tables, "ds");
+    lh.ds_temp_humid.nx = (int32_t)Rf_xlength(list_get(ds, "x"));
+    lh.ds_temp_humid.ny = (int32_t)Rf_xlength(list_get(ds, "y"));
+    lh.ds_temp_humid.x = REAL(list_get(ds, "x"));
+    lh.ds_temp_humid.y = REAL(list_get(ds, "y"));
+    lh.ds_temp_humid.z = REAL(list_get(ds, "z"));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 4));
+    SEXP names = PROTECT(Rf_allocVector(STRSXP, 4));
+    const char *nm[4] = {"mdr", "efd", "das_zerodensity", "ds"};
+    double *dst[4];
+    for (int k = 0; k < 4; ++k) {
+        SEXP v = PROTECT(Rf_allocVector(REALSXP, n));
+        SET_VECTOR_ELT(out, k, v);
+        UNPROTECT(1);
+        SET_STRING_ELT(names, k, Rf_mkChar(nm[k]));
+        dst[k] = REAL(v);
+    }
+    Rf_setAttrib(out, R_NamesSymbol, names);
+    check(mms_lifehistory_vectorised(REAL(water_temperature), REAL(air_temperature), REAL(humidity), (int64_t)n, &lh,
+                                     Rf_asInteger(math_mode), Rf_asInteger(device), dst[0], dst[1], dst[2], dst[3]));
+    UNPROTECT(2);
+    return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
+    {"mms_R_daily_from_monthly", (DL_FUNC)&mms_R_daily_from_monthly, 6},
+    {"mms_R_hourly_from_daily", (DL_FUNC)&mms_R_hourly_from_daily, 5},
+    {"mms_R_lifehistory_vectorised", (DL_FUNC)&mms_R_lifehistory_vectorised, 6},
     {"mms_R_device_count", (DL_FUNC)&mms_R_device_count, 0},
     {"mms_R_water_vectorised", (DL_FUNC)&mms_R_water_vectorised, 9},
     {"mms_R_population_vectorised", (DL_FUNC)&mms_R_population_vectorised, 11},
