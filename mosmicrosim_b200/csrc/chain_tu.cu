@@ -137,9 +137,9 @@ cudaError_t MMS_LAUNCH(launch_lifehistory)(const ChainParams &p, int64_t n, cons
     const size_t smem = sizeof(double) * ((size_t)p.spline.n * 13 + p.ds.nx + p.ds.ny);
     cudaError_t err = cudaFuncSetAttribute(lifehistory_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    const int64_t want = (n + 255) / 256;
+    const int64_t want = (n + 511) / 512;
     const int grid = (int)(want < 2 * (int64_t)n_sm ? want : 2 * (int64_t)n_sm);   // 2 CTAs of 256 per SM (smem bound)
-    lifehistory_kernel<<<grid < 1 ? 1 : grid, 256, smem, stream>>>(p, n, water_t, air_t, humidity, mdr, efd, das0, ds);
+    lifehistory_kernel<<<grid < 1 ? 1 : grid, 512, smem, stream>>>(p, n, water_t, air_t, humidity, mdr, efd, das0, ds);
     return cudaGetLastError();
 }
 

@@ -756,11 +756,14 @@ int mms_daily_from_monthly(const double *monthly, const double *mid_day, const d
     p.monthly = (const double *)d_monthly.p; p.days = (const mms::DayEntry *)d_days.p;
     p.c_stride = cs; p.n_cells = n_cells; p.M = n_months; p.D = n_days;
     p.error_flag = (int32_t *)d_err.p;
+    EventTimer timer(st);
     MMS_CUDA(math_mode ? mms::launch_daily_strict(p, (double *)d_out.p, st) : mms::launch_daily_fast(p, (double *)d_out.p, st));
+    timer.stop();
     if ((rc = copy_out_2d(daily, 8 * n_cells, d_out.p, 8 * cs, 8 * n_cells, (size_t)MMS_NFORCING * n_days, st))) return rc;
     int32_t flag = 0;
     MMS_CUDA(cudaMemcpyAsync(&flag, d_err.p, sizeof flag, cudaMemcpyDeviceToHost, st));
     MMS_CUDA(cudaStreamSynchronize(st));
+    g_stage_kernel_ms = timer.ms();
     cudaStreamDestroy(st);
     if (flag) return fail(MMS_ERR_NONFINITE, "non-finite (NA/NaN/Inf) monthly forcing; R's approx() would drop those knots, "
                           "the GPU backend refuses them");
@@ -788,10 +791,13 @@ int mms_hourly_from_daily(const double *daily, int64_t n_cells, int32_t n_days, 
     mms::ChainParams p{};
     p.c_stride = cs; p.n_cells = n_cells; p.D = n_days;
     fill_hour_tables(p.hr);
+    EventTimer timer(st);
     MMS_CUDA(math_mode ? mms::launch_hourly_strict(p, (const double *)d_in.p, (double *)d_out.p, st)
                        : mms::launch_hourly_fast(p, (const double *)d_in.p, (double *)d_out.p, st));
+    timer.stop();
     if ((rc = copy_out_2d(hourly, 8 * n_cells, d_out.p, 8 * cs, 8 * n_cells, (size_t)6 * 24 * n_days, st))) return rc;
     MMS_CUDA(cudaStreamSynchronize(st));
+    g_stage_kernel_ms = timer.ms();
     cudaStreamDestroy(st);
     return MMS_OK;
 }
@@ -841,12 +847,15 @@ int mms_lifehistory_vectorised(const double *water_temperature, const double *ai
     int n_sm = 0;
     MMS_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
     const bool strict = math_mode != 0 || !tab.uniform;
+    EventTimer timer(st);
     MMS_CUDA(strict ? mms::launch_lifehistory_strict(p, n, (const double *)in[0].p, (const double *)in[1].p, (const double *)in[2].p,
                                                      (double *)out[0].p, (double *)out[1].p, (double *)out[2].p, (double *)out[3].p, n_sm, st)
                     : mms::launch_lifehistory_fast(p, n, (const double *)in[0].p, (const double *)in[1].p, (const double *)in[2].p,
                                                    (double *)out[0].p, (double *)out[1].p, (double *)out[2].p, (double *)out[3].p, n_sm, st));
+    timer.stop();
     for (int k = 0; k < 4; ++k) MMS_CUDA(cudaMemcpyAsync(dst[k], out[k].p, bytes, cudaMemcpyDeviceToHost, st));
     MMS_CUDA(cudaStreamSynchronize(st));
+    g_stage_kernel_ms = timer.ms();
     cudaStreamDestroy(st);
     return MMS_OK;
 }

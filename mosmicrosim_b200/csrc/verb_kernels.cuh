@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(128) hourly_kernel(const __grid_constant__ Cha
 
 // simulate_vector_lifehistory(), R/sim_pop_dynamics.R:100-135: element-wise over n values;
 // out mdr, efd, das_zerodensity, ds.  Spline rows and ds axes in shared memory like the fused kernel.
-__global__ void __launch_bounds__(256) lifehistory_kernel(const __grid_constant__ ChainParams p, int64_t n,
+__global__ void __launch_bounds__(512, 2) lifehistory_kernel(const __grid_constant__ ChainParams p, int64_t n,
                                                           const double *__restrict__ water_t,
                                                           const double *__restrict__ air_t,
                                                           const double *__restrict__ humidity,
