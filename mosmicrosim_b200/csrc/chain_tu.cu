@@ -143,32 +143,97 @@ cudaError_t MMS_LAUNCH(launch_lifehistory)(const ChainParams &p, int64_t n, cons
     return cudaGetLastError();
 }
 
+namespace {
+
+// widest access the series allow: 4 = 32-byte stores, 2 = 16-byte copies, 1 = 8-byte
+int stage_vec(int64_t H, uintptr_t all_pointers)
+{
+    if (H % 4 == 0 && (all_pointers & 31) == 0) return 4;
+    if (H % 2 == 0 && (all_pointers & 15) == 0) return 2;
+    return 1;
+}
+
+// persistent CTAs, one per SM.  The recursions are arithmetic-bound (exp / log / pow per step):
+// the register budget matters more than the warp count, so the default cap is the 16-warp
+// instantiation (128 registers, measured 36.6 vs 58.4 ms for the 80-register 22-warp one on
+// the 100k-pixel population twin), and the warp count is chosen so that the rounds of 32-pixel
+// units come out even (2 x 11 warps beats 16 + 5: 36.6 vs 41.5 ms).
+struct StagePlan { int grid, warps; size_t smem; };
+
+StagePlan stage_plan(int64_t C, int n_inputs, int n_sm, int w_cap)
+{
+    const int64_t n_units = (C + 31) / 32;
+    int w_max = w_cap;
+    bool even = true;
+    if (const char *e = getenv("MMS_STAGE_WARPS")) {                       // tuning aids
+        const int w = atoi(e);
+        if (w >= 1 && w <= kStageMaxWarps) w_max = w;
+    }
+    if (const char *e = getenv("MMS_STAGE_EVEN")) even = atoi(e) != 0;
+    const int64_t per_round = (int64_t)n_sm * w_max;
+    const int64_t rounds = even ? (n_units + per_round - 1) / per_round : 1;
+    int64_t warps = (n_units + (int64_t)n_sm * rounds - 1) / ((int64_t)n_sm * rounds);
+    warps = warps < 1 ? 1 : (warps > w_max ? w_max : warps);
+    const int64_t ctas = (n_units + warps - 1) / warps;
+    return StagePlan{(int)(ctas < n_sm ? ctas : n_sm), (int)warps, stage_smem_bytes(n_inputs, (int)warps)};
+}
+
+template <typename Kern, typename Params>
+cudaError_t launch_stage_kernel(Kern kern, const Params &p, const StagePlan &pl, cudaStream_t stream)
+{
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (err != cudaSuccess) return err;
+    kern<<<pl.grid, pl.warps * 32, pl.smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t device_sm_count(int &n_sm)
+{
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err == cudaSuccess) err = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    return err;
+}
+
+#if MMS_STRICT
+#define MMS_STAGE_DISPATCH(kernel, V, pl)                                                          \
+    launch_stage_kernel(kernel<V, kStageMaxWarps>, p, pl, stream)
+#else
+#define MMS_STAGE_DISPATCH(kernel, V, pl)                                                          \
+    ((pl).warps <= kStageFewWarps ? launch_stage_kernel(kernel<V, kStageFewWarps>, p, pl, stream)   \
+                                  : launch_stage_kernel(kernel<V, kStageMaxWarps>, p, pl, stream))
+#endif
+
+}  // namespace
+
 cudaError_t MMS_LAUNCH(launch_water_stage)(const WaterStageParams &p, cudaStream_t stream)
 {
-    const bool vec2 = (p.H % 2 == 0) &&
-                      ((((uintptr_t)p.rainfall | (uintptr_t)p.air_temperature | (uintptr_t)p.humidity |
-                         (uintptr_t)p.windspeed | (uintptr_t)p.water_surface_area |
-                         (uintptr_t)p.water_volume) & 15) == 0);
-    const unsigned grid = (unsigned)((p.C + kStageCells - 1) / kStageCells);
-    auto kern = vec2 ? water_stage_kernel<2> : water_stage_kernel<1>;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWaterStageSmem);
+    if (p.C <= 0) return cudaSuccess;
+    int n_sm = 0;
+    cudaError_t err = device_sm_count(n_sm);
     if (err != cudaSuccess) return err;
-    kern<<<grid, kStageCells, kWaterStageSmem, stream>>>(p);
-    return cudaGetLastError();
+    const int vec = stage_vec(p.H, (uintptr_t)p.rainfall | (uintptr_t)p.air_temperature | (uintptr_t)p.humidity |
+                                       (uintptr_t)p.windspeed | (uintptr_t)p.water_surface_area |
+                                       (uintptr_t)p.water_volume | (uintptr_t)p.wet);
+    const StagePlan pl = stage_plan(p.C, kWaterInputs, n_sm, kStageFewWarps);
+    if (vec == 4) return MMS_STAGE_DISPATCH(water_stage_kernel, 4, pl);
+    if (vec == 2) return MMS_STAGE_DISPATCH(water_stage_kernel, 2, pl);
+    return MMS_STAGE_DISPATCH(water_stage_kernel, 1, pl);
 }
 
 cudaError_t MMS_LAUNCH(launch_pop_stage)(const PopStageParams &p, cudaStream_t stream)
 {
-    const bool vec2 = (p.H % 2 == 0) &&
-                      ((((uintptr_t)p.larval_habitat_area | (uintptr_t)p.mdr | (uintptr_t)p.efd |
-                         (uintptr_t)p.das_zerodensity | (uintptr_t)p.ds | (uintptr_t)p.aquatic |
-                         (uintptr_t)p.adult) & 15) == 0);
-    const unsigned grid = (unsigned)((p.C + kStageCells - 1) / kStageCells);
-    auto kern = vec2 ? pop_stage_kernel<2> : pop_stage_kernel<1>;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPopStageSmem);
+    if (p.C <= 0) return cudaSuccess;
+    int n_sm = 0;
+    cudaError_t err = device_sm_count(n_sm);
     if (err != cudaSuccess) return err;
-    kern<<<grid, kStageCells, kPopStageSmem, stream>>>(p);
-    return cudaGetLastError();
+    const int vec = stage_vec(p.H, (uintptr_t)p.larval_habitat_area | (uintptr_t)p.mdr | (uintptr_t)p.efd |
+                                       (uintptr_t)p.das_zerodensity | (uintptr_t)p.ds | (uintptr_t)p.aquatic |
+                                       (uintptr_t)p.adult);
+    const StagePlan pl = stage_plan(p.C, kPopInputs, n_sm, kStageFewWarps);
+    if (vec == 4) return MMS_STAGE_DISPATCH(pop_stage_kernel, 4, pl);
+    if (vec == 2) return MMS_STAGE_DISPATCH(pop_stage_kernel, 2, pl);
+    return MMS_STAGE_DISPATCH(pop_stage_kernel, 1, pl);
 }
 
 }  // namespace mms

@@ -4,14 +4,22 @@
 //   simulate_ephemeral_habitat_vectorised()  R/sim_water.R:216-301
 //   simulate_population_vectorised()         R/sim_pop_dynamics.R:208-284
 //
-// One thread integrates one pixel.  Because R's layout is [pixel][time], a
-// warp reading "the same t for adjacent pixels" would be strided by H*8 bytes;
-// instead each CTA stages a tile of kStageCells pixels x kStageT time steps per
-// input through shared memory with cp.async (coalesced 64-byte row segments,
-// transposed on the shared-memory side), integrates the kStageT steps from
-// shared memory, and writes the output tile back the same way.
+// One thread integrates one pixel; the work unit is a warp = 32 pixels, and warps
+// never synchronise with each other.  Because R's layout is [pixel][time], a warp
+// reading "the same t for adjacent pixels" would be strided by H*8 bytes; instead
+// each warp lands a tile of 32 pixels x kStageT steps per input in shared memory
+// with cp.async (whole 32-byte sectors per row), double-buffered so that the
+// copies of tile k+1 are in flight while tile k is integrated.  Each lane then
+// reads its own row (swizzled, conflict-free LDS.128) and writes its kStageT
+// outputs per variable as one 32-byte store = one whole sector of its series.
 //
-// Included by chain_fast.cu / chain_strict.cu.  Citations: reference root.
+// Each step costs an exp / log / pow or three, so with the copies hidden the
+// kernels are FP64-arithmetic-bound, not HBM-bound: the CTA is persistent (one per
+// SM) and the host picks the warp count (chain_tu.cu, stage_plan) so that the
+// units run in evenly filled rounds with a 128-register budget per thread
+// (a 100k-pixel tile: two rounds of 11 warps per SM).
+//
+// Included by chain_tu.cu.  Citations: reference root.
 #pragma once
 
 #include <cuda_pipeline.h>
@@ -21,171 +29,232 @@
 namespace mms {
 namespace MMS_MODE {
 
-constexpr int kStageCells = 128;   // pixels per CTA (= threads)
-constexpr int kStageT = 8;         // time steps per tile: 64-byte row segments
-constexpr int kStagePitch = kStageT + 2;   // doubles; keeps 16-byte alignment, spreads banks
-constexpr size_t kStageTileBytes = sizeof(double) * kStageCells * kStagePitch;
-constexpr size_t kWaterStageSmem = 4 * kStageTileBytes + kStageCells * kStageT;   // + wet flags
-constexpr size_t kPopStageSmem = 5 * kStageTileBytes;
-
-// Copy a [cells x kStageT] tile of a column-major H-by-C matrix into smem
-// tile[cell][kStagePitch].  nt <= kStageT valid steps, nc <= kStageCells valid pixels.
-template <int kVecDoubles>
-__device__ __forceinline__ void stage_load(double *tile, const double *__restrict__ mat, int64_t H,
-                                           int64_t cell0, int nc, int64_t t0, int nt)
+constexpr int kStageT = 4;                       // steps per tile: one 32-byte sector per row
+constexpr int kStageTile = 32 * kStageT;         // doubles per (input, buffer) tile of one warp
+#if MMS_STRICT
+constexpr int kStageMaxWarps = 12;               // CUDA libm paths need the larger register budget
+constexpr int kStageFewWarps = 12;
+#else
+constexpr int kStageMaxWarps = 22;               // registers are allocated per 4 warps: 24 x 32 x 80 = 61 440
+constexpr int kStageFewWarps = 16;               // 128 registers: no spills
+#endif
+constexpr int kWaterInputs = 4, kPopInputs = 5;
+constexpr size_t stage_smem_bytes(int n_inputs, int warps)
 {
-    constexpr int kChunks = kStageT / kVecDoubles;            // chunks per row
-    for (int k = threadIdx.x; k < kStageCells * kChunks; k += blockDim.x) {
-        const int row = k / kChunks, chunk = k % kChunks;
-        const int t = chunk * kVecDoubles;
-        if (row < nc && t < nt) {
-            const double *src = mat + (cell0 + row) * H + t0 + t;
-            double *dst = tile + row * kStagePitch + t;
-            if (kVecDoubles == 2 && t + 1 < nt) {
-                __pipeline_memcpy_async(dst, src, 16);
-            } else {
-                __pipeline_memcpy_async(dst, src, 8);
-                if (kVecDoubles == 2 && t + 1 < nt) __pipeline_memcpy_async(dst + 1, src + 1, 8);
+    return sizeof(double) * 2 * (size_t)n_inputs * kStageTile * (size_t)warps;
+}
+
+// Row r of a tile holds its 4 steps as two 16-byte chunks; chunk c sits at position c ^ ((r >> 2) & 1),
+// so that the 8 lanes of a quarter-warp reading "their" chunk c hit 8 distinct 4-bank groups.
+__device__ __forceinline__ int stage_offset(int row, int t)
+{
+    return row * kStageT + ((((t >> 1) ^ (row >> 2)) & 1) << 1) + (t & 1);
+}
+
+// Issue the copies of one warp tile: steps t0 .. t0+nt-1 of pixels cell0 .. cell0+nc-1.
+// kVec >= 2: 16-byte copies, two lanes per row (each instruction covers 16 whole sectors);
+// kVec == 1: 8-byte copies for series that are not 16-byte aligned (odd H).
+template <int kVec>
+__device__ __forceinline__ void stage_issue(double *tile, const double *__restrict__ mat, int64_t H, int64_t cell0,
+                                            int nc, int64_t t0, int nt, int lane)
+{
+    if (kVec >= 2) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int row = j * 16 + (lane >> 1), t = (lane & 1) * 2;
+            if (row < nc && t < nt) {
+                const double *src = mat + (cell0 + row) * H + t0 + t;
+                double *dst = tile + stage_offset(row, t);
+                if (t + 1 < nt) __pipeline_memcpy_async(dst, src, 16);
+                else __pipeline_memcpy_async(dst, src, 8);
             }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int row = j * 8 + (lane >> 2), t = lane & 3;
+            if (row < nc && t < nt)
+                __pipeline_memcpy_async(tile + stage_offset(row, t), mat + (cell0 + row) * H + t0 + t, 8);
         }
     }
 }
 
-template <int kVecDoubles>
-__device__ __forceinline__ void stage_store(const double *tile, double *__restrict__ mat, int64_t H,
-                                            int64_t cell0, int nc, int64_t t0, int nt)
+// A lane's own row of a tile.
+__device__ __forceinline__ void stage_row(const double *tile, int lane, double (&v)[kStageT])
 {
-    constexpr int kChunks = kStageT / kVecDoubles;
-    for (int k = threadIdx.x; k < kStageCells * kChunks; k += blockDim.x) {
-        const int row = k / kChunks, chunk = k % kChunks;
-        const int t = chunk * kVecDoubles;
-        if (row < nc && t < nt) {
-            double *dst = mat + (cell0 + row) * H + t0 + t;
-            const double *src = tile + row * kStagePitch + t;
-            if (kVecDoubles == 2 && t + 1 < nt) {
-                *reinterpret_cast<double2 *>(dst) = *reinterpret_cast<const double2 *>(src);
-            } else {
-                dst[0] = src[0];
-            }
-        }
+    const double2 a = *reinterpret_cast<const double2 *>(tile + stage_offset(lane, 0));
+    const double2 b = *reinterpret_cast<const double2 *>(tile + stage_offset(lane, 2));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+// Store a lane's kStageT outputs: dst = &out[cell*H + t0].
+template <int kVec>
+__device__ __forceinline__ void stage_put(double *dst, const double (&v)[kStageT], int nt)
+{
+    if (kVec == 4 && nt == kStageT) {
+        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3])
+                     : "memory");
+    } else if (kVec >= 2) {
+        if (nt >= 2) *reinterpret_cast<double2 *>(dst) = make_double2(v[0], v[1]);
+        else if (nt == 1) dst[0] = v[0];
+        if (nt >= 4) *reinterpret_cast<double2 *>(dst + 2) = make_double2(v[2], v[3]);
+        else if (nt == 3) dst[2] = v[2];
+    } else {
+#pragma unroll
+        for (int t = 0; t < kStageT; ++t)
+            if (t < nt) dst[t] = v[t];
     }
 }
 
 // ---- simulate_ephemeral_habitat_vectorised() --------------------------------
-template <int kVecDoubles>
-__global__ void __launch_bounds__(kStageCells)
+// kVec: 4 = H % 4 == 0 and all matrices 32-byte aligned; 2 = H even, 16-byte aligned; 1 = anything
+template <int kVec, int kMaxWarps>
+__global__ void __launch_bounds__(kMaxWarps * 32, 1)
 water_stage_kernel(const __grid_constant__ WaterStageParams p)
 {
-    // dynamic smem: 4 input tiles; the two output tiles alias inputs 0 and 1
-    // (each thread reads all inputs of step t before it writes the outputs of step t)
     extern __shared__ __align__(16) unsigned char stage_smem[];
-    double (*s_in)[kStageCells * kStagePitch] =
-        reinterpret_cast<double (*)[kStageCells * kStagePitch]>(stage_smem);
-    double *s_area = s_in[0];
-    double *s_vol = s_in[1];
-    uint8_t *s_wet = reinterpret_cast<uint8_t *>(s_in[4]);
-
-    const int64_t cell0 = (int64_t)blockIdx.x * kStageCells;
-    const int nc = (int)min((int64_t)kStageCells, p.C - cell0);
-    const int me = threadIdx.x;
-    const bool live = me < nc;
-    const double p_a = live ? air_pressure_kpa(p.altitude[cell0 + me]) : 101.325;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    double *tiles = reinterpret_cast<double *>(stage_smem) + (size_t)warp * 2 * kWaterInputs * kStageTile;
     ::mms::fm::math_tables_init();
-    __syncthreads();
+    __syncthreads();                                                       // the only block-wide barrier
 
-    double volume = p.hab.initial_volume;                                  // R/sim_water.R:277
-    double surface = habitat_surface(p.hab, volume);
-    for (int pass = 0; pass <= p.burnin_years; ++pass) {                   // index, :232-233
-        const bool final_pass = pass == p.burnin_years;
-        const int64_t n_steps = final_pass ? p.H : (int64_t)kHoursPerYear;
-        for (int64_t t0 = 0; t0 < n_steps; t0 += kStageT) {
-            const int nt = (int)min((int64_t)kStageT, n_steps - t0);
-            stage_load<kVecDoubles>(s_in[0], p.rainfall, p.H, cell0, nc, t0, nt);
-            stage_load<kVecDoubles>(s_in[1], p.air_temperature, p.H, cell0, nc, t0, nt);
-            stage_load<kVecDoubles>(s_in[2], p.humidity, p.H, cell0, nc, t0, nt);
-            stage_load<kVecDoubles>(s_in[3], p.windspeed, p.H, cell0, nc, t0, nt);
+    const int64_t n_units = (p.C + 31) / 32;
+    for (int64_t unit = blockIdx.x + (int64_t)gridDim.x * warp; unit < n_units; unit += (int64_t)gridDim.x * n_warps) {
+        const int64_t cell0 = unit * 32;
+        const int nc = (int)min((int64_t)32, p.C - cell0);
+        const bool live = lane < nc;
+        const int64_t cell = cell0 + (live ? lane : 0);
+        const double p_a = air_pressure_kpa(p.altitude[cell]);
+
+        auto issue = [&](int buf, int64_t t0, int nt) {
+            double *b = tiles + buf * kWaterInputs * kStageTile;
+            stage_issue<kVec>(b + 0 * kStageTile, p.rainfall, p.H, cell0, nc, t0, nt, lane);
+            stage_issue<kVec>(b + 1 * kStageTile, p.air_temperature, p.H, cell0, nc, t0, nt, lane);
+            stage_issue<kVec>(b + 2 * kStageTile, p.humidity, p.H, cell0, nc, t0, nt, lane);
+            stage_issue<kVec>(b + 3 * kStageTile, p.windspeed, p.H, cell0, nc, t0, nt, lane);
+        };
+
+        double volume = p.hab.initial_volume;                              // R/sim_water.R:277
+        double surface = habitat_surface(p.hab, volume);
+        for (int pass = 0; pass <= p.burnin_years; ++pass) {               // index, :232-233
+            const bool final_pass = pass == p.burnin_years;
+            const int64_t n_steps = final_pass ? p.H : (int64_t)kHoursPerYear;
+            const int64_t n_tiles = (n_steps + kStageT - 1) / kStageT;
+            if (n_tiles > 0) issue(0, 0, (int)min((int64_t)kStageT, n_steps));
             __pipeline_commit();
-            __pipeline_wait_prior(0);
-            __syncthreads();
-            if (live) {
-                for (int t = 0; t < nt; ++t) {
-                    const int k = me * kStagePitch + t;
-                    const double rain = s_in[0][k], ta = s_in[1][k];
-                    const double rate = evaporation_rate(ta, s_in[2][k], p_a, s_in[3][k]);           // :264-270
-                    const double gain = p.hab.catchment_area * MMS_DIVC(rain, 1000.0);               // :122-123
-                    volume = iterate_volume(p.hab, volume, surface, rate, gain);                     // :279-287
-                    surface = habitat_surface(p.hab, volume);                                        // :294
-                    s_area[k] = surface;
-                    s_vol[k] = volume;
-                    s_wet[me * kStageT + t] = (volume > 0.0) ? 1 : 0;
+            for (int64_t k = 0; k < n_tiles; ++k) {
+                const int64_t t0 = k * kStageT;
+                const int nt = (int)min((int64_t)kStageT, n_steps - t0);
+                if (k + 1 < n_tiles) issue((int)((k + 1) & 1), t0 + kStageT, (int)min((int64_t)kStageT, n_steps - t0 - kStageT));
+                __pipeline_commit();
+                __pipeline_wait_prior(1);                                  // tile k has landed
+                __syncwarp();
+                const double *b = tiles + (int)(k & 1) * kWaterInputs * kStageTile;
+                double rain[kStageT], ta[kStageT], rh[kStageT], ws[kStageT];
+                stage_row(b + 0 * kStageTile, lane, rain);
+                stage_row(b + 1 * kStageTile, lane, ta);
+                stage_row(b + 2 * kStageTile, lane, rh);
+                stage_row(b + 3 * kStageTile, lane, ws);
+                double o_area[kStageT], o_vol[kStageT];
+                uint32_t wet = 0;
+#pragma unroll
+                for (int t = 0; t < kStageT; ++t) {
+                    if (t < nt) {
+                        const double rate = evaporation_rate(ta[t], rh[t], p_a, ws[t]);                  // :264-270
+                        const double gain = p.hab.catchment_area * MMS_DIVC(rain[t], 1000.0);            // :122-123
+                        volume = iterate_volume(p.hab, volume, surface, rate, gain);                     // :279-287
+                        surface = habitat_surface(p.hab, volume);                                        // :294
+                    }
+                    o_area[t] = surface;
+                    o_vol[t] = volume;
+                    wet |= (volume > 0.0 ? 1u : 0u) << (8 * t);
                 }
-            }
-            __syncthreads();
-            if (final_pass) {                                                                        // :290-291
-                stage_store<kVecDoubles>(s_area, p.water_surface_area, p.H, cell0, nc, t0, nt);
-                if (p.water_volume) stage_store<kVecDoubles>(s_vol, p.water_volume, p.H, cell0, nc, t0, nt);
-                if (p.wet) {
-                    for (int k = threadIdx.x; k < kStageCells * kStageT; k += blockDim.x) {
-                        const int row = k / kStageT, t = k % kStageT;
-                        if (row < nc && t < nt) p.wet[(cell0 + row) * p.H + t0 + t] = s_wet[k];
+                if (final_pass && live) {                                                                // :290-291
+                    const int64_t at = cell * p.H + t0;
+                    stage_put<kVec>(p.water_surface_area + at, o_area, nt);
+                    if (p.water_volume) stage_put<kVec>(p.water_volume + at, o_vol, nt);
+                    if (p.wet) {
+                        if (kVec == 4 && nt == kStageT) {
+                            *reinterpret_cast<uint32_t *>(p.wet + at) = wet;
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < kStageT; ++t)
+                                if (t < nt) p.wet[at + t] = (uint8_t)((wet >> (8 * t)) & 1u);
+                        }
                     }
                 }
+                __syncwarp();                                              // buffer k & 1 may be refilled
             }
-            __syncthreads();
         }
     }
 }
 
 // ---- simulate_population_vectorised() ---------------------------------------
-template <int kVecDoubles>
-__global__ void __launch_bounds__(kStageCells)
+template <int kVec, int kMaxWarps>
+__global__ void __launch_bounds__(kMaxWarps * 32, 1)
 pop_stage_kernel(const __grid_constant__ PopStageParams p)
 {
-    // dynamic smem: 5 input tiles; the two output tiles alias inputs 0 and 1
     extern __shared__ __align__(16) unsigned char stage_smem[];
-    double (*s_in)[kStageCells * kStagePitch] =
-        reinterpret_cast<double (*)[kStageCells * kStagePitch]>(stage_smem);
-    double *s_aq = s_in[0];
-    double *s_ad = s_in[1];
-
-    const int64_t cell0 = (int64_t)blockIdx.x * kStageCells;
-    const int nc = (int)min((int64_t)kStageCells, p.C - cell0);
-    const int me = threadIdx.x;
-    const bool live = me < nc;
-
-    double aquatic = p.initial_aquatic, adult = p.initial_adult;           // R/sim_pop_dynamics.R:249-252
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    double *tiles = reinterpret_cast<double *>(stage_smem) + (size_t)warp * 2 * kPopInputs * kStageTile;
     ::mms::fm::math_tables_init();
-    __syncthreads();
-    for (int pass = 0; pass <= p.burnin_years; ++pass) {                   // :225-226
-        const bool final_pass = pass == p.burnin_years;
-        const int64_t n_steps = final_pass ? p.H : (int64_t)kHoursPerYear;
-        for (int64_t t0 = 0; t0 < n_steps; t0 += kStageT) {
-            const int nt = (int)min((int64_t)kStageT, n_steps - t0);
-            stage_load<kVecDoubles>(s_in[0], p.larval_habitat_area, p.H, cell0, nc, t0, nt);
-            stage_load<kVecDoubles>(s_in[1], p.mdr, p.H, cell0, nc, t0, nt);
-            stage_load<kVecDoubles>(s_in[2], p.efd, p.H, cell0, nc, t0, nt);
-            stage_load<kVecDoubles>(s_in[3], p.das_zerodensity, p.H, cell0, nc, t0, nt);
-            stage_load<kVecDoubles>(s_in[4], p.ds, p.H, cell0, nc, t0, nt);
+    __syncthreads();                                                       // the only block-wide barrier
+
+    const int64_t n_units = (p.C + 31) / 32;
+    for (int64_t unit = blockIdx.x + (int64_t)gridDim.x * warp; unit < n_units; unit += (int64_t)gridDim.x * n_warps) {
+        const int64_t cell0 = unit * 32;
+        const int nc = (int)min((int64_t)32, p.C - cell0);
+        const bool live = lane < nc;
+        const int64_t cell = cell0 + (live ? lane : 0);
+
+        auto issue = [&](int buf, int64_t t0, int nt) {
+            double *b = tiles + buf * kPopInputs * kStageTile;
+            stage_issue<kVec>(b + 0 * kStageTile, p.larval_habitat_area, p.H, cell0, nc, t0, nt, lane);
+            stage_issue<kVec>(b + 1 * kStageTile, p.mdr, p.H, cell0, nc, t0, nt, lane);
+            stage_issue<kVec>(b + 2 * kStageTile, p.efd, p.H, cell0, nc, t0, nt, lane);
+            stage_issue<kVec>(b + 3 * kStageTile, p.das_zerodensity, p.H, cell0, nc, t0, nt, lane);
+            stage_issue<kVec>(b + 4 * kStageTile, p.ds, p.H, cell0, nc, t0, nt, lane);
+        };
+
+        double aquatic = p.initial_aquatic, adult = p.initial_adult;       // R/sim_pop_dynamics.R:249-252
+        for (int pass = 0; pass <= p.burnin_years; ++pass) {               // :225-226
+            const bool final_pass = pass == p.burnin_years;
+            const int64_t n_steps = final_pass ? p.H : (int64_t)kHoursPerYear;
+            const int64_t n_tiles = (n_steps + kStageT - 1) / kStageT;
+            if (n_tiles > 0) issue(0, 0, (int)min((int64_t)kStageT, n_steps));
             __pipeline_commit();
-            __pipeline_wait_prior(0);
-            __syncthreads();
-            if (live) {
-                for (int t = 0; t < nt; ++t) {
-                    const int k = me * kStagePitch + t;
-                    const double area = s_in[0][k];
-                    const PopHour ph = pop_hour(p.densmod_type, s_in[1][k], s_in[2][k], s_in[3][k], s_in[4][k]);
-                    iterate_state(aquatic, adult, ph, p.densmod_type, p.dd_effect, p.surface_area_cm2,
-                                  area);                                                              // :259-268
-                    s_aq[k] = aquatic;
-                    s_ad[k] = adult;
+            for (int64_t k = 0; k < n_tiles; ++k) {
+                const int64_t t0 = k * kStageT;
+                const int nt = (int)min((int64_t)kStageT, n_steps - t0);
+                if (k + 1 < n_tiles) issue((int)((k + 1) & 1), t0 + kStageT, (int)min((int64_t)kStageT, n_steps - t0 - kStageT));
+                __pipeline_commit();
+                __pipeline_wait_prior(1);                                  // tile k has landed
+                __syncwarp();
+                const double *b = tiles + (int)(k & 1) * kPopInputs * kStageTile;
+                double area[kStageT], mdr[kStageT], efd[kStageT], das[kStageT], ds[kStageT];
+                stage_row(b + 0 * kStageTile, lane, area);
+                stage_row(b + 1 * kStageTile, lane, mdr);
+                stage_row(b + 2 * kStageTile, lane, efd);
+                stage_row(b + 3 * kStageTile, lane, das);
+                stage_row(b + 4 * kStageTile, lane, ds);
+                double o_aq[kStageT], o_ad[kStageT];
+#pragma unroll
+                for (int t = 0; t < kStageT; ++t) {
+                    if (t < nt) {
+                        const PopHour ph = pop_hour(p.densmod_type, mdr[t], efd[t], das[t], ds[t]);
+                        iterate_state(aquatic, adult, ph, p.densmod_type, p.dd_effect, p.surface_area_cm2,
+                                      area[t]);                                                       // :259-268
+                    }
+                    o_aq[t] = aquatic;
+                    o_ad[t] = adult;
                 }
+                if (final_pass && live) {                                                             // :276-282
+                    const int64_t at = cell * p.H + t0;
+                    stage_put<kVec>(p.aquatic + at, o_aq, nt);
+                    stage_put<kVec>(p.adult + at, o_ad, nt);
+                }
+                __syncwarp();                                              // buffer k & 1 may be refilled
             }
-            __syncthreads();
-            if (final_pass) {                                                                         // :276-282
-                stage_store<kVecDoubles>(s_aq, p.aquatic, p.H, cell0, nc, t0, nt);
-                stage_store<kVecDoubles>(s_ad, p.adult, p.H, cell0, nc, t0, nt);
-            }
-            __syncthreads();
         }
     }
 }

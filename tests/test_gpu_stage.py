@@ -33,17 +33,61 @@ def test_water_twin(gpu, mode, tol, hab, burnin):
     assert np.array_equal(got["wet"], ref["wet"])                   # wet/dry flags bit exact
 
 
-def test_water_twin_ragged_shapes(gpu):
-    """H odd (8-byte copy path), H not a multiple of the time tile, C = 1 and C not a multiple of 128."""
-    case, m = hourly_inputs(n_cells=3)
-    for H, C in ((8759, 3), (101, 1), (8, 2), (7, 3)):
+RAGGED = ((8759, 3), (101, 1), (8, 2), (7, 3), (10, 33), (46, 40), (3, 65), (1, 1), (12, 32))
+
+
+@pytest.mark.parametrize("mode,tol", [("strict", REL_TOL_STRICT), ("fast", REL_TOL_FAST)])
+def test_water_twin_ragged_shapes(gpu, mode, tol):
+    """H odd (8-byte copies), H = 2 mod 4 (16-byte copies, no 32-byte stores), H not a multiple of the
+    time tile, C = 1 and C not a multiple of the 32-pixel unit."""
+    case, m = hourly_inputs(n_cells=65)
+    for H, C in RAGGED:
         sub = {k: np.asfortranarray(v[:H, :C]) for k, v in m.items()}
         ref = oracle.simulate_ephemeral_habitat_vectorised(sub["rainfall"], sub["air_temperature"], sub["humidity"],
                                                            sub["windspeed"], case.altitude[:C], oracle.habitat(), 0)
         got = backend.water_vectorised(sub["rainfall"], sub["air_temperature"], sub["humidity"], sub["windspeed"],
-                                       case.altitude[:C], syn.habitat_cone(), math_mode="strict", want_wet=True)
-        assert rel_err(got["water_surface_area"], ref["water_surface_area"]) <= REL_TOL_STRICT, (H, C)
-        assert np.array_equal(got["wet"], ref["wet"])
+                                       case.altitude[:C], syn.habitat_cone(), math_mode=mode, want_volume=True,
+                                       want_wet=True)
+        assert rel_err(got["water_surface_area"], ref["water_surface_area"]) <= tol, (H, C)
+        assert rel_err(got["water_volume"], ref["water_volume"]) <= tol, (H, C)
+        assert np.array_equal(got["wet"], ref["wet"]), (H, C)
+
+
+@pytest.mark.parametrize("mode,tol", [("strict", REL_TOL_STRICT), ("fast", REL_TOL_FAST)])
+def test_population_twin_ragged_shapes(gpu, mode, tol):
+    case, m = hourly_inputs(n_cells=65)
+    dmh = syn.synthetic_lifehistory("An. gambiae").das_densmod
+    dm = oracle.densmod(dmh.type, dmh.dd_effect, dmh.surface_area_cm2)
+    names = ("larval_habitat_area", "mdr", "efd", "das_zerodensity", "ds")
+    for H, C in RAGGED:
+        sub = [np.asfortranarray(m[k][:H, :C]) for k in names]
+        ref = oracle.simulate_population_vectorised(*sub, dm, burnin_years=0)
+        got = pipeline.simulate_population_vectorised(*sub, dmh, burnin_years=0, math_mode=mode)
+        assert rel_err(got["aquatic"], ref["aquatic"]) <= tol, (H, C)
+        assert rel_err(got["adult"], ref["adult"]) <= tol, (H, C)
+
+
+def test_twins_several_rounds_of_units(gpu):
+    """More 32-pixel units than one round of persistent warps holds (150k pixels, short series)."""
+    rng = np.random.default_rng(5)
+    H, C = 52, 150_001
+    mk = lambda lo, hi: np.asfortranarray(rng.uniform(lo, hi, size=(H, C)))
+    rain, airt, rh, wind, alt = mk(0, 0.4), mk(12, 36), mk(25, 100), mk(0.1, 5), rng.uniform(0, 2500, C)
+    hab = syn.habitat_cone()
+    ref = oracle.simulate_ephemeral_habitat_vectorised(rain, airt, rh, wind, alt, oracle.habitat(**hab), 0)
+    got = backend.water_vectorised(rain, airt, rh, wind, alt, hab, want_volume=True, want_wet=True)
+    assert rel_err(got["water_surface_area"], ref["water_surface_area"]) <= REL_TOL_FAST
+    assert rel_err(got["water_volume"], ref["water_volume"]) <= REL_TOL_FAST
+    assert np.array_equal(got["wet"], ref["wet"])
+    area = ref["water_surface_area"]
+    mdr, efd, das, ds = mk(0, 0.16), mk(0, 10), mk(0.2, 0.95), mk(0.3, 0.9)
+    dmh = syn.synthetic_lifehistory("An. gambiae").das_densmod
+    refp = oracle.simulate_population_vectorised(area, mdr, efd, das, ds,
+                                                 oracle.densmod(dmh.type, dmh.dd_effect, dmh.surface_area_cm2),
+                                                 burnin_years=0)
+    gotp = pipeline.simulate_population_vectorised(area, mdr, efd, das, ds, dmh, burnin_years=0)
+    assert rel_err(gotp["aquatic"], refp["aquatic"]) <= REL_TOL_FAST
+    assert rel_err(gotp["adult"], refp["adult"]) <= REL_TOL_FAST
 
 
 @pytest.mark.parametrize("mode,tol", [("strict", REL_TOL_STRICT), ("fast", REL_TOL_FAST)])
