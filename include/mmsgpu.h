@@ -226,6 +226,26 @@ MMS_API int mms_population_vectorised(const double *larval_habitat_area, const d
                               int32_t math_mode, int32_t device,
                               double *aquatic, double *adult);
 
+/* The scalar twins simulate_ephemeral_habitat(), R/sim_water.R:136-205, and simulate_population(),
+ * R/sim_pop_dynamics.R:138-196: the same recursions for one pixel (n_pixels = 1 gives the R functions'
+ * vector in / vector out; any number of pixels is accepted, same H-by-C layout), but their burn-in
+ * repeats the WHOLE series -- index <- rep(seq_len(n_times), burnin_years + 1), R/sim_water.R:151-152,
+ * R/sim_pop_dynamics.R:147-148 -- not the first 8760 rows, so any n_times is valid. */
+MMS_API int mms_water_series(const double *rainfall, const double *air_temperature,
+                     const double *humidity, const double *windspeed,
+                     const double *altitude, int64_t n_times, int64_t n_pixels,
+                     const mms_habitat *habitat, int32_t burnin_years,
+                     int32_t math_mode, int32_t device,
+                     double *water_surface_area, double *water_volume, uint8_t *wet);
+
+MMS_API int mms_population_series(const double *larval_habitat_area, const double *mdr,
+                          const double *efd, const double *das_zerodensity,
+                          const double *ds, int64_t n_times, int64_t n_pixels,
+                          const mms_densmod *densmod, double initial_adult,
+                          double initial_aquatic, int32_t burnin_years,
+                          int32_t math_mode, int32_t device,
+                          double *aquatic, double *adult);
+
 /* ---- state-free verbs, for callers that want the intermediate products ----------------
  * (layouts with the cell index fastest, like the fused chain)
  *

@@ -87,7 +87,8 @@ EXPORTS = ("mms_abi_version", "mms_device_count", "mms_last_error", "mms_run_cha
            "mms_chain_create", "mms_chain_upload", "mms_chain_launch", "mms_chain_sync",
            "mms_chain_download", "mms_chain_kernel_ms", "mms_chain_launch_count", "mms_chain_destroy",
            "mms_shard_range",
-           "mms_water_vectorised", "mms_population_vectorised", "mms_stage_kernel_ms",
+           "mms_water_vectorised", "mms_population_vectorised", "mms_water_series", "mms_population_series",
+           "mms_stage_kernel_ms",
            "mms_daily_from_monthly", "mms_hourly_from_daily", "mms_lifehistory_vectorised", "mms_host_alloc", "mms_host_free",
            "mms_measure_fp64_peak", "mms_measure_hbm_copy", "mms_flush_l2")
 
@@ -122,6 +123,8 @@ def lib() -> ct.CDLL:
         L.mms_population_vectorised.argtypes = [_dp, _dp, _dp, _dp, _dp, ct.c_int64, ct.c_int64,
                                                 ct.POINTER(Densmod), ct.c_double, ct.c_double,
                                                 ct.c_int32, ct.c_int32, ct.c_int32, _dp, _dp]
+        L.mms_water_series.argtypes = L.mms_water_vectorised.argtypes
+        L.mms_population_series.argtypes = L.mms_population_vectorised.argtypes
         L.mms_stage_kernel_ms.argtypes = [ct.POINTER(ct.c_float)]
         L.mms_daily_from_monthly.argtypes = [_dp, _dp, _dp, ct.c_int64, ct.c_int32, ct.c_int32, ct.c_int32,
                                              ct.c_int32, _dp]
@@ -367,7 +370,9 @@ def run_chain(monthly, altitude, **kwargs):
 
 
 def water_vectorised(rainfall, air_temperature, humidity, windspeed, altitude, habitat, burnin_years=0,
-                     math_mode="fast", device=0, want_volume=False, want_wet=False):
+                     math_mode="fast", device=0, want_volume=False, want_wet=False, whole_series_burnin=False):
+    """mms_water_vectorised(), or mms_water_series() (the scalar twin's burn-in rule: the whole
+    series is repeated) when whole_series_burnin is set."""
     mats = [np.asfortranarray(m, dtype=np.float64) for m in (rainfall, air_temperature, humidity, windspeed)]
     H, C = mats[0].shape
     if any(m.shape != (H, C) for m in mats):
@@ -379,16 +384,19 @@ def water_vectorised(rainfall, air_temperature, humidity, windspeed, altitude, h
     area = np.empty((H, C), order="F")
     vol = np.empty((H, C), order="F") if want_volume else None
     wet = np.empty((H, C), order="F", dtype=np.uint8) if want_wet else None
-    check(lib().mms_water_vectorised(*[m.ctypes.data_as(_dp) for m in mats], _p(alt), H, C, ct.byref(hb),
-                                     int(burnin_years), {"fast": 0, "strict": 1}.get(math_mode, math_mode),
-                                     int(device), area.ctypes.data_as(_dp),
-                                     None if vol is None else vol.ctypes.data_as(_dp),
-                                     None if wet is None else wet.ctypes.data_as(_bp)))
+    fn = lib().mms_water_series if whole_series_burnin else lib().mms_water_vectorised
+    check(fn(*[m.ctypes.data_as(_dp) for m in mats], _p(alt), H, C, ct.byref(hb),
+             int(burnin_years), {"fast": 0, "strict": 1}.get(math_mode, math_mode),
+             int(device), area.ctypes.data_as(_dp),
+             None if vol is None else vol.ctypes.data_as(_dp),
+             None if wet is None else wet.ctypes.data_as(_bp)))
     return {"water_surface_area": area, "water_volume": vol, "wet": wet}
 
 
 def population_vectorised(larval_habitat_area, mdr, efd, das_zerodensity, ds, densmod, initial_adult=100.0,
-                          initial_aquatic=100.0, burnin_years=1, math_mode="fast", device=0):
+                          initial_aquatic=100.0, burnin_years=1, math_mode="fast", device=0,
+                          whole_series_burnin=False):
+    """mms_population_vectorised(), or mms_population_series() when whole_series_burnin is set."""
     mats = [np.asfortranarray(m, dtype=np.float64) for m in (larval_habitat_area, mdr, efd, das_zerodensity, ds)]
     H, C = mats[0].shape
     if any(m.shape != (H, C) for m in mats):
@@ -396,10 +404,11 @@ def population_vectorised(larval_habitat_area, mdr, efd, das_zerodensity, ds, de
     dm = densmod if isinstance(densmod, Densmod) else make_densmod(**densmod)
     aquatic = np.empty((H, C), order="F")
     adult = np.empty((H, C), order="F")
-    check(lib().mms_population_vectorised(*[m.ctypes.data_as(_dp) for m in mats], H, C, ct.byref(dm),
-                                          float(initial_adult), float(initial_aquatic), int(burnin_years),
-                                          {"fast": 0, "strict": 1}.get(math_mode, math_mode), int(device),
-                                          aquatic.ctypes.data_as(_dp), adult.ctypes.data_as(_dp)))
+    fn = lib().mms_population_series if whole_series_burnin else lib().mms_population_vectorised
+    check(fn(*[m.ctypes.data_as(_dp) for m in mats], H, C, ct.byref(dm),
+             float(initial_adult), float(initial_aquatic), int(burnin_years),
+             {"fast": 0, "strict": 1}.get(math_mode, math_mode), int(device),
+             aquatic.ctypes.data_as(_dp), adult.ctypes.data_as(_dp)))
     return {"aquatic": aquatic, "adult": adult}
 
 

@@ -126,6 +126,7 @@ struct WaterStageParams {
     double *water_surface_area, *water_volume;  // [C][H]
     uint8_t *wet;             // [C][H]
     int64_t H, C;
+    int64_t burnin_steps;     // rows repeated per burn-in pass: 8760 (vectorised rule) or H (scalar twins)
     int32_t burnin_years;
     HabitatDev hab;
 };
@@ -133,6 +134,7 @@ struct PopStageParams {
     const double *larval_habitat_area, *mdr, *efd, *das_zerodensity, *ds; // [C][H]
     double *aquatic, *adult;
     int64_t H, C;
+    int64_t burnin_steps;     // as above
     int32_t burnin_years;
     int32_t densmod_type;
     double dd_effect, surface_area_cm2, initial_adult, initial_aquatic;

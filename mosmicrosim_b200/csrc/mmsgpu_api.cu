@@ -632,16 +632,18 @@ struct DevBuf {
     int alloc(size_t bytes) { MMS_CUDA(cudaMalloc(&p, bytes)); return MMS_OK; }
 };
 
-int mms_water_vectorised(const double *rainfall, const double *air_temperature, const double *humidity,
-                         const double *windspeed, const double *altitude, int64_t n_times, int64_t n_pixels,
-                         const mms_habitat *habitat, int32_t burnin_years, int32_t math_mode, int32_t device,
-                         double *water_surface_area, double *water_volume, uint8_t *wet)
+// whole_series: the scalar twins' burn-in rule (every pass repeats all n_times rows) instead of the
+// vectorised functions' "first 8760 rows"
+static int water_twin(const double *rainfall, const double *air_temperature, const double *humidity,
+                      const double *windspeed, const double *altitude, int64_t n_times, int64_t n_pixels,
+                      const mms_habitat *habitat, int32_t burnin_years, bool whole_series, int32_t math_mode,
+                      int32_t device, double *water_surface_area, double *water_volume, uint8_t *wet)
 {
     if (!rainfall || !air_temperature || !humidity || !windspeed || !altitude || !habitat || !water_surface_area)
         return fail(MMS_ERR_INVALID_ARG, "NULL argument");
     if (n_times < 1 || n_pixels < 1) return fail(MMS_ERR_INVALID_ARG, "matrices must have at least one row and column");
     if (burnin_years < 0) return fail(MMS_ERR_INVALID_ARG, "burnin_years must be >= 0");
-    if (burnin_years > 0 && n_times < mms::kHoursPerYear)
+    if (!whole_series && burnin_years > 0 && n_times < mms::kHoursPerYear)
         return fail(MMS_ERR_BURNIN, "burn-in repeats the first %d rows but the matrices have %lld "
                     "(R: subscript out of bounds, R/sim_water.R:240)", mms::kHoursPerYear, (long long)n_times);
     int rc = pick_device(device);
@@ -668,6 +670,7 @@ int mms_water_vectorised(const double *rainfall, const double *air_temperature, 
     p.altitude = (const double *)alt.p;
     p.water_surface_area = (double *)area.p; p.water_volume = (double *)vol.p; p.wet = (uint8_t *)wetb.p;
     p.H = n_times; p.C = n_pixels; p.burnin_years = burnin_years;
+    p.burnin_steps = whole_series ? n_times : (int64_t)mms::kHoursPerYear;
     EventTimer timer(st);
     MMS_CUDA(math_mode ? mms::launch_water_stage_strict(p, st) : mms::launch_water_stage_fast(p, st));
     timer.stop();
@@ -680,17 +683,36 @@ int mms_water_vectorised(const double *rainfall, const double *air_temperature, 
     return MMS_OK;
 }
 
-int mms_population_vectorised(const double *larval_habitat_area, const double *mdr, const double *efd,
-                              const double *das_zerodensity, const double *ds, int64_t n_times, int64_t n_pixels,
-                              const mms_densmod *densmod, double initial_adult, double initial_aquatic,
-                              int32_t burnin_years, int32_t math_mode, int32_t device, double *aquatic, double *adult)
+int mms_water_vectorised(const double *rainfall, const double *air_temperature, const double *humidity,
+                         const double *windspeed, const double *altitude, int64_t n_times, int64_t n_pixels,
+                         const mms_habitat *habitat, int32_t burnin_years, int32_t math_mode, int32_t device,
+                         double *water_surface_area, double *water_volume, uint8_t *wet)
+{
+    return water_twin(rainfall, air_temperature, humidity, windspeed, altitude, n_times, n_pixels, habitat,
+                      burnin_years, false, math_mode, device, water_surface_area, water_volume, wet);
+}
+
+int mms_water_series(const double *rainfall, const double *air_temperature, const double *humidity,
+                     const double *windspeed, const double *altitude, int64_t n_times, int64_t n_pixels,
+                     const mms_habitat *habitat, int32_t burnin_years, int32_t math_mode, int32_t device,
+                     double *water_surface_area, double *water_volume, uint8_t *wet)
+{
+    return water_twin(rainfall, air_temperature, humidity, windspeed, altitude, n_times, n_pixels, habitat,
+                      burnin_years, true, math_mode, device, water_surface_area, water_volume, wet);
+}
+
+static int population_twin(const double *larval_habitat_area, const double *mdr, const double *efd,
+                           const double *das_zerodensity, const double *ds, int64_t n_times, int64_t n_pixels,
+                           const mms_densmod *densmod, double initial_adult, double initial_aquatic,
+                           int32_t burnin_years, bool whole_series, int32_t math_mode, int32_t device,
+                           double *aquatic, double *adult)
 {
     if (!larval_habitat_area || !mdr || !efd || !das_zerodensity || !ds || !densmod || !aquatic || !adult)
         return fail(MMS_ERR_INVALID_ARG, "NULL argument");
     if (n_times < 1 || n_pixels < 1) return fail(MMS_ERR_INVALID_ARG, "matrices must have at least one row and column");
     if (densmod->type != 0 && densmod->type != 1) return fail(MMS_ERR_INVALID_ARG, "densmod type must be 0 (logit) or 1 (cox_ph)");
     if (burnin_years < 0) return fail(MMS_ERR_INVALID_ARG, "burnin_years must be >= 0");
-    if (burnin_years > 0 && n_times < mms::kHoursPerYear)
+    if (!whole_series && burnin_years > 0 && n_times < mms::kHoursPerYear)
         return fail(MMS_ERR_BURNIN, "burn-in repeats the first %d rows but the matrices have %lld "
                     "(R: subscript out of bounds, R/sim_pop_dynamics.R:233)", mms::kHoursPerYear, (long long)n_times);
     int rc = pick_device(device);
@@ -710,6 +732,7 @@ int mms_population_vectorised(const double *larval_habitat_area, const double *m
     p.das_zerodensity = (const double *)in[3].p; p.ds = (const double *)in[4].p;
     p.aquatic = (double *)aq.p; p.adult = (double *)ad.p;
     p.H = n_times; p.C = n_pixels; p.burnin_years = burnin_years;
+    p.burnin_steps = whole_series ? n_times : (int64_t)mms::kHoursPerYear;
     p.densmod_type = densmod->type; p.dd_effect = densmod->dd_effect; p.surface_area_cm2 = densmod->surface_area_cm2;
     p.initial_adult = initial_adult; p.initial_aquatic = initial_aquatic;
     EventTimer timer(st);
@@ -721,6 +744,24 @@ int mms_population_vectorised(const double *larval_habitat_area, const double *m
     g_stage_kernel_ms = timer.ms();
     cudaStreamDestroy(st);
     return MMS_OK;
+}
+
+int mms_population_vectorised(const double *larval_habitat_area, const double *mdr, const double *efd,
+                              const double *das_zerodensity, const double *ds, int64_t n_times, int64_t n_pixels,
+                              const mms_densmod *densmod, double initial_adult, double initial_aquatic,
+                              int32_t burnin_years, int32_t math_mode, int32_t device, double *aquatic, double *adult)
+{
+    return population_twin(larval_habitat_area, mdr, efd, das_zerodensity, ds, n_times, n_pixels, densmod,
+                           initial_adult, initial_aquatic, burnin_years, false, math_mode, device, aquatic, adult);
+}
+
+int mms_population_series(const double *larval_habitat_area, const double *mdr, const double *efd,
+                          const double *das_zerodensity, const double *ds, int64_t n_times, int64_t n_pixels,
+                          const mms_densmod *densmod, double initial_adult, double initial_aquatic,
+                          int32_t burnin_years, int32_t math_mode, int32_t device, double *aquatic, double *adult)
+{
+    return population_twin(larval_habitat_area, mdr, efd, das_zerodensity, ds, n_times, n_pixels, densmod,
+                           initial_adult, initial_aquatic, burnin_years, true, math_mode, device, aquatic, adult);
 }
 
 // ---- state-free verbs ----------------------------------------------------------

@@ -138,7 +138,7 @@ water_stage_kernel(const __grid_constant__ WaterStageParams p)
         double surface = habitat_surface(p.hab, volume);
         for (int pass = 0; pass <= p.burnin_years; ++pass) {               // index, :232-233
             const bool final_pass = pass == p.burnin_years;
-            const int64_t n_steps = final_pass ? p.H : (int64_t)kHoursPerYear;
+            const int64_t n_steps = final_pass ? p.H : p.burnin_steps;
             const int64_t n_tiles = (n_steps + kStageT - 1) / kStageT;
             if (n_tiles > 0) issue(0, 0, (int)min((int64_t)kStageT, n_steps));
             __pipeline_commit();
@@ -219,7 +219,7 @@ pop_stage_kernel(const __grid_constant__ PopStageParams p)
         double aquatic = p.initial_aquatic, adult = p.initial_adult;       // R/sim_pop_dynamics.R:249-252
         for (int pass = 0; pass <= p.burnin_years; ++pass) {               // :225-226
             const bool final_pass = pass == p.burnin_years;
-            const int64_t n_steps = final_pass ? p.H : (int64_t)kHoursPerYear;
+            const int64_t n_steps = final_pass ? p.H : p.burnin_steps;
             const int64_t n_tiles = (n_steps + kStageT - 1) / kStageT;
             if (n_tiles > 0) issue(0, 0, (int)min((int64_t)kStageT, n_steps));
             __pipeline_commit();

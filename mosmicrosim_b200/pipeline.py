@@ -67,6 +67,37 @@ def simulate_population_vectorised(larval_habitat_area_matrix, mdr_matrix, efd_m
                                          math_mode=math_mode, device=device)
 
 
+def simulate_ephemeral_habitat(hourly_climate, altitude, initial_volume=0, burnin_years=0, max_cone_depth=1,
+                               inflow_multiplier=1, *, shape="cone", radius=1.0, leak_per_hour=0.0,
+                               math_mode="fast", device=0):
+    """simulate_ephemeral_habitat(), R/sim_water.R:136-205: one pixel; hourly_climate is a mapping with
+    the columns rainfall, air_temperature, humidity, windspeed (vectors of n_times).  Returns the vector
+    of surface areas.  Unlike the vectorised function the burn-in repeats the whole series (:151-152)."""
+    cols = [np.asarray(hourly_climate[k], dtype=np.float64).reshape(-1, 1)
+            for k in ("rainfall", "air_temperature", "humidity", "windspeed")]
+    hb = backend.make_habitat(shape={"cone": 0, "cylinder": 1}[shape], max_depth=max_cone_depth, radius=radius,
+                              inflow_multiplier=inflow_multiplier, leak_per_hour=leak_per_hour,
+                              initial_volume=initial_volume)
+    res = backend.water_vectorised(*cols, np.array([float(altitude)]), hb, burnin_years=burnin_years,
+                                   math_mode=math_mode, device=device, whole_series_burnin=True)
+    return res["water_surface_area"][:, 0]
+
+
+def simulate_population(hourly_lifehistory, das_densmod_function: SurvDensmod, initial_adult=100,
+                        initial_aquatic=100, burnin_years=1, *, math_mode="fast", device=0):
+    """simulate_population(), R/sim_pop_dynamics.R:138-196: one pixel; hourly_lifehistory is a mapping with
+    the columns larval_habitat_area, mdr, efd, das_zerodensity, ds.  Returns {"aquatic", "adult"} vectors.
+    The burn-in repeats the whole series (:147-148)."""
+    cols = [np.asarray(hourly_lifehistory[k], dtype=np.float64).reshape(-1, 1)
+            for k in ("larval_habitat_area", "mdr", "efd", "das_zerodensity", "ds")]
+    dm = backend.make_densmod(das_densmod_function.type, das_densmod_function.dd_effect,
+                              das_densmod_function.surface_area_cm2)
+    res = backend.population_vectorised(*cols, dm, initial_adult=initial_adult, initial_aquatic=initial_aquatic,
+                                        burnin_years=burnin_years, math_mode=math_mode, device=device,
+                                        whole_series_burnin=True)
+    return {"aquatic": res["aquatic"][:, 0], "adult": res["adult"][:, 0]}
+
+
 # ---------------------------------------------------------------------------
 # the pipeline (tc_to_vectors() after terraclimate_to_monthly_climate())
 # ---------------------------------------------------------------------------

@@ -256,6 +256,27 @@ def simulate_population_vectorised(larval_habitat_area, mdr, efd, das_zerodensit
     return {"aquatic": aquatic, "adult": adult}
 
 
+def simulate_ephemeral_habitat(rainfall, air_temperature, humidity, windspeed, altitude, hb: Habitat,
+                               burnin_years=0):
+    """One-pixel twin (R/sim_water.R:136-205): vectors in, surface-area vector out."""
+    vecs = [_d(v) for v in (rainfall, air_temperature, humidity, windspeed)]
+    out = np.empty(len(vecs[0]))
+    lib().mmso_simulate_ephemeral_habitat(*[_p(v) for v in vecs], ct.c_double(altitude), ct.c_long(len(out)),
+                                          ct.byref(hb), int(burnin_years), _p(out))
+    return out
+
+
+def simulate_population(larval_habitat_area, mdr, efd, das_zerodensity, ds, dm: Densmod,
+                        initial_adult=100.0, initial_aquatic=100.0, burnin_years=1):
+    """One-pixel twin (R/sim_pop_dynamics.R:138-196): vectors in, {"aquatic", "adult"} vectors out."""
+    vecs = [_d(v) for v in (larval_habitat_area, mdr, efd, das_zerodensity, ds)]
+    aquatic, adult = np.empty(len(vecs[0])), np.empty(len(vecs[0]))
+    lib().mmso_simulate_population(*[_p(v) for v in vecs], ct.c_long(len(aquatic)), ct.byref(dm),
+                                   ct.c_double(initial_adult), ct.c_double(initial_aquatic), int(burnin_years),
+                                   _p(aquatic), _p(adult))
+    return {"aquatic": aquatic, "adult": adult}
+
+
 def R_mean(x):
     x = _d(x)
     return lib().mmso_R_mean(_p(x), len(x))

@@ -576,6 +576,51 @@ int mmso_simulate_population_vectorised(
     return 0;
 }
 
+/* simulate_ephemeral_habitat(): R/sim_water.R:136-205, the one-pixel twin.  Its burn-in
+ * index is rep(seq_len(n_times), burnin_years + 1) (:151-152, which overrides :144-149):
+ * the WHOLE series is repeated, and tail(..., n_times_total) keeps the last repeat (:198-199).
+ * Returns cone_volume_to_surface(volumes) (:203). */
+int mmso_simulate_ephemeral_habitat(
+    const double *rainfall, const double *air_temperature, const double *humidity,
+    const double *windspeed, double altitude, long n_times,
+    const mmso_habitat *hb, int burnin_years, double *surface_areas)
+{
+    const double max_volume = mmso_habitat_max_volume(hb);                  /* :164 */
+    const double catchment_area = mmso_habitat_catchment(hb);               /* :168 */
+    double volume = hb->initial_volume;                                     /* :182 */
+    for (int rep = 0; rep <= burnin_years; ++rep) {                         /* :152 */
+        for (long t = 0; t < n_times; ++t) {                                /* :184 */
+            const double rate = mmso_evaporation_rate_kg_h(air_temperature[t], humidity[t], altitude,
+                                                           windspeed[t], 1); /* :171-177 */
+            volume = mmso_iterate_volume(hb, volume, rainfall[t], rate, max_volume, catchment_area); /* :185-194 */
+            if (rep == burnin_years) surface_areas[t] = mmso_habitat_surface(hb, volume); /* :198-203 */
+        }
+    }
+    return 0;
+}
+
+/* simulate_population(): R/sim_pop_dynamics.R:138-196, the one-pixel twin; burn-in index
+ * rep(seq_len(n_times), burnin_years + 1) (:147-148), keep tail(..., n_times) (:187). */
+int mmso_simulate_population(
+    const double *larval_habitat_area, const double *mdr, const double *efd,
+    const double *das_zerodensity, const double *ds, long n_times,
+    const mmso_densmod *dm, double initial_adult, double initial_aquatic,
+    int burnin_years, double *aquatic_out, double *adult_out)
+{
+    double adult = initial_adult, aquatic = initial_aquatic;               /* :161-164 */
+    for (int rep = 0; rep <= burnin_years; ++rep) {
+        for (long t = 0; t < n_times; ++t) {                                /* :169 */
+            mmso_iterate_state(&aquatic, &adult, dm, larval_habitat_area[t], mdr[t], efd[t],
+                               das_zerodensity[t], ds[t]);                  /* :171-180 */
+            if (rep == burnin_years) {                                      /* :187-193 */
+                aquatic_out[t] = aquatic;
+                adult_out[t] = adult;
+            }
+        }
+    }
+    return 0;
+}
+
 /* base-R mean() for doubles: R sources src/main/summary.c real_mean()
  * (long double accumulation plus one correction pass; restated).  Used by
  * aggregate_vectors(), R/pipeline_functions.R:1055-1086. */

@@ -127,6 +127,16 @@ int mmso_simulate_population_vectorised(
     const double *das_zerodensity, const double *ds, long H, long C,
     const mmso_densmod *dm, double initial_adult, double initial_aquatic,
     int burnin_years, double *aquatic, double *adult);
+/* the one-pixel twins, R/sim_water.R:136-205 and R/sim_pop_dynamics.R:138-196 (whole-series burn-in) */
+int mmso_simulate_ephemeral_habitat(
+    const double *rainfall, const double *air_temperature, const double *humidity,
+    const double *windspeed, double altitude, long n_times,
+    const mmso_habitat *hb, int burnin_years, double *surface_areas);
+int mmso_simulate_population(
+    const double *larval_habitat_area, const double *mdr, const double *efd,
+    const double *das_zerodensity, const double *ds, long n_times,
+    const mmso_densmod *dm, double initial_adult, double initial_aquatic,
+    int burnin_years, double *aquatic, double *adult);
 double mmso_R_mean(const double *x, long n);
 
 /* ---- fused chain (composition of the stages above, per cell) ------------ */

@@ -101,6 +101,33 @@ simulate_population_vectorised_gpu <- function(
         PACKAGE = "mosmicrosim")
 }
 
+# simulate_ephemeral_habitat(), R/sim_water.R:136-205 (one pixel; the burn-in repeats the whole series)
+simulate_ephemeral_habitat_gpu <- function(hourly_climate, altitude, initial_volume = 0,
+                                           burnin_years = 0, max_cone_depth = 1,
+                                           inflow_multiplier = 1) {
+  .Call("mms_R_water_series", as.numeric(hourly_climate$rainfall),
+        as.numeric(hourly_climate$air_temperature), as.numeric(hourly_climate$humidity),
+        as.numeric(hourly_climate$windspeed), as.numeric(altitude),
+        mms_habitat(initial_volume = initial_volume, max_cone_depth = max_cone_depth,
+                    inflow_multiplier = inflow_multiplier),
+        as.integer(burnin_years), mms_math_mode(),
+        if (length(mms_devices())) mms_devices()[1] else 0L,
+        PACKAGE = "mosmicrosim")
+}
+
+# simulate_population(), R/sim_pop_dynamics.R:138-196 (one pixel; tibble(aquatic, adult) as at :190-193)
+simulate_population_gpu <- function(hourly_lifehistory, das_densmod_function, initial_adult = 100,
+                                    initial_aquatic = 100, burnin_years = 1) {
+  res <- .Call("mms_R_population_series", as.numeric(hourly_lifehistory$larval_habitat_area),
+               as.numeric(hourly_lifehistory$mdr), as.numeric(hourly_lifehistory$efd),
+               as.numeric(hourly_lifehistory$das_zerodensity), as.numeric(hourly_lifehistory$ds),
+               mms_densmod(das_densmod_function), as.numeric(initial_adult),
+               as.numeric(initial_aquatic), as.integer(burnin_years), mms_math_mode(),
+               if (length(mms_devices())) mms_devices()[1] else 0L,
+               PACKAGE = "mosmicrosim")
+  dplyr::tibble(aquatic = res$aquatic, adult = res$adult)
+}
+
 # ---- state-free verbs (for callers that want the intermediate tibbles) -------------
 
 # daily_from_monthly_climate() for a whole tile, R/sim_microclimate.R:7-64.
@@ -196,6 +223,8 @@ monthly_climate_to_vectors_gpu <- function(pixel_monthly_climate,
 # ---- the switch: one line each in the reference's own functions ------------------
 # R/sim_water.R:216     if (mms_backend() == "gpu") return(simulate_ephemeral_habitat_vectorised_gpu(...))
 # R/sim_pop_dynamics.R:208  if (mms_backend() == "gpu") return(simulate_population_vectorised_gpu(...))
+# R/sim_water.R:136     if (mms_backend() == "gpu") return(simulate_ephemeral_habitat_gpu(...))
+# R/sim_pop_dynamics.R:138  if (mms_backend() == "gpu") return(simulate_population_gpu(...))
 # R/pipeline_functions.R:1099 (tc_to_vectors):
 #   monthly <- terraclimate_to_monthly_climate(pixel_terraclimate_data)
 #   if (mms_backend() == "gpu") return(monthly_climate_to_vectors_gpu(monthly, species, included_dates))

@@ -132,6 +132,51 @@ SEXP mms_R_population_vectorised(SEXP larval_habitat_area, SEXP mdr, SEXP efd, S
     return out;                         /* list(aquatic = , adult = ) like R/sim_pop_dynamics.R:279-282 */
 }
 
+/* simulate_ephemeral_habitat(), R/sim_water.R:136-205: one pixel, plain vectors, whole-series burn-in.
+ * Returns the numeric vector of surface areas (the R function's value, :203). */
+SEXP mms_R_water_series(SEXP rainfall, SEXP air_temperature, SEXP humidity, SEXP windspeed, SEXP altitude,
+                        SEXP habitat, SEXP burnin_years, SEXP math_mode, SEXP device)
+{
+    const int64_t H = Rf_xlength(rainfall);
+    if (Rf_xlength(air_temperature) != H || Rf_xlength(humidity) != H || Rf_xlength(windspeed) != H)
+        Rf_error("all hourly_climate columns must have the same length");
+    mms_habitat hb = habitat_from(habitat);
+    double alt = Rf_asReal(altitude);
+    SEXP area = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)H));
+    check(mms_water_series(REAL(rainfall), REAL(air_temperature), REAL(humidity), REAL(windspeed), &alt, H, 1, &hb,
+                           Rf_asInteger(burnin_years), Rf_asInteger(math_mode), Rf_asInteger(device), REAL(area),
+                           NULL, NULL));
+    UNPROTECT(1);
+    return area;
+}
+
+/* simulate_population(), R/sim_pop_dynamics.R:138-196: one pixel; list(aquatic = , adult = ) which the
+ * R wrapper turns into the tibble of :190-193 */
+SEXP mms_R_population_series(SEXP larval_habitat_area, SEXP mdr, SEXP efd, SEXP das_zerodensity, SEXP ds,
+                             SEXP densmod, SEXP initial_adult, SEXP initial_aquatic, SEXP burnin_years,
+                             SEXP math_mode, SEXP device)
+{
+    const int64_t H = Rf_xlength(larval_habitat_area);
+    if (Rf_xlength(mdr) != H || Rf_xlength(efd) != H || Rf_xlength(das_zerodensity) != H || Rf_xlength(ds) != H)
+        Rf_error("all hourly_lifehistory columns must have the same length");
+    mms_densmod dm = densmod_from(densmod);
+    SEXP aquatic = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)H));
+    SEXP adult = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)H));
+    check(mms_population_series(REAL(larval_habitat_area), REAL(mdr), REAL(efd), REAL(das_zerodensity), REAL(ds),
+                                H, 1, &dm, Rf_asReal(initial_adult), Rf_asReal(initial_aquatic),
+                                Rf_asInteger(burnin_years), Rf_asInteger(math_mode), Rf_asInteger(device),
+                                REAL(aquatic), REAL(adult)));
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SEXP names = PROTECT(Rf_allocVector(STRSXP, 2));
+    SET_VECTOR_ELT(out, 0, aquatic);
+    SET_VECTOR_ELT(out, 1, adult);
+    SET_STRING_ELT(names, 0, Rf_mkChar("aquatic"));
+    SET_STRING_ELT(names, 1, Rf_mkChar("adult"));
+    Rf_setAttrib(out, R_NamesSymbol, names);
+    UNPROTECT(4);
+    return out;
+}
+
 /* The fused chain: interpolate_daily_climate() ... summarise_vectors() for a whole tile,
  * R/pipeline_functions.R:258-1026.
  *   monthly        double [C, M, 9] array (R column-major = [9][M][C] with the cell index fastest)
@@ -274,6 +319,8 @@ static const R_CallMethodDef call_methods[] = {
     {"mms_R_device_count", (DL_FUNC)&mms_R_device_count, 0},
     {"mms_R_water_vectorised", (DL_FUNC)&mms_R_water_vectorised, 9},
     {"mms_R_population_vectorised", (DL_FUNC)&mms_R_population_vectorised, 11},
+    {"mms_R_water_series", (DL_FUNC)&mms_R_water_series, 9},
+    {"mms_R_population_series", (DL_FUNC)&mms_R_population_series, 11},
     {"mms_R_run_chain", (DL_FUNC)&mms_R_run_chain, 13},
     {NULL, NULL, 0}};
 

@@ -173,3 +173,24 @@ def test_full_size_properties_and_sampled_parity(gpu):
     for k, v in enumerate(out["mean_forcing_vars"]):
         assert rel_err(out["mean_forcing"][k][..., pick], ref["mean"][0, ORACLE_VAR[v]]) <= REL_TOL_FAST, v
     assert np.array_equal(out["wet_hours"][..., pick], ref["wet_hours"])
+
+
+@pytest.mark.parametrize("mode,tol", [("strict", REL_TOL_STRICT), ("fast", REL_TOL_FAST)])
+def test_scalar_twins_whole_series_burnin(gpu, mode, tol):
+    """simulate_ephemeral_habitat() / simulate_population(): one pixel, vectors in and out, and the
+    burn-in repeats the whole series (so a 500-step series with burn-in is legal)."""
+    case, m = hourly_inputs(n_cells=2)
+    col = {k: v[:, 1] for k, v in m.items()}
+    dmh = syn.synthetic_lifehistory("An. gambiae").das_densmod
+    dm = oracle.densmod(dmh.type, dmh.dd_effect, dmh.surface_area_cm2)
+    for n, burn in ((case.H, 0), (case.H, 1), (500, 2), (7, 3)):
+        sub = {k: v[:n] for k, v in col.items()}
+        ref = oracle.simulate_ephemeral_habitat(sub["rainfall"], sub["air_temperature"], sub["humidity"],
+                                                sub["windspeed"], float(case.altitude[1]), oracle.habitat(), burn)
+        got = pipeline.simulate_ephemeral_habitat(sub, float(case.altitude[1]), burnin_years=burn, math_mode=mode)
+        assert got.shape == (n,) and rel_err(got, ref) <= tol, (n, burn)
+        refp = oracle.simulate_population(sub["larval_habitat_area"], sub["mdr"], sub["efd"], sub["das_zerodensity"],
+                                          sub["ds"], dm, burnin_years=burn)
+        gotp = pipeline.simulate_population(sub, dmh, burnin_years=burn, math_mode=mode)
+        assert rel_err(gotp["aquatic"], refp["aquatic"]) <= tol, (n, burn)
+        assert rel_err(gotp["adult"], refp["adult"]) <= tol, (n, burn)

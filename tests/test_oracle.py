@@ -201,3 +201,36 @@ def test_golden_vectors():
     assert np.array_equal(ref["wet_hours"], g["wet_hours"])
     sel = g["hourly_steps"]
     np.testing.assert_allclose(ref["hourly"][:, :, sel, :], g["hourly_sample"], rtol=1e-11, atol=1e-15)
+
+
+# ---- the one-pixel twins (whole-series burn-in rule) ------------------------------------------
+
+def test_scalar_twins_burnin_repeats_the_whole_series():
+    """simulate_ephemeral_habitat() / simulate_population() (R/sim_water.R:151-152,
+    R/sim_pop_dynamics.R:147-148): index <- rep(seq_len(n_times), burnin_years + 1)."""
+    case = Case(n_cells=2)
+    h = case.oracle()["hourly"][0]
+    v = {n: h[oracle.VAR_NAMES.index(n)][:, 1] for n in oracle.VAR_NAMES}
+    hb, dm = oracle.habitat(), oracle.densmod(case.densmod["type_"], case.densmod["dd_effect"],
+                                              case.densmod["surface_area_cm2"])
+    wcols = [v[k] for k in ("rainfall", "air_temperature", "humidity", "windspeed")]
+    pcols = [v[k] for k in ("larval_habitat_area", "mdr", "efd", "das_zerodensity", "ds")]
+    alt = float(case.altitude[1])
+    as_mat = lambda cols: [c.reshape(-1, 1) for c in cols]
+    # no burn-in, and one burn-in year on exactly 8760 rows: identical to the vectorised functions
+    for burn in (0, 1):
+        a = oracle.simulate_ephemeral_habitat(*wcols, alt, hb, burn)
+        b = oracle.simulate_ephemeral_habitat_vectorised(*as_mat(wcols), [alt], hb, burn)["water_surface_area"][:, 0]
+        assert np.array_equal(a, b)
+        p = oracle.simulate_population(*pcols, dm, burnin_years=burn)
+        q = oracle.simulate_population_vectorised(*as_mat(pcols), dm, burnin_years=burn)
+        assert np.array_equal(p["adult"], q["adult"][:, 0]) and np.array_equal(p["aquatic"], q["aquatic"][:, 0])
+    # a short series with two burn-in repeats = the series tiled three times, last copy kept
+    n = 500
+    short_w, short_p = [c[:n] for c in wcols], [c[:n] for c in pcols]
+    a = oracle.simulate_ephemeral_habitat(*short_w, alt, hb, 2)
+    b = oracle.simulate_ephemeral_habitat(*[np.tile(c, 3) for c in short_w], alt, hb, 0)[-n:]
+    assert np.array_equal(a, b)
+    p = oracle.simulate_population(*short_p, dm, burnin_years=2)
+    q = oracle.simulate_population(*[np.tile(c, 3) for c in short_p], dm, burnin_years=0)
+    assert np.array_equal(p["adult"], q["adult"][-n:]) and np.array_equal(p["aquatic"], q["aquatic"][-n:])
