@@ -59,6 +59,12 @@ enum {
     MMS_F_CCMIN, MMS_F_CCMAX, MMS_F_RAINFALL_DAILY, MMS_NFORCING
 };
 
+/* raw monthly TerraClimate variables, in the column order of the per-pixel tibble
+ * extract_terraclimate_tile() builds (R/pipeline_functions.R:134-136) */
+enum {
+    MMS_T_TMAX = 0, MMS_T_TMIN, MMS_T_PPT, MMS_T_WS, MMS_T_VPD, MMS_T_SRAD, MMS_NTERRACLIMATE
+};
+
 /* output variables.  0-5 are the reference's vector_variables in its order
  * (R/pipeline_functions.R:1041-1048); 6-7 the water body
  * (R/pipeline_functions.R:879-891 carries larval_habitat_area); 8-12 the hourly
@@ -195,6 +201,18 @@ MMS_API int mms_run_chain(const mms_chain_config *cfg, const double *monthly, co
 typedef struct mms_chain_plan mms_chain_plan;
 MMS_API int  mms_chain_create(const mms_chain_config *cfg, mms_chain_plan **plan);
 MMS_API int  mms_chain_upload(mms_chain_plan *plan, const double *monthly, const double *altitude);
+/* The same upload from the six raw TerraClimate variables: the nine forcing rows are derived on
+ * the device as process_terraclimate_pixel_vars() derives them (R/terraclimate.R:581-643; see
+ * mms_terraclimate_to_monthly below for the arguments). */
+MMS_API int  mms_chain_upload_terraclimate(mms_chain_plan *plan, const double *terraclimate,
+                                           const double *clear_sky, const int32_t *month_id,
+                                           const double *n_days, const double *altitude);
+/* one-shot form of that route (create, upload_terraclimate, launch, download, destroy):
+ * tc_to_vectors() whole, R/pipeline_functions.R:1099-1130 */
+MMS_API int  mms_run_chain_terraclimate(const mms_chain_config *cfg, const double *terraclimate,
+                                        const double *clear_sky, const int32_t *month_id,
+                                        const double *n_days, const double *altitude,
+                                        const mms_chain_outputs *out);
 MMS_API int  mms_chain_launch(mms_chain_plan *plan);          /* asynchronous */
 MMS_API int  mms_chain_sync(mms_chain_plan *plan);            /* waits, reports kernel-side errors */
 MMS_API int  mms_chain_download(mms_chain_plan *plan, const mms_chain_outputs *out);
@@ -249,6 +267,20 @@ MMS_API int mms_population_series(const double *larval_habitat_area, const doubl
 /* ---- state-free verbs, for callers that want the intermediate products ----------------
  * (layouts with the cell index fastest, like the fused chain)
  *
+ * terraclimate_to_monthly_climate() -> process_terraclimate_pixel_vars(), R/pipeline_functions.R:179-252,
+ * R/terraclimate.R:581-643, for all pixels of a tile:
+ *   terraclimate [MMS_NTERRACLIMATE][M][C]  tmax, tmin (deg C), ppt (mm / month), ws (m/s at 10 m), vpd (kPa), srad (W/m2)
+ *   clear_sky    [12][C]                    clear_sky_SOLR of the pixel by calendar month (R/pipeline_functions.R:194-222)
+ *   month_id     [M]                        lubridate::month(start + (end - start) / 2), 1..12 (R/terraclimate.R:591)
+ *   n_days       [M]                        as.numeric(end - start): days in the month MINUS ONE, as the reference has it (:592)
+ *   monthly      [MMS_NFORCING][M][C]       out
+ * Saturation vapour pressure is NicheMapR's VAPPRS (Goff-Gratch), restated: third-party code that is
+ * not part of the reference tree -- parity unpinned, see oracle/mms_oracle.c mmso_vapprs(). */
+MMS_API int mms_terraclimate_to_monthly(const double *terraclimate, const double *clear_sky,
+                                        const int32_t *month_id, const double *n_days, int64_t n_cells,
+                                        int32_t n_months, int32_t math_mode, int32_t device, double *monthly);
+
+/*
  * interpolate_daily_climate() -> daily_from_monthly_climate(), R/pipeline_functions.R:258-275,
  * R/sim_microclimate.R:7-64:  monthly [9][M][C] -> daily [9][D][C] */
 MMS_API int mms_daily_from_monthly(const double *monthly, const double *mid_day, const double *day_predict,

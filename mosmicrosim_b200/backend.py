@@ -14,6 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmmsgpu.so")
 
 NFORCING = 9
+NTERRACLIMATE = 6
+TERRACLIMATE_VARS = ("tmax", "tmin", "ppt", "ws", "vpd", "srad")   # R/pipeline_functions.R:134-136
 NVARS = 13
 VAR_NAMES = ("adult", "aquatic", "mdr", "efd", "das_zerodensity", "ds",
              "larval_habitat_area", "water_volume",
@@ -89,6 +91,7 @@ EXPORTS = ("mms_abi_version", "mms_device_count", "mms_last_error", "mms_run_cha
            "mms_shard_range",
            "mms_water_vectorised", "mms_population_vectorised", "mms_water_series", "mms_population_series",
            "mms_stage_kernel_ms",
+           "mms_chain_upload_terraclimate", "mms_run_chain_terraclimate", "mms_terraclimate_to_monthly",
            "mms_daily_from_monthly", "mms_hourly_from_daily", "mms_lifehistory_vectorised", "mms_host_alloc", "mms_host_free",
            "mms_measure_fp64_peak", "mms_measure_hbm_copy", "mms_flush_l2")
 
@@ -108,6 +111,11 @@ def lib() -> ct.CDLL:
         L.mms_run_chain.argtypes = [ct.POINTER(ChainConfig), _dp, _dp, ct.POINTER(ChainOutputs)]
         L.mms_chain_create.argtypes = [ct.POINTER(ChainConfig), ct.POINTER(vp)]
         L.mms_chain_upload.argtypes = [vp, _dp, _dp]
+        L.mms_chain_upload_terraclimate.argtypes = [vp, _dp, _dp, _ip, _dp, _dp]
+        L.mms_run_chain_terraclimate.argtypes = [ct.POINTER(ChainConfig), _dp, _dp, _ip, _dp, _dp,
+                                                 ct.POINTER(ChainOutputs)]
+        L.mms_terraclimate_to_monthly.argtypes = [_dp, _dp, _ip, _dp, ct.c_int64, ct.c_int32, ct.c_int32,
+                                                  ct.c_int32, _dp]
         L.mms_chain_launch.argtypes = [vp]
         L.mms_chain_sync.argtypes = [vp]
         L.mms_chain_download.argtypes = [vp, ct.POINTER(ChainOutputs)]
@@ -314,6 +322,19 @@ class ChainPlan:
         self._inputs = (monthly, altitude)
         check(lib().mms_chain_upload(self._plan, _p(monthly), _p(altitude)))
 
+    def upload_terraclimate(self, terraclimate, clear_sky, month_id, n_days, altitude):
+        """mms_chain_upload_terraclimate(): the six raw TerraClimate variables [6][M][C] and the pixel's
+        clear-sky radiation by calendar month [12][C]; the nine forcing rows are derived on the device."""
+        tc, cs, nd, altitude = _d(terraclimate), _d(clear_sky), _d(n_days), _d(altitude)
+        mid = np.ascontiguousarray(month_id, dtype=np.int32)
+        if tc.shape != (NTERRACLIMATE, self.M, self.C) or cs.shape != (12, self.C) or altitude.shape != (self.C,):
+            raise ValueError(f"terraclimate must be [6][{self.M}][{self.C}], clear_sky [12][{self.C}], altitude [{self.C}]")
+        if mid.shape != (self.M,) or nd.shape != (self.M,):
+            raise ValueError("month_id and n_days must have one entry per monthly knot")
+        self._inputs = (tc, cs, mid, nd, altitude)
+        check(lib().mms_chain_upload_terraclimate(self._plan, _p(tc), _p(cs), mid.ctypes.data_as(_ip), _p(nd),
+                                                  _p(altitude)))
+
     def launch(self):
         check(lib().mms_chain_launch(self._plan))
 
@@ -369,6 +390,20 @@ def run_chain(monthly, altitude, **kwargs):
         return out
 
 
+def run_chain_terraclimate(terraclimate, clear_sky, month_id, n_days, altitude, **kwargs):
+    """One-shot mms_run_chain_terraclimate(): the raw TerraClimate variables in, summaries out."""
+    tc, cs, nd, altitude = _d(terraclimate), _d(clear_sky), _d(n_days), _d(altitude)
+    mid = np.ascontiguousarray(month_id, dtype=np.int32)
+    with ChainPlan(tc.shape[2], _create=False, **kwargs) as plan:
+        if tc.shape != (NTERRACLIMATE, plan.M, plan.C) or cs.shape != (12, plan.C) or mid.shape != (plan.M,):
+            raise ValueError("terraclimate must be [6][M][C], clear_sky [12][C], month_id [M]")
+        out = plan.allocate_outputs()
+        o = plan._outputs_struct(out)
+        check(lib().mms_run_chain_terraclimate(ct.byref(plan._cfg), _p(tc), _p(cs), mid.ctypes.data_as(_ip), _p(nd),
+                                               _p(altitude), ct.byref(o)))
+        return out
+
+
 def water_vectorised(rainfall, air_temperature, humidity, windspeed, altitude, habitat, burnin_years=0,
                      math_mode="fast", device=0, want_volume=False, want_wet=False, whole_series_burnin=False):
     """mms_water_vectorised(), or mms_water_series() (the scalar twin's burn-in rule: the whole
@@ -414,6 +449,19 @@ def population_vectorised(larval_habitat_area, mdr, efd, das_zerodensity, ds, de
 
 def _mode(math_mode) -> int:
     return {"fast": 0, "strict": 1}.get(math_mode, math_mode)
+
+
+def terraclimate_to_monthly(terraclimate, clear_sky, month_id, n_days, math_mode="fast", device=0):
+    """mms_terraclimate_to_monthly(): terraclimate [6][M][C], clear_sky [12][C] -> monthly [9][M][C]."""
+    tc, cs, nd = _d(terraclimate), _d(clear_sky), _d(n_days)
+    mid = np.ascontiguousarray(month_id, dtype=np.int32)
+    _, M, C = tc.shape
+    if tc.shape[0] != NTERRACLIMATE or cs.shape != (12, C) or mid.shape != (M,) or nd.shape != (M,):
+        raise ValueError("terraclimate must be [6][M][C], clear_sky [12][C], month_id and n_days [M]")
+    monthly = np.empty((NFORCING, M, C))
+    check(lib().mms_terraclimate_to_monthly(_p(tc), _p(cs), mid.ctypes.data_as(_ip), _p(nd), C, M, _mode(math_mode),
+                                            int(device), _p(monthly)))
+    return monthly
 
 
 def daily_from_monthly(monthly, mid_day, day_predict, math_mode="fast", device=0):

@@ -143,6 +143,13 @@ cudaError_t MMS_LAUNCH(launch_lifehistory)(const ChainParams &p, int64_t n, cons
     return cudaGetLastError();
 }
 
+cudaError_t MMS_LAUNCH(launch_terraclimate)(const TerraParams &p, cudaStream_t stream)
+{
+    dim3 grid((unsigned)(p.c_stride / 128), (unsigned)p.M);
+    terraclimate_kernel<<<grid, 128, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
 namespace {
 
 // widest access the series allow: 4 = 32-byte stores, 2 = 16-byte copies, 1 = 8-byte

@@ -120,6 +120,21 @@ cudaError_t launch_lifehistory_strict(const ChainParams &p, int64_t n, const dou
                                       const double *humidity, double *mdr, double *efd, double *das0, double *ds,
                                       int n_sm, cudaStream_t stream);
 
+// process_terraclimate_pixel_vars(), R/terraclimate.R:581-643 (verb_kernels.cuh, terraclimate_kernel)
+struct TerraParams {
+    const double *terraclimate;   // [6][M][c_stride]: tmax, tmin, ppt, ws, vpd, srad
+    const double *clear_sky;      // [12][c_stride]: clear_sky_SOLR by month_id
+    const int32_t *month_id;      // [M], 1..12
+    const double *n_days;         // [M], as.numeric(end - start)
+    double *monthly;              // [9][M][c_stride], MMS_F_* order
+    int64_t c_stride, n_cells;
+    int32_t M;
+    int32_t log1p_rainfall;       // 1: store log1p(rainfall_daily) (what the fused kernel reads, R/sim_microclimate.R:33)
+    double wind_factor;           // (height_required / height_measured) ^ exponent, host libm like R (R/utils.R:132)
+};
+cudaError_t launch_terraclimate_fast(const TerraParams &p, cudaStream_t stream);
+cudaError_t launch_terraclimate_strict(const TerraParams &p, cudaStream_t stream);
+
 struct WaterStageParams {
     const double *rainfall, *air_temperature, *humidity, *windspeed; // [C][H] (R column-major)
     const double *altitude;   // [C]

@@ -231,6 +231,7 @@ struct Shard {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double *d_monthly = nullptr, *d_altitude = nullptr;
+    double *d_terra = nullptr;     // staging of mms_chain_upload_terraclimate(), allocated on first use
     mms::DayEntry *d_days = nullptr;
     int32_t *d_period = nullptr;
     double *d_sx = nullptr, *d_scoef = nullptr, *d_gx = nullptr, *d_gy = nullptr, *d_quad = nullptr;
@@ -273,7 +274,7 @@ void free_shard(Shard &s)
     cudaSetDevice(s.device);
     void *ptrs[] = {s.d_monthly, s.d_altitude, s.d_days, s.d_period, s.d_sx, s.d_scoef, s.d_gx, s.d_gy, s.d_quad,
                     s.d_mean_state, s.d_mean_forcing, s.d_hourly_state, s.d_hourly_forcing, s.d_wet_hours,
-                    s.d_wet_flags, s.d_error};
+                    s.d_wet_flags, s.d_error, s.d_terra};
     for (void *q : ptrs) if (q) cudaFree(q);
     if (s.ev0) cudaEventDestroy(s.ev0);
     if (s.ev1) cudaEventDestroy(s.ev1);
@@ -809,6 +810,114 @@ int mms_daily_from_monthly(const double *monthly, const double *mid_day, const d
     if (flag) return fail(MMS_ERR_NONFINITE, "non-finite (NA/NaN/Inf) monthly forcing; R's approx() would drop those knots, "
                           "the GPU backend refuses them");
     return MMS_OK;
+}
+
+// ---- process_terraclimate_pixel_vars(), R/terraclimate.R:581-643 ----------
+
+static int check_month_ids(const int32_t *month_id, const double *n_days, int32_t n_months)
+{
+    for (int m = 0; m < n_months; ++m) {
+        if (month_id[m] < 1 || month_id[m] > 12)
+            return fail(MMS_ERR_INVALID_ARG, "month_id[%d] = %d is not in 1..12", m, month_id[m]);
+        if (!(n_days[m] == n_days[m])) return fail(MMS_ERR_NONFINITE, "n_days[%d] is NaN", m);
+    }
+    return MMS_OK;
+}
+
+// adjust_wind_speed(ws, height_required = 2, height_measured = 10) on "level grass", R/terraclimate.R:615-617,
+// R/utils.R:123-132: the factor is evaluated with the host libm, as R does
+static double terraclimate_wind_factor() { return std::pow(2.0 / 10.0, 0.15); }
+
+int mms_terraclimate_to_monthly(const double *terraclimate, const double *clear_sky, const int32_t *month_id,
+                                const double *n_days, int64_t n_cells, int32_t n_months, int32_t math_mode,
+                                int32_t device, double *monthly)
+{
+    if (!terraclimate || !clear_sky || !month_id || !n_days || !monthly) return fail(MMS_ERR_INVALID_ARG, "NULL argument");
+    if (n_cells < 1 || n_months < 1) return fail(MMS_ERR_INVALID_ARG, "need cells >= 1 and months >= 1");
+    int rc = check_month_ids(month_id, n_days, n_months);
+    if (rc) return rc;
+    if ((rc = pick_device(device))) return rc;
+    const int64_t cs = ((n_cells + mms::kBlock - 1) / mms::kBlock) * mms::kBlock;
+    DevBuf d_tc, d_cs, d_mid, d_nd, d_out;
+    cudaStream_t st;
+    MMS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    if ((rc = d_tc.alloc(sizeof(double) * MMS_NTERRACLIMATE * n_months * cs)) || (rc = d_cs.alloc(sizeof(double) * 12 * cs)) ||
+        (rc = d_mid.alloc(sizeof(int32_t) * n_months)) || (rc = d_nd.alloc(sizeof(double) * n_months)) ||
+        (rc = d_out.alloc(sizeof(double) * MMS_NFORCING * n_months * cs))) {
+        cudaStreamDestroy(st);
+        return rc;
+    }
+    if ((rc = copy_in_2d(d_tc.p, 8 * cs, terraclimate, 8 * n_cells, 8 * n_cells, (size_t)MMS_NTERRACLIMATE * n_months, st)) ||
+        (rc = copy_in_2d(d_cs.p, 8 * cs, clear_sky, 8 * n_cells, 8 * n_cells, 12, st)))
+        return rc;
+    MMS_CUDA(cudaMemcpyAsync(d_mid.p, month_id, sizeof(int32_t) * n_months, cudaMemcpyHostToDevice, st));
+    MMS_CUDA(cudaMemcpyAsync(d_nd.p, n_days, sizeof(double) * n_months, cudaMemcpyHostToDevice, st));
+    mms::TerraParams p{};
+    p.terraclimate = (const double *)d_tc.p; p.clear_sky = (const double *)d_cs.p;
+    p.month_id = (const int32_t *)d_mid.p; p.n_days = (const double *)d_nd.p; p.monthly = (double *)d_out.p;
+    p.c_stride = cs; p.n_cells = n_cells; p.M = n_months; p.log1p_rainfall = 0;
+    p.wind_factor = terraclimate_wind_factor();
+    EventTimer timer(st);
+    MMS_CUDA(math_mode ? mms::launch_terraclimate_strict(p, st) : mms::launch_terraclimate_fast(p, st));
+    timer.stop();
+    if ((rc = copy_out_2d(monthly, 8 * n_cells, d_out.p, 8 * cs, 8 * n_cells, (size_t)MMS_NFORCING * n_months, st))) return rc;
+    MMS_CUDA(cudaStreamSynchronize(st));
+    g_stage_kernel_ms = timer.ms();
+    cudaStreamDestroy(st);
+    return MMS_OK;
+}
+
+// mms_chain_upload() for callers that hold the six raw TerraClimate variables: the nine forcing rows
+// (rainfall as log1p) are derived on the device, so a third less crosses PCIe
+int mms_chain_upload_terraclimate(mms_chain_plan *pl, const double *terraclimate, const double *clear_sky,
+                                  const int32_t *month_id, const double *n_days, const double *altitude)
+{
+    if (!pl || !terraclimate || !clear_sky || !month_id || !n_days || !altitude)
+        return fail(MMS_ERR_INVALID_ARG, "NULL plan or argument");
+    int rc = check_month_ids(month_id, n_days, pl->M);
+    if (rc) return rc;
+    for (Shard &s : pl->shards) {
+        MMS_CUDA(cudaSetDevice(s.device));
+        if (!s.d_terra) {
+            // [6][M][cs] raw variables, [12][cs] clear-sky values, then n_days [M] and month_id [M]
+            const size_t bytes = sizeof(double) * ((size_t)(MMS_NTERRACLIMATE * pl->M + 12) * s.c_stride + pl->M) +
+                                 sizeof(int32_t) * pl->M;
+            MMS_CUDA(cudaMalloc(&s.d_terra, bytes));
+        }
+        double *d_tc = s.d_terra, *d_cs = d_tc + (size_t)MMS_NTERRACLIMATE * pl->M * s.c_stride;
+        double *d_nd = d_cs + (size_t)12 * s.c_stride;
+        int32_t *d_mid = reinterpret_cast<int32_t *>(d_nd + pl->M);
+        if ((rc = copy_in_2d(d_tc, sizeof(double) * s.c_stride, terraclimate + s.cell0, sizeof(double) * pl->C,
+                             sizeof(double) * s.n_cells, (size_t)MMS_NTERRACLIMATE * pl->M, s.stream)) ||
+            (rc = copy_in_2d(d_cs, sizeof(double) * s.c_stride, clear_sky + s.cell0, sizeof(double) * pl->C,
+                             sizeof(double) * s.n_cells, 12, s.stream)))
+            return rc;
+        MMS_CUDA(cudaMemcpyAsync(d_nd, n_days, sizeof(double) * pl->M, cudaMemcpyHostToDevice, s.stream));
+        MMS_CUDA(cudaMemcpyAsync(d_mid, month_id, sizeof(int32_t) * pl->M, cudaMemcpyHostToDevice, s.stream));
+        MMS_CUDA(cudaMemcpyAsync(s.d_altitude, altitude + s.cell0, sizeof(double) * s.n_cells, cudaMemcpyHostToDevice, s.stream));
+        mms::TerraParams p{};
+        p.terraclimate = d_tc; p.clear_sky = d_cs; p.month_id = d_mid; p.n_days = d_nd; p.monthly = s.d_monthly;
+        p.c_stride = s.c_stride; p.n_cells = s.n_cells; p.M = pl->M; p.log1p_rainfall = 1;
+        p.wind_factor = terraclimate_wind_factor();
+        MMS_CUDA(pl->math_mode ? mms::launch_terraclimate_strict(p, s.stream) : mms::launch_terraclimate_fast(p, s.stream));
+        pl->launches += 1;
+    }
+    pl->uploaded = true;
+    return MMS_OK;
+}
+
+int mms_run_chain_terraclimate(const mms_chain_config *cfg, const double *terraclimate, const double *clear_sky,
+                               const int32_t *month_id, const double *n_days, const double *altitude,
+                               const mms_chain_outputs *out)
+{
+    mms_chain_plan *pl = nullptr;
+    int rc = mms_chain_create(cfg, &pl);
+    if (rc) return rc;
+    rc = mms_chain_upload_terraclimate(pl, terraclimate, clear_sky, month_id, n_days, altitude);
+    if (!rc) rc = mms_chain_launch(pl);
+    if (!rc) rc = mms_chain_download(pl, out);
+    mms_chain_destroy(pl);
+    return rc;
 }
 
 // simulate_hourly_microclimate() / hourly_from_daily_climate_ambient(), R/sim_microclimate.R:126-173

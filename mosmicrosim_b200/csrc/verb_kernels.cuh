@@ -92,6 +92,75 @@ __global__ void __launch_bounds__(128) hourly_kernel(const __grid_constant__ Cha
     }
 }
 
+// ---- process_terraclimate_pixel_vars(), R/terraclimate.R:581-643 -----------------
+// NicheMapR::VAPPRS as restated in oracle/mms_oracle.c (third party, parity unpinned): Goff-Gratch
+// saturation vapour pressure in Pa, over ice at or below the triple point and over water above it.
+// CUDA libm log10 / pow in both math modes: this runs once per monthly knot, not per hour.
+__device__ __forceinline__ double vapprs_pa(double db)
+{
+    const double t = db + 273.16;
+    double loge;
+    if (t <= 273.16) {
+        loge = -9.09718 * (273.16 / t - 1.) - 3.56654 * log10(273.16 / t) +
+               .876793 * (1. - MMS_DIVC(t, 273.16)) + 0.7858350313586662;           // + log10(6.1071)
+    } else {
+        loge = -7.90298 * (373.16 / t - 1.) + 5.02808 * log10(373.16 / t) -
+               1.3816E-07 * (pow(10., 11.344 * (1. - MMS_DIVC(t, 373.16))) - 1.) +
+               8.1328E-03 * (pow(10., -3.49149 * (373.16 / t - 1.)) - 1.) + 3.0057148979490314;   // + log10(1013.246)
+    }
+    return pow(10., loge) * 100;
+}
+
+// relative_humidity(), R/utils.R:80-89 (pmin / pmax keep NaN)
+__device__ __forceinline__ double relative_humidity_pct(double temperature, double vapour_pressure)
+{
+    double rh = vapour_pressure / vapprs_pa(temperature) * 100;
+    rh = rh > 100 ? 100 : rh;
+    rh = rh < 0.01 ? 0.01 : rh;
+    return rh;
+}
+
+// cloud_cover(), R/utils.R:141-147
+__device__ __forceinline__ double cloud_cover_pct(double srad, double clear_sky, double multiplier)
+{
+    double cloud = (1 - srad / clear_sky) * 100;
+    cloud = cloud * multiplier;
+    cloud = cloud > 100 ? 100 : cloud;
+    cloud = cloud < 0 ? 0 : cloud;
+    return cloud;
+}
+
+// grid (c_stride / 128, M).  Padding cells (>= n_cells) get zeros.
+__global__ void __launch_bounds__(128) terraclimate_kernel(const __grid_constant__ TerraParams p)
+{
+    const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.y;
+    if (cell >= p.c_stride) return;
+    const int64_t cs = p.c_stride, plane = (int64_t)p.M * cs, at = (int64_t)m * cs + cell;
+    double o[MMS_NFORCING] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (cell < p.n_cells) {
+        const double tmax = p.terraclimate[0 * plane + at], tmin = p.terraclimate[1 * plane + at];
+        const double ppt = p.terraclimate[2 * plane + at], ws = p.terraclimate[3 * plane + at];
+        const double vpd = p.terraclimate[4 * plane + at], srad = p.terraclimate[5 * plane + at];
+        const double clear = p.clear_sky[(int64_t)(p.month_id[m] - 1) * cs + cell];      // R/terraclimate.R:600-603
+        const double tmean = MMS_DIVC(tmax + tmin, 2.0);                                  // :607
+        // vapour_pressure(), R/utils.R:64-78: WETAIR(db, rh = 100)$e = esat * rh / 100, minus vpd in Pa
+        const double vp = MMS_DIVC(vapprs_pa(tmean) * 100, 100.0) - vpd * 1000;
+        o[MMS_F_TMIN] = tmin;
+        o[MMS_F_TMAX] = tmax;
+        o[MMS_F_RHMAX] = relative_humidity_pct(tmin, vp);                                 // :609
+        o[MMS_F_RHMIN] = relative_humidity_pct(tmax, vp);                                 // :610
+        o[MMS_F_WSMAX] = ws * p.wind_factor;                                              // :615-617
+        o[MMS_F_WSMIN] = o[MMS_F_WSMAX] * 0.1;                                            // :618
+        o[MMS_F_CCMAX] = cloud_cover_pct(srad, clear, 1.2);                               // :624
+        o[MMS_F_CCMIN] = cloud_cover_pct(srad, clear, 0.8);                               // :625
+        const double rain = ppt / p.n_days[m];                                            // :630
+        o[MMS_F_RAINFALL_DAILY] = p.log1p_rainfall ? log1p(rain) : rain;                  // R/sim_microclimate.R:33
+    }
+#pragma unroll
+    for (int v = 0; v < MMS_NFORCING; ++v) p.monthly[v * plane + at] = o[v];
+}
+
 // simulate_vector_lifehistory(), R/sim_pop_dynamics.R:100-135: element-wise over n values;
 // out mdr, efd, das_zerodensity, ds.  Spline rows and ds axes in shared memory like the fused kernel.
 __global__ void __launch_bounds__(512, 2) lifehistory_kernel(const __grid_constant__ ChainParams p, int64_t n,

@@ -80,3 +80,53 @@ def period_index(dates_predict, aggregate_by="month", included_dates=None):
     start = uniq.astype("datetime64[D]")
     end = (uniq + np.timedelta64(1, unit)).astype("datetime64[D]") - np.timedelta64(1, "D")
     return pod, start, end
+
+
+# ---- TerraClimate month bookkeeping --------------------------------------
+
+def terraclimate_month_info(start, end):
+    """(month_id int32[M], n_days float64[M]) as process_terraclimate_pixel_vars() computes them
+    (R/terraclimate.R:591-592): month_id = lubridate::month(start + (end - start) / 2) and
+    n_days = as.numeric(end - start), i.e. the days in the month MINUS ONE (replicated, not fixed)."""
+    s = _as_days(start).astype(np.int64)
+    e = _as_days(end).astype(np.int64)
+    mid = (s + np.floor((e - s) / 2).astype(np.int64)).astype("datetime64[D]")   # month() of an x.5 date floors
+    month_id = (mid.astype("datetime64[M]").astype(np.int64) % 12 + 1).astype(np.int32)
+    return month_id, (e - s).astype(np.float64)
+
+
+def r_mean(x) -> float:
+    """base-R mean() of a double vector (long double sum, then one correction pass)."""
+    x = np.asarray(x, dtype=np.longdouble)
+    if x.size == 0:
+        return float("nan")
+    s = x.sum() / x.size
+    s += (x - s).sum() / x.size
+    return float(s)
+
+
+def pad_last_month(start, end, values, n_previous=3):
+    """pad_last_month(), R/terraclimate.R:519-569: append a synthetic next month whose values are the
+    means of that calendar month in the previous n_previous years of the series (those present).
+    values: [..., M, ...]-shaped arrays are not needed here -- pass [V][M] or [V][M][C] with the month
+    axis second.  Returns (start[M+1], end[M+1], values[V][M+1](...))."""
+    s, e = _as_days(start), _as_days(end)
+    values = np.asarray(values, dtype=np.float64)
+    last_start = s.max()
+    next_start = (last_start.astype("datetime64[M]") + 1).astype("datetime64[D]")        # :525-528
+    next_end = (next_start.astype("datetime64[M]") + 1).astype("datetime64[D]") - np.timedelta64(1, "D")  # :531-534
+    previous = [(next_start.astype("datetime64[M]") - 12 * k).astype("datetime64[D]")
+                for k in range(1, n_previous + 1)]                                        # :537-540
+    rows = np.flatnonzero(np.isin(s, previous))                                           # :544-546
+    sub = values[:, rows]                                                                 # [V][k](...)
+    n_cols = int(np.prod(values.shape[2:], dtype=np.int64))
+    flat = sub.reshape(sub.shape[0], sub.shape[1], n_cols)
+    if len(rows):          # R mean(): long double sum / n, then one correction pass (k <= n_previous terms)
+        ld = flat.astype(np.longdouble)
+        m = ld.sum(axis=1) / len(rows)
+        m += (ld - m[:, None, :]).sum(axis=1) / len(rows)
+        pad = m.astype(np.float64)
+    else:
+        pad = np.full((flat.shape[0], n_cols), np.nan)
+    pad = pad.reshape((values.shape[0], 1) + values.shape[2:])                            # :551-556
+    return (np.append(s, next_start), np.append(e, next_end), np.concatenate([values, pad], axis=1))

@@ -170,6 +170,82 @@ def simulate_hourly_lifehistory(pixel_hourly_conditions, lifehistory_functions, 
     return out
 
 
+def _terraclimate_arrays(pixel_terraclimate_data):
+    """(start, end, terraclimate[6][M][C], clear_sky[12][C], altitude[C]) from the dict form of
+    extract_terraclimate_tile()'s per-pixel tibbles placed side by side."""
+    d = pixel_terraclimate_data
+    start = np.asarray(d["start"], dtype="datetime64[D]")
+    end = np.asarray(d["end"], dtype="datetime64[D]")
+    tc = np.stack([np.asarray(d[name], dtype=np.float64) for name in backend.TERRACLIMATE_VARS], axis=0)
+    clear_sky = np.asarray(d["clear_sky_SOLR"], dtype=np.float64)
+    altitude = np.asarray(d["altitude"], dtype=np.float64)
+    if tc.shape[1] != len(start) or clear_sky.shape != (12, tc.shape[2]) or altitude.shape != (tc.shape[2],):
+        raise ValueError("terraclimate variables must be [M, C], clear_sky_SOLR [12, C] and altitude [C]")
+    return start, end, tc, clear_sky, altitude
+
+
+def terraclimate_to_monthly_climate(pixel_terraclimate_data, *, pad_last=False, math_mode="fast", device=0):
+    """terraclimate_to_monthly_climate() (R/pipeline_functions.R:179-252) for a whole tile.
+
+    pixel_terraclimate_data: dict with start[M], end[M], the six TerraClimate variables tmax, tmin, ppt,
+    ws, vpd, srad as [M, C] arrays, clear_sky_SOLR [12, C] (the pixel's clear-sky radiation by calendar
+    month, R/pipeline_functions.R:194-222), altitude [C] (the reference reads it from its elevation raster,
+    :228-233 -- raster I/O is outside this library), longitude / latitude (carried through).
+    pad_last: apply pad_last_month() first (R/terraclimate.R:519-569; the reference does so when the series
+    ends at the last published month, R/pipeline_functions.R:148-166).
+    Returns the pixel_monthly_climate dict that monthly_climate_to_vectors() takes."""
+    start, end, tc, clear_sky, altitude = _terraclimate_arrays(pixel_terraclimate_data)
+    if pad_last:
+        start, end, tc = dates.pad_last_month(start, end, tc)
+    month_id, n_days = dates.terraclimate_month_info(start, end)
+    monthly = backend.terraclimate_to_monthly(tc, clear_sky, month_id, n_days, math_mode=math_mode, device=device)
+    out = {"start": start, "end": end, "altitude": altitude,
+           "longitude": pixel_terraclimate_data.get("longitude"), "latitude": pixel_terraclimate_data.get("latitude")}
+    for v, name in enumerate(FORCING_VARS):
+        out[name] = monthly[v]
+    return out
+
+
+def _run_vectors(upload, n_cells, start, end, carried, lifehistory_functions, species, included_dates,
+                 aggregate_by, dates_predict, habitats, model_water_temperature, water_shade_proportion,
+                 burnin_years_pop, extra_variables, math_mode, devices):
+    """interpolate_daily_climate() ... summarise_vectors() in one fused launch per device; `upload`
+    puts the monthly knots on the plan (either form)."""
+    species = _match_arg(species, SPECIES, "species")
+    aggregate_by = _match_arg(aggregate_by, ("month", "day"), "aggregate_by")
+    # simulate_hourly_conditions() argument handling, R/pipeline_functions.R:324-338
+    if water_shade_proportion != 1 and not model_water_temperature:
+        warnings.warn("water temperature is not being modelled, so water_shade_proportion argument is ignored")
+    if model_water_temperature:
+        raise NotImplementedError("model of water temperature not yet implemented, "
+                                  "model_water_temperature must be set to FALSE")
+    lh: Lifehistory = lifehistory_functions[{"An. gambiae": "An_gambiae", "An. stephensi": "An_stephensi"}[species]]
+    if dates_predict is None:
+        dates_predict = dates.default_dates_predict(start, end)
+    mid_day, day_predict = dates.datenums(start, end, dates_predict)
+    period_of_day, p_start, p_end = dates.period_index(dates_predict, aggregate_by, included_dates)
+    if habitats is None:      # R/pipeline_functions.R:431-441
+        habitats = [dict(shape=0, max_depth=1.0, radius=1.0, inflow_multiplier=1.0, leak_per_hour=0.0,
+                         initial_volume=0.0)]
+    names = list(VECTOR_VARIABLES) + [v for v in extra_variables if v not in VECTOR_VARIABLES]
+    with backend.ChainPlan(
+            n_cells, mid_day=mid_day, day_predict=day_predict, habitats=habitats,
+            densmod=backend.make_densmod(lh.das_densmod.type, lh.das_densmod.dd_effect, lh.das_densmod.surface_area_cm2),
+            tables=lh.tables(), period_of_day=period_of_day, n_periods=len(p_start), burnin_years_water=0,
+            burnin_years_pop=burnin_years_pop, mean_vars=names, want_wet_hours=True, math_mode=math_mode,
+            devices=devices) as plan:
+        upload(plan)
+        plan.launch()
+        out = plan.download(plan.allocate_outputs())
+    res = {"longitude": carried.get("longitude"), "latitude": carried.get("latitude"),
+           "species": species, "start": p_start, "end": p_end, "wet_hours": out["wet_hours"]}
+    for k, v in enumerate(out["mean_state_vars"]):
+        res[v] = out["mean_state"][:, k] if len(habitats) > 1 else out["mean_state"][0, k]
+    for k, v in enumerate(out["mean_forcing_vars"]):
+        res[v] = out["mean_forcing"][k]
+    return res
+
+
 def monthly_climate_to_vectors(pixel_monthly_climate, lifehistory_functions, species=SPECIES,
                                included_dates=None, aggregate_by="month", dates_predict=None, *,
                                habitats=None, model_water_temperature=False, water_shade_proportion=1,
@@ -187,34 +263,36 @@ def monthly_climate_to_vectors(pixel_monthly_climate, lifehistory_functions, spe
     Returns a dict: longitude, latitude, species, start[P], end[P] and one
     [P, C] array per vector variable -- the `pixel_vectors` tibbles side by side.
     """
-    species = _match_arg(species, SPECIES, "species")
-    aggregate_by = _match_arg(aggregate_by, ("month", "day"), "aggregate_by")
-    # simulate_hourly_conditions() argument handling, R/pipeline_functions.R:324-338
-    if water_shade_proportion != 1 and not model_water_temperature:
-        warnings.warn("water temperature is not being modelled, so water_shade_proportion argument is ignored")
-    if model_water_temperature:
-        raise NotImplementedError("model of water temperature not yet implemented, "
-                                  "model_water_temperature must be set to FALSE")
-    lh: Lifehistory = lifehistory_functions[{"An. gambiae": "An_gambiae", "An. stephensi": "An_stephensi"}[species]]
     start, end, monthly, altitude = _monthly_array(pixel_monthly_climate)
-    if dates_predict is None:
-        dates_predict = dates.default_dates_predict(start, end)
-    mid_day, day_predict = dates.datenums(start, end, dates_predict)
-    period_of_day, p_start, p_end = dates.period_index(dates_predict, aggregate_by, included_dates)
-    if habitats is None:      # R/pipeline_functions.R:431-441
-        habitats = [dict(shape=0, max_depth=1.0, radius=1.0, inflow_multiplier=1.0, leak_per_hour=0.0,
-                         initial_volume=0.0)]
-    names = list(VECTOR_VARIABLES) + [v for v in extra_variables if v not in VECTOR_VARIABLES]
-    out = backend.run_chain(
-        monthly, altitude, mid_day=mid_day, day_predict=day_predict, habitats=habitats,
-        densmod=backend.make_densmod(lh.das_densmod.type, lh.das_densmod.dd_effect, lh.das_densmod.surface_area_cm2),
-        tables=lh.tables(), period_of_day=period_of_day, n_periods=len(p_start), burnin_years_water=0,
-        burnin_years_pop=burnin_years_pop, mean_vars=names, want_wet_hours=True, math_mode=math_mode,
-        devices=devices)
-    res = {"longitude": pixel_monthly_climate.get("longitude"), "latitude": pixel_monthly_climate.get("latitude"),
-           "species": species, "start": p_start, "end": p_end, "wet_hours": out["wet_hours"]}
-    for k, v in enumerate(out["mean_state_vars"]):
-        res[v] = out["mean_state"][:, k] if len(habitats) > 1 else out["mean_state"][0, k]
-    for k, v in enumerate(out["mean_forcing_vars"]):
-        res[v] = out["mean_forcing"][k]
-    return res
+    return _run_vectors(lambda plan: plan.upload(monthly, altitude), monthly.shape[2], start, end,
+                        pixel_monthly_climate, lifehistory_functions, species, included_dates, aggregate_by,
+                        dates_predict, habitats, model_water_temperature, water_shade_proportion,
+                        burnin_years_pop, extra_variables, math_mode, devices)
+
+
+def tc_to_vectors(pixel_terraclimate_data, lifehistory_functions, species=SPECIES, included_dates=None, *,
+                  aggregate_by="month", dates_predict=None, pad_last=False, habitats=None,
+                  model_water_temperature=False, water_shade_proportion=1, burnin_years_pop=1,
+                  extra_variables=(), math_mode="fast", devices=None):
+    """tc_to_vectors(pixel_terraclimate_data, species, included_dates), R/pipeline_functions.R:1099-1130,
+    whole: the six raw TerraClimate variables go to the device and process_terraclimate_pixel_vars()
+    (R/terraclimate.R:581-643) runs there, in front of the fused chain (mms_chain_upload_terraclimate).
+    Input as for terraclimate_to_monthly_climate(); output as for monthly_climate_to_vectors()."""
+    start, end, tc, clear_sky, altitude = _terraclimate_arrays(pixel_terraclimate_data)
+    if pad_last:
+        start, end, tc = dates.pad_last_month(start, end, tc)
+    month_id, n_days = dates.terraclimate_month_info(start, end)
+    return _run_vectors(lambda plan: plan.upload_terraclimate(tc, clear_sky, month_id, n_days, altitude),
+                        tc.shape[2], start, end, pixel_terraclimate_data, lifehistory_functions, species,
+                        included_dates, aggregate_by, dates_predict, habitats, model_water_temperature,
+                        water_shade_proportion, burnin_years_pop, extra_variables, math_mode, devices)
+
+
+def raster_slice(vectors, variable, year, month):
+    """The values create_vector_raster_slice() pulls out of a tile for one (variable, year, month) slice
+    (R/pipeline_functions.R:1262-1303): the row of the period whose start falls in that month, over
+    the tile's pixels in their original order -- one contiguous [C] row of the library's output."""
+    starts = np.asarray(vectors["start"], dtype="datetime64[D]")
+    want = np.datetime64(f"{int(year):04d}-{int(month):02d}", "M")
+    rows = np.flatnonzero(starts.astype("datetime64[M]") == want)          # matches_year & matches_month
+    return vectors[variable][..., rows, :]

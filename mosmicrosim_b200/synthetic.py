@@ -110,6 +110,32 @@ def synthetic_forcing(n_cells: int, start, seed: int = SEED, out_of_range_fracti
     return monthly, altitude
 
 
+def synthetic_terraclimate(n_cells: int, start, seed: int = SEED, out_of_range_fraction: float = 0.01):
+    """Raw TerraClimate-style monthly variables for n_cells cells:
+    returns (terraclimate[6][M][C] in the order tmax, tmin, ppt, ws, vpd, srad; clear_sky[12][C];
+    altitude[C]).  Ranges follow TerraClimate's units: deg C, mm / month, m/s at 10 m, kPa, W/m2."""
+    start = np.asarray(start, dtype="datetime64[D]")
+    M, C = len(start), int(n_cells)
+    rng = np.random.default_rng(seed + 1)
+    month_of_year = (start.astype("datetime64[M]").astype(np.int64) % 12)
+    phase = rng.uniform(0, 2 * np.pi, size=C)
+    season = np.sin(2 * np.pi * month_of_year[:, None] / 12.0 + phase[None, :])
+    tmax = 30.0 + 5.0 * season + rng.normal(0.0, 1.0, size=(M, C))
+    n_bad = int(round(out_of_range_fraction * C))
+    if n_bad:
+        bad = rng.choice(C, size=n_bad, replace=False)
+        tmax[:, bad] += np.where(rng.random(n_bad) < 0.5, 14.0, -24.0)[None, :]
+    tmin = tmax - rng.uniform(8.0, 14.0, size=(M, C))
+    wet_season = np.clip(0.5 + 0.8 * np.sin(2 * np.pi * month_of_year[:, None] / 12.0 + phase[None, :] + 1.0), 0.0, None)
+    ppt = rng.gamma(shape=2.0, scale=60.0, size=(M, C)) * wet_season           # mm / month
+    ws = rng.uniform(0.5, 7.0, size=(M, C))
+    vpd = rng.uniform(0.05, 3.0, size=(M, C))                                  # some exceed esat(tmean): vp < 0 -> rh clamps
+    clear_sky = rng.uniform(180.0, 330.0, size=(12, C))
+    srad = clear_sky[month_of_year] * rng.uniform(0.3, 1.1, size=(M, C))       # > clear sky in places: cloud clamps at 0
+    altitude = rng.uniform(0.0, 2500.0, size=C)
+    return np.stack([tmax, tmin, ppt, ws, vpd, srad]), clear_sky, altitude
+
+
 # habitat settings used by the benchmark configurations ----------------------
 
 def habitat_cone(max_depth=1.0, inflow_multiplier=1.0, leak_per_hour=0.0, initial_volume=0.0):

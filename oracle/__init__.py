@@ -105,6 +105,13 @@ def lib() -> ct.CDLL:
         L.mmso_run_chain.restype = ct.c_int
         L.mmso_run_chain.argtypes = [ct.POINTER(Chain)]
         L.mmso_max_threads.restype = ct.c_int
+        for name, n in (("mmso_vapprs", 1), ("mmso_vapour_pressure", 2), ("mmso_relative_humidity", 2),
+                        ("mmso_adjust_wind_speed", 4), ("mmso_cloud_cover", 3)):
+            getattr(L, name).restype = ct.c_double
+            getattr(L, name).argtypes = [ct.c_double] * n
+        L.mmso_process_terraclimate_pixel_vars.restype = None
+        L.mmso_process_terraclimate_pixel_vars.argtypes = [_dp, _dp, ct.POINTER(ct.c_int), _dp, ct.c_long,
+                                                           ct.c_int, _dp]
         _lib = L
     return _lib
 
@@ -275,6 +282,22 @@ def simulate_population(larval_habitat_area, mdr, efd, das_zerodensity, ds, dm: 
                                    ct.c_double(initial_adult), ct.c_double(initial_aquatic), int(burnin_years),
                                    _p(aquatic), _p(adult))
     return {"aquatic": aquatic, "adult": adult}
+
+
+TERRACLIMATE_VARS = ("tmax", "tmin", "ppt", "ws", "vpd", "srad")      # R/pipeline_functions.R:134-136
+
+
+def process_terraclimate_pixel_vars(terraclimate, clear_sky, month_id, n_days):
+    """process_terraclimate_pixel_vars() (R/terraclimate.R:581-643) for C pixels: terraclimate [6][M][C]
+    (TERRACLIMATE_VARS order), clear_sky [12][C], month_id [M] (1..12), n_days [M] -> monthly [9][M][C]."""
+    tc, cs, nd = _d(terraclimate), _d(clear_sky), _d(n_days)
+    mid = np.ascontiguousarray(month_id, dtype=np.int32)
+    _, M, C = tc.shape
+    assert cs.shape == (12, C) and len(mid) == M and len(nd) == M
+    out = np.empty((9, M, C))
+    lib().mmso_process_terraclimate_pixel_vars(_p(tc), _p(cs), mid.ctypes.data_as(ct.POINTER(ct.c_int)), _p(nd),
+                                               ct.c_long(C), M, _p(out))
+    return out
 
 
 def R_mean(x):

@@ -387,6 +387,104 @@ int mmso_simulate_ephemeral_habitat_vectorised(
 }
 
 /* ========================================================================
+ * T: TerraClimate monthly variables -> the nine monthly forcing variables
+ *    (SURVEY section 8f row N1): process_terraclimate_pixel_vars(),
+ *    R/terraclimate.R:581-643, and its helpers in R/utils.R.
+ * ===================================================================== */
+
+/* NicheMapR::VAPPRS (saturation vapour pressure, Pa), called by NicheMapR::WETAIR for
+ * $esat.  THIRD PARTY, NOT under /root/reference (mrke/NicheMapR, v3.3.1 named at
+ * query_terraclimate.R:4-5; not declared in DESCRIPTION): restated from the published
+ * Goff-Gratch (1946) formulation that VAPPRS uses -- over ice at or below the triple
+ * point, over water above it.  parity unpinned. */
+double mmso_vapprs(double db)
+{
+    const double t = db + 273.16;
+    double loge;
+    if (t <= 273.16) {
+        loge = -9.09718 * (273.16 / t - 1.) - 3.56654 * log10(273.16 / t) +
+               .876793 * (1. - t / 273.16) + log10(6.1071);
+    } else {
+        loge = -7.90298 * (373.16 / t - 1.) + 5.02808 * log10(373.16 / t) -
+               1.3816E-07 * (mmso_R_pow(10., 11.344 * (1. - t / 373.16)) - 1.) +
+               8.1328E-03 * (mmso_R_pow(10., -3.49149 * (373.16 / t - 1.)) - 1.) + log10(1013.246);
+    }
+    return mmso_R_pow(10., loge) * 100;
+}
+
+/* vapour_pressure(): R/utils.R:64-78.  WETAIR(db, rh = 100)$e is esat * rh / 100. */
+double mmso_vapour_pressure(double tmean, double vpd_kpa)
+{
+    const double vapour_pressure = mmso_vapprs(tmean) * 100 / 100;       /* :67-71 */
+    const double vpd_pa = vpd_kpa * 1000;                                /* :76 */
+    return vapour_pressure - vpd_pa;                                     /* :77 */
+}
+
+/* relative_humidity(): R/utils.R:80-89.  pmin / pmax keep NaN. */
+double mmso_relative_humidity(double temperature, double vapour_pressure)
+{
+    const double saturation_vapour_pressure = mmso_vapprs(temperature);  /* :82-83 */
+    double rh = (vapour_pressure / saturation_vapour_pressure) * 100;    /* :85 */
+    if (rh > 100) rh = 100;                                              /* :86 */
+    if (rh < 0.01) rh = 0.01;                                            /* :87 */
+    return rh;
+}
+
+/* adjust_wind_speed(): R/utils.R:97-134; exponent by terrain (:123-127), "level grass" = 0.15 */
+double mmso_adjust_wind_speed(double wind_speed, double height_required, double height_measured,
+                              double exponent)
+{
+    return wind_speed * mmso_R_pow(height_required / height_measured, exponent);   /* :132 */
+}
+
+/* cloud_cover(): R/utils.R:141-147 */
+double mmso_cloud_cover(double solar_radiation, double clear_sky_radiation, double multiplier)
+{
+    double cloud = (1 - solar_radiation / clear_sky_radiation) * 100;    /* :142 */
+    cloud = cloud * multiplier;                                          /* :143 */
+    if (cloud > 100) cloud = 100;                                        /* :144 */
+    if (cloud < 0) cloud = 0;                                            /* :145 */
+    return cloud;
+}
+
+/* process_terraclimate_pixel_vars(): R/terraclimate.R:581-643, for C pixels at once.
+ * terraclimate [6][M][C] in the order tmax, tmin, ppt, ws, vpd, srad (the tibble of
+ * R/pipeline_functions.R:134-136); clear_sky [12][C] = clear_sky_SOLR by month_id;
+ * month_id[M] = lubridate::month(start + (end - start) / 2) (:591), n_days[M] =
+ * as.numeric(end - start) (:592: days in the month MINUS ONE -- replicated, not fixed).
+ * monthly out [9][M][C] in the order of MMSO_F_*. */
+void mmso_process_terraclimate_pixel_vars(const double *terraclimate, const double *clear_sky,
+                                          const int *month_id, const double *n_days,
+                                          long C, int M, double *monthly)
+{
+    const long plane = (long)M * C;
+    for (int m = 0; m < M; ++m) {
+        for (long c = 0; c < C; ++c) {
+            const long at = (long)m * C + c;
+            const double tmax = terraclimate[0 * plane + at], tmin = terraclimate[1 * plane + at];
+            const double ppt = terraclimate[2 * plane + at], ws = terraclimate[3 * plane + at];
+            const double vpd = terraclimate[4 * plane + at], srad = terraclimate[5 * plane + at];
+            const double clear_sky_SOLR = clear_sky[(long)(month_id[m] - 1) * C + c];   /* :600-603 */
+            const double tmean = (tmax + tmin) / 2;                      /* :607 */
+            const double vp = mmso_vapour_pressure(tmean, vpd);          /* :608 */
+            const double rhmax = mmso_relative_humidity(tmin, vp);       /* :609 */
+            const double rhmin = mmso_relative_humidity(tmax, vp);       /* :610 */
+            const double wsmax = mmso_adjust_wind_speed(ws, 2, 10, 0.15);/* :615-617 */
+            const double wsmin = wsmax * 0.1;                            /* :618 */
+            monthly[0 * plane + at] = tmin;
+            monthly[1 * plane + at] = tmax;
+            monthly[2 * plane + at] = rhmin;
+            monthly[3 * plane + at] = rhmax;
+            monthly[4 * plane + at] = wsmin;
+            monthly[5 * plane + at] = wsmax;
+            monthly[6 * plane + at] = mmso_cloud_cover(srad, clear_sky_SOLR, 0.8);   /* ccmin :625 */
+            monthly[7 * plane + at] = mmso_cloud_cover(srad, clear_sky_SOLR, 1.2);   /* ccmax :624 */
+            monthly[8 * plane + at] = ppt / n_days[m];                   /* :630 */
+        }
+    }
+}
+
+/* ========================================================================
  * L: life history
  * ===================================================================== */
 

@@ -110,6 +110,17 @@ int mmso_simulate_ephemeral_habitat_vectorised(
     const mmso_habitat *hb, int burnin_years,
     double *water_surface_area, double *water_volume, unsigned char *wet);
 
+/* ---- T: TerraClimate variables -> monthly forcing (R/terraclimate.R:581-643) ------- */
+double mmso_vapprs(double db);
+double mmso_vapour_pressure(double tmean, double vpd_kpa);
+double mmso_relative_humidity(double temperature, double vapour_pressure);
+double mmso_adjust_wind_speed(double wind_speed, double height_required, double height_measured,
+                              double exponent);
+double mmso_cloud_cover(double solar_radiation, double clear_sky_radiation, double multiplier);
+void mmso_process_terraclimate_pixel_vars(const double *terraclimate, const double *clear_sky,
+                                          const int *month_id, const double *n_days,
+                                          long C, int M, double *monthly);
+
 /* ---- L: life history ---------------------------------------------------- */
 void mmso_fmm_spline(int n, const double *x, const double *y, double *b, double *c, double *d);
 void mmso_spline_eval(const mmso_spline *s, const double *u, long nu, double *v);

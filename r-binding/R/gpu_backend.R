@@ -183,33 +183,44 @@ monthly_climate_to_vectors_gpu <- function(pixel_monthly_climate,
   for (i in seq_len(n_pixels)) {
     monthly[i, , ] <- as.matrix(pixel_monthly_climate$monthly_climate[[i]][, vars])
   }
-  # dates exactly as daily_from_monthly_climate() derives them (R/sim_microclimate.R:12-31)
+  chain <- mms_chain_setup(first, included_dates, aggregate_by)
+  res <- .Call("mms_R_run_chain", monthly, as.numeric(pixel_monthly_climate$altitude),
+               chain$mid_day, chain$day_predict, chain$period_of_day,
+               list(mms_habitat()),                # R/pipeline_functions.R:431-441
+               mms_densmod(lifehistory$das_densmod), mms_lifehistory_tables(lifehistory),
+               63L,                                # the six vector_variables
+               length(chain$periods), 1L, mms_math_mode(), mms_devices(),
+               PACKAGE = "mosmicrosim")
+  mms_vectors_tibble(res, pixel_monthly_climate, species, chain$periods, aggregate_by)
+}
+
+# dates exactly as daily_from_monthly_climate() derives them (R/sim_microclimate.R:12-31) and periods
+# exactly as aggregate_vectors() groups them (R/pipeline_functions.R:1050-1088); `first` is any pixel's
+# monthly tibble (all pixels of a tile share start / end)
+mms_chain_setup <- function(first, included_dates, aggregate_by) {
   midpoint <- first$start + round((first$end - first$start) / 2)
   dates_predict <- seq(from = min(midpoint), to = max(midpoint), by = 1)
   mid_date <- first$start + (first$end - first$start) / 2
-  mid_day <- as.numeric(mid_date - min(mid_date))
-  day_predict <- as.numeric(dates_predict - min(mid_date))
-  # periods exactly as aggregate_vectors() groups them (R/pipeline_functions.R:1050-1088)
   if (is.null(included_dates)) included_dates <- dates_predict
   keep <- dates_predict %in% included_dates
   key <- if (aggregate_by == "month") lubridate::floor_date(dates_predict, "month") else dates_predict
   periods <- sort(unique(key[keep]))
-  period_of_day <- ifelse(keep, match(key, periods) - 1L, -1L)
+  list(mid_day = as.numeric(mid_date - min(mid_date)),
+       day_predict = as.numeric(dates_predict - min(mid_date)),
+       period_of_day = as.integer(ifelse(keep, match(key, periods) - 1L, -1L)),
+       periods = periods)
+}
 
-  res <- .Call("mms_R_run_chain", monthly, as.numeric(pixel_monthly_climate$altitude),
-               mid_day, day_predict, as.integer(period_of_day),
-               list(mms_habitat()),                # R/pipeline_functions.R:431-441
-               mms_densmod(lifehistory$das_densmod), mms_lifehistory_tables(lifehistory),
-               63L,                                # the six vector_variables
-               length(periods), 1L, mms_math_mode(), mms_devices(),
-               PACKAGE = "mosmicrosim")
+# the summarise_vectors() schema from the library's [cell, period, variable] arrays
+mms_vectors_tibble <- function(res, pixels, species, periods, aggregate_by) {
+  n_pixels <- nrow(pixels)
   n_periods <- length(periods)
   state <- array(res$mean_state, dim = c(n_pixels, n_periods, 2))      # adult, aquatic
   forcing <- array(res$mean_forcing, dim = c(n_pixels, n_periods, 4))  # mdr, efd, das_zerodensity, ds
   end <- if (aggregate_by == "month") lubridate::ceiling_date(periods + 1, "month") - 1 else periods
   dplyr::tibble(
-    longitude = pixel_monthly_climate$longitude,
-    latitude = pixel_monthly_climate$latitude,
+    longitude = pixels$longitude,
+    latitude = pixels$latitude,
     species = species,
     pixel_vectors = lapply(seq_len(n_pixels), function(i) {
       dplyr::tibble(start = periods, end = end,
@@ -220,11 +231,54 @@ monthly_climate_to_vectors_gpu <- function(pixel_monthly_climate,
   )
 }
 
+# tc_to_vectors() whole (R/pipeline_functions.R:1099-1130): the raw TerraClimate tibbles of
+# extract_terraclimate_tile() go to the device, where process_terraclimate_pixel_vars()
+# (R/terraclimate.R:581-643) runs in front of the fused chain.  Altitude and the clear-sky lookup are
+# read on the R side exactly as terraclimate_to_monthly_climate() reads them (:183-233).
+tc_to_vectors_gpu <- function(pixel_terraclimate_data,
+                              species = c("An. gambiae", "An. stephensi"),
+                              included_dates = NULL,
+                              aggregate_by = c("month", "day")) {
+  species <- match.arg(species)
+  aggregate_by <- match.arg(aggregate_by)
+  lifehistory <- switch(species,
+                        "An. gambiae" = lifehistory_functions$An_gambiae,
+                        "An. stephensi" = lifehistory_functions$An_stephensi)
+  tc_elev <- terra::unwrap(tc_elev_wrapped)
+  tc_gads <- terra::unwrap(tc_gads_wrapped)
+  coords <- pixel_terraclimate_data[, c("longitude", "latitude")]
+  altitude <- altitude_m(longitude = coords$longitude, latitude = coords$latitude,
+                         altitude_raster = tc_elev)
+  cell_id <- terra::extract(tc_gads, coords, ID = FALSE)[, 1]
+  clear_sky <- t(vapply(match(cell_id, clear_sky_lookup$cell_id),
+                        function(k) as.numeric(clear_sky_lookup$clear_sky_SOLR[[k]]), numeric(12)))
+  first <- pixel_terraclimate_data$monthly_terraclimate[[1]]
+  n_pixels <- nrow(pixel_terraclimate_data)
+  vars <- c("tmax", "tmin", "ppt", "ws", "vpd", "srad")
+  values <- array(NA_real_, dim = c(n_pixels, nrow(first), length(vars)))
+  for (i in seq_len(n_pixels)) {
+    values[i, , ] <- as.matrix(pixel_terraclimate_data$monthly_terraclimate[[i]][, vars])
+  }
+  terraclimate <- list(
+    values = values, clear_sky = clear_sky,
+    month_id = as.integer(lubridate::month(first$start + (first$end - first$start) / 2)),  # R/terraclimate.R:591
+    n_days = as.numeric(first$end - first$start))                                          # :592
+  chain <- mms_chain_setup(first, included_dates, aggregate_by)
+  res <- .Call("mms_R_run_chain_terraclimate", terraclimate, as.numeric(altitude),
+               chain$mid_day, chain$day_predict, chain$period_of_day,
+               list(mms_habitat()), mms_densmod(lifehistory$das_densmod),
+               mms_lifehistory_tables(lifehistory), 63L, length(chain$periods), 1L,
+               mms_math_mode(), mms_devices(), PACKAGE = "mosmicrosim")
+  mms_vectors_tibble(res, pixel_terraclimate_data, species, chain$periods, aggregate_by)
+}
+
 # ---- the switch: one line each in the reference's own functions ------------------
 # R/sim_water.R:216     if (mms_backend() == "gpu") return(simulate_ephemeral_habitat_vectorised_gpu(...))
 # R/sim_pop_dynamics.R:208  if (mms_backend() == "gpu") return(simulate_population_vectorised_gpu(...))
 # R/sim_water.R:136     if (mms_backend() == "gpu") return(simulate_ephemeral_habitat_gpu(...))
 # R/sim_pop_dynamics.R:138  if (mms_backend() == "gpu") return(simulate_population_gpu(...))
 # R/pipeline_functions.R:1099 (tc_to_vectors):
+#   if (mms_backend() == "gpu") return(tc_to_vectors_gpu(pixel_terraclimate_data, species, included_dates))
+# or, keeping terraclimate_to_monthly_climate() on the R side:
 #   monthly <- terraclimate_to_monthly_climate(pixel_terraclimate_data)
 #   if (mms_backend() == "gpu") return(monthly_climate_to_vectors_gpu(monthly, species, included_dates))

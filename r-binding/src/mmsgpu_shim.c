@@ -186,9 +186,9 @@ SEXP mms_R_population_series(SEXP larval_habitat_area, SEXP mdr, SEXP efd, SEXP 
  *   mean_var_mask  integer;  n_periods integer;  burnin_years_pop integer;  math_mode integer
  *   devices        integer vector of CUDA ordinals (length 0 = all)
  * Returns list(mean_state = [C, P, ns, S], mean_forcing = [C, P, nf], wet_hours = [C, P, S]). */
-SEXP mms_R_run_chain(SEXP monthly, SEXP altitude, SEXP mid_day, SEXP day_predict, SEXP period_of_day,
-                     SEXP habitats, SEXP densmod, SEXP tables, SEXP mean_var_mask, SEXP n_periods,
-                     SEXP burnin_years_pop, SEXP math_mode, SEXP devices)
+static SEXP run_chain_impl(SEXP monthly, SEXP terraclimate, SEXP altitude, SEXP mid_day, SEXP day_predict,
+                           SEXP period_of_day, SEXP habitats, SEXP densmod, SEXP tables, SEXP mean_var_mask,
+                           SEXP n_periods, SEXP burnin_years_pop, SEXP math_mode, SEXP devices)
 {
     mms_chain_config cfg;
     memset(&cfg, 0, sizeof cfg);
@@ -197,7 +197,7 @@ SEXP mms_R_run_chain(SEXP monthly, SEXP altitude, SEXP mid_day, SEXP day_predict
     cfg.n_days = (int32_t)Rf_xlength(day_predict);
     cfg.n_settings = (int32_t)Rf_xlength(habitats);
     cfg.n_periods = Rf_asInteger(n_periods);
-    if (Rf_xlength(monthly) != (R_xlen_t)cfg.n_cells * cfg.n_months * MMS_NFORCING)
+    if (terraclimate == R_NilValue && Rf_xlength(monthly) != (R_xlen_t)cfg.n_cells * cfg.n_months * MMS_NFORCING)
         Rf_error("monthly must be a [cells, months, 9] array");
     if (cfg.n_settings < 1 || cfg.n_settings > MMS_MAX_SETTINGS) Rf_error("1 to %d habitat settings", MMS_MAX_SETTINGS);
     cfg.mid_day = REAL(mid_day);
@@ -238,7 +238,20 @@ SEXP mms_R_run_chain(SEXP monthly, SEXP altitude, SEXP mid_day, SEXP day_predict
     out.mean_state = REAL(mean_state);
     out.mean_forcing = REAL(mean_forcing);
     out.wet_hours = (int32_t *)INTEGER(wet_hours);
-    check(mms_run_chain(&cfg, REAL(monthly), REAL(altitude), &out));
+    if (terraclimate == R_NilValue) {
+        check(mms_run_chain(&cfg, REAL(monthly), REAL(altitude), &out));
+    } else {
+        /* list(values = [cells, months, 6], clear_sky = [cells, 12], month_id = integer [months], n_days = double [months]) */
+        SEXP values = list_get(terraclimate, "values"), clear_sky = list_get(terraclimate, "clear_sky");
+        SEXP month_id = list_get(terraclimate, "month_id"), n_days = list_get(terraclimate, "n_days");
+        if (Rf_xlength(values) != (R_xlen_t)cfg.n_cells * cfg.n_months * MMS_NTERRACLIMATE)
+            Rf_error("terraclimate values must be a [cells, months, 6] array");
+        if (Rf_xlength(clear_sky) != (R_xlen_t)cfg.n_cells * 12) Rf_error("clear_sky must be a [cells, 12] matrix");
+        if (Rf_xlength(month_id) != cfg.n_months || Rf_xlength(n_days) != cfg.n_months)
+            Rf_error("month_id and n_days must have one entry per month");
+        check(mms_run_chain_terraclimate(&cfg, REAL(values), REAL(clear_sky), (const int32_t *)INTEGER(month_id),
+                                         REAL(n_days), REAL(altitude), &out));
+    }
 
     SEXP res = PROTECT(Rf_allocVector(VECSXP, 3));
     SEXP names = PROTECT(Rf_allocVector(STRSXP, 3));
@@ -251,6 +264,41 @@ SEXP mms_R_run_chain(SEXP monthly, SEXP altitude, SEXP mid_day, SEXP day_predict
     Rf_setAttrib(res, R_NamesSymbol, names);
     UNPROTECT(5);
     return res;
+}
+
+SEXP mms_R_run_chain(SEXP monthly, SEXP altitude, SEXP mid_day, SEXP day_predict, SEXP period_of_day,
+                     SEXP habitats, SEXP densmod, SEXP tables, SEXP mean_var_mask, SEXP n_periods,
+                     SEXP burnin_years_pop, SEXP math_mode, SEXP devices)
+{
+    return run_chain_impl(monthly, R_NilValue, altitude, mid_day, day_predict, period_of_day, habitats, densmod,
+                          tables, mean_var_mask, n_periods, burnin_years_pop, math_mode, devices);
+}
+
+/* The same from the raw TerraClimate variables (tc_to_vectors() whole, R/pipeline_functions.R:1099-1130):
+ * process_terraclimate_pixel_vars(), R/terraclimate.R:581-643, runs on the device. */
+SEXP mms_R_run_chain_terraclimate(SEXP terraclimate, SEXP altitude, SEXP mid_day, SEXP day_predict,
+                                  SEXP period_of_day, SEXP habitats, SEXP densmod, SEXP tables,
+                                  SEXP mean_var_mask, SEXP n_periods, SEXP burnin_years_pop, SEXP math_mode,
+                                  SEXP devices)
+{
+    return run_chain_impl(R_NilValue, terraclimate, altitude, mid_day, day_predict, period_of_day, habitats,
+                          densmod, tables, mean_var_mask, n_periods, burnin_years_pop, math_mode, devices);
+}
+
+/* process_terraclimate_pixel_vars() for a tile: values [C, M, 6], clear_sky [C, 12] -> monthly [C, M, 9] */
+SEXP mms_R_terraclimate_to_monthly(SEXP values, SEXP clear_sky, SEXP month_id, SEXP n_days, SEXP n_cells,
+                                   SEXP math_mode, SEXP device)
+{
+    const int64_t C = (int64_t)Rf_asReal(n_cells);
+    const int M = (int)Rf_xlength(month_id);
+    if (Rf_xlength(values) != (R_xlen_t)C * M * MMS_NTERRACLIMATE) Rf_error("values must be a [cells, months, 6] array");
+    if (Rf_xlength(clear_sky) != (R_xlen_t)C * 12) Rf_error("clear_sky must be a [cells, 12] matrix");
+    if (Rf_xlength(n_days) != M) Rf_error("month_id and n_days must have one entry per month");
+    SEXP monthly = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)C * M * MMS_NFORCING));
+    check(mms_terraclimate_to_monthly(REAL(values), REAL(clear_sky), (const int32_t *)INTEGER(month_id), REAL(n_days),
+                                      C, M, Rf_asInteger(math_mode), Rf_asInteger(device), REAL(monthly)));
+    UNPROTECT(1);
+    return monthly;
 }
 
 /* interpolate_daily_climate(), R/pipeline_functions.R:258-275: monthly [C, M, 9] -> daily [C, D, 9] */
@@ -322,6 +370,8 @@ static const R_CallMethodDef call_methods[] = {
     {"mms_R_water_series", (DL_FUNC)&mms_R_water_series, 9},
     {"mms_R_population_series", (DL_FUNC)&mms_R_population_series, 11},
     {"mms_R_run_chain", (DL_FUNC)&mms_R_run_chain, 13},
+    {"mms_R_run_chain_terraclimate", (DL_FUNC)&mms_R_run_chain_terraclimate, 13},
+    {"mms_R_terraclimate_to_monthly", (DL_FUNC)&mms_R_terraclimate_to_monthly, 7},
     {NULL, NULL, 0}};
 
 void R_init_mosmicrosim(DllInfo *dll)

@@ -111,3 +111,67 @@ def test_verb_by_verb_pipeline_equals_fused_chain(gpu):
     assert np.array_equal(pop["aquatic"], st["aquatic"], equal_nan=True)
     ref = case.oracle()
     assert rel_err(pop["adult"], ref["hourly"][0, ORACLE_VAR["adult"]]) <= REL_TOL_STRICT
+
+
+# ---- TerraClimate variables -> monthly forcing -----------------------------
+
+@pytest.mark.parametrize("mode,tol", [("strict", REL_TOL_STRICT), ("fast", REL_TOL_FAST)])
+def test_terraclimate_to_monthly_matches_oracle(gpu, mode, tol):
+    from mosmicrosim_b200 import dates
+    start, end = syn.month_table(2001, 2)
+    month_id, n_days = dates.terraclimate_month_info(start, end)
+    for C in (1, 131, 1000):
+        tc, clear_sky, _ = syn.synthetic_terraclimate(C, start)
+        tc[0, 3, 0] = -5.0; tc[1, 3, 0] = -15.0                     # frost: the over-ice branch of VAPPRS
+        ref = oracle.process_terraclimate_pixel_vars(tc, clear_sky, month_id, n_days)
+        got = backend.terraclimate_to_monthly(tc, clear_sky, month_id, n_days, math_mode=mode)
+        for v, name in enumerate(pipeline.FORCING_VARS):
+            assert rel_err(got[v], ref[v]) <= tol, (name, C)
+        # the clamps are hit at identical cells
+        assert np.array_equal(got[2] == 0.01, ref[2] == 0.01) and np.array_equal(got[7] == 0.0, ref[7] == 0.0)
+
+
+def test_tc_to_vectors_equals_the_two_step_route(gpu):
+    """tc_to_vectors() (raw variables up, forcing derived on the device in front of the fused chain) is bit
+    identical to terraclimate_to_monthly_climate() followed by monthly_climate_to_vectors(), and matches
+    the oracle's chain fed with the oracle's own monthly variables."""
+    from mosmicrosim_b200 import dates
+    case = Case(n_cells=40)
+    tc, clear_sky, altitude = syn.synthetic_terraclimate(40, case.start, out_of_range_fraction=0.05)
+    ptd = {"start": case.start, "end": case.end, "altitude": altitude, "clear_sky_SOLR": clear_sky,
+           "longitude": np.arange(40.0), "latitude": -np.arange(40.0)}
+    for v, name in enumerate(backend.TERRACLIMATE_VARS):
+        ptd[name] = tc[v]
+    lhf = {"An_gambiae": case.lh, "An_stephensi": syn.synthetic_lifehistory("An. stephensi")}
+    one = pipeline.tc_to_vectors(ptd, lhf, species="An. gambiae", dates_predict=case.dates_predict)
+    pmc = pipeline.terraclimate_to_monthly_climate(ptd)
+    two = pipeline.monthly_climate_to_vectors(pmc, lhf, species="An. gambiae", dates_predict=case.dates_predict)
+    for name in pipeline.VECTOR_VARIABLES:
+        assert np.array_equal(one[name], two[name], equal_nan=True), name
+    month_id, n_days = dates.terraclimate_month_info(case.start, case.end)
+    monthly = oracle.process_terraclimate_pixel_vars(tc, clear_sky, month_id, n_days)
+    ref = oracle.run_chain(monthly, case.mid_day, case.day_predict, altitude, [oracle.habitat()],
+                           oracle.densmod(case.densmod["type_"], case.densmod["dd_effect"], case.densmod["surface_area_cm2"]),
+                           case.tables, case.period_of_day, case.P, want_hourly=False)
+    for name in pipeline.VECTOR_VARIABLES:
+        assert rel_err(one[name], ref["mean"][0, ORACLE_VAR[name]]) <= REL_TOL_FAST, name
+    feb = pipeline.raster_slice(one, "adult", 2001, 2)
+    assert feb.shape == (1, 40) and np.array_equal(feb[0], one["adult"][1], equal_nan=True)
+
+
+def test_run_chain_terraclimate_one_shot(gpu):
+    """mms_run_chain_terraclimate() == terraclimate_to_monthly + mms_run_chain, bit for bit, over two shards too."""
+    from mosmicrosim_b200 import dates
+    case = Case(n_cells=300, habitats=[syn.habitat_cone(), syn.habitat_cylinder(leak_per_hour=0.002)])
+    tc, clear_sky, altitude = syn.synthetic_terraclimate(300, case.start)
+    month_id, n_days = dates.terraclimate_month_info(case.start, case.end)
+    kw = case.gpu_kwargs(mean_vars=list(backend.VAR_NAMES[:8]), want_wet_hours=True)
+    monthly = backend.terraclimate_to_monthly(tc, clear_sky, month_id, n_days)
+    two = backend.run_chain(monthly, altitude, **kw)
+    for devices in ([0], [0, 0]):
+        one = backend.run_chain_terraclimate(tc, clear_sky, month_id, n_days, altitude, **{**kw, "devices": devices})
+        for k in ("mean_state", "mean_forcing", "wet_hours"):
+            assert np.array_equal(one[k], two[k], equal_nan=True), (k, devices)
+    with pytest.raises(backend.MmsError) as e:
+        backend.run_chain_terraclimate(tc, clear_sky, month_id * 0, n_days, altitude, **kw)
+    assert e.value.code == "MMS_ERR_INVALID_ARG"

@@ -234,3 +234,57 @@ def test_scalar_twins_burnin_repeats_the_whole_series():
     p = oracle.simulate_population(*short_p, dm, burnin_years=2)
     q = oracle.simulate_population(*[np.tile(c, 3) for c in short_p], dm, burnin_years=0)
     assert np.array_equal(p["adult"], q["adult"][-n:]) and np.array_equal(p["aquatic"], q["aquatic"][-n:])
+
+
+# ---- TerraClimate variables -> monthly forcing ------------------------
+
+def test_terraclimate_known_answers():
+    L = oracle.lib()
+    assert L.mmso_vapprs(0.0) == pytest.approx(610.71, rel=1e-12)          # triple point: 10^log10(6.1071) hPa
+    assert L.mmso_vapprs(100.0) == pytest.approx(101324.6, rel=1e-12)      # boiling point: 1013.246 hPa
+    assert L.mmso_vapprs(20.0) == pytest.approx(2338.0, rel=2e-3)          # Goff-Gratch, ~2.34 kPa at 20 C
+    assert L.mmso_vapprs(-10.0) == pytest.approx(259.9, rel=2e-3)          # over ice
+    assert L.mmso_adjust_wind_speed(1.0, 2.0, 10.0, 0.15) == 0.7855150302317644     # SURVEY 8c KAT
+    assert L.mmso_cloud_cover(100.0, 200.0, 1.2) == pytest.approx(60.0) and L.mmso_cloud_cover(100.0, 200.0, 0.8) == pytest.approx(40.0)
+    assert L.mmso_cloud_cover(250.0, 200.0, 1.2) == 0.0 and L.mmso_cloud_cover(1.0, 200.0, 1.2) == 100.0   # clamps
+    vp = L.mmso_vapour_pressure(20.0, 1.0)
+    assert vp == pytest.approx(L.mmso_vapprs(20.0) - 1000.0)
+    assert L.mmso_relative_humidity(20.0, vp) == pytest.approx(100 * vp / L.mmso_vapprs(20.0))
+    assert L.mmso_relative_humidity(20.0, -5.0) == 0.01 and L.mmso_relative_humidity(20.0, 1e6) == 100.0
+
+
+def test_process_terraclimate_pixel_vars_and_month_bookkeeping():
+    from mosmicrosim_b200 import dates
+    start, end = syn.month_table(2001, 1)
+    month_id, n_days = dates.terraclimate_month_info(start, end)
+    assert list(month_id) == [12] + list(range(1, 13)) + [1]
+    assert list(n_days[:4]) == [30.0, 30.0, 27.0, 30.0]                  # days in the month MINUS ONE, as the reference
+    tc, clear_sky, _ = syn.synthetic_terraclimate(7, start)
+    m = oracle.process_terraclimate_pixel_vars(tc, clear_sky, month_id, n_days)
+    names = ["tmin", "tmax", "rhmin", "rhmax", "wsmin", "wsmax", "ccmin", "ccmax", "rainfall_daily"]
+    v = dict(zip(names, m))
+    assert np.array_equal(v["tmax"], tc[0]) and np.array_equal(v["tmin"], tc[1])
+    assert np.all(v["rhmin"] <= v["rhmax"]) and v["rhmin"].min() >= 0.01 and v["rhmax"].max() <= 100.0
+    assert np.array_equal(v["wsmin"], v["wsmax"] * 0.1) and np.allclose(v["wsmax"], tc[3] * 0.7855150302317644, rtol=1e-15)
+    assert np.all(v["ccmin"] <= v["ccmax"]) and v["ccmin"].min() >= 0 and v["ccmax"].max() <= 100
+    assert (v["ccmax"] == 0).any() and (v["rhmin"] == 0.01).any()        # the synthetic data reaches the clamps
+    assert np.array_equal(v["rainfall_daily"], tc[2] / n_days[:, None])
+    # clear-sky values are looked up by calendar month, not by row
+    assert np.array_equal(m[7][0], m[7][12] * 0 + oracle.process_terraclimate_pixel_vars(
+        tc[:, :1], clear_sky, month_id[:1], n_days[:1])[7][0])
+
+
+def test_pad_last_month():
+    from mosmicrosim_b200 import dates
+    start, end = syn.month_table(2001, 3)                                 # Dec 2000 .. Jan 2004
+    vals = np.arange(2 * len(start) * 2, dtype=np.float64).reshape(2, len(start), 2) ** 1.5
+    s2, e2, v2 = dates.pad_last_month(start, end, vals)
+    assert str(s2[-1]) == "2004-02-01" and str(e2[-1]) == "2004-02-29" and v2.shape == (2, len(start) + 1, 2)
+    feb = [i for i, s in enumerate(start) if str(s)[5:7] == "02"]          # Feb 2001, 2002, 2003
+    assert len(feb) == 3
+    np.testing.assert_allclose(v2[:, -1], vals[:, feb].mean(axis=1), rtol=1e-15)
+    assert np.array_equal(v2[:, :-1], vals)
+    assert dates.r_mean([1.0, 2.0, 4.0]) == oracle.R_mean(np.array([1.0, 2.0, 4.0]))
+    # fewer matching years than n_previous: the mean of those present; none: NaN like mean(numeric(0))
+    s3, e3, v3 = dates.pad_last_month(start[:3], end[:3], vals[:, :3])
+    assert str(s3[-1]) == "2001-03-01" and np.isnan(v3[:, -1]).all()
