@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmmsgpu.so")
+LIB_PATH = os.environ.get("MMS_LIB") or os.path.join(_HERE, "libmmsgpu.so")   # MMS_LIB: another build of the same library
 
 NFORCING = 9
 NTERRACLIMATE = 6

@@ -18,6 +18,7 @@ LIB = os.path.join(HERE, "libmmsgpu.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"] + ARCH
+COMMON += os.environ.get("MMS_NVCC_EXTRA", "").split()     # development aid: -D switches for kernel experiments
 
 UNITS = [
     # (source, object, extra flags)

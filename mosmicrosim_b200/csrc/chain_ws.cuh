@@ -25,6 +25,17 @@ namespace mms {
 namespace MMS_MODE {
 
 constexpr int kWsK = 3;              // hours per hand-off (divides 24)
+// unroll factors of the per-hand-off hour loops of the forcing / state warps (kWsK = fully unrolled).
+// Measured on BASELINE configs[1] (ms per launch): F3 S3 61.6, F1 S1 68.1, F3 S1 71.3, F1 S3 58.7 --
+// the state recursion gains from scheduling across hours, the forcing warp from the smaller
+// instruction footprint (the two loops together overflow the 32 KB L1.5 instruction cache otherwise).
+#ifndef MMS_WS_UNROLL_F
+#define MMS_WS_UNROLL_F 1
+#endif
+#ifndef MMS_WS_UNROLL_S
+#define MMS_WS_UNROLL_S 3
+#endif
+constexpr int kWsUnrollF = MMS_WS_UNROLL_F, kWsUnrollS = MMS_WS_UNROLL_S;
 constexpr int kWsFields = 6;         // evap, surv_ad, exp(-mdr/24), egg, link0, gain_m_h
 constexpr int kWsRingDoubles = 2 * kWsK * kWsFields * 32;   // per pair
 
@@ -110,7 +121,7 @@ __device__ __forceinline__ void forcing_pass(const ChainParams &p, const SmemTab
 #pragma unroll 1
         for (int h0 = 0; h0 < 24; h0 += kWsK) {
             double *slot = ring + (size_t)buf * (kWsK * kWsFields * 32) + lane;
-#pragma unroll
+#pragma unroll kWsUnrollF
             for (int k = 0; k < kWsK; ++k) {
                 const int h = h0 + k;
                 const HourF f = hour_forcing<kFull, kWaterOnly>(p, tb, dc, u.p_a, h);
@@ -216,7 +227,7 @@ __device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &
         for (int h0 = 0; h0 < 24; h0 += kWsK) {
             pair_barrier(pair);                      // the forcing warp has filled this buffer
             const double *slot = ring + (size_t)buf * (kWsK * kWsFields * 32) + lane;
-#pragma unroll
+#pragma unroll kWsUnrollS
             for (int k = 0; k < kWsK; ++k) {
                 const double *rec = slot + (size_t)k * (kWsFields * 32);
                 const double evap = rec[0 * 32];
