@@ -172,3 +172,52 @@ def test_errors(gpu):
     with pytest.raises(backend.MmsError) as e:
         backend.run_chain(m, case.altitude, **kw)
     assert e.value.code == "MMS_ERR_NONFINITE"
+
+
+@pytest.mark.parametrize("mode,tol", [("strict", REL_TOL_STRICT), ("fast", REL_TOL_FAST)])
+@pytest.mark.parametrize("species", ["An. gambiae", "An. stephensi"])
+def test_chain_extreme_cells(gpu, mode, tol, species):
+    """Cells that live on the guards of the branch-free math: never any rain (volume 0, log(0), 0/eps density),
+    a deluge (volume pinned at its maximum), frost (all life-history rates 0), heat beyond the ds grid (NA every
+    hour), saturated air (evaporation 0), a gale, and a population driven to extinction / to huge densities."""
+    case = Case(n_cells=8, species=species, out_of_range_fraction=0.0,
+                habitats=[syn.habitat_cone(), syn.habitat_cylinder(radius=0.2, max_depth=0.1, leak_per_hour=0.05)])
+    m = case.monthly
+    F = {n: i for i, n in enumerate(("tmin", "tmax", "rhmin", "rhmax", "wsmin", "wsmax", "ccmin", "ccmax", "rain"))}
+    m[F["rain"], :, 0] = 0.0                                         # never wet
+    m[F["rain"], :, 1] = 80.0                                        # always full
+    m[F["tmin"], :, 2] = -12.0; m[F["tmax"], :, 2] = -1.0            # frost
+    m[F["tmin"], :, 3] = 38.0; m[F["tmax"], :, 3] = 52.0             # beyond the 0-45 C grid for part of every day
+    m[F["rhmin"], :, 4] = 100.0; m[F["rhmax"], :, 4] = 100.0         # saturated air
+    m[F["wsmin"], :, 5] = 4.0; m[F["wsmax"], :, 5] = 40.0            # gale: fast evaporation
+    m[F["rain"], ::2, 6] = 0.0; m[F["rain"], 1::2, 6] = 30.0         # alternating drought / flood months
+    m[F["tmin"], :, 7] = 44.0; m[F["tmax"], :, 7] = 45.0; m[F["rain"], :, 7] = 0.05   # hot trickle: tiny pools, huge densities
+    ref = case.oracle()
+    out = backend.run_chain(m, case.altitude, **case.gpu_kwargs(
+        mean_vars=ALL_VARS, hourly_vars=ALL_VARS, want_wet_hours=True, want_wet_flags=True, math_mode=mode))
+    compare(case, out, ref, tol)
+    wet = ref["wet"]
+    assert wet[0][:, 0].sum() == 0 and wet[0][:, 1].mean() > 0.99       # the cases are what they claim to be
+    assert np.isnan(ref["hourly"][0, ORACLE_VAR["ds"]][:, 3]).any()
+
+
+def test_chain_single_cell(gpu):
+    """BASELINE configs[0]: one cell, one year, every output, both math modes and both species."""
+    for species in ("An. gambiae", "An. stephensi"):
+        case = Case(n_cells=1, species=species, out_of_range_fraction=0.0)
+        ref = case.oracle()
+        for mode, tol in (("strict", REL_TOL_STRICT), ("fast", REL_TOL_FAST)):
+            out = backend.run_chain(case.monthly, case.altitude, **case.gpu_kwargs(
+                mean_vars=ALL_VARS, hourly_vars=ALL_VARS, want_wet_hours=True, want_wet_flags=True, math_mode=mode))
+            compare(case, out, ref, tol)
+
+
+def test_chain_ten_years_monthly(gpu):
+    """BASELINE configs[2] in miniature: ten years (two leap days, 87 648 hourly steps + burn-in), 120 monthly means."""
+    case = Case(n_cells=40, years=10, first_year=1995,
+                habitats=[syn.habitat_cone(), syn.habitat_cylinder(leak_per_hour=0.002)])
+    ref = case.oracle(want_hourly=False)
+    out = backend.run_chain(case.monthly, case.altitude, **case.gpu_kwargs(
+        mean_vars=list(backend.VAR_NAMES[:8]), want_wet_hours=True))
+    assert out["mean_state"].shape[2] == 120
+    compare(case, out, ref, REL_TOL_FAST, what=("mean",))
