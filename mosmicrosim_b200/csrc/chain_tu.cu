@@ -160,23 +160,25 @@ int stage_vec(int64_t H, uintptr_t all_pointers)
     return 1;
 }
 
-// persistent CTAs, one per SM.  The recursions are arithmetic-bound (exp / log / pow per step):
-// the register budget matters more than the warp count, so the default cap is the 16-warp
-// instantiation (128 registers, measured 36.6 vs 58.4 ms for the 80-register 22-warp one on
-// the 100k-pixel population twin), and the warp count is chosen so that the rounds of 32-pixel
-// units come out even (2 x 11 warps beats 16 + 5: 36.6 vs 41.5 ms).
+// persistent CTAs, one per SM.  The recursions are bound by FP64 latency (an exp / log / pow or three per
+// step in a serial chain per pixel), so what counts is independent chains in flight per SM sub-partition
+// within the register budget.  Measured on the 100k-pixel population twin (ms): 2 even rounds x 11 warps at
+// 168 registers 29.0, at 128 registers 31.6; 16 + 5 warps (uneven rounds) 41.5; 22 warps at 80 registers
+// (spills) 58.4; two pixels per thread (kPx = 2, 12 warps) 52.2.  Hence: one pixel per thread, the warp
+// count that makes the rounds of 32-pixel units even, and the 168-register instantiation whenever that
+// count is <= 12.
 struct StagePlan { int grid, warps; size_t smem; };
 
-StagePlan stage_plan(int64_t C, int n_inputs, int n_sm, int w_cap)
+StagePlan stage_plan(int64_t C, int n_inputs, int n_sm)
 {
-    const int64_t n_units = (C + 31) / 32;
-    int w_max = w_cap;
     bool even = true;
-    if (const char *e = getenv("MMS_STAGE_WARPS")) {                       // tuning aids
-        const int w = atoi(e);
-        if (w >= 1 && w <= kStageMaxWarps) w_max = w;
-    }
+    int w_max = 0;
+    if (const char *e = getenv("MMS_STAGE_WARPS")) w_max = atoi(e);       // tuning aids
     if (const char *e = getenv("MMS_STAGE_EVEN")) even = atoi(e) != 0;
+    if (w_max < 1 || w_max > kStageMaxWarps) w_max = kStageMaxWarps;
+    const int w_smem = (int)(kStageSmemBudget / stage_smem_bytes(n_inputs, 1));
+    if (w_max > w_smem) w_max = w_smem;
+    const int64_t n_units = (C + 31) / 32;
     const int64_t per_round = (int64_t)n_sm * w_max;
     const int64_t rounds = even ? (n_units + per_round - 1) / per_round : 1;
     int64_t warps = (n_units + (int64_t)n_sm * rounds - 1) / ((int64_t)n_sm * rounds);
@@ -202,14 +204,9 @@ cudaError_t device_sm_count(int &n_sm)
     return err;
 }
 
-#if MMS_STRICT
-#define MMS_STAGE_DISPATCH(kernel, V, pl)                                                          \
-    launch_stage_kernel(kernel<V, kStageMaxWarps>, p, pl, stream)
-#else
-#define MMS_STAGE_DISPATCH(kernel, V, pl)                                                          \
-    ((pl).warps <= kStageFewWarps ? launch_stage_kernel(kernel<V, kStageFewWarps>, p, pl, stream)   \
-                                  : launch_stage_kernel(kernel<V, kStageMaxWarps>, p, pl, stream))
-#endif
+#define MMS_STAGE_DISPATCH(kernel, V, pl)                                                                 \
+    ((pl).warps <= kStageFewWarps ? launch_stage_kernel(kernel<V, kStageFewWarps, 1>, p, pl, stream)      \
+                                  : launch_stage_kernel(kernel<V, kStageMaxWarps, 1>, p, pl, stream))
 
 }  // namespace
 
@@ -222,7 +219,7 @@ cudaError_t MMS_LAUNCH(launch_water_stage)(const WaterStageParams &p, cudaStream
     const int vec = stage_vec(p.H, (uintptr_t)p.rainfall | (uintptr_t)p.air_temperature | (uintptr_t)p.humidity |
                                        (uintptr_t)p.windspeed | (uintptr_t)p.water_surface_area |
                                        (uintptr_t)p.water_volume | (uintptr_t)p.wet);
-    const StagePlan pl = stage_plan(p.C, kWaterInputs, n_sm, kStageFewWarps);
+    const StagePlan pl = stage_plan(p.C, kWaterInputs, n_sm);
     if (vec == 4) return MMS_STAGE_DISPATCH(water_stage_kernel, 4, pl);
     if (vec == 2) return MMS_STAGE_DISPATCH(water_stage_kernel, 2, pl);
     return MMS_STAGE_DISPATCH(water_stage_kernel, 1, pl);
@@ -237,7 +234,7 @@ cudaError_t MMS_LAUNCH(launch_pop_stage)(const PopStageParams &p, cudaStream_t s
     const int vec = stage_vec(p.H, (uintptr_t)p.larval_habitat_area | (uintptr_t)p.mdr | (uintptr_t)p.efd |
                                        (uintptr_t)p.das_zerodensity | (uintptr_t)p.ds | (uintptr_t)p.aquatic |
                                        (uintptr_t)p.adult);
-    const StagePlan pl = stage_plan(p.C, kPopInputs, n_sm, kStageFewWarps);
+    const StagePlan pl = stage_plan(p.C, kPopInputs, n_sm);
     if (vec == 4) return MMS_STAGE_DISPATCH(pop_stage_kernel, 4, pl);
     if (vec == 2) return MMS_STAGE_DISPATCH(pop_stage_kernel, 2, pl);
     return MMS_STAGE_DISPATCH(pop_stage_kernel, 1, pl);

@@ -194,3 +194,30 @@ def test_scalar_twins_whole_series_burnin(gpu, mode, tol):
         gotp = pipeline.simulate_population(sub, dmh, burnin_years=burn, math_mode=mode)
         assert rel_err(gotp["aquatic"], refp["aquatic"]) <= tol, (n, burn)
         assert rel_err(gotp["adult"], refp["adult"]) <= tol, (n, burn)
+
+
+@pytest.mark.parametrize("mode,tol", [("strict", REL_TOL_STRICT), ("fast", REL_TOL_FAST)])
+def test_twins_ragged_shapes_with_burnin_and_cylinder(gpu, mode, tol):
+    """Both twins on the ragged shapes again, with the other species / water body, a burn-in year where the
+    series allows it, and pixel counts around the 32-pixel unit and the 148-SM grid."""
+    case, m = hourly_inputs(n_cells=131)
+    dmh = syn.synthetic_lifehistory("An. stephensi").das_densmod
+    dm = oracle.densmod(dmh.type, dmh.dd_effect, dmh.surface_area_cm2)
+    names = ("larval_habitat_area", "mdr", "efd", "das_zerodensity", "ds")
+    hab = syn.habitat_cylinder(leak_per_hour=0.003)
+    for H, C in RAGGED + ((8760, 131), (30, 64), (30, 97)):
+        burn = 1 if H >= 8760 else 0
+        sub = {k: np.asfortranarray(v[:H, :C]) for k, v in m.items()}
+        ref = oracle.simulate_ephemeral_habitat_vectorised(sub["rainfall"], sub["air_temperature"], sub["humidity"],
+                                                           sub["windspeed"], case.altitude[:C], oracle.habitat(**hab), burn)
+        got = backend.water_vectorised(sub["rainfall"], sub["air_temperature"], sub["humidity"], sub["windspeed"],
+                                       case.altitude[:C], hab, burnin_years=burn, math_mode=mode, want_volume=True,
+                                       want_wet=True)
+        assert rel_err(got["water_surface_area"], ref["water_surface_area"]) <= tol, (H, C)
+        assert rel_err(got["water_volume"], ref["water_volume"]) <= tol, (H, C)
+        assert np.array_equal(got["wet"], ref["wet"]), (H, C)
+        cols = [sub[k] for k in names]
+        refp = oracle.simulate_population_vectorised(*cols, dm, burnin_years=burn)
+        gotp = pipeline.simulate_population_vectorised(*cols, dmh, burnin_years=burn, math_mode=mode)
+        assert rel_err(gotp["aquatic"], refp["aquatic"]) <= tol, (H, C)
+        assert rel_err(gotp["adult"], refp["adult"]) <= tol, (H, C)
