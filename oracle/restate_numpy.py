@@ -444,3 +444,38 @@ def run_chain(monthly, mid_day, day_predict, altitude, habitats, dm, tables, per
                 for c in range(C):
                     mean[s, v, p, c] = r_mean(hourly[s, v, sel, c])
     return {"hourly": hourly, "wet": wet, "mean": mean, "wet_hours": wet_hours}
+
+
+# ---- T: TerraClimate variables -> monthly forcing (R/terraclimate.R:581-643), vectorised like the R code ----
+
+def vapprs(db):
+    """NicheMapR::VAPPRS (third party, restated: Goff-Gratch; over ice at or below the triple point)."""
+    t = np.asarray(db, dtype=np.float64) + 273.16
+    with np.errstate(all="ignore"):
+        ice = -9.09718 * (273.16 / t - 1.) - 3.56654 * np.log10(273.16 / t) + .876793 * (1. - t / 273.16) + np.log10(6.1071)
+        water = (-7.90298 * (373.16 / t - 1.) + 5.02808 * np.log10(373.16 / t)
+                 - 1.3816E-07 * (np.power(10., 11.344 * (1. - t / 373.16)) - 1.)
+                 + 8.1328E-03 * (np.power(10., -3.49149 * (373.16 / t - 1.)) - 1.) + np.log10(1013.246))
+    loge = np.where(t <= 273.16, ice, water)
+    return np.power(10., loge) * 100                 # R_pow(10, y) is libm pow for these y
+
+
+def process_terraclimate_pixel_vars(terraclimate, clear_sky, month_id, n_days):
+    """terraclimate [6][M][C] (tmax, tmin, ppt, ws, vpd, srad), clear_sky [12][C] -> monthly [9][M][C]."""
+    tmax, tmin, ppt, ws, vpd, srad = (np.asarray(a, dtype=np.float64) for a in terraclimate)
+    clear = np.asarray(clear_sky, dtype=np.float64)[np.asarray(month_id) - 1]          # :600-603
+    tmean = (tmax + tmin) / 2                                                          # :607
+    vp = vapprs(tmean) * 100 / 100 - vpd * 1000                                        # R/utils.R:64-78
+
+    def relative_humidity(temperature):                                                # R/utils.R:80-89
+        rh = (vp / vapprs(temperature)) * 100
+        return np.maximum(np.minimum(rh, 100), 0.01)
+
+    def cloud_cover(multiplier):                                                       # R/utils.R:141-147
+        cloud = (1 - srad / clear) * 100 * multiplier
+        return np.maximum(np.minimum(cloud, 100), 0)
+
+    wsmax = ws * r_pow(2 / 10, 0.15)                                                   # R/utils.R:132
+    n = np.asarray(n_days, dtype=np.float64)[:, None]
+    return np.stack([tmin, tmax, relative_humidity(tmax), relative_humidity(tmin), wsmax * 0.1, wsmax,
+                     cloud_cover(0.8), cloud_cover(1.2), ppt / n])

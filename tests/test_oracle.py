@@ -288,3 +288,16 @@ def test_pad_last_month():
     # fewer matching years than n_previous: the mean of those present; none: NaN like mean(numeric(0))
     s3, e3, v3 = dates.pad_last_month(start[:3], end[:3], vals[:, :3])
     assert str(s3[-1]) == "2001-03-01" and np.isnan(v3[:, -1]).all()
+
+
+def test_terraclimate_c_oracle_matches_numpy_restatement():
+    from mosmicrosim_b200 import dates
+    start, end = syn.month_table(2003, 2)
+    month_id, n_days = dates.terraclimate_month_info(start, end)
+    tc, clear_sky, _ = syn.synthetic_terraclimate(50, start)
+    tc[0, 5, :3] = [-2.0, 0.0, 0.5]; tc[1, 5, :3] = [-20.0, -9.0, -0.5]        # both branches of VAPPRS
+    a = oracle.process_terraclimate_pixel_vars(tc, clear_sky, month_id, n_days)
+    b = rn.process_terraclimate_pixel_vars(tc, clear_sky, month_id, n_days)
+    np.testing.assert_allclose(a, b, rtol=1e-13, atol=0)            # glibc scalar vs numpy log10 / pow last bits
+    for v in (0, 1, 4, 5, 8):                                       # no transcendental involved: bit identical
+        assert np.array_equal(a[v], b[v])
