@@ -54,10 +54,11 @@ cudaError_t launch_one(ChainParams &p, int n_sm, cudaStream_t stream)
 #if !MMS_STRICT
     // Which form?  Measured on B200 (profiles/r01_*): the pair form wins when the launch is
     // short of warps -- several settings per cell and at most two rounds of units per SM (the
-    // 100k-cell tile of BASELINE configs[1]: 61.7 vs 67.4 ms) -- and loses a little when the
-    // monolithic kernel can already fill 16 warps per SM or with one setting per cell.
+    // 100k-cell tile of BASELINE configs[1]: 58.5 vs 67.4 ms) -- and loses a little when the
+    // monolithic kernel can already fill 16 warps per SM, with one setting per cell (100k cells:
+    // 54.0 vs 50.2 ms) or with four settings per thread (132 vs 118 ms).
     const bool ws = p.warp_specialised >= 0 ? p.warp_specialised != 0
-                                            : (kNS >= 2 && p.n_units <= (int64_t)2 * n_sm * kChainMaxPairs);
+                                            : (kNS == 2 && p.n_units <= (int64_t)2 * n_sm * kChainMaxPairs);
     if (ws) {
         // warp-specialised form: a pair of warps (forcing + state) per unit, chain_ws.cuh
         const int pairs_max = p.force_warps > 0 ? p.force_warps : kChainMaxPairs;

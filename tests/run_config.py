@@ -11,8 +11,10 @@ if which == "cfg3":      # Africa 1/24 deg: ~1.5 M land cells, 10 years hourly, 
     total_cells, years, habitats, agg, names = 1_500_000, 10, [syn.habitat_cone()], "month", list(backend.VAR_NAMES[:6])
 elif which == "cfg5":    # 64 water-body / leakage settings x 250k cells x 1 year
     total_cells, years, habitats, agg, names = 250_000, 1, syn.habitat_ensemble(64), "month", ["adult", "aquatic"]
+elif which == "cfg4":    # global land 1/24 deg: ~10 M cells, 5 years hourly, DAILY summaries only (two variables)
+    total_cells, years, habitats, agg, names = 10_000_000, 5, [syn.habitat_cone()], "day", ["adult", "aquatic"]
 else:
-    raise SystemExit("cfg3 | cfg5")
+    raise SystemExit("cfg3 | cfg4 | cfg5")
 C = total_cells // gpus
 lh = syn.synthetic_lifehistory("An. gambiae")
 start, end = syn.month_table(2001, years)
