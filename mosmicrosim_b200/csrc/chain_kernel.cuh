@@ -385,14 +385,20 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
 #pragma unroll
         for (int s = 0; s < kNS; ++s) gain[s] = p.hab[set0 + s].catchment_area * gain_m_h;   // :123
 
-        // state-dependent half of one hour + its outputs
-        auto state_half = [&](const HourF &f, int h) {
+        // the water recursion of one hour: volume, surface <- hour h (needs that hour's evaporation rate only)
+        auto water_step = [&](double evap) {
 #pragma unroll
             for (int s = 0; s < kNS; ++s) {
                 const HabitatDev &hb = p.hab[set0 + s];
-                st.volume[s] = iterate_volume(hb, st.volume[s], st.surface[s], f.evap, gain[s]);   // R/sim_water.R:279-287
+                st.volume[s] = iterate_volume(hb, st.volume[s], st.surface[s], evap, gain[s]);     // R/sim_water.R:279-287
                 st.surface[s] = habitat_surface(hb, st.volume[s]);                                 // :294
-                if (!kWaterOnly)   // larval_habitat_area = water_surface_area, R/sim_pop_dynamics.R:123
+            }
+        };
+        // the population update of hour h (volume, surface are already at hour h) + the outputs of hour h
+        auto pop_and_record = [&](const HourF &f, int h) {
+            if (!kWaterOnly) {
+#pragma unroll
+                for (int s = 0; s < kNS; ++s)   // larval_habitat_area = water_surface_area, R/sim_pop_dynamics.R:123
                     iterate_state(st.aquatic[s], st.adult[s], f.ph, p.densmod_type, p.dd_effect,
                                   p.surface_area_cm2, st.surface[s]);
             }
@@ -448,16 +454,20 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
             }
         };
 
-        // software pipeline over the 24 hours: the state-independent half of hour h + 1 sits in
-        // the same basic block as the state-dependent half of hour h (two independent chains)
+        // software pipeline over the 24 hours, three independent chains per basic block: the
+        // state-independent half of hour h + 1, the water recursion of hour h + 1 (it needs only the
+        // evaporation rate of that hour) and the population update of hour h (it needs the surface of
+        // hour h, which the previous iteration left behind).  Same arithmetic, same results.
         HourF f = hour_forcing<kFull, kWaterOnly>(p, tb, dc, u.p_a, 0);
+        water_step(f.evap);
 #pragma unroll 1
         for (int h = 0; h < 23; ++h) {
             const HourF fn = hour_forcing<kFull, kWaterOnly>(p, tb, dc, u.p_a, h + 1);
-            state_half(f, h);
+            pop_and_record(f, h);
+            water_step(fn.evap);
             f = fn;
         }
-        state_half(f, 23);
+        pop_and_record(f, 23);
 
         // ---- roll the day window
         dc.t_midnight_prev = f.air_t;                // hour-24 value, R/sim_microclimate.R:271
