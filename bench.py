@@ -114,18 +114,24 @@ def cpu_reference(w, n_cells: int, steps: int = 1, warmup: int = 0):
     dm = oracle.densmod(w["densmod"]["type_"], w["densmod"]["dd_effect"], w["densmod"]["surface_area_cm2"])
     monthly = np.ascontiguousarray(w["monthly"][:, :, :n_cells])
     alt = w["altitude"][:n_cells]
+    # every host core this process may use, stated explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers
+    try:
+        n_threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n_threads = os.cpu_count() or 1
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         oracle.run_chain(monthly, w["mid_day"], w["day_predict"], alt, hab, dm, tabs, w["period_of_day"],
-                         w["n_periods"], burnin_years_water=0, burnin_years_pop=1, want_hourly=False)
+                         w["n_periods"], burnin_years_water=0, burnin_years_pop=1, want_hourly=False,
+                         n_threads=n_threads)
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     sec = float(np.mean(times))
-    return {"value": n_cells * YEARS / sec, "unit": "cell-years/s", "cores": oracle.max_threads(),
+    return {"value": n_cells * YEARS / sec, "unit": "cell-years/s", "cores": n_threads,
             "kind": "port", "seconds_per_step": sec,
             "sample": f"first {n_cells} cells of the same tile, same settings and outputs, "
-                      f"{oracle.max_threads()} OpenMP threads over cells (R itself is not installed on this image)"}
+                      f"{n_threads} OpenMP threads over cells (R itself is not installed on this image)"}
 
 
 def main():
