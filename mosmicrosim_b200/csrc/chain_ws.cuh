@@ -24,16 +24,20 @@
 namespace mms {
 namespace MMS_MODE {
 
-constexpr int kWsK = 3;              // hours per hand-off (divides 24)
-// unroll factors of the per-hand-off hour loops of the forcing / state warps (kWsK = fully unrolled).
-// Measured on BASELINE configs[1] (ms per launch): F3 S3 61.6, F1 S1 68.1, F3 S1 71.3, F1 S3 58.7 --
-// the state recursion gains from scheduling across hours, the forcing warp from the smaller
-// instruction footprint (the two loops together overflow the 32 KB L1.5 instruction cache otherwise).
+// Hours per hand-off (divides 24) and unroll factors of the per-hand-off hour loops of the forcing / state
+// warps.  Measured on BASELINE configs[1], ms per launch (K / forcing unroll / state unroll):
+//   3/3/3 61.6   3/1/1 68.1   3/3/1 71.3   3/1/3 58.7   2/1/2 57.2   2/2/2 56.5   1/1/1 55.1
+// -- the smaller the instruction footprint of the two loops (together they overflow the 32 KB L1.5
+// instruction cache when unrolled x3), the better; handing over every hour with static ring offsets wins.
+#ifndef MMS_WS_K
+#define MMS_WS_K 1
+#endif
+constexpr int kWsK = MMS_WS_K;
 #ifndef MMS_WS_UNROLL_F
 #define MMS_WS_UNROLL_F 1
 #endif
 #ifndef MMS_WS_UNROLL_S
-#define MMS_WS_UNROLL_S 3
+#define MMS_WS_UNROLL_S 1
 #endif
 constexpr int kWsUnrollF = MMS_WS_UNROLL_F, kWsUnrollS = MMS_WS_UNROLL_S;
 constexpr int kWsFields = 6;         // evap, surv_ad, exp(-mdr/24), egg, link0, gain_m_h
