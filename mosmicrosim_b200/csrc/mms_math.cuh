@@ -52,13 +52,23 @@ __device__ __forceinline__ double r_pow_pos(double x, double y)
 }
 
 // saturation_vapour_pressure_kpa(), R/sim_water.R:36-38 (Buck)
+#if !MMS_STRICT
+static __constant__ double kEvapC[5] = {0.61121, 18.678, 1.0 / 234.5, 257.14, 0.62198};
+// 3.046474, 0.666667 (R/sim_water.R:30), 1 / 1000 (:107), timestep and -timestep (R/sim_pop_dynamics.R:23)
+static __constant__ double kLitC[5] = {3.046474, 0.666667, 1.0 / 1000.0, 1.0 / 24.0, -(1.0 / 24.0)};
+#define MMS_LIT(i, literal) kLitC[i]
+#else
+#define MMS_LIT(i, literal) (literal)
+#endif
+
 __device__ __forceinline__ double svp_kpa(double t)
 {
 #if MMS_STRICT
     return 0.61121 * exp((18.678 - t / 234.5) * (t / (257.14 + t)));
 #else
     // the exponent is within +-20 for any temperature between -100 and +1000 C: no range guard
-    return 0.61121 * ::mms::fm::exp_core((18.678 - t * (1.0 / 234.5)) * ::mms::fm::div_fast(t, 257.14 + t));
+    // literals through constant memory: as immediates each costs two UMOVs per use in the rolled hour loop
+    return kEvapC[0] * ::mms::fm::exp_core((kEvapC[1] - t * kEvapC[2]) * ::mms::fm::div_fast(t, kEvapC[3] + t));
 #endif
 }
 
@@ -77,7 +87,7 @@ __device__ __forceinline__ double evaporation_rate(double t, double rh, double p
     // xs - x over one denominator (one division instead of two; no cancellation of two
     // rounded quotients): 0.62198 p_a (p_ws - p_w) / ((p_a - p_ws)(p_a - p_w))
     const double p_w = p_ws * (rh * (1.0 / 100.0));
-    const double num = (0.62198 * p_a) * (p_ws - p_w);
+    const double num = (kEvapC[4] * p_a) * (p_ws - p_w);
     const double den = (p_a - p_ws) * (p_a - p_w);
     return theta * ::mms::fm::div_fast(num, den);
 #endif
@@ -104,7 +114,7 @@ __device__ __forceinline__ double ensure_positive(double v)
 // cone_volume_to_surface(), R/sim_water.R:24-31; cylinder is an EXTENSION
 __device__ __forceinline__ double habitat_surface(const HabitatDev &hb, double volume)
 {
-    if (hb.shape == 0) return 3.046474 * r_pow_pos(volume, 0.666667);
+    if (hb.shape == 0) return MMS_LIT(0, 3.046474) * r_pow_pos(volume, MMS_LIT(1, 0.666667));
     return (volume != volume) ? volume : ((volume > 0.0) ? hb.cyl_area : 0.0);
 }
 
@@ -114,7 +124,11 @@ __device__ __forceinline__ double habitat_surface(const HabitatDev &hb, double v
 __device__ __forceinline__ double iterate_volume(const HabitatDev &hb, double volume, double surface,
                                                  double evap_rate, double gain)
 {
-    const double loss = MMS_DIVC(evap_rate * surface, 1000.0); // :107,:113
+#if MMS_STRICT
+    const double loss = (evap_rate * surface) / 1000.0;        // :107,:113
+#else
+    const double loss = (evap_rate * surface) * kLitC[2];
+#endif
     double x = volume - loss;                                  // :116
     x = x - hb.leak_per_hour * volume;                         // EXTENSION (leak = 0: x - 0 == x)
     x = ensure_positive(x);                                    // R/utils.R:159-161
@@ -135,11 +149,11 @@ struct PopHour {
 __device__ __forceinline__ PopHour pop_hour(int densmod_type, double mdr, double efd, double das0, double ds)
 {
     PopHour ph;
-    ph.surv_ad = r_pow_pos(ds, kTimestep);
+    ph.surv_ad = r_pow_pos(ds, MMS_LIT(3, kTimestep));
 #if MMS_STRICT
     const double e = exp(-(kTimestep * mdr));
 #else
-    const double e = ::mms::fm::exp_core(-(kTimestep * mdr));   // mdr is a clamped spline value: 0 <= mdr << 708 * 24
+    const double e = ::mms::fm::exp_core(kLitC[4] * mdr);   // mdr is a clamped spline value: 0 <= mdr << 708 * 24
 #endif
     ph.emf = 1.0 - e;
 #if MMS_STRICT
@@ -147,7 +161,7 @@ __device__ __forceinline__ PopHour pop_hour(int densmod_type, double mdr, double
 #else
     ph.one_m_emf = e;
 #endif
-    ph.egg = efd * kTimestep;
+    ph.egg = efd * MMS_LIT(3, kTimestep);
     if (densmod_type == 1) {
         // cox_ph, R/lifehistory_estimation_functions.R:551-553
         const double daily_mortality_zero_density = 1.0 - das0;
@@ -206,7 +220,7 @@ __device__ __forceinline__ void iterate_state(double &aquatic, double &adult, co
         double z = ::mms::fm::exp_sat(ph.link0 * e1);
         z = ::mms::fm::sel(::mms::fm::is_nan_bits(u), u, z);
         const double das_t = 1.0 - (1.0 - z);
-        surv_aq = ::mms::fm::pow_pos(das_t, kTimestep);
+        surv_aq = ::mms::fm::pow_pos(das_t, kLitC[3]);
     } else {
         // das_t = 1 / (1 + e), e = exp(a), a = -lg;  das_t ^ (1/24) = exp(-log(1 + e) / 24).
         // a is clamped to [-50, 40] for e: below, 1 + e == 1 exactly; above, log(1 + e) == a
@@ -222,7 +236,7 @@ __device__ __forceinline__ void iterate_state(double &aquatic, double &adult, co
         // -L / 24 is within [-29.6, 0] whenever the result is used: beyond a = 709.78 the select
         // below wins (exp(a) = Inf -> das_t = 0); a NaN a propagates through exp_core
         const bool overflow = ahi > 0x40862e42 || (ahi == 0x40862e42 && (unsigned)__double2loint(a) > 0xfefa39efu);
-        surv_aq = ::mms::fm::exp_core(-kTimestep * ::mms::fm::sel(overflow, 0.0, L));
+        surv_aq = ::mms::fm::exp_core(kLitC[4] * ::mms::fm::sel(overflow, 0.0, L));
         surv_aq = ::mms::fm::sel(overflow, 0.0, surv_aq);
         surv_aq = ::mms::fm::sel(::mms::fm::is_nan_bits(a), a, surv_aq);
     }
