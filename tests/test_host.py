@@ -31,12 +31,12 @@ def test_library_exports_every_declared_symbol():
     assert L.mms_abi_version() == 1
 
 
-def test_struct_layouts_match_the_header():
+def test_struct_layouts_match_the_header(tmp_path):
     # sizes the C compiler gives the structs in include/mmsgpu.h
     src = '#include <stdio.h>\n#include "mmsgpu.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu",' \
           "sizeof(mms_habitat),sizeof(mms_densmod),sizeof(mms_spline),sizeof(mms_surface)," \
           "sizeof(mms_lifehistory),sizeof(mms_chain_config),sizeof(mms_chain_outputs));return 0;}"
-    exe = "/tmp/mms_sizes"
+    exe = str(tmp_path / "mms_sizes")
     subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src.encode(),
                    check=True)
     sizes = [int(x) for x in subprocess.run([exe], capture_output=True, check=True).stdout.split()]
