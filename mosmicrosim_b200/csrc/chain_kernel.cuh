@@ -235,9 +235,11 @@ __device__ __forceinline__ void hour_microclimate(const HourTables &hr, const Da
     }
 }
 
+// dens_type: the density-dependence form; callers that know it at compile time pass the constant, so that the
+// other form's code (and the branch around it) disappears from their loop
 template <bool kFull, bool kWaterOnly>
 __device__ __forceinline__ HourF hour_forcing(const ChainParams &p, const SmemTables &tb, const DayCtx &dc,
-                                              double p_a, int h)
+                                              double p_a, int h, int dens_type)
 {
     HourF f;
     hour_microclimate<kFull>(p.hr, dc, h, f);
@@ -271,7 +273,7 @@ __device__ __forceinline__ HourF hour_forcing(const ChainParams &p, const SmemTa
         f.mdr = ensure_positive(c0.x + dx * (c0.y + dx * (c0.z + dx * c0.w)));
         f.efd = ensure_positive(c1.x + dx * (c1.y + dx * (c1.z + dx * c1.w)));
         f.das0 = ensure_positive(c2.x + dx * (c2.y + dx * (c2.z + dx * c2.w)));
-        f.ph = pop_hour(p.densmod_type, f.mdr, f.efd, f.das0, f.ds);
+        f.ph = pop_hour(dens_type, f.mdr, f.efd, f.das0, f.ds);
     }
     return f;
 }
@@ -458,11 +460,11 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
         // state-independent half of hour h + 1, the water recursion of hour h + 1 (it needs only the
         // evaporation rate of that hour) and the population update of hour h (it needs the surface of
         // hour h, which the previous iteration left behind).  Same arithmetic, same results.
-        HourF f = hour_forcing<kFull, kWaterOnly>(p, tb, dc, u.p_a, 0);
+        HourF f = hour_forcing<kFull, kWaterOnly>(p, tb, dc, u.p_a, 0, p.densmod_type);
         water_step(f.evap);
 #pragma unroll 1
         for (int h = 0; h < 23; ++h) {
-            const HourF fn = hour_forcing<kFull, kWaterOnly>(p, tb, dc, u.p_a, h + 1);
+            const HourF fn = hour_forcing<kFull, kWaterOnly>(p, tb, dc, u.p_a, h + 1, p.densmod_type);
             pop_and_record(f, h);
             water_step(fn.evap);
             f = fn;

@@ -33,7 +33,12 @@ cudaError_t launch_kernel(const ChainParams &p, int grid, int warps, cudaStream_
 template <int kNS, bool kFull, bool kHourly, int kMaxPairs>
 cudaError_t launch_kernel_ws(const ChainParams &p, int grid, int pairs, cudaStream_t stream)
 {
-    auto kern = chain_kernel_ws<kNS, kFull, kHourly, kMaxPairs>;
+    // two settings per thread (the form the launcher picks by itself) and summaries only: the density-dependence
+    // form is compiled in; the other instantiations read it from the parameters
+    auto kern = (kNS == 2 && !kFull && !kHourly)
+                    ? (p.densmod_type == 1 ? chain_kernel_ws<kNS, kFull, kHourly, kMaxPairs, (kNS == 2 && !kFull && !kHourly) ? 1 : -1>
+                                           : chain_kernel_ws<kNS, kFull, kHourly, kMaxPairs, (kNS == 2 && !kFull && !kHourly) ? 0 : -1>)
+                    : chain_kernel_ws<kNS, kFull, kHourly, kMaxPairs, -1>;
     const size_t smem = sizeof(double) * ((size_t)p.spline.n * 13 + p.ds.nx + p.ds.ny + (size_t)pairs * kWsRingDoubles) +
                         sizeof(int) * (size_t)pairs;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -71,7 +71,7 @@ struct PeriodCursor {
 };
 
 // ---- forcing warp ---------------------------------------------------------------------------
-template <bool kFull, bool kHourly, bool kWaterOnly, bool kRecord>
+template <bool kFull, bool kHourly, bool kWaterOnly, bool kRecord, int kDens>
 __device__ __forceinline__ void forcing_pass(const ChainParams &p, const SmemTables &tb, const UnitCtx &u,
                                              double *ring, int pair, int n_days, int &bad)
 {
@@ -128,7 +128,7 @@ __device__ __forceinline__ void forcing_pass(const ChainParams &p, const SmemTab
 #pragma unroll kWsUnrollF
             for (int k = 0; k < kWsK; ++k) {
                 const int h = h0 + k;
-                const HourF f = hour_forcing<kFull, kWaterOnly>(p, tb, dc, u.p_a, h);
+                const HourF f = hour_forcing<kFull, kWaterOnly>(p, tb, dc, u.p_a, h, kDens >= 0 ? kDens : p.densmod_type);
                 double *rec = slot + (size_t)k * (kWsFields * 32);
                 rec[0 * 32] = f.evap;
                 rec[1 * 32] = f.ph.surv_ad;
@@ -177,7 +177,7 @@ __device__ __forceinline__ void forcing_pass(const ChainParams &p, const SmemTab
 }
 
 // ---- state warp ------------------------------------------------------------------------------
-template <int kNS, bool kFull, bool kHourly, bool kWaterOnly, bool kRecord>
+template <int kNS, bool kFull, bool kHourly, bool kWaterOnly, bool kRecord, int kDens>
 __device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &u, UnitState<kNS> &st,
                                            const double *ring, int pair, int n_days)
 {
@@ -249,7 +249,7 @@ __device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &
                                                   hb.catchment_area * gain_m_h);             // R/sim_water.R:279-287
                     st.surface[s] = habitat_surface(hb, st.volume[s]);                       // :294
                     if (!kWaterOnly)
-                        iterate_state(st.aquatic[s], st.adult[s], ph, p.densmod_type, p.dd_effect,
+                        iterate_state(st.aquatic[s], st.adult[s], ph, kDens >= 0 ? kDens : p.densmod_type, p.dd_effect,
                                       p.surface_area_cm2, st.surface[s]);
                 }
                 if (kRecord) {
@@ -290,7 +290,9 @@ __device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &
 }
 
 // ---- the kernel: warp 2i = forcing role, warp 2i + 1 = state role of pair i ---------------------
-template <int kNS, bool kFull, bool kHourly, int kMaxPairs>
+// kDens: the density-dependence form when known at compile time (0 logit, 1 cox_ph; -1 = read p.densmod_type):
+// the other form's code and the (uniform, but opaque to the compiler) branches around it leave both loops
+template <int kNS, bool kFull, bool kHourly, int kMaxPairs, int kDens>
 __global__ void __launch_bounds__(kMaxPairs * 64, 1)
 chain_kernel_ws(const __grid_constant__ ChainParams p)
 {
@@ -340,10 +342,10 @@ chain_kernel_ws(const __grid_constant__ ChainParams p)
             u.p_a = air_pressure_kpa(__ldg(p.altitude + u.cell));
             int bad = 0;
             for (int y = 0; y < p.burnin_years_water; ++y)
-                forcing_pass<kFull, kHourly, true, false>(p, tb, u, ring, pair, kDaysPerYear, bad);
+                forcing_pass<kFull, kHourly, true, false, kDens>(p, tb, u, ring, pair, kDaysPerYear, bad);
             for (int y = 0; y < p.burnin_years_pop; ++y)
-                forcing_pass<kFull, kHourly, false, false>(p, tb, u, ring, pair, kDaysPerYear, bad);
-            forcing_pass<kFull, kHourly, false, true>(p, tb, u, ring, pair, p.D, bad);
+                forcing_pass<kFull, kHourly, false, false, kDens>(p, tb, u, ring, pair, kDaysPerYear, bad);
+            forcing_pass<kFull, kHourly, false, true, kDens>(p, tb, u, ring, pair, p.D, bad);
             if (bad && u.live) atomicOr(p.error_flag, 1);
         } else {
             u.p_a = 0.0;
@@ -356,19 +358,19 @@ chain_kernel_ws(const __grid_constant__ ChainParams p)
                 st.surface[s] = habitat_surface(p.hab[u.set0 + s], st.volume[s]);
             }
             for (int y = 0; y < p.burnin_years_water; ++y)
-                state_pass<kNS, kFull, kHourly, true, false>(p, u, st, ring, pair, kDaysPerYear);
+                state_pass<kNS, kFull, kHourly, true, false, kDens>(p, u, st, ring, pair, kDaysPerYear);
             double vol0[kNS];
 #pragma unroll
             for (int s = 0; s < kNS; ++s) vol0[s] = st.volume[s];
             for (int y = 0; y < p.burnin_years_pop; ++y) {
-                state_pass<kNS, kFull, kHourly, false, false>(p, u, st, ring, pair, kDaysPerYear);
+                state_pass<kNS, kFull, kHourly, false, false, kDens>(p, u, st, ring, pair, kDaysPerYear);
 #pragma unroll
                 for (int s = 0; s < kNS; ++s) {
                     st.volume[s] = vol0[s];
                     st.surface[s] = habitat_surface(p.hab[u.set0 + s], vol0[s]);
                 }
             }
-            state_pass<kNS, kFull, kHourly, false, true>(p, u, st, ring, pair, p.D);
+            state_pass<kNS, kFull, kHourly, false, true, kDens>(p, u, st, ring, pair, p.D);
         }
     }
 }

@@ -221,3 +221,14 @@ def test_chain_ten_years_monthly(gpu):
         mean_vars=list(backend.VAR_NAMES[:8]), want_wet_hours=True))
     assert out["mean_state"].shape[2] == 120
     compare(case, out, ref, REL_TOL_FAST, what=("mean",))
+
+
+@pytest.mark.parametrize("species", ["An. gambiae", "An. stephensi"])
+def test_chain_pair_form_with_compiled_in_density_dependence(gpu, species):
+    """Two habitats, summaries of the six reference variables only: the pair kernel instantiations that have the
+    density-dependence form (logit / cox_ph) compiled in."""
+    case = Case(n_cells=200, species=species, habitats=[syn.habitat_cone(), syn.habitat_cylinder(leak_per_hour=0.002)])
+    ref = case.oracle(want_hourly=False)
+    out = backend.run_chain(case.monthly, case.altitude, **case.gpu_kwargs(
+        mean_vars=list(backend.VAR_NAMES[:6]), want_wet_hours=True))
+    compare(case, out, ref, REL_TOL_FAST, what=("mean",))
