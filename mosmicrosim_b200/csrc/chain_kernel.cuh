@@ -300,12 +300,13 @@ __device__ __forceinline__ int out_slot(uint32_t mask, uint32_t class_mask, int 
 // ---- one pass over n_days days ----------------------------------------------------
 // kWaterOnly : water burn-in year (R/sim_water.R:228-233): no life history, no population
 // kRecord    : the final pass over the full series: period summaries / hourly series
-template <int kNS, bool kFull, bool kHourly, bool kWaterOnly, bool kRecord>
+template <int kNS, bool kFull, bool kHourly, bool kWaterOnly, bool kRecord, int kDens>
 __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables &tb, const UnitCtx &u,
                                          UnitState<kNS> &st, int n_days, int &bad)
 {
     constexpr int kNF = kFull ? 9 : 4;
     constexpr uint32_t kState = MMS_STATE_VAR_MASK;
+    const int dens_type = kDens >= 0 ? kDens : p.densmod_type;
     const int64_t cs = u.cs, cell = u.cell;
     const int set0 = u.set0;
 
@@ -401,7 +402,7 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
             if (!kWaterOnly) {
 #pragma unroll
                 for (int s = 0; s < kNS; ++s)   // larval_habitat_area = water_surface_area, R/sim_pop_dynamics.R:123
-                    iterate_state(st.aquatic[s], st.adult[s], f.ph, p.densmod_type, p.dd_effect,
+                    iterate_state(st.aquatic[s], st.adult[s], f.ph, dens_type, p.dd_effect,
                                   p.surface_area_cm2, st.surface[s]);
             }
             if (kRecord) {
@@ -460,11 +461,11 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
         // state-independent half of hour h + 1, the water recursion of hour h + 1 (it needs only the
         // evaporation rate of that hour) and the population update of hour h (it needs the surface of
         // hour h, which the previous iteration left behind).  Same arithmetic, same results.
-        HourF f = hour_forcing<kFull, kWaterOnly>(p, tb, dc, u.p_a, 0, p.densmod_type);
+        HourF f = hour_forcing<kFull, kWaterOnly>(p, tb, dc, u.p_a, 0, dens_type);
         water_step(f.evap);
 #pragma unroll 1
         for (int h = 0; h < 23; ++h) {
-            const HourF fn = hour_forcing<kFull, kWaterOnly>(p, tb, dc, u.p_a, h + 1, p.densmod_type);
+            const HourF fn = hour_forcing<kFull, kWaterOnly>(p, tb, dc, u.p_a, h + 1, dens_type);
             pop_and_record(f, h);
             water_step(fn.evap);
             f = fn;
@@ -484,7 +485,7 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
 }
 
 // ---- one work unit: 32 cells x kNS settings, all passes ---------------------------
-template <int kNS, bool kFull, bool kHourly>
+template <int kNS, bool kFull, bool kHourly, int kDens>
 __device__ __forceinline__ void simulate_unit(const ChainParams &p, const SmemTables &tb, int64_t cell, int set0,
                                               bool write_forcing)
 {
@@ -506,7 +507,7 @@ __device__ __forceinline__ void simulate_unit(const ChainParams &p, const SmemTa
     }
     // water burn-in years: first 8760 steps, water only (R/sim_water.R:228-233)
     for (int y = 0; y < p.burnin_years_water; ++y)
-        run_pass<kNS, kFull, kHourly, true, false>(p, tb, u, st, kDaysPerYear, bad);
+        run_pass<kNS, kFull, kHourly, true, false, kDens>(p, tb, u, st, kDaysPerYear, bad);
     // every later pass re-runs the water model from this volume: the reference computes the
     // water series once and the population burn-in re-indexes its first year
     double vol0[kNS];
@@ -514,7 +515,7 @@ __device__ __forceinline__ void simulate_unit(const ChainParams &p, const SmemTa
     for (int s = 0; s < kNS; ++s) vol0[s] = st.volume[s];
     // population burn-in years: first 8760 steps (R/sim_pop_dynamics.R:221-226)
     for (int y = 0; y < p.burnin_years_pop; ++y) {
-        run_pass<kNS, kFull, kHourly, false, false>(p, tb, u, st, kDaysPerYear, bad);
+        run_pass<kNS, kFull, kHourly, false, false, kDens>(p, tb, u, st, kDaysPerYear, bad);
 #pragma unroll
         for (int s = 0; s < kNS; ++s) {
             st.volume[s] = vol0[s];
@@ -522,7 +523,7 @@ __device__ __forceinline__ void simulate_unit(const ChainParams &p, const SmemTa
         }
     }
     // the full series, recorded
-    run_pass<kNS, kFull, kHourly, false, true>(p, tb, u, st, p.D, bad);
+    run_pass<kNS, kFull, kHourly, false, true, kDens>(p, tb, u, st, p.D, bad);
 
     if (bad && u.live) atomicOr(p.error_flag, 1);
 }
@@ -533,7 +534,8 @@ __device__ __forceinline__ void simulate_unit(const ChainParams &p, const SmemTa
 //           true  = all MMS_NVARS (adds water body and microclimate variables, cloud cover)
 // kHourly : write full hourly series
 // kMaxWarps: largest CTA this instantiation may be launched with (register budget = 64K / threads)
-template <int kNS, bool kFull, bool kHourly, int kMaxWarps>
+// kDens: density-dependence form when the launcher knows it at compile time (0 logit, 1 cox_ph), else -1
+template <int kNS, bool kFull, bool kHourly, int kMaxWarps, int kDens>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
 chain_kernel(const __grid_constant__ ChainParams p)
 {
@@ -557,7 +559,7 @@ chain_kernel(const __grid_constant__ ChainParams p)
         unit = __shfl_sync(0xffffffffu, unit, 0);
         if (unit >= p.n_units) break;
         const int cb = unit % p.n_cell_blocks, g = unit / p.n_cell_blocks;
-        simulate_unit<kNS, kFull, kHourly>(p, tb, (int64_t)cb * 32 + lane, g * kNS, g == 0);
+        simulate_unit<kNS, kFull, kHourly, kDens>(p, tb, (int64_t)cb * 32 + lane, g * kNS, g == 0);
     }
 }
 

@@ -21,7 +21,11 @@ namespace {
 template <int kNS, bool kFull, bool kHourly, int kMaxWarps>
 cudaError_t launch_kernel(const ChainParams &p, int grid, int warps, cudaStream_t stream)
 {
-    auto kern = chain_kernel<kNS, kFull, kHourly, kMaxWarps>;
+    // summaries only (the production shape of the call): the density-dependence form is compiled in
+    constexpr bool kSpecialise = !kFull && !kHourly;
+    auto kern = kSpecialise ? (p.densmod_type == 1 ? chain_kernel<kNS, kFull, kHourly, kMaxWarps, kSpecialise ? 1 : -1>
+                                                   : chain_kernel<kNS, kFull, kHourly, kMaxWarps, kSpecialise ? 0 : -1>)
+                            : chain_kernel<kNS, kFull, kHourly, kMaxWarps, -1>;
     const size_t smem = sizeof(double) * ((size_t)p.spline.n * 13 + p.ds.nx + p.ds.ny);
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
