@@ -306,7 +306,10 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
 {
     constexpr int kNF = kFull ? 9 : 4;
     constexpr uint32_t kState = MMS_STATE_VAR_MASK;
-    const int dens_type = kDens >= 0 ? kDens : p.densmod_type;
+    // kDens packs what the launcher knows at compile time: bit 0 the density-dependence form, bits 1-2 the
+    // water-body shape when all settings share one (1 cone, 2 cylinder; 0 = per setting, from the parameters)
+    const int dens_type = kDens >= 0 ? (kDens & 1) : p.densmod_type;
+    constexpr int kShapeAll = kDens >= 0 ? ((kDens >> 1) & 3) - 1 : -1;
     const int64_t cs = u.cs, cell = u.cell;
     const int set0 = u.set0;
 
@@ -394,7 +397,7 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
             for (int s = 0; s < kNS; ++s) {
                 const HabitatDev &hb = p.hab[set0 + s];
                 st.volume[s] = iterate_volume(hb, st.volume[s], st.surface[s], evap, gain[s]);     // R/sim_water.R:279-287
-                st.surface[s] = habitat_surface(hb, st.volume[s]);                                 // :294
+                st.surface[s] = habitat_surface(hb, st.volume[s], kShapeAll >= 0 ? kShapeAll : hb.shape);   // :294
             }
         };
         // the population update of hour h (volume, surface are already at hour h) + the outputs of hour h
@@ -534,7 +537,7 @@ __device__ __forceinline__ void simulate_unit(const ChainParams &p, const SmemTa
 //           true  = all MMS_NVARS (adds water body and microclimate variables, cloud cover)
 // kHourly : write full hourly series
 // kMaxWarps: largest CTA this instantiation may be launched with (register budget = 64K / threads)
-// kDens: density-dependence form when the launcher knows it at compile time (0 logit, 1 cox_ph), else -1
+// kDens: what the launcher knows at compile time (bit 0: 0 logit / 1 cox_ph; bits 1-2: common shape + 1), else -1
 template <int kNS, bool kFull, bool kHourly, int kMaxWarps, int kDens>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
 chain_kernel(const __grid_constant__ ChainParams p)

@@ -21,11 +21,25 @@ namespace {
 template <int kNS, bool kFull, bool kHourly, int kMaxWarps>
 cudaError_t launch_kernel(const ChainParams &p, int grid, int warps, cudaStream_t stream)
 {
-    // summaries only (the production shape of the call): the density-dependence form is compiled in
+    // summaries only (the production shape of the call): the density-dependence form is compiled in, and with
+    // one setting per thread also the water-body shape when all settings share it (spec = dens | (shape + 1) << 1)
     constexpr bool kSpecialise = !kFull && !kHourly;
-    auto kern = kSpecialise ? (p.densmod_type == 1 ? chain_kernel<kNS, kFull, kHourly, kMaxWarps, kSpecialise ? 1 : -1>
-                                                   : chain_kernel<kNS, kFull, kHourly, kMaxWarps, kSpecialise ? 0 : -1>)
-                            : chain_kernel<kNS, kFull, kHourly, kMaxWarps, -1>;
+    constexpr bool kShapeToo = kSpecialise && kNS == 1;
+    int shape_all = p.hab[0].shape;
+    for (int s = 1; s < p.S; ++s)
+        if (p.hab[s].shape != shape_all) shape_all = -1;
+    const int dens = p.densmod_type == 1 ? 1 : 0;
+    auto kern = chain_kernel<kNS, kFull, kHourly, kMaxWarps, -1>;
+    if (kSpecialise) {
+        kern = dens ? chain_kernel<kNS, kFull, kHourly, kMaxWarps, kSpecialise ? 1 : -1>
+                    : chain_kernel<kNS, kFull, kHourly, kMaxWarps, kSpecialise ? 0 : -1>;
+        if (kShapeToo && shape_all == 0)
+            kern = dens ? chain_kernel<kNS, kFull, kHourly, kMaxWarps, kShapeToo ? 3 : -1>
+                        : chain_kernel<kNS, kFull, kHourly, kMaxWarps, kShapeToo ? 2 : -1>;
+        if (kShapeToo && shape_all == 1)
+            kern = dens ? chain_kernel<kNS, kFull, kHourly, kMaxWarps, kShapeToo ? 5 : -1>
+                        : chain_kernel<kNS, kFull, kHourly, kMaxWarps, kShapeToo ? 4 : -1>;
+    }
     const size_t smem = sizeof(double) * ((size_t)p.spline.n * 13 + p.ds.nx + p.ds.ny);
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;

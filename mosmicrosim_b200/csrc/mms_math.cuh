@@ -112,10 +112,14 @@ __device__ __forceinline__ double ensure_positive(double v)
 }
 
 // cone_volume_to_surface(), R/sim_water.R:24-31; cylinder is an EXTENSION
+__device__ __forceinline__ double habitat_surface(const HabitatDev &hb, double volume, int shape)
+{
+    if (shape == 0) return MMS_LIT(0, 3.046474) * r_pow_pos(volume, MMS_LIT(1, 0.666667));
+    return (volume != volume) ? volume : ((volume > 0.0) ? hb.cyl_area : 0.0);
+}
 __device__ __forceinline__ double habitat_surface(const HabitatDev &hb, double volume)
 {
-    if (hb.shape == 0) return MMS_LIT(0, 3.046474) * r_pow_pos(volume, MMS_LIT(1, 0.666667));
-    return (volume != volume) ? volume : ((volume > 0.0) ? hb.cyl_area : 0.0);
+    return habitat_surface(hb, volume, hb.shape);
 }
 
 // iterate_cone_volume(), R/sim_water.R:94-132; `surface` is

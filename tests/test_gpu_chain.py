@@ -232,3 +232,17 @@ def test_chain_pair_form_with_compiled_in_density_dependence(gpu, species):
     out = backend.run_chain(case.monthly, case.altitude, **case.gpu_kwargs(
         mean_vars=list(backend.VAR_NAMES[:6]), want_wet_hours=True))
     compare(case, out, ref, REL_TOL_FAST, what=("mean",))
+
+
+@pytest.mark.parametrize("species", ["An. gambiae", "An. stephensi"])
+@pytest.mark.parametrize("hab", [syn.habitat_cone(), syn.habitat_cylinder(leak_per_hour=0.001)])
+def test_chain_one_setting_specialised_instantiations(gpu, species, hab):
+    """One habitat per cell, summaries only: the monolithic instantiations with the density-dependence form and
+    the water-body shape compiled in (all four combinations), and three same-shape settings (shape compiled in,
+    one setting per thread)."""
+    for habitats in ([hab], [hab, dict(hab, inflow_multiplier=2.0), dict(hab, max_depth=0.3)]):
+        case = Case(n_cells=100, species=species, habitats=habitats)
+        ref = case.oracle(want_hourly=False)
+        out = backend.run_chain(case.monthly, case.altitude, **case.gpu_kwargs(
+            mean_vars=list(backend.VAR_NAMES[:6]), want_wet_hours=True))
+        compare(case, out, ref, REL_TOL_FAST, what=("mean",))
