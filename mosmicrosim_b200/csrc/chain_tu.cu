@@ -228,9 +228,12 @@ cudaError_t device_sm_count(int &n_sm)
     return err;
 }
 
-#define MMS_STAGE_DISPATCH(kernel, V, pl)                                                                 \
-    ((pl).warps <= kStageFewWarps ? launch_stage_kernel(kernel<V, kStageFewWarps, 1>, p, pl, stream)      \
-                                  : launch_stage_kernel(kernel<V, kStageMaxWarps, 1>, p, pl, stream))
+// spec: the water-body shape (water twin) / the density-dependence form (population twin), compiled in
+#define MMS_STAGE_DISPATCH1(kernel, V, SPEC, pl)                                                          \
+    ((pl).warps <= kStageFewWarps ? launch_stage_kernel(kernel<V, kStageFewWarps, SPEC>, p, pl, stream)   \
+                                  : launch_stage_kernel(kernel<V, kStageMaxWarps, SPEC>, p, pl, stream))
+#define MMS_STAGE_DISPATCH(kernel, V, spec, pl)                                                           \
+    ((spec) == 1 ? MMS_STAGE_DISPATCH1(kernel, V, 1, pl) : MMS_STAGE_DISPATCH1(kernel, V, 0, pl))
 
 }  // namespace
 
@@ -244,9 +247,9 @@ cudaError_t MMS_LAUNCH(launch_water_stage)(const WaterStageParams &p, cudaStream
                                        (uintptr_t)p.windspeed | (uintptr_t)p.water_surface_area |
                                        (uintptr_t)p.water_volume | (uintptr_t)p.wet);
     const StagePlan pl = stage_plan(p.C, kWaterInputs, n_sm);
-    if (vec == 4) return MMS_STAGE_DISPATCH(water_stage_kernel, 4, pl);
-    if (vec == 2) return MMS_STAGE_DISPATCH(water_stage_kernel, 2, pl);
-    return MMS_STAGE_DISPATCH(water_stage_kernel, 1, pl);
+    if (vec == 4) return MMS_STAGE_DISPATCH(water_stage_kernel, 4, p.hab.shape, pl);
+    if (vec == 2) return MMS_STAGE_DISPATCH(water_stage_kernel, 2, p.hab.shape, pl);
+    return MMS_STAGE_DISPATCH(water_stage_kernel, 1, p.hab.shape, pl);
 }
 
 cudaError_t MMS_LAUNCH(launch_pop_stage)(const PopStageParams &p, cudaStream_t stream)
@@ -259,9 +262,9 @@ cudaError_t MMS_LAUNCH(launch_pop_stage)(const PopStageParams &p, cudaStream_t s
                                        (uintptr_t)p.das_zerodensity | (uintptr_t)p.ds | (uintptr_t)p.aquatic |
                                        (uintptr_t)p.adult);
     const StagePlan pl = stage_plan(p.C, kPopInputs, n_sm);
-    if (vec == 4) return MMS_STAGE_DISPATCH(pop_stage_kernel, 4, pl);
-    if (vec == 2) return MMS_STAGE_DISPATCH(pop_stage_kernel, 2, pl);
-    return MMS_STAGE_DISPATCH(pop_stage_kernel, 1, pl);
+    if (vec == 4) return MMS_STAGE_DISPATCH(pop_stage_kernel, 4, p.densmod_type, pl);
+    if (vec == 2) return MMS_STAGE_DISPATCH(pop_stage_kernel, 2, p.densmod_type, pl);
+    return MMS_STAGE_DISPATCH(pop_stage_kernel, 1, p.densmod_type, pl);
 }
 
 }  // namespace mms

@@ -109,14 +109,17 @@ __device__ __forceinline__ void stage_put(double *dst, const double (&v)[kStageT
 
 // ---- simulate_ephemeral_habitat_vectorised() --------------------------------
 // kVec: 4 = H % 4 == 0 and all matrices 32-byte aligned; 2 = H even, 16-byte aligned; 1 = anything.
-// kPx: pixels per thread.  A unit is 32 * kPx adjacent pixels; lane l integrates pixels l, l + 32, ...
-// of it as kPx independent recursions.  Only kPx = 1 is instantiated: two pixels per thread measured
-// slower (52.2 vs 31.6 ms on the 100k-pixel population twin) -- the second chain costs more in registers
-// and shared memory (half the warps) than its interleaving gains.
-template <int kVec, int kMaxWarps, int kPx>
+// kShape: the water-body shape (0 cone, 1 cylinder), a template parameter so that the other shape's code and
+// the branch around it leave the recursion.
+// kPx: pixels per thread (a unit is 32 * kPx adjacent pixels; lane l integrates pixels l, l + 32, ... of it as
+// kPx independent recursions).  Fixed at 1: two pixels per thread measured slower (52.2 vs 31.6 ms on the
+// 100k-pixel population twin) -- the second chain costs more in registers and shared memory (half the warps)
+// than its interleaving gains.
+template <int kVec, int kMaxWarps, int kShape>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
 water_stage_kernel(const __grid_constant__ WaterStageParams p)
 {
+    constexpr int kPx = 1;
     extern __shared__ __align__(16) unsigned char stage_smem[];
     constexpr int kBuf = kPx * kWaterInputs * kStageTile;                  // doubles per buffer of one warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
@@ -139,7 +142,7 @@ water_stage_kernel(const __grid_constant__ WaterStageParams p)
             cell[q] = live[q] ? cell0[q] + lane : 0;
             p_a[q] = air_pressure_kpa(p.altitude[cell[q]]);
             volume[q] = p.hab.initial_volume;                              // R/sim_water.R:277
-            surface[q] = habitat_surface(p.hab, volume[q]);
+            surface[q] = habitat_surface(p.hab, volume[q], kShape);
         }
 
         auto issue = [&](int buf, int64_t t0, int nt) {
@@ -191,7 +194,7 @@ water_stage_kernel(const __grid_constant__ WaterStageParams p)
                     for (int q = 0; q < kPx; ++q) {
                         if (t < nt) {
                             volume[q] = iterate_volume(p.hab, volume[q], surface[q], rate[q][t], gain[q][t]);   // :279-287
-                            surface[q] = habitat_surface(p.hab, volume[q]);                                     // :294
+                            surface[q] = habitat_surface(p.hab, volume[q], kShape);                                     // :294
                         }
                         o_area[q][t] = surface[q];
                         o_vol[q][t] = volume[q];
@@ -222,10 +225,12 @@ water_stage_kernel(const __grid_constant__ WaterStageParams p)
 }
 
 // ---- simulate_population_vectorised() ---------------------------------------
-template <int kVec, int kMaxWarps, int kPx>
+// kDens: the density-dependence form (0 logit, 1 cox_ph), compiled in like kShape above
+template <int kVec, int kMaxWarps, int kDens>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
 pop_stage_kernel(const __grid_constant__ PopStageParams p)
 {
+    constexpr int kPx = 1;
     extern __shared__ __align__(16) unsigned char stage_smem[];
     constexpr int kBuf = kPx * kPopInputs * kStageTile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
@@ -292,8 +297,8 @@ pop_stage_kernel(const __grid_constant__ PopStageParams p)
                             const double2 d0 = *reinterpret_cast<const double2 *>(b + 3 * kStageTile + at);
                             const double2 d = *reinterpret_cast<const double2 *>(b + 4 * kStageTile + at);
                             area[q][j] = a.x; area[q][j + 1] = a.y;
-                            ph[q][j] = pop_hour(p.densmod_type, m.x, e.x, d0.x, d.x);          // state independent
-                            ph[q][j + 1] = pop_hour(p.densmod_type, m.y, e.y, d0.y, d.y);
+                            ph[q][j] = pop_hour(kDens, m.x, e.x, d0.x, d.x);          // state independent
+                            ph[q][j + 1] = pop_hour(kDens, m.y, e.y, d0.y, d.y);
                         }
                     }
 #pragma unroll
@@ -301,7 +306,7 @@ pop_stage_kernel(const __grid_constant__ PopStageParams p)
 #pragma unroll
                         for (int q = 0; q < kPx; ++q) {
                             if (h + j < nt)
-                                iterate_state(aquatic[q], adult[q], ph[q][j], p.densmod_type, p.dd_effect,
+                                iterate_state(aquatic[q], adult[q], ph[q][j], kDens, p.dd_effect,
                                               p.surface_area_cm2, area[q][j]);                        // :259-268
                             o_aq[q][h + j] = aquatic[q];
                             o_ad[q][h + j] = adult[q];
