@@ -68,3 +68,40 @@ class Case:
 
 # oracle variable id (12 vars) for each product variable name
 ORACLE_VAR = {n: i for i, n in enumerate(oracle.VAR_NAMES)}
+
+
+# ---- the plain-C caller of the ABI (tests/c_driver/abi_driver.c) ------------------------------------------
+
+def build_c_driver(tmp_path) -> str:
+    """gcc -std=c99 -Wall -Wextra -Werror on the driver, linked against the in-tree libmmsgpu.so."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "abi_driver")
+    libdir = os.path.join(root, "mosmicrosim_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "c_driver", "abi_driver.c"), "-o", exe, "-L", libdir, "-lmmsgpu",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    return exe
+
+
+def write_c_driver_inputs(case, names, d, ns, nf):
+    """The driver's input directory: dims.txt and raw little-endian arrays / structs."""
+    from mosmicrosim_b200 import backend
+    t = case.tables
+    (d / "dims.txt").write_text(f"{case.C} {len(case.mid_day)} {case.D} {len(case.habitats)} {case.P} "
+                                f"{len(t['mdr']['x'])} {len(t['ds']['x'])} {len(t['ds']['y'])} "
+                                f"{backend.var_mask(names)} {ns} {nf}\n")
+
+    def f64(name, a):
+        np.ascontiguousarray(a, dtype=np.float64).tofile(str(d / name))
+
+    f64("mid_day.f64", case.mid_day); f64("day_predict.f64", case.day_predict)
+    np.ascontiguousarray(case.period_of_day, dtype=np.int32).tofile(str(d / "period_of_day.i32"))
+    (d / "habitats.bin").write_bytes(b"".join(bytes(backend.make_habitat(**h)) for h in case.habitats))
+    (d / "densmod.bin").write_bytes(bytes(backend.make_densmod(**case.densmod)))
+    for stem in ("mdr", "efd", "das"):
+        for part in "xybcd":
+            f64(f"{stem}_{part}.f64", t[stem][part])
+    f64("ds_x.f64", t["ds"]["x"]); f64("ds_y.f64", t["ds"]["y"]); f64("ds_z.f64", t["ds"]["z"])
+    f64("monthly.f64", case.monthly); f64("altitude.f64", case.altitude)

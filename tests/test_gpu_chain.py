@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from helpers import ABS_FLOOR, ORACLE_VAR, REL_TOL_FAST, REL_TOL_STRICT, Case, rel_err
+from helpers import ABS_FLOOR, ORACLE_VAR, REL_TOL_FAST, REL_TOL_STRICT, Case, build_c_driver, rel_err, write_c_driver_inputs
 from mosmicrosim_b200 import backend, synthetic as syn
 
 pytestmark = pytest.mark.gpu
@@ -246,3 +246,24 @@ def test_chain_one_setting_specialised_instantiations(gpu, species, hab):
         out = backend.run_chain(case.monthly, case.altitude, **case.gpu_kwargs(
             mean_vars=list(backend.VAR_NAMES[:6]), want_wet_hours=True))
         compare(case, out, ref, REL_TOL_FAST, what=("mean",))
+
+
+def test_plain_c_caller(gpu, tmp_path):
+    """tests/c_driver/abi_driver.c -- a C99 program that fills the structs of include/mmsgpu.h by hand and calls
+    mms_run_chain like the .Call shim does -- gives bit-identical results to the ctypes route (and an invalid
+    call comes back as a status code with a message)."""
+    import subprocess
+    exe = build_c_driver(tmp_path)
+    case = Case(n_cells=150, habitats=[syn.habitat_cone(), syn.habitat_cylinder(leak_per_hour=0.002)])
+    names = list(backend.VAR_NAMES[:6])
+    ref = backend.run_chain(case.monthly, case.altitude, **case.gpu_kwargs(mean_vars=names, want_wet_hours=True))
+    d = tmp_path
+    write_c_driver_inputs(case, names, d, ref["mean_state"].shape[1], ref["mean_forcing"].shape[0])
+    r = subprocess.run([exe, str(d)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), (r.returncode, r.stdout, r.stderr)
+    got_state = np.fromfile(str(d / "mean_state.f64")).reshape(ref["mean_state"].shape)
+    got_forc = np.fromfile(str(d / "mean_forcing.f64")).reshape(ref["mean_forcing"].shape)
+    got_wet = np.fromfile(str(d / "wet_hours.i32"), dtype=np.int32).reshape(ref["wet_hours"].shape)
+    assert np.array_equal(got_state, ref["mean_state"], equal_nan=True)
+    assert np.array_equal(got_forc, ref["mean_forcing"], equal_nan=True)
+    assert np.array_equal(got_wet, ref["wet_hours"])

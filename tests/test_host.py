@@ -218,3 +218,17 @@ def test_two_rank_sharding_equals_single_run(tmp_path):
                        capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "SHARDS_OK" in r.stdout
+
+
+def test_plain_c_caller_builds_and_fails_loudly_without_a_device(tmp_path):
+    """tests/c_driver/abi_driver.c compiles as C99 with -Wall -Wextra -Werror against include/mmsgpu.h and links
+    against libmmsgpu.so; on a box without a GPU its argument check still answers (status + message) and the
+    real call comes back with MMS_ERR_NO_DEVICE -- no CPU fallback."""
+    from helpers import Case, build_c_driver, write_c_driver_inputs
+    exe = build_c_driver(tmp_path)
+    if backend.lib().mms_device_count() > 0:
+        pytest.skip("a GPU is visible: the run itself is tests/test_gpu_chain.py::test_plain_c_caller")
+    case = Case(n_cells=4)
+    write_c_driver_inputs(case, list(backend.VAR_NAMES[:6]), tmp_path, 2, 4)
+    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 5 and "no CUDA device" in r.stderr, (r.returncode, r.stdout, r.stderr)
