@@ -48,15 +48,35 @@ cudaError_t launch_kernel(const ChainParams &p, int grid, int warps, cudaStream_
 }
 
 #if !MMS_STRICT
+// the specialised instantiations of the pair kernel: two settings per thread, summaries only.  spec = density-
+// dependence form | (shape of setting 0 + 1) << 1 | (shape of setting 1 + 1) << 3 (chain_ws.cuh); the shapes are
+// compiled in only in the kChainMaxPairs instantiation and when every unit has the same pair of shapes.
+template <int kNS, bool kFull, bool kHourly, int kMaxPairs>
+auto pick_kernel_ws(const ChainParams &p) -> void (*)(ChainParams)
+{
+    constexpr bool kSpecialise = kNS == 2 && !kFull && !kHourly;
+    constexpr bool kShapes = kSpecialise && kMaxPairs == kChainMaxPairs;
+    if (!kSpecialise) return chain_kernel_ws<kNS, kFull, kHourly, kMaxPairs, -1>;
+    const int dens = p.densmod_type == 1 ? 1 : 0;
+    bool periodic = kShapes;
+    for (int s = kNS; s < p.S && periodic; ++s) periodic = p.hab[s].shape == p.hab[s % kNS].shape;
+    if (periodic) {
+        switch (dens | (p.hab[0].shape + 1) << 1 | (p.hab[kNS > 1 ? 1 : 0].shape + 1) << 3) {
+#define MMS_WS_CASE(v) case v: return chain_kernel_ws<kNS, kFull, kHourly, kMaxPairs, kShapes ? v : -1>;
+            MMS_WS_CASE(10) MMS_WS_CASE(11) MMS_WS_CASE(12) MMS_WS_CASE(13)      // (cone | cylinder, cone)
+            MMS_WS_CASE(18) MMS_WS_CASE(19) MMS_WS_CASE(20) MMS_WS_CASE(21)      // (cone | cylinder, cylinder)
+#undef MMS_WS_CASE
+        default: break;
+        }
+    }
+    return dens ? chain_kernel_ws<kNS, kFull, kHourly, kMaxPairs, kSpecialise ? 1 : -1>
+                : chain_kernel_ws<kNS, kFull, kHourly, kMaxPairs, kSpecialise ? 0 : -1>;
+}
+
 template <int kNS, bool kFull, bool kHourly, int kMaxPairs>
 cudaError_t launch_kernel_ws(const ChainParams &p, int grid, int pairs, cudaStream_t stream)
 {
-    // two settings per thread (the form the launcher picks by itself) and summaries only: the density-dependence
-    // form is compiled in; the other instantiations read it from the parameters
-    auto kern = (kNS == 2 && !kFull && !kHourly)
-                    ? (p.densmod_type == 1 ? chain_kernel_ws<kNS, kFull, kHourly, kMaxPairs, (kNS == 2 && !kFull && !kHourly) ? 1 : -1>
-                                           : chain_kernel_ws<kNS, kFull, kHourly, kMaxPairs, (kNS == 2 && !kFull && !kHourly) ? 0 : -1>)
-                    : chain_kernel_ws<kNS, kFull, kHourly, kMaxPairs, -1>;
+    auto kern = pick_kernel_ws<kNS, kFull, kHourly, kMaxPairs>(p);
     const size_t smem = sizeof(double) * ((size_t)p.spline.n * 13 + p.ds.nx + p.ds.ny + (size_t)pairs * kWsRingDoubles) +
                         sizeof(int) * (size_t)pairs;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -128,7 +128,7 @@ __device__ __forceinline__ void forcing_pass(const ChainParams &p, const SmemTab
 #pragma unroll kWsUnrollF
             for (int k = 0; k < kWsK; ++k) {
                 const int h = h0 + k;
-                const HourF f = hour_forcing<kFull, kWaterOnly>(p, tb, dc, u.p_a, h, kDens >= 0 ? kDens : p.densmod_type);
+                const HourF f = hour_forcing<kFull, kWaterOnly>(p, tb, dc, u.p_a, h, kDens >= 0 ? (kDens & 1) : p.densmod_type);
                 double *rec = slot + (size_t)k * (kWsFields * 32);
                 rec[0 * 32] = f.evap;
                 rec[1 * 32] = f.ph.surv_ad;
@@ -247,9 +247,11 @@ __device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &
                     const HabitatDev &hb = p.hab[u.set0 + s];
                     st.volume[s] = iterate_volume(hb, st.volume[s], st.surface[s], evap,
                                                   hb.catchment_area * gain_m_h);             // R/sim_water.R:279-287
-                    st.surface[s] = habitat_surface(hb, st.volume[s]);                       // :294
+                    // shape of setting s: compiled in when the launcher knew it (two bits per setting, 0 = run time)
+                    const int shape_bits = kDens >= 0 ? (kDens >> (1 + 2 * s)) & 3 : 0;
+                    st.surface[s] = habitat_surface(hb, st.volume[s], shape_bits ? shape_bits - 1 : hb.shape);   // :294
                     if (!kWaterOnly)
-                        iterate_state(st.aquatic[s], st.adult[s], ph, kDens >= 0 ? kDens : p.densmod_type, p.dd_effect,
+                        iterate_state(st.aquatic[s], st.adult[s], ph, kDens >= 0 ? (kDens & 1) : p.densmod_type, p.dd_effect,
                                       p.surface_area_cm2, st.surface[s]);
                 }
                 if (kRecord) {
@@ -290,8 +292,9 @@ __device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &
 }
 
 // ---- the kernel: warp 2i = forcing role, warp 2i + 1 = state role of pair i ---------------------
-// kDens: the density-dependence form when known at compile time (0 logit, 1 cox_ph; -1 = read p.densmod_type):
-// the other form's code and the (uniform, but opaque to the compiler) branches around it leave both loops
+// kDens: what the launcher knows at compile time, or -1 (read the parameters): bit 0 the density-dependence form
+// (0 logit, 1 cox_ph), then two bits per setting of a unit with its water-body shape + 1 (0 = read hab[].shape).
+// The other form's / shape's code and the (uniform, but opaque to the compiler) branches around it leave both loops
 template <int kNS, bool kFull, bool kHourly, int kMaxPairs, int kDens>
 __global__ void __launch_bounds__(kMaxPairs * 64, 1)
 chain_kernel_ws(const __grid_constant__ ChainParams p)

@@ -267,3 +267,16 @@ def test_plain_c_caller(gpu, tmp_path):
     assert np.array_equal(got_state, ref["mean_state"], equal_nan=True)
     assert np.array_equal(got_forc, ref["mean_forcing"], equal_nan=True)
     assert np.array_equal(got_wet, ref["wet_hours"])
+
+
+@pytest.mark.parametrize("shapes", ["cone,cone", "cylinder,cone", "cylinder,cylinder"])
+def test_chain_pair_form_shape_patterns(gpu, shapes):
+    """The pair-kernel instantiations with both water-body shapes compiled in ((cone, cylinder) is covered above)."""
+    mk = {"cone": lambda k: syn.habitat_cone(max_depth=1.0 - 0.3 * k),
+          "cylinder": lambda k: syn.habitat_cylinder(leak_per_hour=0.001 * (k + 1))}
+    pair = [mk[name](k) for k, name in enumerate(shapes.split(","))]
+    case = Case(n_cells=150, habitats=pair)
+    ref = case.oracle(want_hourly=False)
+    out = backend.run_chain(case.monthly, case.altitude, **case.gpu_kwargs(
+        mean_vars=list(backend.VAR_NAMES[:6]), want_wet_hours=True))
+    compare(case, out, ref, REL_TOL_FAST, what=("mean",))
