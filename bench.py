@@ -251,7 +251,7 @@ def main():
                 "frac": achieved / peak_fp64,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, one launch,
                 # from the committed capture profiles/r01_ncu_chain_ws.txt (91.4 MB + 54.9 MB)
-                "traffic": 147.2e6, "traffic_unit": "bytes per launch (ncu, profiles/r01_ncu_chain_ws.txt)",
+                "traffic": 147.5e6, "traffic_unit": "bytes per launch (ncu, profiles/r01_ncu_chain_ws.txt)",
                 "peak_source": "measured live: dependent-free DFMA loop on this GPU (mms_measure_fp64_peak); "
                                "FP64 is not in MEASURED_PEAKS.json",
                 "flop_per_cell_hour": FLOP_SHARED + FLOP_CONE + FLOP_CYLINDER,
