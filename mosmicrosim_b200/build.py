@@ -3,7 +3,9 @@
     python -m mosmicrosim_b200.build [--force]
 
 The kernel translation unit csrc/chain_tu.cu is compiled twice: "fast"
-(FMA contraction on) and "strict" (-fmad=false, literal operation order).
+(FMA contraction on) and "strict" (-fmad=false, literal operation order);
+csrc/chain_ws_tu.cu holds the warp-pair form of the fused kernel (fast only).
+All units compile in parallel (about two minutes).
 """
 from __future__ import annotations
 
@@ -23,6 +25,7 @@ COMMON += os.environ.get("MMS_NVCC_EXTRA", "").split()     # development aid: -D
 UNITS = [
     # (source, object, extra flags)
     ("chain_tu.cu", "chain_fast.o", ["-DMMS_STRICT=0"]),
+    ("chain_ws_tu.cu", "chain_ws_fast.o", ["-DMMS_STRICT=0"]),
     ("chain_tu.cu", "chain_strict.o", ["-DMMS_STRICT=1", "-fmad=false"]),
     ("mmsgpu_api.cu", "mmsgpu_api.o", []),
     ("measure.cu", "measure.o", []),

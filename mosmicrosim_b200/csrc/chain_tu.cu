@@ -1,8 +1,9 @@
 // chain_tu.cu -- kernel translation unit, compiled twice by build.py:
 //   -DMMS_STRICT=0              -> chain_fast.o   (launch_*_fast)
 //   -DMMS_STRICT=1 -fmad=false  -> chain_strict.o (launch_*_strict)
+// (the warp-pair form of the fused kernel is a translation unit of its own, chain_ws_tu.cu, so that the
+// two long compilations run side by side)
 #include "chain_kernel.cuh"
-#include "chain_ws.cuh"
 #include "stage_kernels.cuh"
 #include "verb_kernels.cuh"
 
@@ -47,44 +48,6 @@ cudaError_t launch_kernel(const ChainParams &p, int grid, int warps, cudaStream_
     return cudaGetLastError();
 }
 
-#if !MMS_STRICT
-// the specialised instantiations of the pair kernel: two settings per thread, summaries only.  spec = density-
-// dependence form | (shape of setting 0 + 1) << 1 | (shape of setting 1 + 1) << 3 (chain_ws.cuh); the shapes are
-// compiled in only in the kChainMaxPairs instantiation and when every unit has the same pair of shapes.
-template <int kNS, bool kFull, bool kHourly, int kMaxPairs>
-auto pick_kernel_ws(const ChainParams &p) -> void (*)(ChainParams)
-{
-    constexpr bool kSpecialise = kNS == 2 && !kFull && !kHourly;
-    constexpr bool kShapes = kSpecialise && kMaxPairs == kChainMaxPairs;
-    if (!kSpecialise) return chain_kernel_ws<kNS, kFull, kHourly, kMaxPairs, -1>;
-    const int dens = p.densmod_type == 1 ? 1 : 0;
-    bool periodic = kShapes;
-    for (int s = kNS; s < p.S && periodic; ++s) periodic = p.hab[s].shape == p.hab[s % kNS].shape;
-    if (periodic) {
-        switch (dens | (p.hab[0].shape + 1) << 1 | (p.hab[kNS > 1 ? 1 : 0].shape + 1) << 3) {
-#define MMS_WS_CASE(v) case v: return chain_kernel_ws<kNS, kFull, kHourly, kMaxPairs, kShapes ? v : -1>;
-            MMS_WS_CASE(10) MMS_WS_CASE(11) MMS_WS_CASE(12) MMS_WS_CASE(13)      // (cone | cylinder, cone)
-            MMS_WS_CASE(18) MMS_WS_CASE(19) MMS_WS_CASE(20) MMS_WS_CASE(21)      // (cone | cylinder, cylinder)
-#undef MMS_WS_CASE
-        default: break;
-        }
-    }
-    return dens ? chain_kernel_ws<kNS, kFull, kHourly, kMaxPairs, kSpecialise ? 1 : -1>
-                : chain_kernel_ws<kNS, kFull, kHourly, kMaxPairs, kSpecialise ? 0 : -1>;
-}
-
-template <int kNS, bool kFull, bool kHourly, int kMaxPairs>
-cudaError_t launch_kernel_ws(const ChainParams &p, int grid, int pairs, cudaStream_t stream)
-{
-    auto kern = pick_kernel_ws<kNS, kFull, kHourly, kMaxPairs>(p);
-    const size_t smem = sizeof(double) * ((size_t)p.spline.n * 13 + p.ds.nx + p.ds.ny + (size_t)pairs * kWsRingDoubles) +
-                        sizeof(int) * (size_t)pairs;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
-    kern<<<grid, pairs * 64, smem, stream>>>(p);
-    return cudaGetLastError();
-}
-#endif
 
 template <int kNS, bool kFull, bool kHourly>
 cudaError_t launch_one(ChainParams &p, int n_sm, cudaStream_t stream)
@@ -111,8 +74,7 @@ cudaError_t launch_one(ChainParams &p, int n_sm, cudaStream_t stream)
         pairs = pairs < 1 ? 1 : (pairs > pairs_max ? pairs_max : pairs);
         const int64_t ctas = (p.n_units + pairs - 1) / pairs;
         const int grid = (int)(ctas < n_sm ? ctas : n_sm);
-        if (pairs <= kChainFewPairs) return launch_kernel_ws<kNS, kFull, kHourly, kChainFewPairs>(p, grid, pairs, stream);
-        return launch_kernel_ws<kNS, kFull, kHourly, kChainMaxPairs>(p, grid, pairs, stream);
+        return launch_chain_ws_fast(p, kNS, kFull, kHourly, grid, pairs, stream);
     }
 #endif
     const int w_max = p.force_warps > 0 ? p.force_warps : kChainMaxWarps;

@@ -104,6 +104,9 @@ struct ChainParams {
 // (p.unit_counter must be zero when the kernel starts; n_units / n_cell_blocks are filled in here)
 cudaError_t launch_chain_fast(ChainParams &p, int n_sm, cudaStream_t stream);
 cudaError_t launch_chain_strict(ChainParams &p, int n_sm, cudaStream_t stream);
+// the warp-pair form (chain_ws_tu.cu), called by launch_chain_fast when it picks that form
+cudaError_t launch_chain_ws_fast(const ChainParams &p, int settings_per_thread, bool full, bool hourly, int grid,
+                                 int pairs, cudaStream_t stream);
 // monthly rainfall -> log1p(rainfall) in place (R/sim_microclimate.R:33)
 cudaError_t launch_log1p_rows_fast(double *rows, int64_t n, cudaStream_t stream);
 cudaError_t launch_log1p_rows_strict(double *rows, int64_t n, cudaStream_t stream);
