@@ -23,6 +23,13 @@ thread_local std::string g_error;
 thread_local float g_stage_kernel_ms = 0.f;   // device time of the last stage-twin kernel on this thread
 
 // CUDA-event bracket around one kernel launch on a stream
+// a stream that is destroyed on every way out of the function that made it
+struct Stream {
+    cudaStream_t s = nullptr;
+    ~Stream() { if (s) cudaStreamDestroy(s); }
+    operator cudaStream_t() const { return s; }
+};
+
 struct EventTimer {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     cudaStream_t st;
@@ -654,17 +661,15 @@ static int water_twin(const double *rainfall, const double *air_temperature, con
     const size_t bytes = sizeof(double) * (size_t)n_times * (size_t)n_pixels;
     DevBuf in[4], alt, area, vol, wetb;
     const double *src[4] = {rainfall, air_temperature, humidity, windspeed};
-    cudaStream_t st;
-    MMS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    Stream st;
+    MMS_CUDA(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
     for (int k = 0; k < 4; ++k) {
-        if ((rc = in[k].alloc(bytes))) { cudaStreamDestroy(st); return rc; }
+        if ((rc = in[k].alloc(bytes))) return rc;
         MMS_CUDA(cudaMemcpyAsync(in[k].p, src[k], bytes, cudaMemcpyHostToDevice, st));
     }
     if ((rc = alt.alloc(sizeof(double) * n_pixels)) || (rc = area.alloc(bytes)) ||
-        (water_volume && (rc = vol.alloc(bytes))) || (wet && (rc = wetb.alloc((size_t)n_times * n_pixels)))) {
-        cudaStreamDestroy(st);
+        (water_volume && (rc = vol.alloc(bytes))) || (wet && (rc = wetb.alloc((size_t)n_times * n_pixels))))
         return rc;
-    }
     MMS_CUDA(cudaMemcpyAsync(alt.p, altitude, sizeof(double) * n_pixels, cudaMemcpyHostToDevice, st));
     p.rainfall = (const double *)in[0].p; p.air_temperature = (const double *)in[1].p;
     p.humidity = (const double *)in[2].p; p.windspeed = (const double *)in[3].p;
@@ -680,7 +685,6 @@ static int water_twin(const double *rainfall, const double *air_temperature, con
     if (wet) MMS_CUDA(cudaMemcpyAsync(wet, wetb.p, (size_t)n_times * n_pixels, cudaMemcpyDeviceToHost, st));
     MMS_CUDA(cudaStreamSynchronize(st));
     g_stage_kernel_ms = timer.ms();
-    cudaStreamDestroy(st);
     return MMS_OK;
 }
 
@@ -721,13 +725,13 @@ static int population_twin(const double *larval_habitat_area, const double *mdr,
     const size_t bytes = sizeof(double) * (size_t)n_times * (size_t)n_pixels;
     DevBuf in[5], aq, ad;
     const double *src[5] = {larval_habitat_area, mdr, efd, das_zerodensity, ds};
-    cudaStream_t st;
-    MMS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    Stream st;
+    MMS_CUDA(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
     for (int k = 0; k < 5; ++k) {
-        if ((rc = in[k].alloc(bytes))) { cudaStreamDestroy(st); return rc; }
+        if ((rc = in[k].alloc(bytes))) return rc;
         MMS_CUDA(cudaMemcpyAsync(in[k].p, src[k], bytes, cudaMemcpyHostToDevice, st));
     }
-    if ((rc = aq.alloc(bytes)) || (rc = ad.alloc(bytes))) { cudaStreamDestroy(st); return rc; }
+    if ((rc = aq.alloc(bytes)) || (rc = ad.alloc(bytes))) return rc;
     mms::PopStageParams p{};
     p.larval_habitat_area = (const double *)in[0].p; p.mdr = (const double *)in[1].p; p.efd = (const double *)in[2].p;
     p.das_zerodensity = (const double *)in[3].p; p.ds = (const double *)in[4].p;
@@ -743,7 +747,6 @@ static int population_twin(const double *larval_habitat_area, const double *mdr,
     MMS_CUDA(cudaMemcpyAsync(adult, ad.p, bytes, cudaMemcpyDeviceToHost, st));
     MMS_CUDA(cudaStreamSynchronize(st));
     g_stage_kernel_ms = timer.ms();
-    cudaStreamDestroy(st);
     return MMS_OK;
 }
 
@@ -780,13 +783,11 @@ int mms_daily_from_monthly(const double *monthly, const double *mid_day, const d
     if ((rc = build_day_table(mid_day, n_months, day_predict, n_days, days))) return rc;
     const int64_t cs = ((n_cells + mms::kBlock - 1) / mms::kBlock) * mms::kBlock;
     DevBuf d_monthly, d_days, d_out, d_err;
-    cudaStream_t st;
-    MMS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    Stream st;
+    MMS_CUDA(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
     if ((rc = d_monthly.alloc(sizeof(double) * MMS_NFORCING * n_months * cs)) || (rc = d_days.alloc(sizeof(mms::DayEntry) * n_days)) ||
-        (rc = d_out.alloc(sizeof(double) * MMS_NFORCING * n_days * cs)) || (rc = d_err.alloc(2 * sizeof(int32_t)))) {
-        cudaStreamDestroy(st);
+        (rc = d_out.alloc(sizeof(double) * MMS_NFORCING * n_days * cs)) || (rc = d_err.alloc(2 * sizeof(int32_t))))
         return rc;
-    }
     MMS_CUDA(cudaMemsetAsync(d_monthly.p, 0, sizeof(double) * MMS_NFORCING * n_months * cs, st));
     MMS_CUDA(cudaMemsetAsync(d_err.p, 0, 2 * sizeof(int32_t), st));
     if ((rc = copy_in_2d(d_monthly.p, 8 * cs, monthly, 8 * n_cells, 8 * n_cells, (size_t)MMS_NFORCING * n_months, st))) return rc;
@@ -806,7 +807,6 @@ int mms_daily_from_monthly(const double *monthly, const double *mid_day, const d
     MMS_CUDA(cudaMemcpyAsync(&flag, d_err.p, sizeof flag, cudaMemcpyDeviceToHost, st));
     MMS_CUDA(cudaStreamSynchronize(st));
     g_stage_kernel_ms = timer.ms();
-    cudaStreamDestroy(st);
     if (flag) return fail(MMS_ERR_NONFINITE, "non-finite (NA/NaN/Inf) monthly forcing; R's approx() would drop those knots, "
                           "the GPU backend refuses them");
     return MMS_OK;
@@ -839,14 +839,12 @@ int mms_terraclimate_to_monthly(const double *terraclimate, const double *clear_
     if ((rc = pick_device(device))) return rc;
     const int64_t cs = ((n_cells + mms::kBlock - 1) / mms::kBlock) * mms::kBlock;
     DevBuf d_tc, d_cs, d_mid, d_nd, d_out;
-    cudaStream_t st;
-    MMS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    Stream st;
+    MMS_CUDA(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
     if ((rc = d_tc.alloc(sizeof(double) * MMS_NTERRACLIMATE * n_months * cs)) || (rc = d_cs.alloc(sizeof(double) * 12 * cs)) ||
         (rc = d_mid.alloc(sizeof(int32_t) * n_months)) || (rc = d_nd.alloc(sizeof(double) * n_months)) ||
-        (rc = d_out.alloc(sizeof(double) * MMS_NFORCING * n_months * cs))) {
-        cudaStreamDestroy(st);
+        (rc = d_out.alloc(sizeof(double) * MMS_NFORCING * n_months * cs)))
         return rc;
-    }
     if ((rc = copy_in_2d(d_tc.p, 8 * cs, terraclimate, 8 * n_cells, 8 * n_cells, (size_t)MMS_NTERRACLIMATE * n_months, st)) ||
         (rc = copy_in_2d(d_cs.p, 8 * cs, clear_sky, 8 * n_cells, 8 * n_cells, 12, st)))
         return rc;
@@ -863,7 +861,6 @@ int mms_terraclimate_to_monthly(const double *terraclimate, const double *clear_
     if ((rc = copy_out_2d(monthly, 8 * n_cells, d_out.p, 8 * cs, 8 * n_cells, (size_t)MMS_NFORCING * n_months, st))) return rc;
     MMS_CUDA(cudaStreamSynchronize(st));
     g_stage_kernel_ms = timer.ms();
-    cudaStreamDestroy(st);
     return MMS_OK;
 }
 
@@ -930,12 +927,10 @@ int mms_hourly_from_daily(const double *daily, int64_t n_cells, int32_t n_days, 
     if (rc) return rc;
     const int64_t cs = ((n_cells + mms::kBlock - 1) / mms::kBlock) * mms::kBlock;
     DevBuf d_in, d_out;
-    cudaStream_t st;
-    MMS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    if ((rc = d_in.alloc(sizeof(double) * MMS_NFORCING * n_days * cs)) || (rc = d_out.alloc(sizeof(double) * 6 * 24 * n_days * cs))) {
-        cudaStreamDestroy(st);
+    Stream st;
+    MMS_CUDA(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
+    if ((rc = d_in.alloc(sizeof(double) * MMS_NFORCING * n_days * cs)) || (rc = d_out.alloc(sizeof(double) * 6 * 24 * n_days * cs)))
         return rc;
-    }
     MMS_CUDA(cudaMemsetAsync(d_in.p, 0, sizeof(double) * MMS_NFORCING * n_days * cs, st));
     if ((rc = copy_in_2d(d_in.p, 8 * cs, daily, 8 * n_cells, 8 * n_cells, (size_t)MMS_NFORCING * n_days, st))) return rc;
     mms::ChainParams p{};
@@ -948,7 +943,6 @@ int mms_hourly_from_daily(const double *daily, int64_t n_cells, int32_t n_days, 
     if ((rc = copy_out_2d(hourly, 8 * n_cells, d_out.p, 8 * cs, 8 * n_cells, (size_t)6 * 24 * n_days, st))) return rc;
     MMS_CUDA(cudaStreamSynchronize(st));
     g_stage_kernel_ms = timer.ms();
-    cudaStreamDestroy(st);
     return MMS_OK;
 }
 
@@ -968,20 +962,18 @@ int mms_lifehistory_vectorised(const double *water_temperature, const double *ai
     DevBuf in[3], out[4], d_sx, d_scoef, d_gx, d_gy, d_quad;
     const double *src[3] = {water_temperature, air_temperature, humidity};
     double *dst[4] = {mdr, efd, das_zerodensity, ds};
-    cudaStream_t st;
-    MMS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    Stream st;
+    MMS_CUDA(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
     const size_t bytes = sizeof(double) * (size_t)n;
     for (int k = 0; k < 3; ++k) {
-        if ((rc = in[k].alloc(bytes))) { cudaStreamDestroy(st); return rc; }
+        if ((rc = in[k].alloc(bytes))) return rc;
         MMS_CUDA(cudaMemcpyAsync(in[k].p, src[k], bytes, cudaMemcpyHostToDevice, st));
     }
     for (int k = 0; k < 4; ++k)
-        if ((rc = out[k].alloc(bytes))) { cudaStreamDestroy(st); return rc; }
+        if ((rc = out[k].alloc(bytes))) return rc;
     if ((rc = d_sx.alloc(8 * tab.sx.size())) || (rc = d_scoef.alloc(8 * tab.scoef.size())) || (rc = d_gx.alloc(8 * (size_t)g.nx)) ||
-        (rc = d_gy.alloc(8 * (size_t)g.ny)) || (rc = d_quad.alloc(8 * tab.quad.size()))) {
-        cudaStreamDestroy(st);
+        (rc = d_gy.alloc(8 * (size_t)g.ny)) || (rc = d_quad.alloc(8 * tab.quad.size())))
         return rc;
-    }
     MMS_CUDA(cudaMemcpyAsync(d_sx.p, tab.sx.data(), 8 * tab.sx.size(), cudaMemcpyHostToDevice, st));
     MMS_CUDA(cudaMemcpyAsync(d_scoef.p, tab.scoef.data(), 8 * tab.scoef.size(), cudaMemcpyHostToDevice, st));
     MMS_CUDA(cudaMemcpyAsync(d_gx.p, g.x, 8 * (size_t)g.nx, cudaMemcpyHostToDevice, st));
@@ -1006,7 +998,6 @@ int mms_lifehistory_vectorised(const double *water_temperature, const double *ai
     for (int k = 0; k < 4; ++k) MMS_CUDA(cudaMemcpyAsync(dst[k], out[k].p, bytes, cudaMemcpyDeviceToHost, st));
     MMS_CUDA(cudaStreamSynchronize(st));
     g_stage_kernel_ms = timer.ms();
-    cudaStreamDestroy(st);
     return MMS_OK;
 }
 
