@@ -149,9 +149,11 @@ def main():
         if rank != 0:
             return 0
         w = workload(0)
-        cb = cpu_reference(w, CPU_SAMPLE_CELLS, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
+        timed, warm = max(1, min(args.steps, 3)), min(args.warmup, 1)     # bounded: each step is 10-30 s of CPU work
+        cb = cpu_reference(w, CPU_SAMPLE_CELLS, steps=timed, warmup=warm)
         line = {"impl": "reference", "metric": "cell-years/sec (hourly steps)", "value": cb["value"],
-                "unit": "cell-years/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
+                "unit": "cell-years/s", "n_gpus": args.gpus, "gpus_used": 0, "steps": args.steps, "warmup": args.warmup,
+                "timed_steps": timed, "untimed_steps": warm,
                 "ms_per_step": cb["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": CONFIG,
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
