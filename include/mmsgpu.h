@@ -264,6 +264,16 @@ MMS_API int mms_population_series(const double *larval_habitat_area, const doubl
                           int32_t math_mode, int32_t device,
                           double *aquatic, double *adult);
 
+/* summarise_vectors() -> aggregate_vectors(), R/pipeline_functions.R:995-1091: period means of hourly series.
+ *   hourly        [n_vars][24 * n_days][C]   cell fastest (the layout of the hourly outputs above)
+ *   period_of_day [n_days]                   period of each day, -1 = not in included_dates; non-negative entries
+ *                                            non-decreasing (by date, or by floor_date(date, "month"))
+ *   means         [n_vars][n_periods][C]     out; NaN for a period without a day
+ * sum / n in the order of the hours, in double, exactly as the fused chain accumulates its summaries
+ * (the reference: R mean(), long-double two-pass -- the difference is far below the 1e-9 tolerance). */
+MMS_API int mms_summarise_vectors(const double *hourly, int64_t n_cells, int32_t n_days, int32_t n_vars,
+                                  const int32_t *period_of_day, int32_t n_periods, int32_t device, double *means);
+
 /* ---- state-free verbs, for callers that want the intermediate products ----------------
  * (layouts with the cell index fastest, like the fused chain)
  *

@@ -92,6 +92,7 @@ EXPORTS = ("mms_abi_version", "mms_device_count", "mms_last_error", "mms_run_cha
            "mms_water_vectorised", "mms_population_vectorised", "mms_water_series", "mms_population_series",
            "mms_stage_kernel_ms",
            "mms_chain_upload_terraclimate", "mms_run_chain_terraclimate", "mms_terraclimate_to_monthly",
+           "mms_summarise_vectors",
            "mms_daily_from_monthly", "mms_hourly_from_daily", "mms_lifehistory_vectorised", "mms_host_alloc", "mms_host_free",
            "mms_measure_fp64_peak", "mms_measure_hbm_copy", "mms_flush_l2")
 
@@ -114,6 +115,7 @@ def lib() -> ct.CDLL:
         L.mms_chain_upload_terraclimate.argtypes = [vp, _dp, _dp, _ip, _dp, _dp]
         L.mms_run_chain_terraclimate.argtypes = [ct.POINTER(ChainConfig), _dp, _dp, _ip, _dp, _dp,
                                                  ct.POINTER(ChainOutputs)]
+        L.mms_summarise_vectors.argtypes = [_dp, ct.c_int64, ct.c_int32, ct.c_int32, _ip, ct.c_int32, ct.c_int32, _dp]
         L.mms_terraclimate_to_monthly.argtypes = [_dp, _dp, _ip, _dp, ct.c_int64, ct.c_int32, ct.c_int32,
                                                   ct.c_int32, _dp]
         L.mms_chain_launch.argtypes = [vp]
@@ -462,6 +464,19 @@ def terraclimate_to_monthly(terraclimate, clear_sky, month_id, n_days, math_mode
     check(lib().mms_terraclimate_to_monthly(_p(tc), _p(cs), mid.ctypes.data_as(_ip), _p(nd), C, M, _mode(math_mode),
                                             int(device), _p(monthly)))
     return monthly
+
+
+def summarise_vectors(hourly, period_of_day, n_periods, device=0):
+    """mms_summarise_vectors(): hourly [n_vars][24 D][C] -> period means [n_vars][P][C]."""
+    hourly = _d(hourly)
+    nv, H, C = hourly.shape
+    pod = np.ascontiguousarray(period_of_day, dtype=np.int32)
+    if H != 24 * len(pod):
+        raise ValueError("hourly must have 24 steps per entry of period_of_day")
+    means = np.empty((nv, int(n_periods), C))
+    check(lib().mms_summarise_vectors(_p(hourly), C, len(pod), nv, pod.ctypes.data_as(_ip), int(n_periods), int(device),
+                                      _p(means)))
+    return means
 
 
 def daily_from_monthly(monthly, mid_day, day_predict, math_mode="fast", device=0):

@@ -149,6 +149,14 @@ cudaError_t MMS_LAUNCH(launch_lifehistory)(const ChainParams &p, int64_t n, cons
     return cudaGetLastError();
 }
 
+cudaError_t MMS_LAUNCH(launch_summarise)(const double *hourly, const int32_t *period_of_day, int64_t c_stride, int32_t D,
+                                         int32_t P, int32_t n_vars, double *means, cudaStream_t stream)
+{
+    dim3 grid((unsigned)(c_stride / 128), (unsigned)n_vars);
+    summarise_kernel<<<grid, 128, 0, stream>>>(hourly, period_of_day, c_stride, D, P, means);
+    return cudaGetLastError();
+}
+
 cudaError_t MMS_LAUNCH(launch_terraclimate)(const TerraParams &p, cudaStream_t stream)
 {
     dim3 grid((unsigned)(p.c_stride / 128), (unsigned)p.M);

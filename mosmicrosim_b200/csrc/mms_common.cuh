@@ -123,6 +123,12 @@ cudaError_t launch_lifehistory_strict(const ChainParams &p, int64_t n, const dou
                                       const double *humidity, double *mdr, double *efd, double *das0, double *ds,
                                       int n_sm, cudaStream_t stream);
 
+// summarise_vectors() / aggregate_vectors(), R/pipeline_functions.R:995-1091 (verb_kernels.cuh, summarise_kernel)
+cudaError_t launch_summarise_fast(const double *hourly, const int32_t *period_of_day, int64_t c_stride, int32_t D,
+                                  int32_t P, int32_t n_vars, double *means, cudaStream_t stream);
+cudaError_t launch_summarise_strict(const double *hourly, const int32_t *period_of_day, int64_t c_stride, int32_t D,
+                                    int32_t P, int32_t n_vars, double *means, cudaStream_t stream);
+
 // process_terraclimate_pixel_vars(), R/terraclimate.R:581-643 (verb_kernels.cuh, terraclimate_kernel)
 struct TerraParams {
     const double *terraclimate;   // [6][M][c_stride]: tmax, tmin, ppt, ws, vpd, srad

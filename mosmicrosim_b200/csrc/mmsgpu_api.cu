@@ -946,6 +946,44 @@ int mms_hourly_from_daily(const double *daily, int64_t n_cells, int32_t n_days, 
     return MMS_OK;
 }
 
+// summarise_vectors() / aggregate_vectors(), R/pipeline_functions.R:995-1091
+int mms_summarise_vectors(const double *hourly, int64_t n_cells, int32_t n_days, int32_t n_vars,
+                          const int32_t *period_of_day, int32_t n_periods, int32_t device, double *means)
+{
+    if (!hourly || !period_of_day || !means) return fail(MMS_ERR_INVALID_ARG, "NULL argument");
+    if (n_cells < 1 || n_days < 1 || n_vars < 1 || n_periods < 1)
+        return fail(MMS_ERR_INVALID_ARG, "need cells, days, variables and periods >= 1");
+    int last = -1;
+    for (int d = 0; d < n_days; ++d) {
+        const int q = period_of_day[d];
+        if (q >= n_periods) return fail(MMS_ERR_INVALID_ARG, "period_of_day[%d] = %d >= n_periods", d, q);
+        if (q >= 0 && q < last) return fail(MMS_ERR_INVALID_ARG, "period_of_day must be non-decreasing over its non-negative entries");
+        if (q >= 0) last = q;
+    }
+    int rc = pick_device(device);
+    if (rc) return rc;
+    const int64_t cs = ((n_cells + mms::kBlock - 1) / mms::kBlock) * mms::kBlock;
+    const size_t n_in = (size_t)n_vars * 24 * n_days * cs, n_out = (size_t)n_vars * n_periods * cs;
+    DevBuf d_in, d_out, d_pod;
+    Stream st;
+    MMS_CUDA(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
+    if ((rc = d_in.alloc(sizeof(double) * n_in)) || (rc = d_out.alloc(sizeof(double) * n_out)) ||
+        (rc = d_pod.alloc(sizeof(int32_t) * n_days)))
+        return rc;
+    MMS_CUDA(cudaMemsetAsync(d_in.p, 0, sizeof(double) * n_in, st));
+    MMS_CUDA(cudaMemsetAsync(d_out.p, 0xFF, sizeof(double) * n_out, st));          // periods without a day: NaN
+    if ((rc = copy_in_2d(d_in.p, 8 * cs, hourly, 8 * n_cells, 8 * n_cells, (size_t)n_vars * 24 * n_days, st))) return rc;
+    MMS_CUDA(cudaMemcpyAsync(d_pod.p, period_of_day, sizeof(int32_t) * n_days, cudaMemcpyHostToDevice, st));
+    EventTimer timer(st);
+    MMS_CUDA(mms::launch_summarise_fast((const double *)d_in.p, (const int32_t *)d_pod.p, cs, n_days, n_periods, n_vars,
+                                        (double *)d_out.p, st));
+    timer.stop();
+    if ((rc = copy_out_2d(means, 8 * n_cells, d_out.p, 8 * cs, 8 * n_cells, (size_t)n_vars * n_periods, st))) return rc;
+    MMS_CUDA(cudaStreamSynchronize(st));
+    g_stage_kernel_ms = timer.ms();
+    return MMS_OK;
+}
+
 // simulate_hourly_lifehistory() / simulate_vector_lifehistory(), R/sim_pop_dynamics.R:100-135
 int mms_lifehistory_vectorised(const double *water_temperature, const double *air_temperature, const double *humidity,
                                int64_t n, const mms_lifehistory *lh, int32_t math_mode, int32_t device,

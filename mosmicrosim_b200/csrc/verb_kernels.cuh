@@ -161,6 +161,36 @@ __global__ void __launch_bounds__(128) terraclimate_kernel(const __grid_constant
     for (int v = 0; v < MMS_NFORCING; ++v) p.monthly[v * plane + at] = o[v];
 }
 
+// ---- summarise_vectors() -> aggregate_vectors(), R/pipeline_functions.R:995-1091 ---------------------------
+// Period means of hourly series: hourly [n_vars][24 D][cs] -> means [n_vars][P][cs].  One thread per (cell,
+// variable) walks its series once (a warp reads 256 contiguous bytes per hour: an HBM-bound streaming kernel) and
+// accumulates hour by hour in the order of the fused kernel, so both give the same bits.  period_of_day: -1 = day
+// not in included_dates; non-negative entries non-decreasing (checked on the host).  Periods without a day keep
+// the NaN the output was filled with.  grid (cs / 128, n_vars).
+__global__ void __launch_bounds__(128) summarise_kernel(const double *__restrict__ hourly, const int32_t *__restrict__ period_of_day,
+                                                        int64_t cs, int32_t D, int32_t P, double *__restrict__ means)
+{
+    const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= cs) return;
+    const double *src = hourly + (int64_t)blockIdx.y * 24 * D * cs + cell;
+    double *dst = means + (int64_t)blockIdx.y * P * cs + cell;
+    double acc = 0.0;
+    int n = 0, cur = -1;
+    for (int day = 0; day < D; ++day) {
+        const int period = period_of_day[day];
+        if (period < 0) continue;                                          // filter(date %in% included_dates), :1052-1054
+        if (period != cur) {
+            if (cur >= 0) dst[(int64_t)cur * cs] = acc / (double)n;        // mean by period, :1055-1064 / :1070-1086
+            cur = period; acc = 0.0; n = 0;
+        }
+        const double *row = src + (int64_t)day * 24 * cs;
+#pragma unroll 8
+        for (int h = 0; h < 24; ++h) acc += row[(int64_t)h * cs];
+        n += 24;
+    }
+    if (cur >= 0) dst[(int64_t)cur * cs] = acc / (double)n;
+}
+
 // simulate_vector_lifehistory(), R/sim_pop_dynamics.R:100-135: element-wise over n values;
 // out mdr, efd, das_zerodensity, ds.  Spline rows and ds axes in shared memory like the fused kernel.
 __global__ void __launch_bounds__(512, 2) lifehistory_kernel(const __grid_constant__ ChainParams p, int64_t n,

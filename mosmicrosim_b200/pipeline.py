@@ -170,6 +170,51 @@ def simulate_hourly_lifehistory(pixel_hourly_conditions, lifehistory_functions, 
     return out
 
 
+def simulate_hourly_conditions(pixel_hourly_microclimate, model_water_temperature=False,
+                               water_shade_proportion=1, *, math_mode="fast", device=0):
+    """simulate_hourly_conditions(), R/pipeline_functions.R:319-538: adds water_surface_area to the hourly
+    microclimate of every pixel (the reference's cone, depth 1, no burn-in: :431-441).  pixel_hourly_microclimate
+    is the dict simulate_hourly_microclimate() returns ([H, C] arrays and the pixels' altitude)."""
+    if water_shade_proportion != 1 and not model_water_temperature:           # :329-331
+        warnings.warn("water temperature is not being modelled, so water_shade_proportion argument is ignored")
+    if model_water_temperature:                                                # :335-337
+        raise NotImplementedError("model of water temperature not yet implemented, "
+                                  "model_water_temperature must be set to FALSE")
+    m = pixel_hourly_microclimate
+    area = simulate_ephemeral_habitat_vectorised(m["rainfall"], m["air_temperature"], m["humidity"], m["windspeed"],
+                                                 m["altitude"], math_mode=math_mode, device=device)["water_surface_area"]
+    out = dict(m)
+    out["water_surface_area"] = area
+    return out
+
+
+def simulate_hourly_vectors(pixel_hourly_lifehistory, *, burnin_years=1, math_mode="fast", device=0):
+    """simulate_hourly_vectors(), R/pipeline_functions.R:691-906: the population model on the hourly life-history
+    parameters of every pixel; adds adult and aquatic ([H, C])."""
+    lhp = pixel_hourly_lifehistory
+    pop = simulate_population_vectorised(lhp["larval_habitat_area"], lhp["mdr"], lhp["efd"], lhp["das_zerodensity"],
+                                         lhp["ds"], lhp["das_densmod_function"], burnin_years=burnin_years,
+                                         math_mode=math_mode, device=device)
+    out = dict(lhp)
+    out.update(pop)
+    return out
+
+
+def summarise_vectors(pixel_hourly_vectors, aggregate_by="month", included_dates=None, *, device=0):
+    """summarise_vectors() -> aggregate_vectors(), R/pipeline_functions.R:995-1091: means of the six vector
+    variables by date or by month over included_dates, on the device (mms_summarise_vectors).
+    pixel_hourly_vectors: dict of [H, C] arrays; returns start[P], end[P] and one [P, C] array per variable."""
+    aggregate_by = _match_arg(aggregate_by, ("month", "day"), "aggregate_by")
+    dates_predict = np.asarray(pixel_hourly_vectors["date"], "datetime64[D]")[::24]      # one entry per simulated day
+    period_of_day, p_start, p_end = dates.period_index(dates_predict, aggregate_by, included_dates)
+    hourly = np.stack([np.asarray(pixel_hourly_vectors[v], dtype=np.float64) for v in VECTOR_VARIABLES], axis=0)
+    means = backend.summarise_vectors(hourly, period_of_day, len(p_start), device=device)
+    out = {"start": p_start, "end": p_end}
+    for k, v in enumerate(VECTOR_VARIABLES):
+        out[v] = means[k]
+    return out
+
+
 def _terraclimate_arrays(pixel_terraclimate_data):
     """(start, end, terraclimate[6][M][C], clear_sky[12][C], altitude[C]) from the dict form of
     extract_terraclimate_tile()'s per-pixel tibbles placed side by side."""

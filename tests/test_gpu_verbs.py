@@ -175,3 +175,51 @@ def test_run_chain_terraclimate_one_shot(gpu):
     with pytest.raises(backend.MmsError) as e:
         backend.run_chain_terraclimate(tc, clear_sky, month_id * 0, n_days, altitude, **kw)
     assert e.value.code == "MMS_ERR_INVALID_ARG"
+
+
+@pytest.mark.parametrize("aggregate_by", ["month", "day"])
+def test_all_six_verbs_one_gpu_call_each(gpu, aggregate_by):
+    """interpolate_daily_climate |> simulate_hourly_microclimate |> simulate_hourly_conditions |>
+    simulate_hourly_lifehistory |> simulate_hourly_vectors |> summarise_vectors with the reference's signatures,
+    one GPU call per verb; the summaries equal the fused chain's bit for bit (same device functions, same order of
+    the hourly accumulation), with included_dates dropping days."""
+    case = Case(n_cells=37)
+    pmc = {"start": case.start, "end": case.end, "altitude": case.altitude,
+           "longitude": np.arange(37.0), "latitude": np.arange(37.0)}
+    for v, name in enumerate(pipeline.FORCING_VARS):
+        pmc[name] = case.monthly[v]
+    lhf = {"An_gambiae": case.lh, "An_stephensi": syn.synthetic_lifehistory("An. stephensi")}
+    included = np.concatenate([case.dates_predict[:40], case.dates_predict[100:333]])
+    kw = dict(math_mode="strict")
+    vec = pipeline.simulate_hourly_vectors(
+        pipeline.simulate_hourly_lifehistory(
+            pipeline.simulate_hourly_conditions(
+                pipeline.simulate_hourly_microclimate(
+                    pipeline.interpolate_daily_climate(pmc, dates_predict=case.dates_predict, **kw), **kw), **kw),
+            lhf, species="An. gambiae", **kw), **kw)
+    got = pipeline.summarise_vectors(vec, aggregate_by=aggregate_by, included_dates=included)
+    fused = pipeline.monthly_climate_to_vectors(pmc, lhf, species="An. gambiae", included_dates=included,
+                                                aggregate_by=aggregate_by, dates_predict=case.dates_predict, **kw)
+    assert np.array_equal(got["start"], fused["start"]) and np.array_equal(got["end"], fused["end"])
+    assert len(got["start"]) == (273 if aggregate_by == "day" else 10)       # Jan, Feb, Apr .. Nov
+    for name in pipeline.VECTOR_VARIABLES:
+        assert np.array_equal(got[name], fused[name], equal_nan=True), name
+    # and against the oracle's long-double two-pass mean() of the same periods
+    from mosmicrosim_b200 import dates as mms_dates
+    pod, _, _ = mms_dates.period_index(case.dates_predict, aggregate_by, included)
+    ref = oracle.run_chain(case.monthly, case.mid_day, case.day_predict, case.altitude, [oracle.habitat()],
+                           oracle.densmod(case.densmod["type_"], case.densmod["dd_effect"], case.densmod["surface_area_cm2"]),
+                           case.tables, pod, len(got["start"]), want_hourly=False)
+    for name in pipeline.VECTOR_VARIABLES:
+        assert rel_err(got[name], ref["mean"][0, ORACLE_VAR[name]]) <= REL_TOL_STRICT, name
+
+
+def test_summarise_vectors_argument_checks(gpu):
+    h = np.zeros((2, 48, 5))
+    with pytest.raises(backend.MmsError) as e:
+        backend.summarise_vectors(h, [1, 0], 2)                 # decreasing periods
+    assert e.value.code == "MMS_ERR_INVALID_ARG"
+    with pytest.raises(backend.MmsError):
+        backend.summarise_vectors(h, [0, 3], 2)                 # period >= n_periods
+    m = backend.summarise_vectors(h + 2.5, [-1, 1], 3)          # periods 0 and 2 have no day: NaN
+    assert np.isnan(m[:, 0]).all() and np.isnan(m[:, 2]).all() and np.all(m[:, 1] == 2.5)
