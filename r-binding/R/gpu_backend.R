@@ -159,6 +159,25 @@ simulate_vector_lifehistory_gpu <- function(hourly_conditions, lifehistory) {
                 larval_habitat_area = hourly_conditions$water_surface_area)
 }
 
+# summarise_vectors() -> aggregate_vectors() for a whole tile, R/pipeline_functions.R:995-1091.
+# hourly: [cells, 24 * days, variables] array; dates_predict: the simulated days; returns
+# list(start, end, means = [cells, periods, variables])
+summarise_vectors_gpu <- function(hourly, dates_predict, aggregate_by = c("month", "day"),
+                                  included_dates = NULL) {
+  aggregate_by <- match.arg(aggregate_by)
+  if (is.null(included_dates)) included_dates <- dates_predict
+  keep <- dates_predict %in% included_dates
+  key <- if (aggregate_by == "month") lubridate::floor_date(dates_predict, "month") else dates_predict
+  periods <- sort(unique(key[keep]))
+  period_of_day <- as.integer(ifelse(keep, match(key, periods) - 1L, -1L))
+  m <- .Call("mms_R_summarise_vectors", hourly, period_of_day, length(periods),
+             as.numeric(dim(hourly)[1]), as.integer(dim(hourly)[3]),
+             if (length(mms_devices())) mms_devices()[1] else 0L, PACKAGE = "mosmicrosim")
+  end <- if (aggregate_by == "month") lubridate::ceiling_date(periods + 1, "month") - 1 else periods
+  list(start = periods, end = end,
+       means = array(m, dim = c(dim(hourly)[1], length(periods), dim(hourly)[3])))
+}
+
 # ---- the fused pipeline --------------------------------------------------------
 # tc_to_vectors() (R/pipeline_functions.R:1099-1130) from interpolate_daily_climate()
 # on, for the whole tile in one call.  pixel_monthly_climate is the tibble that

@@ -301,6 +301,20 @@ SEXP mms_R_terraclimate_to_monthly(SEXP values, SEXP clear_sky, SEXP month_id, S
     return monthly;
 }
 
+/* summarise_vectors() -> aggregate_vectors(), R/pipeline_functions.R:995-1091:
+ * hourly [C, 24 D, n_vars] array, period_of_day integer [D] (-1 = excluded) -> means [C, P, n_vars] */
+SEXP mms_R_summarise_vectors(SEXP hourly, SEXP period_of_day, SEXP n_periods, SEXP n_cells, SEXP n_vars, SEXP device)
+{
+    const int64_t C = (int64_t)Rf_asReal(n_cells);
+    const int D = (int)Rf_xlength(period_of_day), V = Rf_asInteger(n_vars), P = Rf_asInteger(n_periods);
+    if (Rf_xlength(hourly) != (R_xlen_t)C * 24 * D * V) Rf_error("hourly must be a [cells, 24 * days, variables] array");
+    SEXP means = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)C * P * V));
+    check(mms_summarise_vectors(REAL(hourly), C, D, V, (const int32_t *)INTEGER(period_of_day), P, Rf_asInteger(device),
+                                REAL(means)));
+    UNPROTECT(1);
+    return means;
+}
+
 /* interpolate_daily_climate(), R/pipeline_functions.R:258-275: monthly [C, M, 9] -> daily [C, D, 9] */
 SEXP mms_R_daily_from_monthly(SEXP monthly, SEXP mid_day, SEXP day_predict, SEXP n_cells, SEXP math_mode, SEXP device)
 {
@@ -372,6 +386,7 @@ static const R_CallMethodDef call_methods[] = {
     {"mms_R_run_chain", (DL_FUNC)&mms_R_run_chain, 13},
     {"mms_R_run_chain_terraclimate", (DL_FUNC)&mms_R_run_chain_terraclimate, 13},
     {"mms_R_terraclimate_to_monthly", (DL_FUNC)&mms_R_terraclimate_to_monthly, 7},
+    {"mms_R_summarise_vectors", (DL_FUNC)&mms_R_summarise_vectors, 6},
     {NULL, NULL, 0}};
 
 void R_init_mosmicrosim(DllInfo *dll)
