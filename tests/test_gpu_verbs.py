@@ -223,3 +223,18 @@ def test_summarise_vectors_argument_checks(gpu):
         backend.summarise_vectors(h, [0, 3], 2)                 # period >= n_periods
     m = backend.summarise_vectors(h + 2.5, [-1, 1], 3)          # periods 0 and 2 have no day: NaN
     assert np.isnan(m[:, 0]).all() and np.isnan(m[:, 2]).all() and np.all(m[:, 1] == 2.5)
+
+
+def test_golden_front_end_and_twins_gpu(gpu):
+    """The committed golden vectors of the TerraClimate front end and of the one-pixel twins
+    (tests/golden/front_end_and_twins.npz, from the numpy restatement) against the CUDA path."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "front_end_and_twins.npz"))
+    got = backend.terraclimate_to_monthly(g["terraclimate"], g["clear_sky"], g["month_id"], g["n_days"])
+    assert rel_err(got, g["monthly"]) <= REL_TOL_FAST
+    s = dict(zip(oracle.VAR_NAMES, g["series"]))
+    area = pipeline.simulate_ephemeral_habitat(s, float(g["altitude"]), burnin_years=2)
+    assert rel_err(area, g["water_surface_area_burnin2"]) <= REL_TOL_FAST
+    pop = pipeline.simulate_population(s, syn.synthetic_lifehistory("An. gambiae").das_densmod, burnin_years=2)
+    assert rel_err(pop["aquatic"], g["aquatic_burnin2"]) <= REL_TOL_FAST
+    assert rel_err(pop["adult"], g["adult_burnin2"]) <= REL_TOL_FAST

@@ -301,3 +301,22 @@ def test_terraclimate_c_oracle_matches_numpy_restatement():
     np.testing.assert_allclose(a, b, rtol=1e-13, atol=0)            # glibc scalar vs numpy log10 / pow last bits
     for v in (0, 1, 4, 5, 8):                                       # no transcendental involved: bit identical
         assert np.array_equal(a[v], b[v])
+
+
+def test_golden_front_end_and_twins():
+    """tests/golden/front_end_and_twins.npz (written by the numpy restatement, make_golden.py): the TerraClimate front
+    end and the one-pixel twins with two whole-series burn-in repeats, against the C oracle."""
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), "front_end_and_twins.npz"))
+    got = oracle.process_terraclimate_pixel_vars(g["terraclimate"], g["clear_sky"], g["month_id"], g["n_days"])
+    np.testing.assert_allclose(got, g["monthly"], rtol=1e-13, atol=0)
+    s = dict(zip(oracle.VAR_NAMES, g["series"]))
+    case = Case(n_cells=2)
+    hab = oracle.habitat(**syn.habitat_cone())
+    dm = oracle.densmod(case.densmod["type_"], case.densmod["dd_effect"], case.densmod["surface_area_cm2"])
+    area = oracle.simulate_ephemeral_habitat(s["rainfall"], s["air_temperature"], s["humidity"], s["windspeed"],
+                                             float(g["altitude"]), hab, 2)
+    np.testing.assert_allclose(area, g["water_surface_area_burnin2"], rtol=1e-11, atol=1e-15)
+    pop = oracle.simulate_population(s["larval_habitat_area"], s["mdr"], s["efd"], s["das_zerodensity"], s["ds"], dm,
+                                     burnin_years=2)
+    np.testing.assert_allclose(pop["aquatic"], g["aquatic_burnin2"], rtol=1e-11, atol=1e-15)
+    np.testing.assert_allclose(pop["adult"], g["adult_burnin2"], rtol=1e-11, atol=1e-15)
