@@ -195,9 +195,20 @@ MMS_API int mms_run_chain(const mms_chain_config *cfg, const double *monthly, co
                   const mms_chain_outputs *out);
 
 /* Resident ("plan") form of the same call, for callers that keep a tile on
- * the device across several launches (species, habitat ensembles) and for
- * benchmarking the kernel with inputs already in HBM.  A plan shards the cells
- * contiguously over cfg->devices; every call below is issued to all shards. */
+ * the device across several launches (species, habitat ensembles), for tile
+ * loops that reuse one plan (mms_chain_run per tile), and for benchmarking the
+ * kernel with inputs already in HBM.  A plan shards the cells contiguously over
+ * cfg->devices and owns a team of host threads per device, so the shards of a
+ * multi-GPU plan are fed, run and drained concurrently: one call on one
+ * process replaces the reference's furrr fan-out over pixel batches
+ * (query_terraclimate.R:117-123,166-175,196-241).
+ *
+ * Host buffers: every call below RETURNS ONLY WHEN IT NO LONGER NEEDS THE HOST
+ * BUFFERS IT WAS GIVEN (uploads have left them, downloads have filled them);
+ * mms_chain_launch alone is asynchronous.  Buffers from mms_host_alloc (or
+ * cudaHostRegister'ed memory) are copied by DMA in place; ordinary pageable
+ * memory -- R vectors, numpy arrays -- goes through the plan's pinned bounce
+ * buffers, several host threads per device. */
 typedef struct mms_chain_plan mms_chain_plan;
 MMS_API int  mms_chain_create(const mms_chain_config *cfg, mms_chain_plan **plan);
 MMS_API int  mms_chain_upload(mms_chain_plan *plan, const double *monthly, const double *altitude);
@@ -207,7 +218,17 @@ MMS_API int  mms_chain_upload(mms_chain_plan *plan, const double *monthly, const
 MMS_API int  mms_chain_upload_terraclimate(mms_chain_plan *plan, const double *terraclimate,
                                            const double *clear_sky, const int32_t *month_id,
                                            const double *n_days, const double *altitude);
-/* one-shot form of that route (create, upload_terraclimate, launch, download, destroy):
+/* upload + launch + download as ONE pipelined call: the shard of every device is cut into
+ * chunks of about one round of the persistent kernel, and the host-to-device copy of chunk
+ * k+1, the kernel of chunk k and the device-to-host copy of chunk k-1 overlap.  This is what
+ * mms_run_chain() does between create and destroy. */
+MMS_API int  mms_chain_run(mms_chain_plan *plan, const double *monthly, const double *altitude,
+                           const mms_chain_outputs *out);
+MMS_API int  mms_chain_run_terraclimate(mms_chain_plan *plan, const double *terraclimate,
+                                        const double *clear_sky, const int32_t *month_id,
+                                        const double *n_days, const double *altitude,
+                                        const mms_chain_outputs *out);
+/* one-shot form of that route (create, run_terraclimate, destroy):
  * tc_to_vectors() whole, R/pipeline_functions.R:1099-1130 */
 MMS_API int  mms_run_chain_terraclimate(const mms_chain_config *cfg, const double *terraclimate,
                                         const double *clear_sky, const int32_t *month_id,
@@ -216,7 +237,10 @@ MMS_API int  mms_run_chain_terraclimate(const mms_chain_config *cfg, const doubl
 MMS_API int  mms_chain_launch(mms_chain_plan *plan);          /* asynchronous */
 MMS_API int  mms_chain_sync(mms_chain_plan *plan);            /* waits, reports kernel-side errors */
 MMS_API int  mms_chain_download(mms_chain_plan *plan, const mms_chain_outputs *out);
-MMS_API int  mms_chain_kernel_ms(mms_chain_plan *plan, float *ms);   /* max over shards, last launch */
+MMS_API int  mms_chain_kernel_ms(mms_chain_plan *plan, float *ms);   /* max over shards, last launch (mms_chain_run: sum over its chunks) */
+/* how the plan cut the work: shards (devices), chunks of the first shard, host threads per shard */
+MMS_API int  mms_chain_plan_info(mms_chain_plan *plan, int32_t *n_shards, int32_t *n_chunks_per_shard,
+                                 int32_t *n_workers_per_shard);
 MMS_API int  mms_chain_launch_count(mms_chain_plan *plan, int64_t *n);/* kernels launched so far */
 MMS_API void mms_chain_destroy(mms_chain_plan *plan);
 /* the contiguous cell range [cell0, cell0 + count) that shard `index` of `n_shards` owns
@@ -312,8 +336,8 @@ MMS_API int mms_lifehistory_vectorised(const double *water_temperature, const do
 MMS_API int mms_stage_kernel_ms(float *ms);
 
 /* ---- pinned host buffers --------------------------------------------------
- * Optional: host<->device copies of buffers obtained here run asynchronously at
- * full PCIe speed; any other host memory works too (staged by the driver). */
+ * Optional: host<->device copies of buffers obtained here are DMA'd in place;
+ * any other host memory works too (staged through the plan's bounce buffers). */
 MMS_API int mms_host_alloc(void **ptr, uint64_t bytes);
 MMS_API int mms_host_free(void *ptr);
 
@@ -321,6 +345,7 @@ MMS_API int mms_host_free(void *ptr);
 MMS_API int mms_measure_fp64_peak(int32_t device, double *tflops);  /* dependent-free DFMA loop */
 MMS_API int mms_measure_hbm_copy(int32_t device, double *gbs);      /* device-to-device copy, read+write bytes */
 MMS_API int mms_flush_l2(int32_t device);                           /* overwrite a buffer larger than L2 */
+MMS_API int mms_device_info(int32_t device, int32_t *n_sm, int32_t *sm_clock_khz_max, uint64_t *memory_bytes);
 
 #ifdef __cplusplus
 }

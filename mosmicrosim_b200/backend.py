@@ -87,6 +87,7 @@ class ChainOutputs(ct.Structure):
 
 EXPORTS = ("mms_abi_version", "mms_device_count", "mms_last_error", "mms_run_chain",
            "mms_chain_create", "mms_chain_upload", "mms_chain_launch", "mms_chain_sync",
+           "mms_chain_run", "mms_chain_run_terraclimate", "mms_chain_plan_info",
            "mms_chain_download", "mms_chain_kernel_ms", "mms_chain_launch_count", "mms_chain_destroy",
            "mms_shard_range",
            "mms_water_vectorised", "mms_population_vectorised", "mms_water_series", "mms_population_series",
@@ -94,7 +95,7 @@ EXPORTS = ("mms_abi_version", "mms_device_count", "mms_last_error", "mms_run_cha
            "mms_chain_upload_terraclimate", "mms_run_chain_terraclimate", "mms_terraclimate_to_monthly",
            "mms_summarise_vectors",
            "mms_daily_from_monthly", "mms_hourly_from_daily", "mms_lifehistory_vectorised", "mms_host_alloc", "mms_host_free",
-           "mms_measure_fp64_peak", "mms_measure_hbm_copy", "mms_flush_l2")
+           "mms_measure_fp64_peak", "mms_measure_hbm_copy", "mms_flush_l2", "mms_device_info")
 
 _lib = None
 
@@ -119,6 +120,9 @@ def lib() -> ct.CDLL:
         L.mms_terraclimate_to_monthly.argtypes = [_dp, _dp, _ip, _dp, ct.c_int64, ct.c_int32, ct.c_int32,
                                                   ct.c_int32, _dp]
         L.mms_chain_launch.argtypes = [vp]
+        L.mms_chain_run.argtypes = [vp, _dp, _dp, ct.POINTER(ChainOutputs)]
+        L.mms_chain_run_terraclimate.argtypes = [vp, _dp, _dp, _ip, _dp, _dp, ct.POINTER(ChainOutputs)]
+        L.mms_chain_plan_info.argtypes = [vp, _ip, _ip, _ip]
         L.mms_chain_sync.argtypes = [vp]
         L.mms_chain_download.argtypes = [vp, ct.POINTER(ChainOutputs)]
         L.mms_chain_kernel_ms.argtypes = [vp, ct.POINTER(ct.c_float)]
@@ -146,6 +150,7 @@ def lib() -> ct.CDLL:
         L.mms_measure_fp64_peak.argtypes = [ct.c_int32, ct.POINTER(ct.c_double)]
         L.mms_measure_hbm_copy.argtypes = [ct.c_int32, ct.POINTER(ct.c_double)]
         L.mms_flush_l2.argtypes = [ct.c_int32]
+        L.mms_device_info.argtypes = [ct.c_int32, _ip, _ip, ct.POINTER(ct.c_uint64)]
         _lib = L
     return _lib
 
@@ -359,9 +364,32 @@ class ChainPlan:
         return int(n.value)
 
     def run(self, monthly, altitude, out=None):
-        self.upload(monthly, altitude)
-        self.launch()
-        return self.download(out if out is not None else self.allocate_outputs())
+        """mms_chain_run(): upload, kernels and download pipelined over the chunks of every shard."""
+        monthly, altitude = _d(monthly), _d(altitude)
+        if monthly.shape != (NFORCING, self.M, self.C) or altitude.shape != (self.C,):
+            raise ValueError(f"monthly must be [9][{self.M}][{self.C}] and altitude [{self.C}]")
+        out = out if out is not None else self.allocate_outputs()
+        o = self._outputs_struct(out)
+        check(lib().mms_chain_run(self._plan, _p(monthly), _p(altitude), ct.byref(o)))
+        return out
+
+    def run_terraclimate(self, terraclimate, clear_sky, month_id, n_days, altitude, out=None):
+        """mms_chain_run_terraclimate(): the same from the six raw TerraClimate variables."""
+        tc, cs, nd, altitude = _d(terraclimate), _d(clear_sky), _d(n_days), _d(altitude)
+        mid = np.ascontiguousarray(month_id, dtype=np.int32)
+        if tc.shape != (NTERRACLIMATE, self.M, self.C) or cs.shape != (12, self.C) or altitude.shape != (self.C,):
+            raise ValueError(f"terraclimate must be [6][{self.M}][{self.C}], clear_sky [12][{self.C}], altitude [{self.C}]")
+        out = out if out is not None else self.allocate_outputs()
+        o = self._outputs_struct(out)
+        check(lib().mms_chain_run_terraclimate(self._plan, _p(tc), _p(cs), mid.ctypes.data_as(_ip), _p(nd),
+                                               _p(altitude), ct.byref(o)))
+        return out
+
+    def info(self):
+        """(shards, chunks of the first shard, host threads per shard)"""
+        a, b, c = ct.c_int32(), ct.c_int32(), ct.c_int32()
+        check(lib().mms_chain_plan_info(self._plan, ct.byref(a), ct.byref(b), ct.byref(c)))
+        return {"shards": a.value, "chunks_per_shard": b.value, "workers_per_shard": c.value}
 
     def close(self):
         if getattr(self, "_plan", None):
@@ -540,6 +568,12 @@ def measure_hbm_copy(device=0) -> float:
     v = ct.c_double()
     check(lib().mms_measure_hbm_copy(int(device), ct.byref(v)))
     return float(v.value)
+
+
+def device_info(device=0) -> dict:
+    n_sm, khz, mem = ct.c_int32(), ct.c_int32(), ct.c_uint64()
+    check(lib().mms_device_info(int(device), ct.byref(n_sm), ct.byref(khz), ct.byref(mem)))
+    return {"n_sm": n_sm.value, "sm_clock_mhz_max": khz.value / 1000.0, "memory_bytes": mem.value}
 
 
 def flush_l2(device=0) -> None:

@@ -28,6 +28,8 @@ UNITS = [
     ("chain_ws_tu.cu", "chain_ws_fast.o", ["-DMMS_STRICT=0"]),
     ("chain_tu.cu", "chain_strict.o", ["-DMMS_STRICT=1", "-fmad=false"]),
     ("mmsgpu_api.cu", "mmsgpu_api.o", []),
+    ("api_common.cu", "api_common.o", []),
+    ("api_twins.cu", "api_twins.o", []),
     ("measure.cu", "measure.o", []),
 ]
 
@@ -51,8 +53,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     os.makedirs(BUILD, exist_ok=True)
     procs = []
+    headers = [os.path.join(HERE, "..", "include", "mmsgpu.h")]
+    headers += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    newest_header = max(os.path.getmtime(h) for h in headers)
+    flags_tag = " ".join(COMMON)
     for src, obj, extra in UNITS:
-        cmd = [NVCC] + COMMON + extra + ["-c", os.path.join(CSRC, src), "-o", os.path.join(BUILD, obj)]
+        o = os.path.join(BUILD, obj)
+        tag = o + ".flags"
+        # a unit is rebuilt when its source, any header or the flags changed
+        if (not force and os.path.exists(o) and os.path.exists(tag) and open(tag).read() == flags_tag + " ".join(extra)
+                and os.path.getmtime(o) > max(newest_header, os.path.getmtime(os.path.join(CSRC, src)))):
+            continue
+        with open(tag, "w") as f:
+            f.write(flags_tag + " ".join(extra))
+        cmd = [NVCC] + COMMON + extra + ["-c", os.path.join(CSRC, src), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)

@@ -55,7 +55,7 @@ cudaError_t launch_one(ChainParams &p, int n_sm, cudaStream_t stream)
     // work units: 32 cells x one group of kNS settings.  Pick the number of warps
     // per persistent CTA so that the rounds come out even: the fewest rounds that
     // fit the largest CTA, then the fewest warps that still need only that many.
-    p.n_cell_blocks = (int32_t)(p.c_stride / 32);
+    p.n_cell_blocks = (int32_t)(p.n_cols / 32);
     p.n_units = p.n_cell_blocks * (p.S / kNS);
 #if !MMS_STRICT
     // Which form?  Measured on B200 (profiles/r01_*): the pair form wins when the launch is
@@ -96,10 +96,11 @@ cudaError_t launch_ns(ChainParams &p, int n_sm, bool full, bool hourly, cudaStre
     return hourly ? launch_one<kNS, false, true>(p, n_sm, stream) : launch_one<kNS, false, false>(p, n_sm, stream);
 }
 
-__global__ void log1p_rows_kernel(double *rows, int64_t n)
+__global__ void log1p_rows_kernel(double *rows, int64_t width, int64_t pitch)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) rows[i] = log1p(rows[i]);                  // R/sim_microclimate.R:33
+    double *row = rows + (int64_t)blockIdx.y * pitch;
+    if (i < width) row[i] = log1p(row[i]);                // R/sim_microclimate.R:33
 }
 
 }  // namespace
@@ -115,10 +116,11 @@ cudaError_t MMS_LAUNCH(launch_chain)(ChainParams &p, int n_sm, cudaStream_t stre
     return launch_ns<1>(p, n_sm, full, hourly, stream);
 }
 
-cudaError_t MMS_LAUNCH(launch_log1p_rows)(double *rows, int64_t n, cudaStream_t stream)
+cudaError_t MMS_LAUNCH(launch_log1p_rows)(double *rows, int64_t n_rows, int64_t width, int64_t pitch, cudaStream_t stream)
 {
-    if (n <= 0) return cudaSuccess;
-    log1p_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(rows, n);
+    if (n_rows <= 0 || width <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((width + 255) / 256), (unsigned)n_rows);
+    log1p_rows_kernel<<<grid, 256, 0, stream>>>(rows, width, pitch);
     return cudaGetLastError();
 }
 
@@ -159,7 +161,7 @@ cudaError_t MMS_LAUNCH(launch_summarise)(const double *hourly, const int32_t *pe
 
 cudaError_t MMS_LAUNCH(launch_terraclimate)(const TerraParams &p, cudaStream_t stream)
 {
-    dim3 grid((unsigned)(p.c_stride / 128), (unsigned)p.M);
+    dim3 grid((unsigned)((p.n_cols + 127) / 128), (unsigned)p.M);
     terraclimate_kernel<<<grid, 128, 0, stream>>>(p);
     return cudaGetLastError();
 }

@@ -101,6 +101,23 @@ int mms_measure_hbm_copy(int32_t device, double *gbs)
     return MMS_OK;
 }
 
+// SM count and the maximum SM clock of a device: the nominal FP64 peak is n_sm x 64 FMA/clk x 2 x clock
+int mms_device_info(int32_t device, int32_t *n_sm, int32_t *sm_clock_khz_max, uint64_t *memory_bytes)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) return MMS_ERR_NO_DEVICE;
+    if (device < 0 || device >= n) return MMS_ERR_INVALID_ARG;
+    int v = 0;
+    if (n_sm) { if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return MMS_ERR_CUDA; *n_sm = v; }
+    if (sm_clock_khz_max) { if (cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, device) != cudaSuccess) return MMS_ERR_CUDA; *sm_clock_khz_max = v; }
+    if (memory_bytes) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return MMS_ERR_CUDA;
+        *memory_bytes = (uint64_t)prop.totalGlobalMem;
+    }
+    return MMS_OK;
+}
+
 int mms_flush_l2(int32_t device)
 {
     int n = 0;

@@ -75,8 +75,10 @@ struct ChainParams {
     const double *altitude;    // [c_stride]
     const DayEntry *days;      // [D]
     const int32_t *period_of_day; // [D] or nullptr
-    int64_t c_stride;          // padded number of cells of this shard
-    int64_t n_cells;           // real cells of this shard
+    int64_t c_stride;          // row stride of every [...][cell] array of this shard (its padded number of cells)
+    int64_t n_cells;           // real cells of this launch (a launch covers a column window of the shard's arrays:
+                               // all pointers below are already offset to the window's first cell)
+    int64_t n_cols;            // columns this launch integrates (n_cells rounded up to whole 32-cell units, <= c_stride)
     int32_t M, D, S, P;
     int32_t burnin_years_water, burnin_years_pop;
     double initial_adult, initial_aquatic;
@@ -93,7 +95,7 @@ struct ChainParams {
     int32_t *error_flag;       // set non-zero by the kernel on non-finite forcing
     int32_t *unit_counter;     // work-unit dispenser, zeroed before every launch
     int32_t n_units;           // n_cell_blocks * (S / settings per thread)
-    int32_t n_cell_blocks;     // c_stride / 32
+    int32_t n_cell_blocks;     // n_cols / 32
     int32_t force_warps;       // > 0: cap on warps (pairs) per CTA (tuning aid, env MMS_CHAIN_WARPS)
     int32_t warp_specialised;  // fast mode: 1 = chain_ws.cuh (forcing / state warp pairs), 0 = monolithic, -1 = auto
     HourTables hr;
@@ -107,9 +109,19 @@ cudaError_t launch_chain_strict(ChainParams &p, int n_sm, cudaStream_t stream);
 // the warp-pair form (chain_ws_tu.cu), called by launch_chain_fast when it picks that form
 cudaError_t launch_chain_ws_fast(const ChainParams &p, int settings_per_thread, bool full, bool hourly, int grid,
                                  int pairs, cudaStream_t stream);
-// monthly rainfall -> log1p(rainfall) in place (R/sim_microclimate.R:33)
-cudaError_t launch_log1p_rows_fast(double *rows, int64_t n, cudaStream_t stream);
-cudaError_t launch_log1p_rows_strict(double *rows, int64_t n, cudaStream_t stream);
+// monthly rainfall -> log1p(rainfall) in place (R/sim_microclimate.R:33): n_rows rows of `width` doubles, `pitch` apart
+cudaError_t launch_log1p_rows_fast(double *rows, int64_t n_rows, int64_t width, int64_t pitch, cudaStream_t stream);
+cudaError_t launch_log1p_rows_strict(double *rows, int64_t n_rows, int64_t width, int64_t pitch, cudaStream_t stream);
+
+// work units (32 cells x one group of settings) one round of the persistent fused kernel holds on a device with
+// n_sm SMs, and the settings a thread integrates -- what the host pipeline sizes its chunks with (chain_tu.cu
+// launch_one picks the same forms)
+inline int chain_settings_per_thread(int S) { return S % 4 == 0 ? 4 : (S % 2 == 0 ? 2 : 1); }
+inline int chain_round_units(int S, bool strict, int n_sm)
+{
+    const bool pairs = !strict && chain_settings_per_thread(S) == 2;
+    return n_sm * (pairs ? kChainMaxPairs : kChainMaxWarps);
+}
 
 // state-free verbs (verb_kernels.cuh); p carries monthly / days / hr / tables as for the chain
 cudaError_t launch_daily_fast(const ChainParams &p, double *out_daily, cudaStream_t stream);
@@ -136,7 +148,8 @@ struct TerraParams {
     const int32_t *month_id;      // [M], 1..12
     const double *n_days;         // [M], as.numeric(end - start)
     double *monthly;              // [9][M][c_stride], MMS_F_* order
-    int64_t c_stride, n_cells;
+    int64_t c_stride, n_cells;    // row stride; real cells of this launch (pointers offset to its first cell)
+    int64_t n_cols;               // columns written (cells beyond n_cells get zeros), <= c_stride
     int32_t M;
     int32_t log1p_rainfall;       // 1: store log1p(rainfall_daily) (what the fused kernel reads, R/sim_microclimate.R:33)
     double wind_factor;           // (height_required / height_measured) ^ exponent, host libm like R (R/utils.R:132)

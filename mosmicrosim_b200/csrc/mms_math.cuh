@@ -172,7 +172,13 @@ __device__ __forceinline__ PopHour pop_hour(int densmod_type, double mdr, double
 #if MMS_STRICT
         ph.link0 = log(-log(1.0 - daily_mortality_zero_density));
 #else
-        ph.link0 = ::mms::fm::log_nonneg(1.0 - daily_mortality_zero_density);   // log p'; exp(loghaz) = -log p' * exp(dd*D)
+        // log p'; exp(loghaz) = -log p' * exp(dd*D).  A spline that overshoots 1 (positive_spline clamps at 0 only):
+        // p' > 1 -> the reference takes log(-log p') of a negative number: NaN; p' == 1 -> log(-0) = -Inf, das_t = 1:
+        // log p' must be an exact 0 for that (the table-driven log(1) is ~1e-17, and dd*D may be huge)
+        const double pp = 1.0 - daily_mortality_zero_density;
+        double lp = ::mms::fm::log_nonneg(pp);
+        lp = ::mms::fm::sel(pp == 1.0, 0.0, lp);
+        ph.link0 = ::mms::fm::sel(pp > 1.0, ::mms::fm::make_nan(), lp);
 #endif
     } else {
 #if MMS_STRICT

@@ -130,12 +130,12 @@ __device__ __forceinline__ double cloud_cover_pct(double srad, double clear_sky,
     return cloud;
 }
 
-// grid (c_stride / 128, M).  Padding cells (>= n_cells) get zeros.
+// grid (ceil(n_cols / 128), M).  Padding cells (>= n_cells) get zeros.
 __global__ void __launch_bounds__(128) terraclimate_kernel(const __grid_constant__ TerraParams p)
 {
     const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int m = blockIdx.y;
-    if (cell >= p.c_stride) return;
+    if (cell >= p.n_cols) return;
     const int64_t cs = p.c_stride, plane = (int64_t)p.M * cs, at = (int64_t)m * cs + cell;
     double o[MMS_NFORCING] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (cell < p.n_cells) {

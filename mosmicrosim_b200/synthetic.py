@@ -110,6 +110,27 @@ def synthetic_forcing(n_cells: int, start, seed: int = SEED, out_of_range_fracti
     return monthly, altitude
 
 
+def synthetic_forcing_large(n_cells: int, start, seed: int = SEED, base_cells: int = 100_000,
+                            out_of_range_fraction: float = 0.01):
+    """The same kind of forcing for the multi-million-cell configurations, generated fast: a base tile of
+    base_cells cells from synthetic_forcing(), repeated with a replica-specific temperature shift, rainfall
+    scale and altitude offset (so no two replicas are the same cells).  Returns (monthly[9][M][C], altitude[C])."""
+    C = int(n_cells)
+    base, alt = synthetic_forcing(min(base_cells, C), start, seed=seed, out_of_range_fraction=out_of_range_fraction)
+    nb = base.shape[2]
+    if nb == C:
+        return base, alt
+    monthly = np.empty((9, base.shape[1], C))
+    altitude = np.empty(C)
+    for k, c0 in enumerate(range(0, C, nb)):
+        n = min(nb, C - c0)
+        monthly[:, :, c0:c0 + n] = base[:, :, :n]
+        monthly[0:2, :, c0:c0 + n] += 0.37 * ((k * 7) % 11 - 5)          # tmin, tmax: -1.85 .. +1.85 deg C
+        monthly[8, :, c0:c0 + n] *= 1.0 + 0.05 * ((k * 5) % 9 - 4)        # rainfall: x 0.8 .. 1.2
+        altitude[c0:c0 + n] = (alt[:n] + 137.0 * k) % 2500.0
+    return monthly, altitude
+
+
 def synthetic_terraclimate(n_cells: int, start, seed: int = SEED, out_of_range_fraction: float = 0.01):
     """Raw TerraClimate-style monthly variables for n_cells cells:
     returns (terraclimate[6][M][C] in the order tmax, tmin, ppt, ws, vpd, srad; clear_sky[12][C];
