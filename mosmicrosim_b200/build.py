@@ -30,6 +30,7 @@ UNITS = [
     ("mmsgpu_api.cu", "mmsgpu_api.o", []),
     ("api_common.cu", "api_common.o", []),
     ("api_twins.cu", "api_twins.o", []),
+    ("host_copy.cpp", "host_copy.o", []),       # g++ only (AVX2 streaming stores behind a run-time check)
     ("measure.cu", "measure.o", []),
 ]
 
@@ -67,6 +68,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         with open(tag, "w") as f:
             f.write(flags_tag + " ".join(extra))
         cmd = [NVCC] + COMMON + extra + ["-c", os.path.join(CSRC, src), "-o", o]
+        if src.endswith(".cpp"):
+            cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O3", "-fPIC", "-fvisibility=hidden", "-c",
+                   os.path.join(CSRC, src), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)

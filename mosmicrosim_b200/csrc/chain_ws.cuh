@@ -41,12 +41,178 @@ constexpr int kWsK = MMS_WS_K;
 #endif
 constexpr int kWsUnrollF = MMS_WS_UNROLL_F, kWsUnrollS = MMS_WS_UNROLL_S;
 constexpr int kWsFields = 6;         // evap, surv_ad, exp(-mdr/24), egg, link0, gain_m_h
-constexpr int kWsRingDoubles = 2 * kWsK * kWsFields * 32;   // per pair
+
+// The hand-off: two slots and one named barrier per pair (bar.sync id, 64) at every hour.  ncu (profiles/r01_*,
+// per-role stall samples in profiles/r02_pair_kernel_binder.md) shows the state warps waiting 11 % of their time at
+// that barrier and the forcing warps 3 %, so round 2 tried to decouple the roles: MMS_WS_RING = 4 replaces the
+// barrier by a ring of four slots with a full / empty pair of shared-memory mbarriers per slot (every lane arrives),
+// so that the forcing warp can run up to four hours ahead.  MEASURED (BASELINE configs[1], one B200): 54.4 ms against
+// 52.8 ms for the barrier form -- the try_wait / arrive pairs and the slot arithmetic cost more issue slots and
+// latency on the two in-order instruction streams than the lock-step loses.  Kept behind the switch (parity-tested),
+// off by default.
+#ifndef MMS_WS_RING
+#define MMS_WS_RING 0
+#endif
+constexpr int kWsRing = MMS_WS_RING;             // slots (a power of two), or 0
+constexpr int kWsSlots = kWsRing > 0 ? kWsRing : 2;
+static_assert(kWsRing == 0 || (kWsRing & (kWsRing - 1)) == 0, "the ring needs a power-of-two number of slots");
+static_assert(kWsRing == 0 || MMS_WS_K == 1, "the mbarrier ring hands over one hour at a time");
+constexpr int kWsRingDoubles = kWsSlots * kWsK * kWsFields * 32 + 2 * kWsSlots;   // per pair: slots, then full[] / empty[] mbarriers
+
+// The ds(T, RH) quad table (2 MB) lives in L2: its look-up is the one long-latency load of the forcing warp's hour
+// (19 % of the forcing warps' stall samples sit on the first use of the quad).  Round 2 tried to request the quad of
+// hour h + 1 at the top of hour h.  MEASURED (same workload): carrying the requested quad in registers 63.4 ms
+// (the forcing role is at its 80-register cap -- 22 warps x 2560 registers -- and the carried values spill inside the
+// hour loop); a bare prefetch.global.L1 of the record, nothing carried, 57.9 ms (the ~35 instructions that find the
+// next hour's record cost more than the latency they hide: both instruction streams are in-order and bound by
+// FP64 dependent-issue latency, so every added instruction lengthens the hour).  Off by default.
+// (1 = carry the requested quad in registers; 2 = only a prefetch.global.L1 of its two sectors, nothing carried.)
+#ifndef MMS_WS_DSPREFETCH
+#define MMS_WS_DSPREFETCH 0
+#endif
+
+// prefetch.global.L1 of the quad record the ds look-up of (temperature, humidity) will read
+__device__ __forceinline__ void ds_prefetch_l1(const SurfaceDev &g, double temperature, double humidity)
+{
+    const double fx = (temperature - g.x0) * g.inv_dx, fy = (humidity - g.y0) * g.inv_dy;
+    int i = __double2int_rd(fx), j = __double2int_rd(fy);
+    i = min(max(i, 0), g.nx - 2);
+    j = min(max(j, 0), g.ny - 2);
+    const double *q = g.quad + (size_t)(i + (g.nx - 1) * j) * 4;       // one 32-byte record = one sector
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+}
 
 __device__ __forceinline__ void pair_barrier(int pair)
 {
     asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");   // barrier 0 is __syncthreads()
 }
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(bar) : "memory");
+}
+
+// wait until the phase with this parity of the barrier has completed (try_wait suspends the warp for a
+// hardware-defined time before it reports failure: no busy spin on the issue slots of the sub-partition)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MMS_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MMS_DONE_%=;\n"
+        "bra MMS_WAIT_%=;\n"
+        "MMS_DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// one end of a pair's ring: where the slots and the barriers are, and how many hand-offs this warp has made
+// (both roles make the same hand-offs in the same order, over all passes and all units of the kernel)
+struct RingEnd {
+    double *slots;          // [kWsSlots][kWsFields][32], this lane's column
+    uint32_t full, empty;   // shared-memory addresses of full[0], empty[0]
+    uint32_t it;            // hand-offs so far
+    int pair;
+};
+
+__device__ __forceinline__ RingEnd ring_end(double *ring, int pair, int lane)
+{
+    RingEnd r;
+    r.slots = ring + lane;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ring + kWsSlots * kWsK * kWsFields * 32);
+    r.full = smem_u32(bars);
+    r.empty = smem_u32(bars + kWsSlots);
+    r.it = 0;
+    r.pair = pair;
+    return r;
+}
+
+// forcing warp: the slot to fill next (waits until the state warp has drained it)
+__device__ __forceinline__ double *ring_acquire_empty(RingEnd &r)
+{
+    if (kWsRing > 0) {
+        const uint32_t slot = r.it & (kWsSlots - 1);
+        mbar_wait(r.empty + 8 * slot, ((r.it / kWsSlots) & 1) ^ 1);
+        return r.slots + (size_t)slot * (kWsFields * 32);
+    }
+    return r.slots + (size_t)(r.it & 1) * (kWsK * kWsFields * 32);
+}
+__device__ __forceinline__ void ring_publish(RingEnd &r)
+{
+    if (kWsRing > 0) mbar_arrive(r.full + 8 * (r.it & (kWsSlots - 1)));
+    else pair_barrier(r.pair);                       // the state warp may now read this buffer
+    r.it += 1;
+}
+// state warp: the slot to read next (waits until the forcing warp has filled it)
+__device__ __forceinline__ const double *ring_acquire_full(RingEnd &r)
+{
+    if (kWsRing > 0) {
+        const uint32_t slot = r.it & (kWsSlots - 1);
+        mbar_wait(r.full + 8 * slot, (r.it / kWsSlots) & 1);
+        return r.slots + (size_t)slot * (kWsFields * 32);
+    }
+    pair_barrier(r.pair);                            // the forcing warp has filled this buffer
+    return r.slots + (size_t)(r.it & 1) * (kWsK * kWsFields * 32);
+}
+__device__ __forceinline__ void ring_release(RingEnd &r)
+{
+    if (kWsRing > 0) mbar_arrive(r.empty + 8 * (r.it & (kWsSlots - 1)));
+    r.it += 1;
+}
+
+#if MMS_WS_DSPREFETCH == 1
+// the microclimate of an hour and (requested, not yet used) its ds quad
+struct HourAhead {
+    double air_t, rh, wind, cloud;
+    DsFetch dsf;
+};
+
+template <bool kFull, bool kWaterOnly>
+__device__ __forceinline__ HourAhead hour_ahead(const ChainParams &p, const DayCtx &dc, int h)
+{
+    HourF f;
+    hour_microclimate<kFull>(p.hr, dc, h, f);
+    HourAhead a;
+    a.air_t = f.air_t; a.rh = f.rh; a.wind = f.wind; a.cloud = f.cloud;
+    if (!kWaterOnly) a.dsf = ds_fetch(p.ds, f.air_t, f.rh);
+    return a;
+}
+
+// hour_forcing() (chain_kernel.cuh) from a microclimate evaluated, and a quad requested, an hour earlier
+template <bool kFull, bool kWaterOnly>
+__device__ __forceinline__ HourF hour_forcing_from(const ChainParams &p, const SmemTables &tb, const HourAhead &a,
+                                                   double p_a, int dens_type)
+{
+    HourF f;
+    f.air_t = a.air_t; f.rh = a.rh; f.wind = a.wind; f.cloud = a.cloud;
+    f.mdr = f.efd = f.das0 = f.ds = 0.0;
+    double dx = 0.0;
+    double4 c0 = make_double4(0, 0, 0, 0), c1 = c0, c2 = c0;
+    if (!kWaterOnly) {
+        const int i = spline_interval(p.spline, tb.sx, f.air_t);
+        dx = f.air_t - tb.sx[i];
+        const double4 *cf = reinterpret_cast<const double4 *>(tb.coef + (size_t)i * 12);
+        c0 = cf[0]; c1 = cf[1]; c2 = cf[2];
+    }
+    f.evap = evaporation_rate(f.air_t, f.rh, p_a, f.wind);      // R/sim_water.R:264-270 (air temperature)
+    if (!kWaterOnly) {
+        f.ds = ds_blend(a.dsf);
+        f.mdr = ensure_positive(c0.x + dx * (c0.y + dx * (c0.z + dx * c0.w)));
+        f.efd = ensure_positive(c1.x + dx * (c1.y + dx * (c1.z + dx * c1.w)));
+        f.das0 = ensure_positive(c2.x + dx * (c2.y + dx * (c2.z + dx * c2.w)));
+        f.ph = pop_hour(dens_type, f.mdr, f.efd, f.das0, f.ds);
+    }
+    return f;
+}
+#endif
 
 // period bookkeeping shared by both roles (aggregate_vectors(), R/pipeline_functions.R:1050-1088)
 struct PeriodCursor {
@@ -73,7 +239,7 @@ struct PeriodCursor {
 // ---- forcing warp ---------------------------------------------------------------------------
 template <bool kFull, bool kHourly, bool kWaterOnly, bool kRecord, int kDens>
 __device__ __forceinline__ void forcing_pass(const ChainParams &p, const SmemTables &tb, const UnitCtx &u,
-                                             double *ring, int pair, int n_days, int &bad)
+                                             RingEnd &ring, int n_days, int &bad)
 {
     constexpr int kNF = kFull ? 9 : 4;
     constexpr uint32_t kState = MMS_STATE_VAR_MASK;
@@ -107,7 +273,7 @@ __device__ __forceinline__ void forcing_pass(const ChainParams &p, const SmemTab
     dc.t_midnight_prev = (dc.t_sunset - dc.nxt.tmin) / p.hr.exp_e[23] + dc.nxt.tmin;   // :271-272
     dc.rhmin_prev = dc.cur.rhmin; dc.wsmax_prev = dc.cur.wsmax; dc.ccmin_prev = dc.cur.ccmin;
 
-    int buf = 0;
+    (void)lane;
     for (int day = 0; day < n_days; ++day) {
         if (kRecord) {
             bool fresh;
@@ -122,13 +288,31 @@ __device__ __forceinline__ void forcing_pass(const ChainParams &p, const SmemTab
         const double rain_h = dc.cur.rain * (1.0 / 24.0);                 // R/sim_microclimate.R:132
         const double gain_m_h = rain_h * (1.0 / 1000.0);                  // R/sim_water.R:122
         double air_t_last = 0.0;
+#if MMS_WS_DSPREFETCH == 1
+        HourAhead ahead = hour_ahead<kFull, kWaterOnly>(p, dc, 0);
+#endif
 #pragma unroll 1
         for (int h0 = 0; h0 < 24; h0 += kWsK) {
-            double *slot = ring + (size_t)buf * (kWsK * kWsFields * 32) + lane;
+#if MMS_WS_DSPREFETCH == 1
+            // the quad of the hour to come is requested before this hour's arithmetic starts
+            const HourAhead now = ahead;
+            if (h0 + kWsK < 24) ahead = hour_ahead<kFull, kWaterOnly>(p, dc, h0 + kWsK);
+#elif MMS_WS_DSPREFETCH == 2
+            if (!kWaterOnly && h0 + kWsK < 24) {
+                HourF fa;
+                hour_microclimate<false>(p.hr, dc, h0 + kWsK, fa);
+                ds_prefetch_l1(p.ds, fa.air_t, fa.rh);
+            }
+#endif
+            double *slot = ring_acquire_empty(ring);
 #pragma unroll kWsUnrollF
             for (int k = 0; k < kWsK; ++k) {
                 const int h = h0 + k;
+#if MMS_WS_DSPREFETCH == 1
+                const HourF f = hour_forcing_from<kFull, kWaterOnly>(p, tb, now, u.p_a, kDens >= 0 ? (kDens & 1) : p.densmod_type);
+#else
                 const HourF f = hour_forcing<kFull, kWaterOnly>(p, tb, dc, u.p_a, h, kDens >= 0 ? (kDens & 1) : p.densmod_type);
+#endif
                 double *rec = slot + (size_t)k * (kWsFields * 32);
                 rec[0 * 32] = f.evap;
                 rec[1 * 32] = f.ph.surv_ad;
@@ -161,8 +345,7 @@ __device__ __forceinline__ void forcing_pass(const ChainParams &p, const SmemTab
                     }
                 }
             }
-            pair_barrier(pair);                      // the state warp may now read this buffer
-            buf ^= 1;
+            ring_publish(ring);
         }
         // ---- roll the day window
         dc.t_midnight_prev = air_t_last;             // hour-24 value, R/sim_microclimate.R:271
@@ -179,7 +362,7 @@ __device__ __forceinline__ void forcing_pass(const ChainParams &p, const SmemTab
 // ---- state warp ------------------------------------------------------------------------------
 template <int kNS, bool kFull, bool kHourly, bool kWaterOnly, bool kRecord, int kDens>
 __device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &u, UnitState<kNS> &st,
-                                           const double *ring, int pair, int n_days)
+                                           RingEnd &ring, int n_days)
 {
     constexpr uint32_t kState = MMS_STATE_VAR_MASK;
     const int lane = threadIdx.x & 31;
@@ -216,7 +399,7 @@ __device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &
         }
     };
 
-    int buf = 0;
+    (void)lane;
     for (int day = 0; day < n_days; ++day) {
         if (kRecord) {
             bool fresh;
@@ -229,8 +412,7 @@ __device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &
         }
 #pragma unroll 1
         for (int h0 = 0; h0 < 24; h0 += kWsK) {
-            pair_barrier(pair);                      // the forcing warp has filled this buffer
-            const double *slot = ring + (size_t)buf * (kWsK * kWsFields * 32) + lane;
+            const double *slot = ring_acquire_full(ring);
 #pragma unroll kWsUnrollS
             for (int k = 0; k < kWsK; ++k) {
                 const double *rec = slot + (size_t)k * (kWsFields * 32);
@@ -242,6 +424,7 @@ __device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &
                 ph.egg = rec[3 * 32];
                 ph.link0 = rec[4 * 32];
                 const double gain_m_h = rec[5 * 32];
+                if (k == kWsK - 1) ring_release(ring);   // the values are in registers: the forcing warp may refill the slot
 #pragma unroll
                 for (int s = 0; s < kNS; ++s) {
                     const HabitatDev &hb = p.hab[u.set0 + s];
@@ -285,7 +468,6 @@ __device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &
                     }
                 }
             }
-            buf ^= 1;
         }
     }
     if (kRecord && pc.cur_period >= 0) flush(pc.cur_period);
@@ -312,6 +494,10 @@ chain_kernel_ws(const __grid_constant__ ChainParams p)
     for (int k = threadIdx.x; k < p.ds.nx; k += blockDim.x) s_gx[k] = p.ds.x[k];
     for (int k = threadIdx.x; k < p.ds.ny; k += blockDim.x) s_gy[k] = p.ds.y[k];
     ::mms::fm::math_tables_init();
+    if (kWsRing > 0 && (int)threadIdx.x < n_pairs) {
+        uint64_t *bars = reinterpret_cast<uint64_t *>(s_ring + (size_t)threadIdx.x * kWsRingDoubles + kWsSlots * kWsK * kWsFields * 32);
+        for (int k = 0; k < 2 * kWsSlots; ++k) mbar_init(bars + k, 32);    // every lane of the arriving warp arrives
+    }
     __syncthreads();
     SmemTables tb{s_x, s_coef, s_gx, s_gy};
 
@@ -323,7 +509,7 @@ chain_kernel_ws(const __grid_constant__ ChainParams p)
     const bool tail = (n_pairs & 1) && warp >= 2 * (n_pairs - 1);
     const int pair = tail ? n_pairs - 1 : (warp & 1) + ((warp >> 2) << 1);
     const bool forcing_role = tail ? (warp & 1) == 0 : (warp & 2) == 0;
-    double *ring = s_ring + (size_t)pair * kWsRingDoubles;
+    RingEnd ring = ring_end(s_ring + (size_t)pair * kWsRingDoubles, pair, lane);
 
     for (;;) {
         if (forcing_role && lane == 0) s_unit[pair] = atomicAdd(p.unit_counter, 1);
@@ -345,10 +531,10 @@ chain_kernel_ws(const __grid_constant__ ChainParams p)
             u.p_a = air_pressure_kpa(__ldg(p.altitude + u.cell));
             int bad = 0;
             for (int y = 0; y < p.burnin_years_water; ++y)
-                forcing_pass<kFull, kHourly, true, false, kDens>(p, tb, u, ring, pair, kDaysPerYear, bad);
+                forcing_pass<kFull, kHourly, true, false, kDens>(p, tb, u, ring, kDaysPerYear, bad);
             for (int y = 0; y < p.burnin_years_pop; ++y)
-                forcing_pass<kFull, kHourly, false, false, kDens>(p, tb, u, ring, pair, kDaysPerYear, bad);
-            forcing_pass<kFull, kHourly, false, true, kDens>(p, tb, u, ring, pair, p.D, bad);
+                forcing_pass<kFull, kHourly, false, false, kDens>(p, tb, u, ring, kDaysPerYear, bad);
+            forcing_pass<kFull, kHourly, false, true, kDens>(p, tb, u, ring, p.D, bad);
             if (bad && u.live) atomicOr(p.error_flag, 1);
         } else {
             u.p_a = 0.0;
@@ -361,19 +547,19 @@ chain_kernel_ws(const __grid_constant__ ChainParams p)
                 st.surface[s] = habitat_surface(p.hab[u.set0 + s], st.volume[s]);
             }
             for (int y = 0; y < p.burnin_years_water; ++y)
-                state_pass<kNS, kFull, kHourly, true, false, kDens>(p, u, st, ring, pair, kDaysPerYear);
+                state_pass<kNS, kFull, kHourly, true, false, kDens>(p, u, st, ring, kDaysPerYear);
             double vol0[kNS];
 #pragma unroll
             for (int s = 0; s < kNS; ++s) vol0[s] = st.volume[s];
             for (int y = 0; y < p.burnin_years_pop; ++y) {
-                state_pass<kNS, kFull, kHourly, false, false, kDens>(p, u, st, ring, pair, kDaysPerYear);
+                state_pass<kNS, kFull, kHourly, false, false, kDens>(p, u, st, ring, kDaysPerYear);
 #pragma unroll
                 for (int s = 0; s < kNS; ++s) {
                     st.volume[s] = vol0[s];
                     st.surface[s] = habitat_surface(p.hab[u.set0 + s], vol0[s]);
                 }
             }
-            state_pass<kNS, kFull, kHourly, false, true, kDens>(p, u, st, ring, pair, p.D);
+            state_pass<kNS, kFull, kHourly, false, true, kDens>(p, u, st, ring, p.D);
         }
     }
 }

@@ -30,11 +30,16 @@
 
 using namespace mms_api;
 
+namespace mms_api {
+// host_copy.cpp: streaming-store row copy between caller memory and the pinned bounce buffers
+void copy_rows(char *dst, size_t dpitch, const char *src, size_t spitch, size_t width, size_t rows);
+}
+
 namespace {
 
 constexpr size_t kSlotBytes = (size_t)16 << 20;   // one pinned bounce buffer
 constexpr int kSlots = 2;                         // bounce buffers per worker and direction
-constexpr int kMaxWorkers = 4;                    // host threads per device
+constexpr int kMaxWorkers = 8;                    // host threads per device
 constexpr int kMaxChunks = 64;                    // chunks per shard
 
 // a host <-> device array with the cell index fastest: `rows` rows of cells, this shard's part
@@ -347,12 +352,6 @@ bool ensure_slots(Worker *wk, bool in)
         if (!evs[k]) MMS_CUDA_W(s, cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming));
     }
     return true;
-}
-
-void copy_rows(char *dst, size_t dpitch, const char *src, size_t spitch, size_t width, size_t rows)
-{
-    if (dpitch == width && spitch == width) { std::memcpy(dst, src, width * rows); return; }
-    for (size_t r = 0; r < rows; ++r) std::memcpy(dst + r * dpitch, src + r * spitch, width);
 }
 
 // host -> device: the worker's columns of one array
@@ -701,8 +700,9 @@ int plan_workers(int n_shards)
     return std::max(1, std::min(kMaxWorkers, per));
 }
 
-// chunks of one shard: about one round of the persistent kernel each (at most kMaxChunks), equal numbers of
-// 32-cell units so that every chunk's launch fills its rounds evenly
+// chunks of one shard: at most one round of the persistent kernel each (every warp slot of the device gets one
+// unit; a chunk that needed a second, partly filled round would run at about half the warps per SM), equal numbers
+// of 32-cell units, at most kMaxChunks (then each chunk is several even rounds)
 void plan_chunks(mms_chain_plan *pl, Shard *s, int n_sm_guess)
 {
     const int64_t blocks = s->c_stride / 32;
@@ -710,7 +710,7 @@ void plan_chunks(mms_chain_plan *pl, Shard *s, int n_sm_guess)
     const int64_t units = blocks * (pl->S / kns);
     const bool strict = pl->math_mode != 0 || !pl->tab.uniform;
     const int64_t round_units = mms::chain_round_units(pl->S, strict, n_sm_guess);
-    int64_t n = (units + round_units / 2) / round_units;
+    int64_t n = (units + round_units - 1) / round_units;
     if (const char *e = std::getenv("MMS_CHAIN_CHUNKS")) {
         const int64_t f = std::atoll(e);
         if (f >= 1) n = f;
