@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MMS_ABI_VERSION 1
+#define MMS_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define MMS_API __attribute__((visibility("default")))
@@ -68,17 +68,20 @@ enum {
 /* output variables.  0-5 are the reference's vector_variables in its order
  * (R/pipeline_functions.R:1041-1048); 6-7 the water body
  * (R/pipeline_functions.R:879-891 carries larval_habitat_area); 8-12 the hourly
- * microclimate (R/sim_microclimate.R:139-169). */
+ * microclimate (R/sim_microclimate.R:139-169); 13 the water temperature (the
+ * air temperature, R/sim_microclimate.R:163, unless it is modelled). */
 enum {
     MMS_V_ADULT = 0, MMS_V_AQUATIC, MMS_V_MDR, MMS_V_EFD, MMS_V_DAS_ZERODENSITY, MMS_V_DS,
     MMS_V_LARVAL_HABITAT_AREA, MMS_V_WATER_VOLUME,
     MMS_V_AIR_TEMPERATURE, MMS_V_HUMIDITY, MMS_V_WINDSPEED, MMS_V_RAINFALL, MMS_V_CLOUDCOVER,
+    MMS_V_WATER_TEMPERATURE,
     MMS_NVARS
 };
 /* variables that depend on the habitat setting (one series per setting);
  * all others depend on the forcing only (one series per cell) */
 #define MMS_STATE_VAR_MASK ((1u << MMS_V_ADULT) | (1u << MMS_V_AQUATIC) | \
-                            (1u << MMS_V_LARVAL_HABITAT_AREA) | (1u << MMS_V_WATER_VOLUME))
+                            (1u << MMS_V_LARVAL_HABITAT_AREA) | (1u << MMS_V_WATER_VOLUME) | \
+                            (1u << MMS_V_WATER_TEMPERATURE))
 #define MMS_PIPELINE_VAR_MASK 0x3Fu   /* the six vector_variables */
 #define MMS_MAX_SETTINGS 64
 
@@ -127,6 +130,27 @@ typedef struct mms_lifehistory {
     mms_surface ds_temp_humid; /* (air temperature, humidity), :116-119 */
 } mms_lifehistory;
 
+/* Water-temperature model -- an EXTENSION.  The reference only sketches it (comments,
+ * query_terraclimate.R:370-497), stop()s on simulate_hourly_conditions(model_water_temperature =
+ * TRUE) (R/pipeline_functions.R:334-338) and uses the air temperature (R/sim_microclimate.R:163).
+ * The spec is authored in DESIGN.md section 5 from that prose: hourly energy balance of the water
+ * body -- evaporative loss, long-wave exchange with the air, solar gain from the pixel's clear-sky
+ * radiation distributed over the day by the solar zenith angle (latitude, day of year, hour),
+ * reduced by the hourly cloud cover (Angstrom) and by the shade.  Parity unpinned by construction.
+ * With enabled = 0 (the default) every result is the reference's, bit for bit.  Needs
+ * mms_chain_set_location() and n_settings == 1 (the rates that take the water temperature become
+ * a property of the water body). */
+typedef struct mms_water_temperature {
+    int32_t enabled;               /* model_water_temperature */
+    int32_t reserved;
+    double  shade_proportion;      /* water_shade_proportion in [0, 1]; 1 = fully shaded (no solar gain) */
+    double  albedo;                /* of the water surface; the notes assume "very low": 0 */
+    double  emissivity;            /* 0.97 */
+    double  convection_w_m2_k;     /* sensible heat exchange with the air, W / m2 / K; 0 = the notes' model (none) */
+    const int32_t *day_of_year;    /* [D] doy(date), R/utils.R:46-48 */
+    const int32_t *month_of_day;   /* [D] calendar month 1..12 of each day (row of clear_sky) */
+} mms_water_temperature;
+
 /* Everything about a fused-chain run except the per-cell data. */
 typedef struct mms_chain_config {
     int64_t n_cells;           /* C */
@@ -154,6 +178,7 @@ typedef struct mms_chain_config {
                                       1 = strict (no contraction, literal operation order) */
     int32_t  n_devices;            /* 0 = all visible devices */
     const int32_t *devices;        /* [n_devices] CUDA ordinals, or NULL for 0..n_devices-1 */
+    mms_water_temperature water_temperature;   /* EXTENSION (ABI 2); all zero = the reference */
 } mms_chain_config;
 
 /* ---- library ------------------------------------------------------------ */
@@ -234,6 +259,10 @@ MMS_API int  mms_run_chain_terraclimate(const mms_chain_config *cfg, const doubl
                                         const double *clear_sky, const int32_t *month_id,
                                         const double *n_days, const double *altitude,
                                         const mms_chain_outputs *out);
+/* per-cell inputs of the water-temperature model: latitude [C] (degrees) and the pixel's clear-sky
+ * radiation by calendar month [12][C] (clear_sky_radiation_12mo(), the array the TerraClimate route
+ * takes too); resident on the device until the plan is destroyed */
+MMS_API int  mms_chain_set_location(mms_chain_plan *plan, const double *latitude, const double *clear_sky);
 MMS_API int  mms_chain_launch(mms_chain_plan *plan);          /* asynchronous */
 MMS_API int  mms_chain_sync(mms_chain_plan *plan);            /* waits, reports kernel-side errors */
 MMS_API int  mms_chain_download(mms_chain_plan *plan, const mms_chain_outputs *out);

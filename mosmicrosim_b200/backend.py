@@ -16,12 +16,12 @@ LIB_PATH = os.environ.get("MMS_LIB") or os.path.join(_HERE, "libmmsgpu.so")   # 
 NFORCING = 9
 NTERRACLIMATE = 6
 TERRACLIMATE_VARS = ("tmax", "tmin", "ppt", "ws", "vpd", "srad")   # R/pipeline_functions.R:134-136
-NVARS = 13
+NVARS = 14
 VAR_NAMES = ("adult", "aquatic", "mdr", "efd", "das_zerodensity", "ds",
              "larval_habitat_area", "water_volume",
-             "air_temperature", "humidity", "windspeed", "rainfall", "cloudcover")
+             "air_temperature", "humidity", "windspeed", "rainfall", "cloudcover", "water_temperature")
 VAR_INDEX = {n: i for i, n in enumerate(VAR_NAMES)}
-STATE_VAR_MASK = (1 << 0) | (1 << 1) | (1 << 6) | (1 << 7)
+STATE_VAR_MASK = (1 << 0) | (1 << 1) | (1 << 6) | (1 << 7) | (1 << 13)
 PIPELINE_VAR_MASK = 0x3F
 MAX_SETTINGS = 64
 
@@ -67,6 +67,13 @@ class LifehistoryC(ct.Structure):
     _fields_ = [("mdr_temp", Spline), ("efd_temp", Spline), ("das_temp", Spline), ("ds_temp_humid", Surface)]
 
 
+class WaterTemperature(ct.Structure):
+    """mms_water_temperature: the water-temperature EXTENSION (include/mmsgpu.h)."""
+    _fields_ = [("enabled", ct.c_int32), ("reserved", ct.c_int32), ("shade_proportion", ct.c_double),
+                ("albedo", ct.c_double), ("emissivity", ct.c_double), ("convection_w_m2_k", ct.c_double),
+                ("day_of_year", _ip), ("month_of_day", _ip)]
+
+
 class ChainConfig(ct.Structure):
     _fields_ = [("n_cells", ct.c_int64), ("n_months", ct.c_int32), ("n_days", ct.c_int32),
                 ("n_settings", ct.c_int32), ("n_periods", ct.c_int32),
@@ -77,7 +84,8 @@ class ChainConfig(ct.Structure):
                 ("densmod", Densmod), ("lifehistory", LifehistoryC),
                 ("mean_var_mask", ct.c_uint32), ("hourly_var_mask", ct.c_uint32),
                 ("want_wet_hours", ct.c_int32), ("want_wet_flags", ct.c_int32),
-                ("math_mode", ct.c_int32), ("n_devices", ct.c_int32), ("devices", _ip)]
+                ("math_mode", ct.c_int32), ("n_devices", ct.c_int32), ("devices", _ip),
+                ("water_temperature", WaterTemperature)]
 
 
 class ChainOutputs(ct.Structure):
@@ -87,7 +95,7 @@ class ChainOutputs(ct.Structure):
 
 EXPORTS = ("mms_abi_version", "mms_device_count", "mms_last_error", "mms_run_chain",
            "mms_chain_create", "mms_chain_upload", "mms_chain_launch", "mms_chain_sync",
-           "mms_chain_run", "mms_chain_run_terraclimate", "mms_chain_plan_info",
+           "mms_chain_run", "mms_chain_run_terraclimate", "mms_chain_plan_info", "mms_chain_set_location",
            "mms_chain_download", "mms_chain_kernel_ms", "mms_chain_launch_count", "mms_chain_destroy",
            "mms_shard_range",
            "mms_water_vectorised", "mms_population_vectorised", "mms_water_series", "mms_population_series",
@@ -123,6 +131,7 @@ def lib() -> ct.CDLL:
         L.mms_chain_run.argtypes = [vp, _dp, _dp, ct.POINTER(ChainOutputs)]
         L.mms_chain_run_terraclimate.argtypes = [vp, _dp, _dp, _ip, _dp, _dp, ct.POINTER(ChainOutputs)]
         L.mms_chain_plan_info.argtypes = [vp, _ip, _ip, _ip]
+        L.mms_chain_set_location.argtypes = [vp, _dp, _dp]
         L.mms_chain_sync.argtypes = [vp]
         L.mms_chain_download.argtypes = [vp, ct.POINTER(ChainOutputs)]
         L.mms_chain_kernel_ms.argtypes = [vp, ct.POINTER(ct.c_float)]
@@ -232,7 +241,7 @@ class ChainPlan:
     def __init__(self, n_cells, mid_day, day_predict, habitats, densmod, tables, period_of_day=None,
                  n_periods=0, burnin_years_water=0, burnin_years_pop=1, initial_adult=100.0,
                  initial_aquatic=100.0, mean_vars=(), hourly_vars=(), want_wet_hours=False,
-                 want_wet_flags=False, math_mode="fast", devices=None, _create=True):
+                 want_wet_flags=False, math_mode="fast", devices=None, water_temperature=None, _create=True):
         self._keep = []
         cfg = ChainConfig()
         self.C = int(n_cells)
@@ -275,10 +284,34 @@ class ChainPlan:
             dv = np.ascontiguousarray(devices, dtype=np.int32)
             self._keep.append(dv)
             cfg.n_devices, cfg.devices = len(dv), dv.ctypes.data_as(_ip)
+        self._location = None
+        if water_temperature is not None:
+            # EXTENSION: dict(shade_proportion, albedo, emissivity, convection_w_m2_k, day_of_year[D], month_of_day[D],
+            #                 latitude[C], clear_sky[12][C])
+            w = water_temperature
+            doy = np.ascontiguousarray(w["day_of_year"], dtype=np.int32)
+            mon = np.ascontiguousarray(w["month_of_day"], dtype=np.int32)
+            if doy.shape != (self.D,) or mon.shape != (self.D,):
+                raise ValueError("day_of_year and month_of_day must have one entry per simulated day")
+            self._keep += [doy, mon]
+            cfg.water_temperature = WaterTemperature(1, 0, float(w.get("shade_proportion", 1.0)), float(w.get("albedo", 0.0)),
+                                                     float(w.get("emissivity", 0.97)), float(w.get("convection_w_m2_k", 0.0)),
+                                                     doy.ctypes.data_as(_ip), mon.ctypes.data_as(_ip))
+            if "latitude" in w:
+                self._location = (_d(w["latitude"]), _d(w["clear_sky"]))
         self._cfg = cfg
         self._plan = ct.c_void_p()
         if _create:
             check(lib().mms_chain_create(ct.byref(cfg), ct.byref(self._plan)))
+            if self._location is not None:
+                self.set_location(*self._location)
+
+    def set_location(self, latitude, clear_sky):
+        """mms_chain_set_location(): latitude [C] and clear-sky radiation by calendar month [12][C]."""
+        lat, cs = _d(latitude), _d(clear_sky)
+        if lat.shape != (self.C,) or cs.shape != (12, self.C):
+            raise ValueError(f"latitude must be [{self.C}] and clear_sky [12][{self.C}]")
+        check(lib().mms_chain_set_location(self._plan, _p(lat), _p(cs)))
 
     # -- output buffers -------------------------------------------------------
     def allocate_outputs(self, pinned=False):
@@ -412,6 +445,10 @@ class ChainPlan:
 def run_chain(monthly, altitude, **kwargs):
     """One-shot mms_run_chain(): host buffers in, host buffers out."""
     monthly = _d(monthly)
+    if kwargs.get("water_temperature") is not None:
+        # the water-temperature EXTENSION takes per-cell location inputs: create, set_location, run, destroy
+        with ChainPlan(monthly.shape[2], **kwargs) as plan:
+            return plan.run(monthly, altitude)
     with ChainPlan(monthly.shape[2], _create=False, **kwargs) as plan:
         out = plan.allocate_outputs()
         o = plan._outputs_struct(out)

@@ -183,6 +183,8 @@ __device__ __forceinline__ double ds_blend(const DsFetch &d)
 struct DayCtx {          // everything the hourly curves need about yesterday / today / tomorrow
     Daily cur, nxt;
     double A, t_sunset, t_midnight_prev, rhmin_prev, wsmax_prev, ccmin_prev;
+    // water-temperature EXTENSION: clear-sky irradiance of hour h = sol_scale * max(0, sol_a * cos_hour_angle[h] + sol_b)
+    double sol_a, sol_b, sol_scale;
 };
 
 struct HourF {
@@ -237,12 +239,14 @@ __device__ __forceinline__ void hour_microclimate(const HourTables &hr, const Da
 
 // dens_type: the density-dependence form; callers that know it at compile time pass the constant, so that the
 // other form's code (and the branch around it) disappears from their loop
-template <bool kFull, bool kWaterOnly>
+// kWT (water-temperature EXTENSION): the two rates that take the water temperature (mdr, das_zerodensity) and what
+// follows from them are left to the water step, which knows that temperature; the hourly cloud cover is needed
+template <bool kFull, bool kWaterOnly, bool kWT = false>
 __device__ __forceinline__ HourF hour_forcing(const ChainParams &p, const SmemTables &tb, const DayCtx &dc,
                                               double p_a, int h, int dens_type)
 {
     HourF f;
-    hour_microclimate<kFull>(p.hr, dc, h, f);
+    hour_microclimate<kFull || kWT>(p.hr, dc, h, f);
     // ---- life-history parameters, R/sim_pop_dynamics.R:100-135
     // water_temperature = air_temperature, R/sim_microclimate.R:163.  The table look-ups
     // (L2-resident ds quad table, shared-memory spline rows) are issued first so that their
@@ -270,10 +274,14 @@ __device__ __forceinline__ HourF hour_forcing(const ChainParams &p, const SmemTa
 #if !MMS_STRICT
         f.ds = ds_blend(dsf);
 #endif
-        f.mdr = ensure_positive(c0.x + dx * (c0.y + dx * (c0.z + dx * c0.w)));
         f.efd = ensure_positive(c1.x + dx * (c1.y + dx * (c1.z + dx * c1.w)));
-        f.das0 = ensure_positive(c2.x + dx * (c2.y + dx * (c2.z + dx * c2.w)));
-        f.ph = pop_hour(dens_type, f.mdr, f.efd, f.das0, f.ds);
+        if (kWT) {
+            pop_hour_air(f.ph, f.efd, f.ds);
+        } else {
+            f.mdr = ensure_positive(c0.x + dx * (c0.y + dx * (c0.z + dx * c0.w)));
+            f.das0 = ensure_positive(c2.x + dx * (c2.y + dx * (c2.z + dx * c2.w)));
+            f.ph = pop_hour(dens_type, f.mdr, f.efd, f.das0, f.ds);
+        }
     }
     return f;
 }
@@ -282,6 +290,7 @@ __device__ __forceinline__ HourF hour_forcing(const ChainParams &p, const SmemTa
 template <int kNS>
 struct UnitState {
     double volume[kNS], surface[kNS], aquatic[kNS], adult[kNS];
+    double water_t[kNS];      // water temperature: the hour's air temperature unless the EXTENSION models it
 };
 
 struct UnitCtx {
@@ -300,10 +309,11 @@ __device__ __forceinline__ int out_slot(uint32_t mask, uint32_t class_mask, int 
 // ---- one pass over n_days days ----------------------------------------------------
 // kWaterOnly : water burn-in year (R/sim_water.R:228-233): no life history, no population
 // kRecord    : the final pass over the full series: period summaries / hourly series
-template <int kNS, bool kFull, bool kHourly, bool kWaterOnly, bool kRecord, int kDens>
+template <int kNS, bool kFull, bool kHourly, bool kWaterOnly, bool kRecord, int kDens, bool kWT = false>
 __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables &tb, const UnitCtx &u,
                                          UnitState<kNS> &st, int n_days, int &bad)
 {
+    static_assert(!kWT || (kNS == 1 && kFull), "the water-temperature model runs one setting per thread, all variables");
     constexpr int kNF = kFull ? 9 : 4;
     constexpr uint32_t kState = MMS_STATE_VAR_MASK;
     // kDens packs what the launcher knows at compile time: bit 0 the density-dependence form, bits 1-2 the
@@ -314,7 +324,7 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
     const int set0 = u.set0;
 
     // period accumulators (aggregate_vectors(), R/pipeline_functions.R:1030-1091)
-    double acc_state[kNS][4];      // adult, aquatic, area, volume
+    double acc_state[kNS][5];      // adult, aquatic, area, volume, water temperature
     double acc_forc[kNF];          // mdr, efd, das0, ds [, airT, RH, wind, rain, cloud]
     int acc_wet[kNS];
     int acc_n = 0, cur_period = -1;
@@ -323,7 +333,7 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
         for (int s = 0; s < kNS; ++s) {
             acc_wet[s] = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) acc_state[s][k] = 0.0;
+            for (int k = 0; k < 5; ++k) acc_state[s][k] = 0.0;
         }
 #pragma unroll
         for (int k = 0; k < kNF; ++k) acc_forc[k] = 0.0;
@@ -337,9 +347,10 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
         const double n = (double)acc_n;
 #pragma unroll
         for (int s = 0; s < kNS; ++s) {
-            const int vid[4] = {MMS_V_ADULT, MMS_V_AQUATIC, MMS_V_LARVAL_HABITAT_AREA, MMS_V_WATER_VOLUME};
+            const int vid[5] = {MMS_V_ADULT, MMS_V_AQUATIC, MMS_V_LARVAL_HABITAT_AREA, MMS_V_WATER_VOLUME,
+                                MMS_V_WATER_TEMPERATURE};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 5; ++k) {
                 if (!kFull && k >= 2) continue;
                 if (p.mean_mask & (1u << vid[k])) {
                     const int64_t row = (int64_t)(set0 + s) * u.n_mean_state + out_slot(p.mean_mask, kState, vid[k]);
@@ -385,6 +396,21 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
             acc_inc = (period >= 0) ? 1 : 0;
         }
 
+        if (kWT) {
+            // the day's clear-sky curve: the pixel's clear-sky radiation of the calendar month (a daily mean) spread
+            // over the 24 hours in proportion to max(0, cos Z), cos Z = cos(lat) cos(delta) cos(h) + sin(lat) sin(delta)
+            const double2 sun = p.wt.sun_day[day];
+            dc.sol_a = __ldg(p.wt.cos_lat + cell) * sun.y;
+            dc.sol_b = __ldg(p.wt.sin_lat + cell) * sun.x;
+            double w = 0.0;
+#pragma unroll 4
+            for (int k = 0; k < 24; ++k) {
+                const double cz = dc.sol_a * p.hr.cos_hour_angle[k] + dc.sol_b;
+                w += (cz > 0.0) ? cz : 0.0;
+            }
+            const double clear = __ldg(p.wt.clear_sky + (int64_t)(p.wt.month_of_day[day] - 1) * cs + cell);
+            dc.sol_scale = (w > 0.0) ? clear * 24.0 / w : 0.0;
+        }
         const double rain_h = MMS_DIVC(dc.cur.rain, 24.0);                // R/sim_microclimate.R:132
         const double gain_m_h = MMS_DIVC(rain_h, 1000.0);                 // R/sim_water.R:122
         double gain[kNS];
@@ -392,11 +418,32 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
         for (int s = 0; s < kNS; ++s) gain[s] = p.hab[set0 + s].catchment_area * gain_m_h;   // :123
 
         // the water recursion of one hour: volume, surface <- hour h (needs that hour's evaporation rate only)
-        auto water_step = [&](double evap) {
+        auto water_step = [&](HourF &fx, int h) {
 #pragma unroll
             for (int s = 0; s < kNS; ++s) {
                 const HabitatDev &hb = p.hab[set0 + s];
-                st.volume[s] = iterate_volume(hb, st.volume[s], st.surface[s], evap, gain[s]);     // R/sim_water.R:279-287
+                if (kWT) {
+                    // EXTENSION: volume and temperature together, then the rates that take the water temperature
+                    const double cz = dc.sol_a * p.hr.cos_hour_angle[h] + dc.sol_b;
+                    const double i_clear = dc.sol_scale * ((cz > 0.0) ? cz : 0.0);
+                    double tw = st.water_t[s];
+                    tw = (tw != tw) ? fx.air_t : tw;             // first step: the water starts at the air's temperature
+                    st.volume[s] = iterate_volume_temperature(hb, p.wt, st.volume[s], st.surface[s], tw, fx.evap, gain[s],
+                                                              fx.air_t, fx.cloud, i_clear);
+                    st.water_t[s] = tw;
+                    if (!kWaterOnly) {
+                        const int i = spline_interval(p.spline, tb.sx, tw);        // R/sim_pop_dynamics.R:108,114
+                        const double dx = tw - tb.sx[i];
+                        const double4 *cf = reinterpret_cast<const double4 *>(tb.coef + (size_t)i * 12);
+                        const double4 c0 = cf[0], c2 = cf[2];
+                        fx.mdr = ensure_positive(c0.x + dx * (c0.y + dx * (c0.z + dx * c0.w)));
+                        fx.das0 = ensure_positive(c2.x + dx * (c2.y + dx * (c2.z + dx * c2.w)));
+                        pop_hour_water(fx.ph, dens_type, fx.mdr, fx.das0);
+                    }
+                } else {
+                    st.volume[s] = iterate_volume(hb, st.volume[s], st.surface[s], fx.evap, gain[s]);     // R/sim_water.R:279-287
+                    if (kFull) st.water_t[s] = fx.air_t;         // water_temperature = air_temperature, R/sim_microclimate.R:163
+                }
                 st.surface[s] = habitat_surface(hb, st.volume[s], kShapeAll >= 0 ? kShapeAll : hb.shape);   // :294
             }
         };
@@ -417,6 +464,7 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
                     if (kFull) {
                         acc_state[s][2] += (acc_on ? st.surface[s] : 0.0);
                         acc_state[s][3] += (acc_on ? st.volume[s] : 0.0);
+                        acc_state[s][4] += (acc_on ? st.water_t[s] : 0.0);
                     }
                     acc_wet[s] += (st.volume[s] > 0.0) ? acc_inc : 0;
                 }
@@ -431,10 +479,11 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
                     const int64_t tc = (int64_t)(day * 24 + h) * cs + cell;
 #pragma unroll
                     for (int s = 0; s < kNS; ++s) {
-                        const double val[4] = {st.adult[s], st.aquatic[s], st.surface[s], st.volume[s]};
-                        const int vid[4] = {MMS_V_ADULT, MMS_V_AQUATIC, MMS_V_LARVAL_HABITAT_AREA, MMS_V_WATER_VOLUME};
+                        const double val[5] = {st.adult[s], st.aquatic[s], st.surface[s], st.volume[s], st.water_t[s]};
+                        const int vid[5] = {MMS_V_ADULT, MMS_V_AQUATIC, MMS_V_LARVAL_HABITAT_AREA, MMS_V_WATER_VOLUME,
+                                            MMS_V_WATER_TEMPERATURE};
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
+                        for (int k = 0; k < 5; ++k) {
                             if (!kFull && k >= 2) continue;
                             if (p.hourly_mask & (1u << vid[k])) {
                                 const int64_t row = (int64_t)(set0 + s) * u.n_hourly_state + out_slot(p.hourly_mask, kState, vid[k]);
@@ -464,13 +513,13 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
         // state-independent half of hour h + 1, the water recursion of hour h + 1 (it needs only the
         // evaporation rate of that hour) and the population update of hour h (it needs the surface of
         // hour h, which the previous iteration left behind).  Same arithmetic, same results.
-        HourF f = hour_forcing<kFull, kWaterOnly>(p, tb, dc, u.p_a, 0, dens_type);
-        water_step(f.evap);
+        HourF f = hour_forcing<kFull, kWaterOnly, kWT>(p, tb, dc, u.p_a, 0, dens_type);
+        water_step(f, 0);
 #pragma unroll 1
         for (int h = 0; h < 23; ++h) {
-            const HourF fn = hour_forcing<kFull, kWaterOnly>(p, tb, dc, u.p_a, h + 1, dens_type);
+            HourF fn = hour_forcing<kFull, kWaterOnly, kWT>(p, tb, dc, u.p_a, h + 1, dens_type);
             pop_and_record(f, h);
-            water_step(fn.evap);
+            water_step(fn, h + 1);
             f = fn;
         }
         pop_and_record(f, 23);
@@ -488,7 +537,7 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
 }
 
 // ---- one work unit: 32 cells x kNS settings, all passes ---------------------------
-template <int kNS, bool kFull, bool kHourly, int kDens>
+template <int kNS, bool kFull, bool kHourly, int kDens, bool kWT = false>
 __device__ __forceinline__ void simulate_unit(const ChainParams &p, const SmemTables &tb, int64_t cell, int set0,
                                               bool write_forcing)
 {
@@ -507,26 +556,28 @@ __device__ __forceinline__ void simulate_unit(const ChainParams &p, const SmemTa
         st.adult[s] = p.initial_adult;
         st.volume[s] = p.hab[set0 + s].initial_volume;   // R/sim_water.R:277
         st.surface[s] = habitat_surface(p.hab[set0 + s], st.volume[s]);
+        st.water_t[s] = __longlong_as_double(0x7ff8000000000000LL);   // "not set yet": the first step takes the air's temperature
     }
     // water burn-in years: first 8760 steps, water only (R/sim_water.R:228-233)
     for (int y = 0; y < p.burnin_years_water; ++y)
-        run_pass<kNS, kFull, kHourly, true, false, kDens>(p, tb, u, st, kDaysPerYear, bad);
-    // every later pass re-runs the water model from this volume: the reference computes the
+        run_pass<kNS, kFull, kHourly, true, false, kDens, kWT>(p, tb, u, st, kDaysPerYear, bad);
+    // every later pass re-runs the water model from this volume [and temperature]: the reference computes the
     // water series once and the population burn-in re-indexes its first year
-    double vol0[kNS];
+    double vol0[kNS], tw0[kNS];
 #pragma unroll
-    for (int s = 0; s < kNS; ++s) vol0[s] = st.volume[s];
+    for (int s = 0; s < kNS; ++s) { vol0[s] = st.volume[s]; tw0[s] = st.water_t[s]; }
     // population burn-in years: first 8760 steps (R/sim_pop_dynamics.R:221-226)
     for (int y = 0; y < p.burnin_years_pop; ++y) {
-        run_pass<kNS, kFull, kHourly, false, false, kDens>(p, tb, u, st, kDaysPerYear, bad);
+        run_pass<kNS, kFull, kHourly, false, false, kDens, kWT>(p, tb, u, st, kDaysPerYear, bad);
 #pragma unroll
         for (int s = 0; s < kNS; ++s) {
             st.volume[s] = vol0[s];
             st.surface[s] = habitat_surface(p.hab[set0 + s], vol0[s]);
+            st.water_t[s] = tw0[s];
         }
     }
     // the full series, recorded
-    run_pass<kNS, kFull, kHourly, false, true, kDens>(p, tb, u, st, p.D, bad);
+    run_pass<kNS, kFull, kHourly, false, true, kDens, kWT>(p, tb, u, st, p.D, bad);
 
     if (bad && u.live) atomicOr(p.error_flag, 1);
 }
@@ -538,7 +589,8 @@ __device__ __forceinline__ void simulate_unit(const ChainParams &p, const SmemTa
 // kHourly : write full hourly series
 // kMaxWarps: largest CTA this instantiation may be launched with (register budget = 64K / threads)
 // kDens: what the launcher knows at compile time (bit 0: 0 logit / 1 cox_ph; bits 1-2: common shape + 1), else -1
-template <int kNS, bool kFull, bool kHourly, int kMaxWarps, int kDens>
+// kWT: the water-temperature EXTENSION (one setting per thread, all variables)
+template <int kNS, bool kFull, bool kHourly, int kMaxWarps, int kDens, bool kWT = false>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
 chain_kernel(const __grid_constant__ ChainParams p)
 {
@@ -562,7 +614,7 @@ chain_kernel(const __grid_constant__ ChainParams p)
         unit = __shfl_sync(0xffffffffu, unit, 0);
         if (unit >= p.n_units) break;
         const int cb = unit % p.n_cell_blocks, g = unit / p.n_cell_blocks;
-        simulate_unit<kNS, kFull, kHourly, kDens>(p, tb, (int64_t)cb * 32 + lane, g * kNS, g == 0);
+        simulate_unit<kNS, kFull, kHourly, kDens, kWT>(p, tb, (int64_t)cb * 32 + lane, g * kNS, g == 0);
     }
 }
 

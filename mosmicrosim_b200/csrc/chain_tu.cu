@@ -31,6 +31,8 @@ cudaError_t launch_kernel(const ChainParams &p, int grid, int warps, cudaStream_
         if (p.hab[s].shape != shape_all) shape_all = -1;
     const int dens = p.densmod_type == 1 ? 1 : 0;
     auto kern = chain_kernel<kNS, kFull, kHourly, kMaxWarps, -1>;
+    // the water-temperature EXTENSION: one setting per thread, the all-variables instantiation (launch_chain sees to both)
+    if (p.wt.enabled) kern = chain_kernel<kNS, kFull, kHourly, kMaxWarps, -1, (kNS == 1 && kFull)>;
     if (kSpecialise) {
         kern = dens ? chain_kernel<kNS, kFull, kHourly, kMaxWarps, kSpecialise ? 1 : -1>
                     : chain_kernel<kNS, kFull, kHourly, kMaxWarps, kSpecialise ? 0 : -1>;
@@ -63,8 +65,10 @@ cudaError_t launch_one(ChainParams &p, int n_sm, cudaStream_t stream)
     // 100k-cell tile of BASELINE configs[1]: 58.5 vs 67.4 ms) -- and loses a little when the
     // monolithic kernel can already fill 16 warps per SM, with one setting per cell (100k cells:
     // 54.0 vs 50.2 ms) or with four settings per thread (132 vs 118 ms).
-    const bool ws = p.warp_specialised >= 0 ? p.warp_specialised != 0
-                                            : (kNS == 2 && p.n_units <= (int64_t)2 * n_sm * kChainMaxPairs);
+    bool ws = p.warp_specialised >= 0 ? p.warp_specialised != 0
+                                      : (kNS == 2 && p.n_units <= (int64_t)2 * n_sm * kChainMaxPairs);
+    // the water temperature (as an output, or modelled) lives in the monolithic form only
+    if (p.wt.enabled || ((p.mean_mask | p.hourly_mask) & (1u << MMS_V_WATER_TEMPERATURE))) ws = false;
     if (ws) {
         // warp-specialised form: a pair of warps (forcing + state) per unit, chain_ws.cuh
         const int pairs_max = p.force_warps > 0 ? p.force_warps : kChainMaxPairs;
@@ -108,8 +112,9 @@ __global__ void log1p_rows_kernel(double *rows, int64_t width, int64_t pitch)
 cudaError_t MMS_LAUNCH(launch_chain)(ChainParams &p, int n_sm, cudaStream_t stream)
 {
     const uint32_t all = p.mean_mask | p.hourly_mask;
-    const bool full = (all & ~MMS_PIPELINE_VAR_MASK) != 0;
+    const bool full = (all & ~MMS_PIPELINE_VAR_MASK) != 0 || p.wt.enabled;
     const bool hourly = p.hourly_mask != 0 || p.wet_flags != nullptr;
+    if (p.wt.enabled) return launch_ns<1>(p, n_sm, true, hourly, stream);      // host checked S == 1
     // settings per thread: the largest of 4, 2, 1 that divides S
     if (p.S % 4 == 0) return launch_ns<4>(p, n_sm, full, hourly, stream);
     if (p.S % 2 == 0) return launch_ns<2>(p, n_sm, full, hourly, stream);

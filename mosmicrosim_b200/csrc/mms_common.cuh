@@ -28,6 +28,19 @@ struct HourTables {
     double w_vsine_inv[24];// 1 - weight, :498-500
     double air_coef[24];   // fast mode: predawn[h] | z_light[h] | 1 / exp_e[h] by segment
     double z_night;        // :210
+    double cos_hour_angle[24];  // water-temperature EXTENSION: cos(15 (hour - 12) degrees), query_terraclimate.R:459-466
+};
+
+// Water-temperature model (EXTENSION): per-launch constants and per-day / per-cell tables
+struct WaterTempDev {
+    int32_t enabled; int32_t pad;
+    double solar_gain;           // (1 - shade)(1 - albedo)
+    double sigma_eps;            // 5.67e-8 * emissivity
+    double convection;           // W / m2 / K
+    const double2 *sun_day;      // [D] (sin delta, cos delta) of each day
+    const int32_t *month_of_day; // [D] 1..12
+    const double *sin_lat, *cos_lat;   // [c_stride]
+    const double *clear_sky;     // [12][c_stride]
 };
 
 // Per-setting water-body constants, derived on the host exactly as
@@ -98,6 +111,7 @@ struct ChainParams {
     int32_t n_cell_blocks;     // n_cols / 32
     int32_t force_warps;       // > 0: cap on warps (pairs) per CTA (tuning aid, env MMS_CHAIN_WARPS)
     int32_t warp_specialised;  // fast mode: 1 = chain_ws.cuh (forcing / state warp pairs), 0 = monolithic, -1 = auto
+    WaterTempDev wt;
     HourTables hr;
     HabitatDev hab[MMS_MAX_SETTINGS];
 };

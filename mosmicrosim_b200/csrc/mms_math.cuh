@@ -150,10 +150,16 @@ struct PopHour {
     double link0;       // logit(das0) / cox_ph link of das0: the state independent part of densmod
 };
 
-__device__ __forceinline__ PopHour pop_hour(int densmod_type, double mdr, double efd, double das0, double ds)
+// the part that takes the AIR temperature / humidity rates: adult survival, eggs
+__device__ __forceinline__ void pop_hour_air(PopHour &ph, double efd, double ds)
 {
-    PopHour ph;
     ph.surv_ad = r_pow_pos(ds, MMS_LIT(3, kTimestep));
+    ph.egg = efd * MMS_LIT(3, kTimestep);
+}
+
+// the part that takes the WATER temperature rates (R/sim_pop_dynamics.R:108,114): emergence, density-free link
+__device__ __forceinline__ void pop_hour_water(PopHour &ph, int densmod_type, double mdr, double das0)
+{
 #if MMS_STRICT
     const double e = exp(-(kTimestep * mdr));
 #else
@@ -165,7 +171,6 @@ __device__ __forceinline__ PopHour pop_hour(int densmod_type, double mdr, double
 #else
     ph.one_m_emf = e;
 #endif
-    ph.egg = efd * MMS_LIT(3, kTimestep);
     if (densmod_type == 1) {
         // cox_ph, R/lifehistory_estimation_functions.R:551-553
         const double daily_mortality_zero_density = 1.0 - das0;
@@ -190,7 +195,56 @@ __device__ __forceinline__ PopHour pop_hour(int densmod_type, double mdr, double
         ph.link0 = ::mms::fm::log_nonneg(odds);
 #endif
     }
+}
+
+__device__ __forceinline__ PopHour pop_hour(int densmod_type, double mdr, double efd, double das0, double ds)
+{
+    PopHour ph;
+    pop_hour_air(ph, efd, ds);
+    pop_hour_water(ph, densmod_type, mdr, das0);
     return ph;
+}
+
+// ---- water temperature (EXTENSION; oracle: mmso_iterate_volume_temperature) ------------------
+// One hour of the water body WITH its temperature: the water present at the start of the hour (volume, surface
+// `surface` = S(volume), temperature tw) exchanges evaporative, long-wave, solar [and sensible] heat with a linearly
+// implicit step, then the volume step of iterate_volume() with the same arithmetic, then the rain that arrives (at
+// air temperature) is mixed in by mass.  Plain IEEE arithmetic in both math modes (an optional model, off the
+// benchmarked path); returns the new volume, updates tw.
+__device__ __forceinline__ double iterate_volume_temperature(const HabitatDev &hb, const WaterTempDev &wt, double volume,
+                                                             double surface, double &tw, double evap_rate, double gain,
+                                                             double air_t, double cloud_pct, double i_clear)
+{
+    double tw_pre;
+    if (!(volume > 0.0)) {
+        tw_pre = air_t;
+    } else {
+        const double dt = 3600.0, se = wt.sigma_eps;
+        const double mass = 1000.0 * volume;
+        const double q_evap = 2.26e6 * (evap_rate * surface);
+        const double twk = tw + 273.15, tak = air_t + 273.15;
+        const double twk2 = twk * twk, tak2 = tak * tak;
+        const double q_rad = se * surface * (twk2 * twk2 - tak2 * tak2) * dt;
+        const double angstrom = 0.36 + 0.64 * (1.0 - cloud_pct / 100.0);
+        const double q_sol = wt.solar_gain * i_clear * angstrom * surface * dt;
+        const double q_conv = wt.convection * surface * (air_t - tw) * dt;
+        const double k = 4.0 * se * (twk2 * twk) * surface * dt + wt.convection * surface * dt;
+        tw_pre = tw + (q_sol - q_evap - q_rad + q_conv) / (mass * 4184.0 + k);
+        if (tw_pre < 0.0) tw_pre = 0.0;
+        if (tw_pre > 100.0) tw_pre = 100.0;
+    }
+#if MMS_STRICT
+    const double loss = (evap_rate * surface) / 1000.0;
+#else
+    const double loss = (evap_rate * surface) * kLitC[2];
+#endif
+    double x = volume - loss;
+    x = x - hb.leak_per_hour * volume;
+    x = ensure_positive(x);
+    double y = x + gain;
+    tw = (y > 0.0) ? (x * tw_pre + gain * air_t) / y : air_t;
+    y = (y > hb.max_volume) ? hb.max_volume : y;
+    return y;
 }
 
 // iterate_state(), R/sim_pop_dynamics.R:14-96 (state dependent part)

@@ -104,6 +104,10 @@ struct Shard {
     int32_t *d_wet_hours = nullptr;
     uint8_t *d_wet_flags = nullptr;
     int32_t *d_error = nullptr;    // [chunk][2]: error flag, work-unit counter
+    // water-temperature EXTENSION: per-day tables, per-cell location inputs (mms_chain_set_location)
+    double2 *d_sun_day = nullptr;
+    int32_t *d_month_of_day = nullptr;
+    double *d_sin_lat = nullptr, *d_cos_lat = nullptr, *d_clear_sky = nullptr;
     int n_sm = 0;
     bool launched = false;
     std::vector<Chunk> chunks;
@@ -153,6 +157,11 @@ struct mms_chain_plan {
     std::atomic<int64_t> launches{0};
     bool uploaded = false;
     int n_workers = 1;
+    // water-temperature EXTENSION
+    mms_water_temperature wt{};
+    std::vector<double2> sun_day;          // (sin delta, cos delta) of every day, host libm
+    std::vector<int32_t> month_of_day;
+    bool location_set = false;
 };
 
 namespace {
@@ -214,6 +223,14 @@ bool setup_shard(Shard *s)
     if (!dev_alloc(s, &s->d_hourly_forcing, (size_t)pl->n_hourly_forcing * H * cs)) return false;
     if (pl->want_wet_hours && !dev_alloc(s, &s->d_wet_hours, (size_t)pl->S * pl->P * cs)) return false;
     if (pl->want_wet_flags && !dev_alloc(s, &s->d_wet_flags, (size_t)pl->S * H * cs)) return false;
+    if (pl->wt.enabled) {
+        if (!dev_upload(s, &s->d_sun_day, pl->sun_day, st)) return false;
+        if (!dev_upload(s, &s->d_month_of_day, pl->month_of_day, st)) return false;
+        if (!dev_alloc(s, &s->d_sin_lat, cs) || !dev_alloc(s, &s->d_cos_lat, cs) || !dev_alloc(s, &s->d_clear_sky, 12 * cs)) return false;
+        MMS_CUDA_W(s, cudaMemsetAsync(s->d_sin_lat, 0, sizeof(double) * cs, st));
+        MMS_CUDA_W(s, cudaMemsetAsync(s->d_cos_lat, 0, sizeof(double) * cs, st));
+        MMS_CUDA_W(s, cudaMemsetAsync(s->d_clear_sky, 0, sizeof(double) * 12 * cs, st));
+    }
     if (!dev_alloc(s, &s->d_error, 2 * s->chunks.size())) return false;
     MMS_CUDA_W(s, cudaMemsetAsync(s->d_error, 0, 2 * s->chunks.size() * sizeof(int32_t), st));
     MMS_CUDA_W(s, cudaDeviceGetAttribute(&s->n_sm, cudaDevAttrMultiProcessorCount, s->device));
@@ -233,7 +250,8 @@ void free_shard_device(Shard *s)
     cudaSetDevice(s->device);
     void *ptrs[] = {s->d_monthly, s->d_altitude, s->d_days, s->d_period, s->d_sx, s->d_scoef, s->d_gx, s->d_gy, s->d_quad,
                     s->d_mean_state, s->d_mean_forcing, s->d_hourly_state, s->d_hourly_forcing, s->d_wet_hours,
-                    s->d_wet_flags, s->d_error, s->d_terra};
+                    s->d_wet_flags, s->d_error, s->d_terra, s->d_sun_day, s->d_month_of_day, s->d_sin_lat, s->d_cos_lat,
+                    s->d_clear_sky};
     for (void *q : ptrs) if (q) cudaFree(q);
     for (Chunk &c : s->chunks) {
         if (c.ev_kernel) cudaEventDestroy(c.ev_kernel);
@@ -303,6 +321,14 @@ bool enqueue_chain(Shard *s, int64_t c0, int64_t n_cols, int64_t n_cells, int er
     p.wet_hours = s->d_wet_hours ? s->d_wet_hours + c0 : nullptr;
     p.wet_flags = s->d_wet_flags ? s->d_wet_flags + c0 : nullptr;
     p.mean_mask = pl->mean_mask; p.hourly_mask = pl->hourly_mask;
+    if (pl->wt.enabled) {
+        p.wt.enabled = 1;
+        p.wt.solar_gain = (1.0 - pl->wt.shade_proportion) * (1.0 - pl->wt.albedo);
+        p.wt.sigma_eps = 5.67e-8 * pl->wt.emissivity;
+        p.wt.convection = pl->wt.convection_w_m2_k;
+        p.wt.sun_day = s->d_sun_day; p.wt.month_of_day = s->d_month_of_day;
+        p.wt.sin_lat = s->d_sin_lat + c0; p.wt.cos_lat = s->d_cos_lat + c0; p.wt.clear_sky = s->d_clear_sky + c0;
+    }
     p.error_flag = s->d_error + 2 * err_slot;
     p.unit_counter = s->d_error + 2 * err_slot + 1;
     if (const char *fw = std::getenv("MMS_CHAIN_WARPS")) p.force_warps = std::atoi(fw);
@@ -822,6 +848,31 @@ int mms_chain_create(const mms_chain_config *cfg, mms_chain_plan **out)
         pl->all_periods_present = std::all_of(seen.begin(), seen.end(), [](char c) { return c != 0; });
     }
     if (!rc) rc = pack_tables(cfg->lifehistory, pl->tab);
+    if (!rc && cfg->water_temperature.enabled) {
+        // EXTENSION: the water-temperature model
+        const mms_water_temperature &w = cfg->water_temperature;
+        if (pl->S != 1)
+            rc = fail(MMS_ERR_UNSUPPORTED, "model_water_temperature needs n_settings == 1: the rates that take the water "
+                      "temperature become a property of the water body (run one habitat setting per call)");
+        else if (!w.day_of_year || !w.month_of_day) rc = fail(MMS_ERR_INVALID_ARG, "water temperature: NULL day_of_year or month_of_day");
+        else if (!(w.shade_proportion >= 0 && w.shade_proportion <= 1)) rc = fail(MMS_ERR_INVALID_ARG, "water_shade_proportion must be in [0, 1]");
+        else if (!(w.albedo >= 0 && w.albedo <= 1) || !(w.emissivity > 0 && w.emissivity <= 1) || !(w.convection_w_m2_k >= 0))
+            rc = fail(MMS_ERR_INVALID_ARG, "water temperature: albedo in [0, 1], emissivity in (0, 1], convection >= 0");
+        pl->wt = w;
+        pl->wt.day_of_year = nullptr; pl->wt.month_of_day = nullptr;     // copied below; the caller's arrays are not kept
+        for (int d = 0; d < pl->D && !rc; ++d) {
+            const int doy = w.day_of_year[d], mon = w.month_of_day[d];
+            if (doy < 1 || doy > 366 || mon < 1 || mon > 12) { rc = fail(MMS_ERR_INVALID_ARG, "water temperature: day_of_year[%d] / month_of_day[%d] out of range", d, d); break; }
+            // zeta = omega (doy - 80) + 2 eps (sin(omega doy) - sin(omega 80)), delta = asin(0.39784993 sin zeta)
+            // (query_terraclimate.R:434-457), host libm
+            const double omega = 2 * 3.141592653589793 / 365, eps = 0.01675;
+            const double zeta = omega * (doy - 80) + 2 * eps * (std::sin(omega * doy) - std::sin(omega * 80));
+            const double delta = std::asin(0.39784993 * std::sin(zeta));
+            pl->sun_day.push_back(make_double2(std::sin(delta), std::cos(delta)));
+            pl->month_of_day.push_back(mon);
+        }
+        for (int k = 1; k <= 24; ++k) pl->hr.cos_hour_angle[k - 1] = std::cos(15.0 * (k - 12) * (3.141592653589793 / 180));   // :459-466
+    }
     if (rc) return rc;
     pl->ds_nx = cfg->lifehistory.ds_temp_humid.nx; pl->ds_ny = cfg->lifehistory.ds_temp_humid.ny;
     pl->gx.assign(cfg->lifehistory.ds_temp_humid.x, cfg->lifehistory.ds_temp_humid.x + pl->ds_nx);
@@ -893,10 +944,37 @@ int mms_chain_upload_terraclimate(mms_chain_plan *pl, const double *terraclimate
     return MMS_OK;
 }
 
+// latitude and clear-sky radiation of every cell (water-temperature EXTENSION); sin / cos of the latitude are taken
+// here with the host libm.  Small (14 doubles per cell): one synchronous copy per shard.
+int mms_chain_set_location(mms_chain_plan *pl, const double *latitude, const double *clear_sky)
+{
+    if (!pl || !latitude || !clear_sky) return fail(MMS_ERR_INVALID_ARG, "NULL plan, latitude or clear_sky");
+    if (!pl->wt.enabled) return fail(MMS_ERR_INVALID_ARG, "the plan was not created with the water-temperature model enabled");
+    for (auto &sp : pl->shards) {
+        Shard *s = sp.get();
+        MMS_CUDA(cudaSetDevice(s->device));
+        std::vector<double> sl((size_t)s->n_cells), cl((size_t)s->n_cells);
+        for (int64_t c = 0; c < s->n_cells; ++c) {
+            const double lat = latitude[s->cell0 + c];
+            if (!(lat >= -90 && lat <= 90)) return fail(MMS_ERR_INVALID_ARG, "latitude of cell %lld is not in [-90, 90]", (long long)(s->cell0 + c));
+            const double phi = lat * (3.141592653589793 / 180);
+            sl[(size_t)c] = std::sin(phi);
+            cl[(size_t)c] = std::cos(phi);
+        }
+        MMS_CUDA(cudaMemcpy(s->d_sin_lat, sl.data(), sizeof(double) * s->n_cells, cudaMemcpyHostToDevice));
+        MMS_CUDA(cudaMemcpy(s->d_cos_lat, cl.data(), sizeof(double) * s->n_cells, cudaMemcpyHostToDevice));
+        MMS_CUDA(cudaMemcpy2D(s->d_clear_sky, sizeof(double) * s->c_stride, clear_sky + s->cell0, sizeof(double) * pl->C,
+                              sizeof(double) * s->n_cells, 12, cudaMemcpyHostToDevice));
+    }
+    pl->location_set = true;
+    return MMS_OK;
+}
+
 int mms_chain_launch(mms_chain_plan *pl)
 {
     if (!pl) return fail(MMS_ERR_INVALID_ARG, "NULL plan");
     if (!pl->uploaded) return fail(MMS_ERR_INVALID_ARG, "mms_chain_upload has not been called on this plan");
+    if (pl->wt.enabled && !pl->location_set) return fail(MMS_ERR_INVALID_ARG, "the water-temperature model needs mms_chain_set_location() first");
     for (auto &sp : pl->shards) {
         Shard *s = sp.get();
         MMS_CUDA(cudaSetDevice(s->device));
@@ -941,6 +1019,7 @@ int mms_chain_download(mms_chain_plan *pl, const mms_chain_outputs *out)
 
 static int run_pipelined(mms_chain_plan *pl, std::vector<Job> &jobs, const mms_chain_outputs *out)
 {
+    if (pl->wt.enabled && !pl->location_set) return fail(MMS_ERR_INVALID_ARG, "the water-temperature model needs mms_chain_set_location() first");
     for (size_t g = 0; g < pl->shards.size(); ++g) add_outputs(pl, pl->shards[g].get(), out, jobs[g]);
     classify(pl, jobs);
     for (auto &sp : pl->shards) { sp->timing_chunks = true; sp->launched = true; }

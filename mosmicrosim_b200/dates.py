@@ -84,6 +84,18 @@ def period_index(dates_predict, aggregate_by="month", included_dates=None):
 
 # ---- TerraClimate month bookkeeping --------------------------------------
 
+def day_of_year(dates) -> np.ndarray:
+    """doy(): as.integer(format(date, "%j")), R/utils.R:46-48 (1-based)."""
+    d = np.asarray(dates, dtype="datetime64[D]")
+    return ((d - d.astype("datetime64[Y]")).astype(np.int64) + 1).astype(np.int32)
+
+
+def month_of_year(dates) -> np.ndarray:
+    """lubridate::month(date): 1..12."""
+    d = np.asarray(dates, dtype="datetime64[D]")
+    return (d.astype("datetime64[M]").astype(np.int64) % 12 + 1).astype(np.int32)
+
+
 def terraclimate_month_info(start, end):
     """(month_id int32[M], n_days float64[M]) as process_terraclimate_pixel_vars() computes them
     (R/terraclimate.R:591-592): month_id = lubridate::month(start + (end - start) / 2) and

@@ -177,9 +177,12 @@ def simulate_hourly_conditions(pixel_hourly_microclimate, model_water_temperatur
     is the dict simulate_hourly_microclimate() returns ([H, C] arrays and the pixels' altitude)."""
     if water_shade_proportion != 1 and not model_water_temperature:           # :329-331
         warnings.warn("water temperature is not being modelled, so water_shade_proportion argument is ignored")
-    if model_water_temperature:                                                # :335-337
-        raise NotImplementedError("model of water temperature not yet implemented, "
-                                  "model_water_temperature must be set to FALSE")
+    if model_water_temperature:
+        # the reference stop()s here (:335-337).  The GPU backend does model the water temperature (DESIGN.md section 5),
+        # but inside the fused chain, where the water body, its temperature and the rates that depend on it advance
+        # together: monthly_climate_to_vectors() / tc_to_vectors(model_water_temperature = TRUE)
+        raise NotImplementedError("model_water_temperature = TRUE is available through monthly_climate_to_vectors() / "
+                                  "tc_to_vectors() (the fused chain), not through this stage-level verb")
     m = pixel_hourly_microclimate
     area = simulate_ephemeral_habitat_vectorised(m["rainfall"], m["air_temperature"], m["humidity"], m["windspeed"],
                                                  m["altitude"], math_mode=math_mode, device=device)["water_surface_area"]
@@ -251,19 +254,16 @@ def terraclimate_to_monthly_climate(pixel_terraclimate_data, *, pad_last=False, 
     return out
 
 
-def _run_vectors(upload, n_cells, start, end, carried, lifehistory_functions, species, included_dates,
+def _run_vectors(run, n_cells, start, end, carried, lifehistory_functions, species, included_dates,
                  aggregate_by, dates_predict, habitats, model_water_temperature, water_shade_proportion,
-                 burnin_years_pop, extra_variables, math_mode, devices):
-    """interpolate_daily_climate() ... summarise_vectors() in one fused launch per device; `upload`
-    puts the monthly knots on the plan (either form)."""
+                 burnin_years_pop, extra_variables, math_mode, devices, water_temperature_options=None):
+    """interpolate_daily_climate() ... summarise_vectors() in one pipelined call (mms_chain_run[_terraclimate]);
+    `run(plan, out)` hands the monthly knots (either form) and the output buffers to the plan."""
     species = _match_arg(species, SPECIES, "species")
     aggregate_by = _match_arg(aggregate_by, ("month", "day"), "aggregate_by")
     # simulate_hourly_conditions() argument handling, R/pipeline_functions.R:324-338
     if water_shade_proportion != 1 and not model_water_temperature:
         warnings.warn("water temperature is not being modelled, so water_shade_proportion argument is ignored")
-    if model_water_temperature:
-        raise NotImplementedError("model of water temperature not yet implemented, "
-                                  "model_water_temperature must be set to FALSE")
     lh: Lifehistory = lifehistory_functions[{"An. gambiae": "An_gambiae", "An. stephensi": "An_stephensi"}[species]]
     if dates_predict is None:
         dates_predict = dates.default_dates_predict(start, end)
@@ -273,15 +273,26 @@ def _run_vectors(upload, n_cells, start, end, carried, lifehistory_functions, sp
         habitats = [dict(shape=0, max_depth=1.0, radius=1.0, inflow_multiplier=1.0, leak_per_hour=0.0,
                          initial_volume=0.0)]
     names = list(VECTOR_VARIABLES) + [v for v in extra_variables if v not in VECTOR_VARIABLES]
+    wt = None
+    if model_water_temperature:
+        # EXTENSION (the reference stop()s, R/pipeline_functions.R:334-338): the model sketched in
+        # query_terraclimate.R:370-497, DESIGN.md section 5.  Needs the pixels' latitude and clear-sky radiation.
+        if carried.get("latitude") is None or carried.get("clear_sky_SOLR") is None:
+            raise ValueError("model_water_temperature = TRUE needs the pixels' latitude and clear_sky_SOLR [12, C]")
+        dp = np.asarray(dates_predict, dtype="datetime64[D]")
+        wt = dict(water_temperature_options or {})
+        wt.update(shade_proportion=float(water_shade_proportion), day_of_year=dates.day_of_year(dp),
+                  month_of_day=dates.month_of_year(dp), latitude=np.asarray(carried["latitude"], dtype=np.float64),
+                  clear_sky=np.asarray(carried["clear_sky_SOLR"], dtype=np.float64))
+        if "water_temperature" not in names:
+            names.append("water_temperature")
     with backend.ChainPlan(
             n_cells, mid_day=mid_day, day_predict=day_predict, habitats=habitats,
             densmod=backend.make_densmod(lh.das_densmod.type, lh.das_densmod.dd_effect, lh.das_densmod.surface_area_cm2),
             tables=lh.tables(), period_of_day=period_of_day, n_periods=len(p_start), burnin_years_water=0,
             burnin_years_pop=burnin_years_pop, mean_vars=names, want_wet_hours=True, math_mode=math_mode,
-            devices=devices) as plan:
-        upload(plan)
-        plan.launch()
-        out = plan.download(plan.allocate_outputs())
+            devices=devices, water_temperature=wt) as plan:
+        out = run(plan, plan.allocate_outputs())
     res = {"longitude": carried.get("longitude"), "latitude": carried.get("latitude"),
            "species": species, "start": p_start, "end": p_end, "wet_hours": out["wet_hours"]}
     for k, v in enumerate(out["mean_state_vars"]):
@@ -294,7 +305,8 @@ def _run_vectors(upload, n_cells, start, end, carried, lifehistory_functions, sp
 def monthly_climate_to_vectors(pixel_monthly_climate, lifehistory_functions, species=SPECIES,
                                included_dates=None, aggregate_by="month", dates_predict=None, *,
                                habitats=None, model_water_temperature=False, water_shade_proportion=1,
-                               burnin_years_pop=1, extra_variables=(), math_mode="fast", devices=None):
+                               burnin_years_pop=1, extra_variables=(), math_mode="fast", devices=None,
+                               water_temperature_options=None):
     """tc_to_vectors() (R/pipeline_functions.R:1099-1130) from
     interpolate_daily_climate() to summarise_vectors(), for a whole tile in one
     fused kernel launch per device.
@@ -309,16 +321,16 @@ def monthly_climate_to_vectors(pixel_monthly_climate, lifehistory_functions, spe
     [P, C] array per vector variable -- the `pixel_vectors` tibbles side by side.
     """
     start, end, monthly, altitude = _monthly_array(pixel_monthly_climate)
-    return _run_vectors(lambda plan: plan.upload(monthly, altitude), monthly.shape[2], start, end,
+    return _run_vectors(lambda plan, out: plan.run(monthly, altitude, out), monthly.shape[2], start, end,
                         pixel_monthly_climate, lifehistory_functions, species, included_dates, aggregate_by,
                         dates_predict, habitats, model_water_temperature, water_shade_proportion,
-                        burnin_years_pop, extra_variables, math_mode, devices)
+                        burnin_years_pop, extra_variables, math_mode, devices, water_temperature_options)
 
 
 def tc_to_vectors(pixel_terraclimate_data, lifehistory_functions, species=SPECIES, included_dates=None, *,
                   aggregate_by="month", dates_predict=None, pad_last=False, habitats=None,
                   model_water_temperature=False, water_shade_proportion=1, burnin_years_pop=1,
-                  extra_variables=(), math_mode="fast", devices=None):
+                  extra_variables=(), math_mode="fast", devices=None, water_temperature_options=None):
     """tc_to_vectors(pixel_terraclimate_data, species, included_dates), R/pipeline_functions.R:1099-1130,
     whole: the six raw TerraClimate variables go to the device and process_terraclimate_pixel_vars()
     (R/terraclimate.R:581-643) runs there, in front of the fused chain (mms_chain_upload_terraclimate).
@@ -327,10 +339,11 @@ def tc_to_vectors(pixel_terraclimate_data, lifehistory_functions, species=SPECIE
     if pad_last:
         start, end, tc = dates.pad_last_month(start, end, tc)
     month_id, n_days = dates.terraclimate_month_info(start, end)
-    return _run_vectors(lambda plan: plan.upload_terraclimate(tc, clear_sky, month_id, n_days, altitude),
+    return _run_vectors(lambda plan, out: plan.run_terraclimate(tc, clear_sky, month_id, n_days, altitude, out),
                         tc.shape[2], start, end, pixel_terraclimate_data, lifehistory_functions, species,
                         included_dates, aggregate_by, dates_predict, habitats, model_water_temperature,
-                        water_shade_proportion, burnin_years_pop, extra_variables, math_mode, devices)
+                        water_shade_proportion, burnin_years_pop, extra_variables, math_mode, devices,
+                        water_temperature_options)
 
 
 def raster_slice(vectors, variable, year, month):

@@ -18,10 +18,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libmms_oracle.so")
 
 NFORCING = 9
-NVARS = 12
+NVARS = 13
 VAR_NAMES = ("adult", "aquatic", "mdr", "efd", "das_zerodensity", "ds",
              "larval_habitat_area", "water_volume", "air_temperature", "humidity",
-             "windspeed", "rainfall")
+             "windspeed", "rainfall", "water_temperature")
 
 _dp = ct.POINTER(ct.c_double)
 _ip = ct.POINTER(ct.c_int)
@@ -50,6 +50,13 @@ class Lifehistory(ct.Structure):
     _fields_ = [("mdr", Spline), ("efd", Spline), ("das", Spline), ("ds", Surface)]
 
 
+class WaterTemperature(ct.Structure):
+    """EXTENSION (mms_oracle.h mmso_water_temperature): the model sketched in query_terraclimate.R:370-497."""
+    _fields_ = [("enabled", ct.c_int), ("shade_proportion", ct.c_double), ("albedo", ct.c_double),
+                ("emissivity", ct.c_double), ("convection_w_m2_k", ct.c_double), ("day_of_year", _ip), ("month_of_day", _ip),
+                ("latitude", _dp), ("clear_sky", _dp)]
+
+
 class Chain(ct.Structure):
     _fields_ = [("M", ct.c_int), ("D", ct.c_int), ("C", ct.c_int), ("S", ct.c_int), ("P", ct.c_int),
                 ("monthly", _dp), ("mid_day", _dp), ("day_predict", _dp), ("altitude", _dp),
@@ -57,7 +64,7 @@ class Chain(ct.Structure):
                 ("burnin_years_water", ct.c_int), ("burnin_years_pop", ct.c_int),
                 ("initial_adult", ct.c_double), ("initial_aquatic", ct.c_double),
                 ("densmod", Densmod), ("lh", Lifehistory),
-                ("period_of_day", _ip),
+                ("period_of_day", _ip), ("wt", WaterTemperature),
                 ("out_mean", _dp), ("out_wet_hours", _ip), ("out_hourly", _dp), ("out_wet", _bp),
                 ("n_threads", ct.c_int)]
 
@@ -105,6 +112,12 @@ def lib() -> ct.CDLL:
         L.mmso_run_chain.restype = ct.c_int
         L.mmso_run_chain.argtypes = [ct.POINTER(Chain)]
         L.mmso_max_threads.restype = ct.c_int
+        L.mmso_solar_declination.restype = None
+        L.mmso_solar_declination.argtypes = [ct.c_int, _dp, _dp]
+        L.mmso_cos_hour_angle.restype = ct.c_double
+        L.mmso_cos_hour_angle.argtypes = [ct.c_int]
+        L.mmso_clear_sky_hourly.restype = None
+        L.mmso_clear_sky_hourly.argtypes = [ct.c_double, ct.c_int, ct.c_double, _dp]
         for name, n in (("mmso_vapprs", 1), ("mmso_vapour_pressure", 2), ("mmso_relative_humidity", 2),
                         ("mmso_adjust_wind_speed", 4), ("mmso_cloud_cover", 3)):
             getattr(L, name).restype = ct.c_double
@@ -300,6 +313,24 @@ def process_terraclimate_pixel_vars(terraclimate, clear_sky, month_id, n_days):
     return out
 
 
+def solar_declination(doy):
+    """(sin delta, cos delta) of a day of the year (EXTENSION: water-temperature model)"""
+    sd, cd = ct.c_double(), ct.c_double()
+    lib().mmso_solar_declination(int(doy), ct.byref(sd), ct.byref(cd))
+    return sd.value, cd.value
+
+
+def cos_hour_angle(hour):
+    return lib().mmso_cos_hour_angle(int(hour))
+
+
+def clear_sky_hourly(latitude, doy, clear_sky_mean):
+    """Clear-sky irradiance of the 24 hours of a day whose daily mean is clear_sky_mean."""
+    out = np.empty(24)
+    lib().mmso_clear_sky_hourly(float(latitude), int(doy), float(clear_sky_mean), _p(out))
+    return out
+
+
 def R_mean(x):
     x = _d(x)
     return lib().mmso_R_mean(_p(x), len(x))
@@ -312,7 +343,7 @@ def max_threads() -> int:
 def run_chain(monthly, mid_day, day_predict, altitude, habitats, densmod_, tables,
               period_of_day=None, n_periods=0, burnin_years_water=0, burnin_years_pop=1,
               initial_adult=100.0, initial_aquatic=100.0, want_mean=True, want_hourly=False,
-              n_threads=0):
+              n_threads=0, water_temperature=None):
     """Fused chain for C cells.  monthly is [9][M][C]; tables is the dict made
     by mosmicrosim_b200.synthetic.synthetic_lifehistory (or any dict with the
     same keys).  Returns a dict of numpy arrays laid out [S][var][period|t][C]."""
@@ -336,6 +367,17 @@ def run_chain(monthly, mid_day, day_predict, altitude, habitats, densmod_, table
     ch.lh = Lifehistory(make_spline(tables["mdr"]), make_spline(tables["efd"]),
                         make_spline(tables["das"]), make_surface(tables["ds"]))
     ch.period_of_day = pod.ctypes.data_as(_ip)
+    if water_temperature is not None:
+        # dict(shade_proportion, albedo, emissivity, convection_w_m2_k, day_of_year[D], month_of_day[D], latitude[C], clear_sky[12][C])
+        w = water_temperature
+        doy = np.ascontiguousarray(w["day_of_year"], dtype=np.int32)
+        mon = np.ascontiguousarray(w["month_of_day"], dtype=np.int32)
+        lat, cs = _d(w["latitude"]), _d(w["clear_sky"])
+        assert doy.shape == (D,) and mon.shape == (D,) and lat.shape == (C,) and cs.shape == (12, C)
+        ch.wt = WaterTemperature(1, float(w.get("shade_proportion", 1.0)), float(w.get("albedo", 0.0)),
+                                 float(w.get("emissivity", 0.97)), float(w.get("convection_w_m2_k", 0.0)),
+                                 doy.ctypes.data_as(_ip), mon.ctypes.data_as(_ip),
+                                 _p(lat), _p(cs))
     out = {}
     if want_mean and P > 0:
         out["mean"] = np.empty((S, NVARS, P, C))

@@ -387,6 +387,132 @@ int mmso_simulate_ephemeral_habitat_vectorised(
 }
 
 /* ========================================================================
+ * Water temperature -- EXTENSION.  The reference only sketches this model, as
+ * comments (query_terraclimate.R:370-497), stop()s when it is requested
+ * (R/pipeline_functions.R:334-338) and copies the air temperature instead
+ * (R/sim_microclimate.R:163).  The spec below is authored in DESIGN.md
+ * section 5 from that prose; parity is unpinned by construction.
+ * ===================================================================== */
+
+/* zeta = omega (doy - 80) + 2 eps (sin(omega doy) - sin(omega 80)), delta = asin(0.39784993 sin zeta),
+ * omega = 2 pi / 365, eps = 0.01675 (query_terraclimate.R:434-457) */
+void mmso_solar_declination(int doy, double *sin_delta, double *cos_delta)
+{
+    const double omega = 2 * 3.141592653589793 / 365, eps = 0.01675;
+    const double zeta = omega * (doy - 80) + 2 * eps * (sin(omega * doy) - sin(omega * 80));
+    const double delta = asin(0.39784993 * sin(zeta));
+    *sin_delta = sin(delta);
+    *cos_delta = cos(delta);
+}
+
+/* h = 15 (t_d - 12) degrees, t_d the hour of the day (:459-466); the hourly series carries hour = 1..24 */
+double mmso_cos_hour_angle(int hour)
+{
+    return cos(15.0 * (hour - 12) * (3.141592653589793 / 180));
+}
+
+/* The monthly clear-sky value is a daily mean; over the day it follows cos Z = cos(phi) cos(delta) cos(h) +
+ * sin(phi) sin(delta) (:468-472; the notes' "cos(delta * h)" is read as the astronomical-triangle product), zero
+ * while the sun is below the horizon.  (a/r)^2 (:425-432) is common to the 24 hours and cancels. */
+void mmso_clear_sky_hourly(double latitude_deg, int doy, double clear_sky_mean, double *irr)
+{
+    double sd, cd;
+    mmso_solar_declination(doy, &sd, &cd);
+    const double phi = latitude_deg * (3.141592653589793 / 180);
+    const double a = cos(phi) * cd, b = sin(phi) * sd;
+    double w = 0;
+    for (int k = 1; k <= 24; ++k) {
+        const double cz = a * mmso_cos_hour_angle(k) + b;
+        irr[k - 1] = (cz > 0) ? cz : 0;
+        w += irr[k - 1];
+    }
+    const double scale = (w > 0) ? clear_sky_mean * 24 / w : 0;
+    for (int k = 0; k < 24; ++k) irr[k] = scale * irr[k];
+}
+
+/* One hour of the water body with its temperature:
+ *   water present at the start of the hour (volume V, surface A = S(V), mass m = 1000 V kg) exchanges
+ *     Q_evap  = lambda E,  E = rate A kg evaporated (the loss of R/sim_water.R:107), lambda = 2.26e6 J/kg   (:388-393)
+ *     Q_rad   = sigma eps A (Tw_K^4 - Ta_K^4) dt,  sigma = 5.67e-8, dt = 3600 s                             (:395-401)
+ *     Q_solar = (1 - shade)(1 - albedo) I_clear (0.36 + 0.64 (1 - cloud / 100)) A dt   (Angstrom, :414-419)
+ *   and its temperature moves by (Q_solar - Q_evap - Q_rad) / (m c + k), c = 4184 J/kg/K (:489-494), with
+ *   k = 4 sigma eps Tw_K^3 A dt the derivative of Q_rad: the notes' explicit dT = Q / (m c) made linearly implicit
+ *   in the radiative term, which is what keeps a film of water stable (m c -> 0); liquid water: clamped to
+ *   [0, 100] C.  A dry body has the air's temperature.  Then the volume step of iterate_cone_volume(), and the rain
+ *   that arrives (at air temperature) is mixed in by mass. */
+void mmso_iterate_volume_temperature(const mmso_habitat *hb, const mmso_water_temperature *wt,
+                                     double *volume_io, double *tw_io, double rainfall_mm_h,
+                                     double evap_rate, double air_t, double cloud_pct, double i_clear,
+                                     double max_volume, double catchment_area)
+{
+    const double volume = *volume_io, tw = *tw_io;
+    const double area = mmso_habitat_surface(hb, volume);
+    double tw_pre;
+    if (!(volume > 0)) {
+        tw_pre = air_t;
+    } else {
+        const double dt = 3600, se = 5.67e-8 * wt->emissivity;
+        const double mass = 1000 * volume;
+        const double q_evap = 2.26e6 * (evap_rate * area);
+        const double twk = tw + 273.15, tak = air_t + 273.15;
+        const double twk2 = twk * twk, tak2 = tak * tak;
+        const double q_rad = se * area * (twk2 * twk2 - tak2 * tak2) * dt;
+        const double angstrom = 0.36 + 0.64 * (1 - cloud_pct / 100);
+        const double q_sol = (1 - wt->shade_proportion) * (1 - wt->albedo) * i_clear * angstrom * area * dt;
+        /* optional sensible heat exchange h_c A (Ta - Tw) dt (absent from the notes; h_c = 0 by default), implicit like
+         * the radiative term */
+        const double q_conv = wt->convection_w_m2_k * area * (air_t - tw) * dt;
+        const double k = 4 * se * (twk2 * twk) * area * dt + wt->convection_w_m2_k * area * dt;
+        tw_pre = tw + (q_sol - q_evap - q_rad + q_conv) / (mass * 4184 + k);
+        if (tw_pre < 0) tw_pre = 0;
+        if (tw_pre > 100) tw_pre = 100;
+    }
+    /* iterate_cone_volume(), R/sim_water.R:94-132, as in mmso_iterate_volume() */
+    const double loss = (evap_rate * area) / 1000;
+    double x = volume - loss;
+    x = x - hb->leak_per_hour * volume;
+    x = x * ((x > 0) ? 1.0 : 0.0);
+    const double gain = catchment_area * (rainfall_mm_h / 1000);
+    double y = x + gain;
+    *tw_io = (y > 0) ? (x * tw_pre + gain * air_t) / y : air_t;
+    if (y > max_volume) y = max_volume;
+    *volume_io = y;
+}
+
+/* the vectorised water simulation of one pixel with the temperature model on: same burn-in rule
+ * (the first 8760 steps are repeated, R/sim_water.R:228-233), temperature carried like the volume */
+static int simulate_habitat_temperature_one(const mmso_chain *ch, long c, const mmso_habitat *hb,
+                                            const double *rain, const double *air_t, const double *rh,
+                                            const double *wind, const double *cloud,
+                                            double *area, double *volume, unsigned char *wet, double *water_t)
+{
+    const long H = 24L * ch->D, n_times_year = 365 * 24;
+    if (ch->burnin_years_water > 0 && H < n_times_year) return -1;
+    const double max_volume = mmso_habitat_max_volume(hb), catchment_area = mmso_habitat_catchment(hb);
+    double vol = hb->initial_volume, tw = air_t[0];
+    double irr[24];
+    for (int pass = 0; pass <= ch->burnin_years_water; ++pass) {
+        const long n = (pass < ch->burnin_years_water) ? n_times_year : H;
+        for (long t = 0; t < n; ++t) {
+            const int d = (int)(t / 24), h = (int)(t % 24);
+            if (h == 0)
+                mmso_clear_sky_hourly(ch->wt.latitude[c], ch->wt.day_of_year[d],
+                                      ch->wt.clear_sky[(size_t)(ch->wt.month_of_day[d] - 1) * ch->C + c], irr);
+            const double rate = mmso_evaporation_rate_kg_h(air_t[t], rh[t], ch->altitude[c], wind[t], 1);
+            mmso_iterate_volume_temperature(hb, &ch->wt, &vol, &tw, rain[t], rate, air_t[t], cloud[t], irr[h],
+                                            max_volume, catchment_area);
+            if (pass == ch->burnin_years_water) {
+                area[t] = mmso_habitat_surface(hb, vol);
+                volume[t] = vol;
+                wet[t] = (unsigned char)(vol > 0);
+                water_t[t] = tw;
+            }
+        }
+    }
+    return 0;
+}
+
+/* ========================================================================
  * T: TerraClimate monthly variables -> the nine monthly forcing variables
  *    (SURVEY section 8f row N1): process_terraclimate_pixel_vars(),
  *    R/terraclimate.R:581-643, and its helpers in R/utils.R.
@@ -791,10 +917,20 @@ static int chain_one_cell(const mmso_chain *ch, long c, double *work)
     const double altitude = ch->altitude[c];
     for (int s = 0; s < S; ++s) {
         /* simulate_hourly_conditions(), R/pipeline_functions.R:319-538 */
+        if (ch->wt.enabled) {
+            /* EXTENSION: model_water_temperature = TRUE.  The water temperature is a state of the water body, so
+             * the two rates that take it (R/sim_pop_dynamics.R:108,114) are evaluated per setting */
+            rc = simulate_habitat_temperature_one(ch, c, &ch->habitats[s], rain, air_t, rh, wind, cloud,
+                                                  area, volume, wet, water_t);
+            if (rc) return rc;
+            mmso_positive_spline(&ch->lh.mdr, water_t, H, mdr);
+            mmso_positive_spline(&ch->lh.das, water_t, H, das0);
+        } else {
         rc = mmso_simulate_ephemeral_habitat_vectorised(rain, air_t, rh, wind, &altitude, H, 1,
                                                         &ch->habitats[s], ch->burnin_years_water,
                                                         area, volume, wet);
         if (rc) return rc;
+        }
         /* simulate_hourly_vectors(), :691-906; larval_habitat_area =
          * water_surface_area (R/sim_pop_dynamics.R:123) */
         rc = mmso_simulate_population_vectorised(area, mdr, efd, das0, ds, H, 1, &ch->densmod,
@@ -803,7 +939,7 @@ static int chain_one_cell(const mmso_chain *ch, long c, double *work)
         if (rc) return rc;
 
         const double *series[MMSO_NVARS] = { adult, aquatic, mdr, efd, das0, ds,
-                                             area, volume, air_t, rh, wind, rain };
+                                             area, volume, air_t, rh, wind, rain, water_t };
         if (ch->out_hourly) {
             for (int v = 0; v < MMSO_NVARS; ++v)
                 for (long t = 0; t < H; ++t)

@@ -38,6 +38,7 @@ enum {
 enum {
     MMSO_V_ADULT = 0, MMSO_V_AQUATIC, MMSO_V_MDR, MMSO_V_EFD, MMSO_V_DAS0, MMSO_V_DS,
     MMSO_V_AREA, MMSO_V_VOLUME, MMSO_V_AIRT, MMSO_V_RH, MMSO_V_WIND, MMSO_V_RAIN,
+    MMSO_V_WATERT,            /* water temperature: the air temperature (R/sim_microclimate.R:163) unless modelled */
     MMSO_NVARS
 };
 
@@ -110,6 +111,34 @@ int mmso_simulate_ephemeral_habitat_vectorised(
     const mmso_habitat *hb, int burnin_years,
     double *water_surface_area, double *water_volume, unsigned char *wet);
 
+/* ---- water temperature (EXTENSION: the model sketched in query_terraclimate.R:370-497; the reference itself
+ * stop()s on model_water_temperature = TRUE, R/pipeline_functions.R:334-338, and copies the air temperature,
+ * R/sim_microclimate.R:163).  Spec authored in DESIGN.md section 5; parity unpinned by construction. ---- */
+typedef struct {
+    int    enabled;            /* model_water_temperature */
+    double shade_proportion;   /* water_shade_proportion in [0, 1]; 1 = fully shaded, no solar gain */
+    double albedo;             /* of the water surface ("assume very low albedo for water") */
+    double emissivity;         /* "water is ~0.97-0.99" */
+    double convection_w_m2_k;  /* sensible heat exchange with the air; 0 = the notes' model (none) */
+    const int *day_of_year;    /* [D] doy(date), R/utils.R:46-48 */
+    const int *month_of_day;   /* [D] calendar month 1..12 (row of clear_sky) */
+    const double *latitude;    /* [C] degrees */
+    const double *clear_sky;   /* [12][C] clear-sky radiation by calendar month, W/m2 (clear_sky_radiation_12mo()) */
+} mmso_water_temperature;
+/* sin / cos of the solar declination of a day of the year (query_terraclimate.R:434-457) */
+void mmso_solar_declination(int doy, double *sin_delta, double *cos_delta);
+/* cos of the hour angle of hour-of-day k = 1..24: h = 15 (k - 12) degrees (:459-466) */
+double mmso_cos_hour_angle(int hour_1_to_24);
+/* clear-sky irradiance of each of the 24 hours of a day whose daily MEAN is clear_sky_mean (W/m2): distributed in
+ * proportion to max(0, cos Z), cos Z = cos(lat) cos(delta) cos(h) + sin(lat) sin(delta) (:468-472) */
+void mmso_clear_sky_hourly(double latitude_deg, int doy, double clear_sky_mean, double *irradiance24);
+/* one hourly step of water volume AND water temperature */
+void mmso_iterate_volume_temperature(const mmso_habitat *hb, const mmso_water_temperature *wt,
+                                     double *volume_io, double *water_temperature_io,
+                                     double rainfall_mm_h, double evap_rate_kg_h_m2, double air_temperature,
+                                     double cloud_cover_pct, double clear_sky_irradiance,
+                                     double max_volume, double catchment_area);
+
 /* ---- T: TerraClimate variables -> monthly forcing (R/terraclimate.R:581-643) ------- */
 double mmso_vapprs(double db);
 double mmso_vapour_pressure(double tmean, double vpd_kpa);
@@ -164,6 +193,7 @@ typedef struct {
     mmso_densmod densmod;
     mmso_lifehistory lh;
     const int *period_of_day;   /* [D]; -1 = excluded (included_dates filter) */
+    mmso_water_temperature wt;  /* EXTENSION; enabled = 0: water temperature = air temperature (the reference) */
     /* outputs, any may be NULL */
     double *out_mean;           /* [S][MMSO_NVARS][P][C] period means */
     int    *out_wet_hours;      /* [S][P][C] hours with volume > 0 */

@@ -57,7 +57,7 @@ int main(int argc, char **argv)
         return 2;
     }
     fclose(f);
-    if (mms_abi_version() != 1) { fprintf(stderr, "unexpected ABI version\n"); return 3; }
+    if (mms_abi_version() != MMS_ABI_VERSION) { fprintf(stderr, "unexpected ABI version\n"); return 3; }
 
     mms_chain_config cfg;
     memset(&cfg, 0, sizeof cfg);

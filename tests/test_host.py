@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in sorted(declared) if not hasattr(L, n)]
     assert not missing, missing
     assert declared == set(backend.EXPORTS), declared ^ set(backend.EXPORTS)
-    assert L.mms_abi_version() == 1
+    assert L.mms_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header(tmp_path):
@@ -157,8 +157,12 @@ def test_pipeline_argument_handling_mirrors_the_reference():
     lhf = {"An_gambiae": case.lh, "An_stephensi": syn.synthetic_lifehistory("An. stephensi")}
     with pytest.raises(ValueError):
         pipeline.monthly_climate_to_vectors(pmc, lhf, species="An. funestus")
-    with pytest.raises(NotImplementedError):                     # R/pipeline_functions.R:334-338
+    # the reference stop()s on model_water_temperature = TRUE (R/pipeline_functions.R:334-338); here it is modelled
+    # (an extension) and needs the pixels' clear-sky radiation next to their latitude
+    with pytest.raises(ValueError, match="clear_sky_SOLR"):
         pipeline.monthly_climate_to_vectors(pmc, lhf, model_water_temperature=True)
+    with pytest.raises(NotImplementedError):                     # the stage-level verb points to the fused chain
+        pipeline.simulate_hourly_conditions({}, model_water_temperature=True)
     if backend.device_count() == 0:
         with warnings.catch_warnings(record=True) as wlist:      # R/pipeline_functions.R:327-332
             warnings.simplefilter("always")
@@ -184,7 +188,7 @@ sub = oracle.run_chain(np.ascontiguousarray(case.monthly[:, :, c0:c0 + n]), case
                        case.altitude[c0:c0 + n], [oracle.habitat(**h) for h in case.habitats],
                        oracle.densmod(case.densmod["type_"], case.densmod["dd_effect"], case.densmod["surface_area_cm2"]),
                        case.tables, case.period_of_day, case.P, want_hourly=False, n_threads=2)
-mine = torch.zeros((1, 12, case.P, 256), dtype=torch.float64)
+mine = torch.zeros((1, oracle.NVARS, case.P, 256), dtype=torch.float64)
 mine[..., :n] = torch.from_numpy(sub["mean"])
 parts = [torch.zeros_like(mine) for _ in range(world)]
 dist.all_gather(parts, mine)                   # the gather at the end: the only communication

@@ -176,7 +176,7 @@ def test_c_oracle_matches_numpy_restatement(species):
               surface_area_cm2=case.densmod["surface_area_cm2"])
     alt = rn.run_chain(case.monthly, case.mid_day, case.day_predict, case.altitude, case.habitats, dm,
                        case.tables, case.period_of_day, case.P)
-    for v, name in enumerate(oracle.VAR_NAMES):
+    for v, name in enumerate(rn.VAR_NAMES):      # (the oracle's 13th, water_temperature, is the air temperature here)
         a, b = ref["hourly"][:, v], alt["hourly"][:, v]
         assert np.array_equal(np.isnan(a), np.isnan(b)), name
         ok = ~np.isnan(a)
@@ -187,7 +187,7 @@ def test_c_oracle_matches_numpy_restatement(species):
         v = oracle.VAR_NAMES.index(name)
         assert np.array_equal(ref["hourly"][0, v], alt["hourly"][0, v], equal_nan=True), name
     assert np.array_equal(ref["wet"], alt["wet"]) and np.array_equal(ref["wet_hours"], alt["wet_hours"])
-    np.testing.assert_allclose(ref["mean"], alt["mean"], rtol=1e-11, atol=1e-15)
+    np.testing.assert_allclose(ref["mean"][:, :len(rn.VAR_NAMES)], alt["mean"], rtol=1e-11, atol=1e-15)
 
 
 # ---- golden vectors ----------------------------------------------------------------------
@@ -197,10 +197,11 @@ def test_golden_vectors():
     case = Case(n_cells=int(g["n_cells"]), habitats=[syn.habitat_cone(), syn.habitat_cylinder(leak_per_hour=0.002)])
     assert np.array_equal(case.monthly, g["monthly"]) and np.array_equal(case.altitude, g["altitude"])
     ref = case.oracle(want_hourly=True)
-    np.testing.assert_allclose(ref["mean"], g["mean"], rtol=1e-11, atol=1e-15)
+    nv = g["mean"].shape[1]                      # the golden file holds the restatement's 12 variables
+    np.testing.assert_allclose(ref["mean"][:, :nv], g["mean"], rtol=1e-11, atol=1e-15)
     assert np.array_equal(ref["wet_hours"], g["wet_hours"])
     sel = g["hourly_steps"]
-    np.testing.assert_allclose(ref["hourly"][:, :, sel, :], g["hourly_sample"], rtol=1e-11, atol=1e-15)
+    np.testing.assert_allclose(ref["hourly"][:, :nv][:, :, sel, :], g["hourly_sample"], rtol=1e-11, atol=1e-15)
 
 
 # ---- the one-pixel twins (whole-series burn-in rule) ------------------------------------------
@@ -320,3 +321,52 @@ def test_golden_front_end_and_twins():
                                      burnin_years=2)
     np.testing.assert_allclose(pop["aquatic"], g["aquatic_burnin2"], rtol=1e-11, atol=1e-15)
     np.testing.assert_allclose(pop["adult"], g["adult_burnin2"], rtol=1e-11, atol=1e-15)
+
+
+# ---- water-temperature EXTENSION (query_terraclimate.R:370-497) ------------------------------
+
+def test_solar_geometry_known_answers():
+    """Declination: ~0 at the March equinox (doy 80), +-23.44 degrees at the solstices; hour angles symmetric about
+    noon; the hourly clear-sky curve keeps the daily mean it is given, is zero at night and peaks at noon."""
+    sd, cd = oracle.solar_declination(80)
+    assert abs(sd) < 1e-12 and abs(cd - 1) < 1e-12                       # zeta = 0 exactly on day 80
+    assert abs(np.degrees(np.arcsin(oracle.solar_declination(172)[0])) - 23.44) < 0.05
+    assert abs(np.degrees(np.arcsin(oracle.solar_declination(355)[0])) + 23.44) < 0.05
+    assert oracle.cos_hour_angle(12) == 1.0 and abs(oracle.cos_hour_angle(18)) < 1e-15
+    assert oracle.cos_hour_angle(7) == pytest.approx(oracle.cos_hour_angle(17), abs=1e-15)
+    for lat, doy in ((0.0, 80), (-33.0, 200), (52.0, 355), (66.0, 172)):
+        irr = oracle.clear_sky_hourly(lat, doy, 250.0)
+        assert irr.mean() == pytest.approx(250.0, rel=1e-12) and irr.min() == 0.0 and irr.argmax() == 11
+    eq = oracle.clear_sky_hourly(0.0, 80, 250.0)                          # equator, equinox: cos Z = cos h, sun up 7h..17h
+    assert np.count_nonzero(eq > 1e-9) == 11 and eq[11] == pytest.approx(250.0 * 24 / sum(max(0.0, np.cos(np.radians(15 * (k - 12)))) for k in range(1, 25)))
+    assert np.all(oracle.clear_sky_hourly(80.0, 355, 250.0) == 0.0)       # polar night
+
+
+def test_water_temperature_model_properties():
+    """Default off: the water temperature is the air temperature and nothing else changes.  On: a fully shaded water
+    body is never warmer than the air (evaporative loss, no solar gain); sun warms it; strong convection ties it to
+    the air; a deep, full body barely moves in an hour; the volume series does not depend on the temperature model."""
+    from helpers import Case, ORACLE_VAR
+    from mosmicrosim_b200 import dates
+    case = Case(n_cells=6, out_of_range_fraction=0.0)
+    dm = case.densmod
+    args = (case.monthly, case.mid_day, case.day_predict, case.altitude, [oracle.habitat()],
+            oracle.densmod(dm["type_"], dm["dd_effect"], dm["surface_area_cm2"]), case.tables, case.period_of_day, case.P)
+    base = oracle.run_chain(*args, want_hourly=True)
+    h0 = base["hourly"][0]
+    assert np.array_equal(h0[ORACLE_VAR["water_temperature"]], h0[ORACLE_VAR["air_temperature"]])
+    wt = dict(day_of_year=dates.day_of_year(case.dates_predict), month_of_day=dates.month_of_year(case.dates_predict),
+              latitude=np.linspace(-30, 30, 6), clear_sky=np.full((12, 6), 280.0))
+
+    def run(**over):
+        h = oracle.run_chain(*args, want_hourly=True, water_temperature=dict(wt, **over))["hourly"][0]
+        return h[ORACLE_VAR["water_temperature"]], h[ORACLE_VAR["air_temperature"]], h[ORACLE_VAR["water_volume"]]
+
+    tw, ta, vol = run(shade_proportion=1.0)
+    assert np.array_equal(vol, h0[ORACLE_VAR["water_volume"]])           # same water, whatever its temperature
+    assert np.all(tw <= ta + 1e-9) and (ta - tw).mean() > 5.0            # the notes' shaded model: evaporative cooling
+    tw_sun, _, _ = run(shade_proportion=0.0)
+    assert (tw_sun - tw).max() > 10.0 and np.all(tw_sun >= tw - 1e-9)
+    tw_conv, _, _ = run(shade_proportion=1.0, convection_w_m2_k=1e4)
+    assert np.abs(tw_conv - ta).max() < 0.5
+    assert np.array_equal(tw[vol == 0.0], ta[vol == 0.0])                # a dry body has the air's temperature
