@@ -179,6 +179,16 @@ typedef struct mms_chain_config {
     int32_t  n_devices;            /* 0 = all visible devices */
     const int32_t *devices;        /* [n_devices] CUDA ordinals, or NULL for 0..n_devices-1 */
     mms_water_temperature water_temperature;   /* EXTENSION (ABI 2); all zero = the reference */
+    /* Output rows in RASTER cell order (ABI 2): with raster_cell_idx != NULL every output row has
+     * n_raster_cells columns instead of C, the value of pixel c lands in column raster_cell_idx[c]
+     * (0-based: terra's cell number minus one) and raster cells that are not pixels of the tile
+     * hold NaN (0 in the integer outputs) -- one row is one raster slice, what
+     * create_vector_raster_slice() builds with raster[cell_idx] <- values
+     * (R/pipeline_functions.R:1283-1325, cell_idx at :1316-1322).  The scatter happens on the device,
+     * in the kernel's stores.  raster_cell_idx [C] must be strictly increasing (pixels in raster
+     * order, as terra::cells() returns them). */
+    const int64_t *raster_cell_idx;
+    int64_t n_raster_cells;
 } mms_chain_config;
 
 /* ---- library ------------------------------------------------------------ */
@@ -201,7 +211,8 @@ MMS_API const char *mms_last_error(void);              /* message of the last fa
  * altitude [C] host
  * Outputs (host, caller-allocated, any may be NULL when not requested).  With
  * ns = number of state variables selected in the mask (ascending variable
- * id), nf = number of forcing-only variables selected, H = 24*D:
+ * id), nf = number of forcing-only variables selected, H = 24*D (and C replaced
+ * by n_raster_cells when cfg->raster_cell_idx is given):
  *   out_mean_state    [S][ns][P][C]   out_mean_forcing   [nf][P][C]
  *   out_hourly_state  [S][ns][H][C]   out_hourly_forcing [nf][H][C]
  *   out_wet_hours     [S][P][C] int32 out_wet_flags      [S][H][C] uint8

@@ -85,7 +85,8 @@ class ChainConfig(ct.Structure):
                 ("mean_var_mask", ct.c_uint32), ("hourly_var_mask", ct.c_uint32),
                 ("want_wet_hours", ct.c_int32), ("want_wet_flags", ct.c_int32),
                 ("math_mode", ct.c_int32), ("n_devices", ct.c_int32), ("devices", _ip),
-                ("water_temperature", WaterTemperature)]
+                ("water_temperature", WaterTemperature),
+                ("raster_cell_idx", ct.POINTER(ct.c_int64)), ("n_raster_cells", ct.c_int64)]
 
 
 class ChainOutputs(ct.Structure):
@@ -241,7 +242,8 @@ class ChainPlan:
     def __init__(self, n_cells, mid_day, day_predict, habitats, densmod, tables, period_of_day=None,
                  n_periods=0, burnin_years_water=0, burnin_years_pop=1, initial_adult=100.0,
                  initial_aquatic=100.0, mean_vars=(), hourly_vars=(), want_wet_hours=False,
-                 want_wet_flags=False, math_mode="fast", devices=None, water_temperature=None, _create=True):
+                 want_wet_flags=False, math_mode="fast", devices=None, water_temperature=None,
+                 raster_cell_idx=None, n_raster_cells=None, _create=True):
         self._keep = []
         cfg = ChainConfig()
         self.C = int(n_cells)
@@ -284,6 +286,14 @@ class ChainPlan:
             dv = np.ascontiguousarray(devices, dtype=np.int32)
             self._keep.append(dv)
             cfg.n_devices, cfg.devices = len(dv), dv.ctypes.data_as(_ip)
+        self.R = self.C                  # columns of an output row
+        if raster_cell_idx is not None:
+            idx = np.ascontiguousarray(raster_cell_idx, dtype=np.int64)
+            if idx.shape != (self.C,):
+                raise ValueError("raster_cell_idx must have one entry per cell")
+            self._keep.append(idx)
+            self.R = int(n_raster_cells)
+            cfg.raster_cell_idx, cfg.n_raster_cells = idx.ctypes.data_as(ct.POINTER(ct.c_int64)), self.R
         self._location = None
         if water_temperature is not None:
             # EXTENSION: dict(shade_proportion, albedo, emissivity, convection_w_m2_k, day_of_year[D], month_of_day[D],
@@ -318,12 +328,12 @@ class ChainPlan:
         ms, mf = split_mask(self.mean_mask)
         hs, hf = split_mask(self.hourly_mask)
         shapes = {
-            "mean_state": ((self.S, len(ms), self.P, self.C), np.float64) if ms and self.P else None,
-            "mean_forcing": ((len(mf), self.P, self.C), np.float64) if mf and self.P else None,
-            "hourly_state": ((self.S, len(hs), self.H, self.C), np.float64) if hs else None,
-            "hourly_forcing": ((len(hf), self.H, self.C), np.float64) if hf else None,
-            "wet_hours": ((self.S, self.P, self.C), np.int32) if self.want_wet_hours and self.P else None,
-            "wet_flags": ((self.S, self.H, self.C), np.uint8) if self.want_wet_flags else None,
+            "mean_state": ((self.S, len(ms), self.P, self.R), np.float64) if ms and self.P else None,
+            "mean_forcing": ((len(mf), self.P, self.R), np.float64) if mf and self.P else None,
+            "hourly_state": ((self.S, len(hs), self.H, self.R), np.float64) if hs else None,
+            "hourly_forcing": ((len(hf), self.H, self.R), np.float64) if hf else None,
+            "wet_hours": ((self.S, self.P, self.R), np.int32) if self.want_wet_hours and self.P else None,
+            "wet_flags": ((self.S, self.H, self.R), np.uint8) if self.want_wet_flags else None,
         }
         out, keep = {}, []
         for k, spec in shapes.items():

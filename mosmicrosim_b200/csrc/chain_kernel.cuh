@@ -294,7 +294,9 @@ struct UnitState {
 };
 
 struct UnitCtx {
-    int64_t cell, cs;
+    int64_t cell, cs;       // the thread's cell (column of the input arrays) and their row stride
+    int64_t ocell, os;      // its column in the OUTPUT arrays and their row stride: the same, unless the outputs are
+                            // scattered into raster cell order (ChainParams::out_col)
     int set0, H;
     bool live, write_forcing;
     double p_a;
@@ -343,7 +345,7 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
 
     auto flush = [&](int period) {
         if (!u.live) return;
-        const int64_t pc = (int64_t)period * cs + cell;
+        const int64_t pc = (int64_t)period * u.os + u.ocell;
         const double n = (double)acc_n;
 #pragma unroll
         for (int s = 0; s < kNS; ++s) {
@@ -354,10 +356,10 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
                 if (!kFull && k >= 2) continue;
                 if (p.mean_mask & (1u << vid[k])) {
                     const int64_t row = (int64_t)(set0 + s) * u.n_mean_state + out_slot(p.mean_mask, kState, vid[k]);
-                    p.mean_state[row * p.P * cs + pc] = acc_state[s][k] / n;
+                    p.mean_state[row * p.P * u.os + pc] = acc_state[s][k] / n;
                 }
             }
-            if (p.wet_hours) p.wet_hours[(int64_t)(set0 + s) * p.P * cs + pc] = acc_wet[s];
+            if (p.wet_hours) p.wet_hours[(int64_t)(set0 + s) * p.P * u.os + pc] = acc_wet[s];
         }
         if (u.write_forcing) {
             const int vid[9] = {MMS_V_MDR, MMS_V_EFD, MMS_V_DAS_ZERODENSITY, MMS_V_DS, MMS_V_AIR_TEMPERATURE,
@@ -366,7 +368,7 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
             for (int k = 0; k < kNF; ++k) {
                 if (p.mean_mask & (1u << vid[k])) {
                     const int64_t row = out_slot(p.mean_mask, ~kState, vid[k]);
-                    p.mean_forcing[row * p.P * cs + pc] = acc_forc[k] / n;
+                    p.mean_forcing[row * p.P * u.os + pc] = acc_forc[k] / n;
                 }
             }
         }
@@ -476,7 +478,7 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
                 }
                 acc_n += acc_inc;
                 if (kHourly && u.live) {
-                    const int64_t tc = (int64_t)(day * 24 + h) * cs + cell;
+                    const int64_t tc = (int64_t)(day * 24 + h) * u.os + u.ocell;
 #pragma unroll
                     for (int s = 0; s < kNS; ++s) {
                         const double val[5] = {st.adult[s], st.aquatic[s], st.surface[s], st.volume[s], st.water_t[s]};
@@ -487,11 +489,11 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
                             if (!kFull && k >= 2) continue;
                             if (p.hourly_mask & (1u << vid[k])) {
                                 const int64_t row = (int64_t)(set0 + s) * u.n_hourly_state + out_slot(p.hourly_mask, kState, vid[k]);
-                                p.hourly_state[row * u.H * cs + tc] = val[k];
+                                p.hourly_state[row * u.H * u.os + tc] = val[k];
                             }
                         }
                         if (p.wet_flags)
-                            p.wet_flags[(int64_t)(set0 + s) * u.H * cs + tc] = (st.volume[s] > 0.0) ? 1 : 0;
+                            p.wet_flags[(int64_t)(set0 + s) * u.H * u.os + tc] = (st.volume[s] > 0.0) ? 1 : 0;
                     }
                     if (u.write_forcing) {
                         const double val[9] = {f.mdr, f.efd, f.das0, f.ds, f.air_t, f.rh, f.wind, rain_h, f.cloud};
@@ -501,7 +503,7 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
                         for (int k = 0; k < kNF; ++k) {
                             if (p.hourly_mask & (1u << vid[k])) {
                                 const int64_t row = out_slot(p.hourly_mask, ~kState, vid[k]);
-                                p.hourly_forcing[row * u.H * cs + tc] = val[k];
+                                p.hourly_forcing[row * u.H * u.os + tc] = val[k];
                             }
                         }
                     }
@@ -544,6 +546,8 @@ __device__ __forceinline__ void simulate_unit(const ChainParams &p, const SmemTa
     UnitCtx u;
     u.cell = cell; u.cs = p.c_stride; u.set0 = set0; u.H = 24 * p.D;
     u.live = cell < p.n_cells; u.write_forcing = write_forcing;
+    u.os = p.out_stride;
+    u.ocell = (p.out_col && u.live) ? __ldg(p.out_col + cell) : cell;
     u.p_a = air_pressure_kpa(__ldg(p.altitude + cell));
     u.n_mean_state = __popc(p.mean_mask & MMS_STATE_VAR_MASK);
     u.n_hourly_state = __popc(p.hourly_mask & MMS_STATE_VAR_MASK);

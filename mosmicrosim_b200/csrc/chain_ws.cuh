@@ -252,7 +252,7 @@ __device__ __forceinline__ void forcing_pass(const ChainParams &p, const SmemTab
 
     auto flush = [&](int period) {
         if (!u.live || !u.write_forcing) return;
-        const int64_t at = (int64_t)period * u.cs + u.cell;
+        const int64_t at = (int64_t)period * u.os + u.ocell;
         const double n = (double)pc.acc_n;
         const int vid[9] = {MMS_V_MDR, MMS_V_EFD, MMS_V_DAS_ZERODENSITY, MMS_V_DS, MMS_V_AIR_TEMPERATURE,
                             MMS_V_HUMIDITY, MMS_V_WINDSPEED, MMS_V_RAINFALL, MMS_V_CLOUDCOVER};
@@ -260,7 +260,7 @@ __device__ __forceinline__ void forcing_pass(const ChainParams &p, const SmemTab
         for (int k = 0; k < kNF; ++k) {
             if (p.mean_mask & (1u << vid[k])) {
                 const int64_t row = out_slot(p.mean_mask, ~kState, vid[k]);
-                p.mean_forcing[row * p.P * u.cs + at] = acc[k] / n;
+                p.mean_forcing[row * p.P * u.os + at] = acc[k] / n;
             }
         }
     };
@@ -331,7 +331,7 @@ __device__ __forceinline__ void forcing_pass(const ChainParams &p, const SmemTab
                     }
                     pc.acc_n += pc.acc_inc;
                     if (kHourly && u.live && u.write_forcing) {
-                        const int64_t tc = (int64_t)(day * 24 + h) * u.cs + u.cell;
+                        const int64_t tc = (int64_t)(day * 24 + h) * u.os + u.ocell;
                         const double val[9] = {f.mdr, f.efd, f.das0, f.ds, f.air_t, f.rh, f.wind, rain_h, f.cloud};
                         const int vid[9] = {MMS_V_MDR, MMS_V_EFD, MMS_V_DAS_ZERODENSITY, MMS_V_DS, MMS_V_AIR_TEMPERATURE,
                                             MMS_V_HUMIDITY, MMS_V_WINDSPEED, MMS_V_RAINFALL, MMS_V_CLOUDCOVER};
@@ -339,7 +339,7 @@ __device__ __forceinline__ void forcing_pass(const ChainParams &p, const SmemTab
                         for (int q = 0; q < kNF; ++q) {
                             if (p.hourly_mask & (1u << vid[q])) {
                                 const int64_t row = out_slot(p.hourly_mask, ~kState, vid[q]);
-                                p.hourly_forcing[row * u.H * u.cs + tc] = val[q];
+                                p.hourly_forcing[row * u.H * u.os + tc] = val[q];
                             }
                         }
                     }
@@ -382,7 +382,7 @@ __device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &
 
     auto flush = [&](int period) {
         if (!u.live) return;
-        const int64_t at = (int64_t)period * u.cs + u.cell;
+        const int64_t at = (int64_t)period * u.os + u.ocell;
         const double n = (double)pc.acc_n;
 #pragma unroll
         for (int s = 0; s < kNS; ++s) {
@@ -392,10 +392,10 @@ __device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &
                 if (!kFull && k >= 2) continue;
                 if (p.mean_mask & (1u << vid[k])) {
                     const int64_t row = (int64_t)(u.set0 + s) * u.n_mean_state + out_slot(p.mean_mask, kState, vid[k]);
-                    p.mean_state[row * p.P * u.cs + at] = acc[s][k] / n;
+                    p.mean_state[row * p.P * u.os + at] = acc[s][k] / n;
                 }
             }
-            if (p.wet_hours) p.wet_hours[(int64_t)(u.set0 + s) * p.P * u.cs + at] = acc_wet[s];
+            if (p.wet_hours) p.wet_hours[(int64_t)(u.set0 + s) * p.P * u.os + at] = acc_wet[s];
         }
     };
 
@@ -450,7 +450,7 @@ __device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &
                     }
                     pc.acc_n += pc.acc_inc;
                     if (kHourly && u.live) {
-                        const int64_t tc = (int64_t)(day * 24 + h0 + k) * u.cs + u.cell;
+                        const int64_t tc = (int64_t)(day * 24 + h0 + k) * u.os + u.ocell;
 #pragma unroll
                         for (int s = 0; s < kNS; ++s) {
                             const double val[4] = {st.adult[s], st.aquatic[s], st.surface[s], st.volume[s]};
@@ -460,10 +460,10 @@ __device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &
                                 if (!kFull && q >= 2) continue;
                                 if (p.hourly_mask & (1u << vid[q])) {
                                     const int64_t row = (int64_t)(u.set0 + s) * u.n_hourly_state + out_slot(p.hourly_mask, kState, vid[q]);
-                                    p.hourly_state[row * u.H * u.cs + tc] = val[q];
+                                    p.hourly_state[row * u.H * u.os + tc] = val[q];
                                 }
                             }
-                            if (p.wet_flags) p.wet_flags[(int64_t)(u.set0 + s) * u.H * u.cs + tc] = (st.volume[s] > 0.0) ? 1 : 0;
+                            if (p.wet_flags) p.wet_flags[(int64_t)(u.set0 + s) * u.H * u.os + tc] = (st.volume[s] > 0.0) ? 1 : 0;
                         }
                     }
                 }
@@ -522,6 +522,8 @@ chain_kernel_ws(const __grid_constant__ ChainParams p)
         UnitCtx u;
         u.cell = (int64_t)cb * 32 + lane; u.cs = p.c_stride; u.set0 = g * kNS; u.H = 24 * p.D;
         u.live = u.cell < p.n_cells; u.write_forcing = g == 0;
+        u.os = p.out_stride;
+        u.ocell = (p.out_col && u.live) ? __ldg(p.out_col + u.cell) : u.cell;
         u.n_mean_state = __popc(p.mean_mask & MMS_STATE_VAR_MASK);
         u.n_hourly_state = __popc(p.hourly_mask & MMS_STATE_VAR_MASK);
         // passes: water burn-in years (R/sim_water.R:228-233), population burn-in years

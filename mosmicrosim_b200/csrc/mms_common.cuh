@@ -100,7 +100,10 @@ struct ChainParams {
     double dd_effect, surface_area_cm2;
     SplineDev spline;
     SurfaceDev ds;
-    // outputs (device) -- same layouts as the host ones with C -> c_stride
+    // outputs (device) -- same layouts as the host ones with C -> out_stride (= c_stride unless the outputs are
+    // scattered into raster cell order: then cell c of the launch writes column out_col[c] of rows out_stride long)
+    int64_t out_stride;
+    const int64_t *out_col;    // [n_cols] or nullptr (column = cell)
     double *mean_state, *mean_forcing, *hourly_state, *hourly_forcing;
     int32_t *wet_hours;
     uint8_t *wet_flags;

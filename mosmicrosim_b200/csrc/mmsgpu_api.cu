@@ -92,6 +92,10 @@ struct Shard {
     mms_chain_plan *plan = nullptr;
     int device = 0;
     int64_t cell0 = 0, n_cells = 0, c_stride = 0;
+    // output geometry: rows of out_stride columns; the shard's first column is column out_col0 of the caller's rows.
+    // Without a scatter that is the cell geometry again (out_col0 = cell0, out_stride = c_stride).
+    int64_t out_col0 = 0, out_cols = 0, out_stride = 0;
+    int64_t *d_out_col = nullptr;     // [c_stride] column of every cell relative to out_col0 (scatter only)
     cudaStream_t s_compute = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // whole-shard launch (mms_chain_launch)
     bool timing_chunks = false;                 // kernel time = sum over chunks (mms_chain_run) or ev0..ev1
@@ -157,6 +161,10 @@ struct mms_chain_plan {
     std::atomic<int64_t> launches{0};
     bool uploaded = false;
     int n_workers = 1;
+    // outputs scattered into raster cell order (N2): cell c -> column cell_idx[c] of rows R long
+    bool scatter = false;
+    std::vector<int64_t> cell_idx;
+    int64_t R = 0;                         // columns of the caller's output rows (C without a scatter)
     // water-temperature EXTENSION
     mms_water_temperature wt{};
     std::vector<double2> sun_day;          // (sin delta, cos delta) of every day, host libm
@@ -165,6 +173,18 @@ struct mms_chain_plan {
 };
 
 namespace {
+
+// First output column owned by the cells from global index b on: a window of cells [a, b) owns the columns
+// [out_boundary(a), out_boundary(b)) of the caller's rows -- its cells' own columns plus the gap (raster cells that
+// are not pixels of the tile) up to the next window's first cell; the first window also owns the leading gap, the
+// last one the trailing gap.  Any partition of the cells into windows therefore tiles the rows exactly.
+int64_t out_boundary(const mms_chain_plan *pl, int64_t b)
+{
+    if (!pl->scatter) return b;
+    if (b <= 0) return 0;
+    if (b >= pl->C) return pl->R;
+    return pl->cell_idx[(size_t)b];
+}
 
 // CUDA call inside a worker / the pipeline: record the failure in the shard and leave
 #define MMS_CUDA_W(shard, call)                                                                   \
@@ -203,9 +223,15 @@ bool setup_shard(Shard *s)
     MMS_CUDA_W(s, cudaStreamCreateWithFlags(&s->s_compute, cudaStreamNonBlocking));
     MMS_CUDA_W(s, cudaEventCreate(&s->ev0));
     MMS_CUDA_W(s, cudaEventCreate(&s->ev1));
-    const size_t cs = (size_t)s->c_stride;
+    const size_t cs = (size_t)s->c_stride, os = (size_t)s->out_stride;
     const size_t H = (size_t)24 * pl->D;
     cudaStream_t st = s->s_compute;
+    if (pl->scatter) {
+        std::vector<int64_t> col((size_t)s->c_stride, 0);
+        for (int64_t c = 0; c < s->n_cells; ++c) col[(size_t)c] = pl->cell_idx[(size_t)(s->cell0 + c)] - s->out_col0;
+        if (!dev_upload(s, &s->d_out_col, col, st)) return false;
+        MMS_CUDA_W(s, cudaStreamSynchronize(st));          // `col` goes out of scope
+    }
     if (!dev_alloc(s, &s->d_monthly, (size_t)MMS_NFORCING * pl->M * cs)) return false;
     if (!dev_alloc(s, &s->d_altitude, cs)) return false;
     MMS_CUDA_W(s, cudaMemsetAsync(s->d_monthly, 0, sizeof(double) * MMS_NFORCING * pl->M * cs, st));
@@ -217,12 +243,12 @@ bool setup_shard(Shard *s)
     if (!dev_upload(s, &s->d_gx, pl->gx, st)) return false;
     if (!dev_upload(s, &s->d_gy, pl->gy, st)) return false;
     if (!dev_upload(s, &s->d_quad, pl->tab.quad, st)) return false;
-    if (!dev_alloc(s, &s->d_mean_state, (size_t)pl->S * pl->n_mean_state * pl->P * cs)) return false;
-    if (!dev_alloc(s, &s->d_mean_forcing, (size_t)pl->n_mean_forcing * pl->P * cs)) return false;
-    if (!dev_alloc(s, &s->d_hourly_state, (size_t)pl->S * pl->n_hourly_state * H * cs)) return false;
-    if (!dev_alloc(s, &s->d_hourly_forcing, (size_t)pl->n_hourly_forcing * H * cs)) return false;
-    if (pl->want_wet_hours && !dev_alloc(s, &s->d_wet_hours, (size_t)pl->S * pl->P * cs)) return false;
-    if (pl->want_wet_flags && !dev_alloc(s, &s->d_wet_flags, (size_t)pl->S * H * cs)) return false;
+    if (!dev_alloc(s, &s->d_mean_state, (size_t)pl->S * pl->n_mean_state * pl->P * os)) return false;
+    if (!dev_alloc(s, &s->d_mean_forcing, (size_t)pl->n_mean_forcing * pl->P * os)) return false;
+    if (!dev_alloc(s, &s->d_hourly_state, (size_t)pl->S * pl->n_hourly_state * H * os)) return false;
+    if (!dev_alloc(s, &s->d_hourly_forcing, (size_t)pl->n_hourly_forcing * H * os)) return false;
+    if (pl->want_wet_hours && !dev_alloc(s, &s->d_wet_hours, (size_t)pl->S * pl->P * os)) return false;
+    if (pl->want_wet_flags && !dev_alloc(s, &s->d_wet_flags, (size_t)pl->S * H * os)) return false;
     if (pl->wt.enabled) {
         if (!dev_upload(s, &s->d_sun_day, pl->sun_day, st)) return false;
         if (!dev_upload(s, &s->d_month_of_day, pl->month_of_day, st)) return false;
@@ -250,7 +276,7 @@ void free_shard_device(Shard *s)
     cudaSetDevice(s->device);
     void *ptrs[] = {s->d_monthly, s->d_altitude, s->d_days, s->d_period, s->d_sx, s->d_scoef, s->d_gx, s->d_gy, s->d_quad,
                     s->d_mean_state, s->d_mean_forcing, s->d_hourly_state, s->d_hourly_forcing, s->d_wet_hours,
-                    s->d_wet_flags, s->d_error, s->d_terra, s->d_sun_day, s->d_month_of_day, s->d_sin_lat, s->d_cos_lat,
+                    s->d_wet_flags, s->d_error, s->d_terra, s->d_out_col, s->d_sun_day, s->d_month_of_day, s->d_sin_lat, s->d_cos_lat,
                     s->d_clear_sky};
     for (void *q : ptrs) if (q) cudaFree(q);
     for (Chunk &c : s->chunks) {
@@ -299,8 +325,18 @@ bool enqueue_chain(Shard *s, int64_t c0, int64_t n_cols, int64_t n_cells, int er
     mms_chain_plan *pl = s->plan;
     if (n_cols <= 0) return true;
     cudaStream_t st = s->s_compute;
-    const size_t cs = (size_t)s->c_stride;
+    const size_t os = (size_t)s->out_stride;
+    const size_t H = (size_t)24 * pl->D;
+    // output columns of this window, relative to the shard's first output column
+    const int64_t ga = s->cell0 + std::min(c0, s->n_cells), gb = s->cell0 + std::min(c0 + n_cells, s->n_cells);
+    const int64_t o0 = out_boundary(pl, ga) - s->out_col0;
+    const size_t ow = pl->scatter ? (size_t)(out_boundary(pl, gb) - out_boundary(pl, ga)) : (size_t)n_cols;
+    // without a scatter the kernel addresses the window's columns (all pointers offset to its first cell); with one,
+    // out_col[] holds shard-relative columns, so the output pointers stay at the shard's origin
+    const int64_t ob = pl->scatter ? 0 : c0;
     mms::ChainParams p{};
+    p.out_stride = s->out_stride;
+    p.out_col = pl->scatter ? s->d_out_col + c0 : nullptr;
     p.monthly = s->d_monthly + c0; p.altitude = s->d_altitude + c0; p.days = s->d_days;
     p.period_of_day = s->d_period;
     p.c_stride = s->c_stride; p.n_cells = n_cells; p.n_cols = n_cols;
@@ -314,12 +350,12 @@ bool enqueue_chain(Shard *s, int64_t c0, int64_t n_cols, int64_t n_cells, int er
     p.ds.x0 = pl->gx[0]; p.ds.inv_dx = (pl->ds_nx - 1) / (pl->gx[pl->ds_nx - 1] - pl->gx[0]);
     p.ds.y0 = pl->gy[0]; p.ds.inv_dy = (pl->ds_ny - 1) / (pl->gy[pl->ds_ny - 1] - pl->gy[0]);
     p.ds.x1 = pl->gx[pl->ds_nx - 1]; p.ds.y1 = pl->gy[pl->ds_ny - 1];
-    p.mean_state = s->d_mean_state ? s->d_mean_state + c0 : nullptr;
-    p.mean_forcing = s->d_mean_forcing ? s->d_mean_forcing + c0 : nullptr;
-    p.hourly_state = s->d_hourly_state ? s->d_hourly_state + c0 : nullptr;
-    p.hourly_forcing = s->d_hourly_forcing ? s->d_hourly_forcing + c0 : nullptr;
-    p.wet_hours = s->d_wet_hours ? s->d_wet_hours + c0 : nullptr;
-    p.wet_flags = s->d_wet_flags ? s->d_wet_flags + c0 : nullptr;
+    p.mean_state = s->d_mean_state ? s->d_mean_state + ob : nullptr;
+    p.mean_forcing = s->d_mean_forcing ? s->d_mean_forcing + ob : nullptr;
+    p.hourly_state = s->d_hourly_state ? s->d_hourly_state + ob : nullptr;
+    p.hourly_forcing = s->d_hourly_forcing ? s->d_hourly_forcing + ob : nullptr;
+    p.wet_hours = s->d_wet_hours ? s->d_wet_hours + ob : nullptr;
+    p.wet_flags = s->d_wet_flags ? s->d_wet_flags + ob : nullptr;
     p.mean_mask = pl->mean_mask; p.hourly_mask = pl->hourly_mask;
     if (pl->wt.enabled) {
         p.wt.enabled = 1;
@@ -339,11 +375,16 @@ bool enqueue_chain(Shard *s, int64_t c0, int64_t n_cols, int64_t n_cells, int er
     MMS_CUDA_W(s, cudaMemsetAsync(s->d_error + 2 * err_slot, 0, 2 * sizeof(int32_t), st));
     p.hr = pl->hr;
     for (int k = 0; k < pl->S; ++k) p.hab[k] = pl->hab[k];
-    // periods that never occur stay NaN (all-ones bit pattern) / 0
-    if (!pl->all_periods_present) {
-        if (p.mean_state) MMS_CUDA_W(s, cudaMemset2DAsync(p.mean_state, 8 * cs, 0xFF, 8 * (size_t)n_cols, (size_t)pl->S * pl->n_mean_state * pl->P, st));
-        if (p.mean_forcing) MMS_CUDA_W(s, cudaMemset2DAsync(p.mean_forcing, 8 * cs, 0xFF, 8 * (size_t)n_cols, (size_t)pl->n_mean_forcing * pl->P, st));
-        if (p.wet_hours) MMS_CUDA_W(s, cudaMemset2DAsync(p.wet_hours, 4 * cs, 0, 4 * (size_t)n_cols, (size_t)pl->S * pl->P, st));
+    // periods that never occur, and raster cells that are not pixels of the tile, stay NaN (all-ones bit pattern) / 0
+    if ((!pl->all_periods_present || pl->scatter) && ow > 0) {
+        if (s->d_mean_state) MMS_CUDA_W(s, cudaMemset2DAsync(s->d_mean_state + o0, 8 * os, 0xFF, 8 * ow, (size_t)pl->S * pl->n_mean_state * pl->P, st));
+        if (s->d_mean_forcing) MMS_CUDA_W(s, cudaMemset2DAsync(s->d_mean_forcing + o0, 8 * os, 0xFF, 8 * ow, (size_t)pl->n_mean_forcing * pl->P, st));
+        if (s->d_wet_hours) MMS_CUDA_W(s, cudaMemset2DAsync(s->d_wet_hours + o0, 4 * os, 0, 4 * ow, (size_t)pl->S * pl->P, st));
+    }
+    if (pl->scatter && ow > 0) {
+        if (s->d_hourly_state) MMS_CUDA_W(s, cudaMemset2DAsync(s->d_hourly_state + o0, 8 * os, 0xFF, 8 * ow, (size_t)pl->S * pl->n_hourly_state * H, st));
+        if (s->d_hourly_forcing) MMS_CUDA_W(s, cudaMemset2DAsync(s->d_hourly_forcing + o0, 8 * os, 0xFF, 8 * ow, (size_t)pl->n_hourly_forcing * H, st));
+        if (s->d_wet_flags) MMS_CUDA_W(s, cudaMemset2DAsync(s->d_wet_flags + o0, os, 0, ow, (size_t)pl->S * H, st));
     }
     // the fast kernels index the tables arithmetically, which needs equally spaced knots /
     // axes (true for every table the reference builds); anything else runs the strict
@@ -365,6 +406,15 @@ void worker_window(const Chunk &c, int w, int workers, int64_t &w0, int64_t &wn)
     const int64_t b = std::min<int64_t>((int64_t)(w + 1) * per * 32, c.n_cells);
     w0 = c.c0 + a;
     wn = b - a;
+}
+
+// the output columns (relative to the shard's first output column) that go with the cell window [w0, w0 + wn)
+void out_window(const Shard *s, int64_t w0, int64_t wn, int64_t &o0, int64_t &on)
+{
+    const mms_chain_plan *pl = s->plan;
+    const int64_t a = out_boundary(pl, s->cell0 + w0), b = out_boundary(pl, s->cell0 + w0 + wn);
+    o0 = a - s->out_col0;
+    on = wn > 0 ? b - a : 0;
 }
 
 bool ensure_slots(Worker *wk, bool in)
@@ -512,10 +562,11 @@ bool do_out(Worker *wk, const Job &job, int k)
     }
     if (s->failed.load()) return false;
     if (c.kernel_recorded) MMS_CUDA_W(s, cudaStreamWaitEvent(wk->s_out, c.ev_kernel, 0));
-    int64_t w0 = 0, wn = 0;
+    int64_t w0 = 0, wn = 0, o0 = 0, on = 0;
     if (wk->id < job.workers) worker_window(c, wk->id, job.workers, w0, wn);
+    out_window(s, w0, wn, o0, on);
     for (const Mat &m : job.out)
-        if (!stage_out(wk, m, w0, wn)) return false;
+        if (!stage_out(wk, m, o0, on)) return false;
     while (!wk->pending.empty())
         if (!drain_one(wk)) return false;
     return true;
@@ -631,21 +682,34 @@ Mat make_mat(const void *host, size_t host_cells, void *dev, const Shard *s, siz
     return m;
 }
 
+// an output array: rows of R columns on the host (R = C without a scatter), of out_stride on the device
+Mat make_out_mat(const mms_chain_plan *pl, void *host, void *dev, const Shard *s, size_t rows, int elem)
+{
+    Mat m;
+    m.host = (char *)host + (size_t)s->out_col0 * elem;
+    m.host_pitch = (size_t)pl->R * elem;
+    m.dev = (char *)dev;
+    m.dev_pitch = (size_t)s->out_stride * elem;
+    m.rows = rows;
+    m.elem = elem;
+    return m;
+}
+
 void add_outputs(mms_chain_plan *pl, const Shard *s, const mms_chain_outputs *out, Job &job)
 {
-    const size_t H = (size_t)24 * pl->D, C = (size_t)pl->C;
+    const size_t H = (size_t)24 * pl->D;
     if (out->mean_state && s->d_mean_state)
-        job.out.push_back(make_mat(out->mean_state, C, s->d_mean_state, s, (size_t)pl->S * pl->n_mean_state * pl->P, 8));
+        job.out.push_back(make_out_mat(pl, out->mean_state, s->d_mean_state, s, (size_t)pl->S * pl->n_mean_state * pl->P, 8));
     if (out->mean_forcing && s->d_mean_forcing)
-        job.out.push_back(make_mat(out->mean_forcing, C, s->d_mean_forcing, s, (size_t)pl->n_mean_forcing * pl->P, 8));
+        job.out.push_back(make_out_mat(pl, out->mean_forcing, s->d_mean_forcing, s, (size_t)pl->n_mean_forcing * pl->P, 8));
     if (out->hourly_state && s->d_hourly_state)
-        job.out.push_back(make_mat(out->hourly_state, C, s->d_hourly_state, s, (size_t)pl->S * pl->n_hourly_state * H, 8));
+        job.out.push_back(make_out_mat(pl, out->hourly_state, s->d_hourly_state, s, (size_t)pl->S * pl->n_hourly_state * H, 8));
     if (out->hourly_forcing && s->d_hourly_forcing)
-        job.out.push_back(make_mat(out->hourly_forcing, C, s->d_hourly_forcing, s, (size_t)pl->n_hourly_forcing * H, 8));
+        job.out.push_back(make_out_mat(pl, out->hourly_forcing, s->d_hourly_forcing, s, (size_t)pl->n_hourly_forcing * H, 8));
     if (out->wet_hours && s->d_wet_hours)
-        job.out.push_back(make_mat(out->wet_hours, C, s->d_wet_hours, s, (size_t)pl->S * pl->P, 4));
+        job.out.push_back(make_out_mat(pl, out->wet_hours, s->d_wet_hours, s, (size_t)pl->S * pl->P, 4));
     if (out->wet_flags && s->d_wet_flags)
-        job.out.push_back(make_mat(out->wet_flags, C, s->d_wet_flags, s, (size_t)pl->S * H, 1));
+        job.out.push_back(make_out_mat(pl, out->wet_flags, s->d_wet_flags, s, (size_t)pl->S * H, 1));
 }
 
 // pinned or pageable?  One driver query per host array; a job whose arrays are all pinned needs one worker
@@ -873,6 +937,21 @@ int mms_chain_create(const mms_chain_config *cfg, mms_chain_plan **out)
         }
         for (int k = 1; k <= 24; ++k) pl->hr.cos_hour_angle[k - 1] = std::cos(15.0 * (k - 12) * (3.141592653589793 / 180));   // :459-466
     }
+    pl->R = pl->C;
+    if (!rc && cfg->raster_cell_idx) {
+        // N2: scatter the output rows into raster cell order (cell_idx of R/pipeline_functions.R:1316-1322)
+        pl->scatter = true;
+        pl->R = cfg->n_raster_cells;
+        pl->cell_idx.assign(cfg->raster_cell_idx, cfg->raster_cell_idx + pl->C);
+        if (pl->R < pl->C) rc = fail(MMS_ERR_INVALID_ARG, "n_raster_cells (%lld) is smaller than n_cells", (long long)pl->R);
+        for (int64_t c = 0; c < pl->C && !rc; ++c) {
+            const int64_t k = pl->cell_idx[(size_t)c];
+            if (k < 0 || k >= pl->R) rc = fail(MMS_ERR_INVALID_ARG, "raster_cell_idx[%lld] = %lld is outside 0..n_raster_cells-1", (long long)c, (long long)k);
+            else if (c > 0 && k <= pl->cell_idx[(size_t)c - 1])
+                rc = fail(MMS_ERR_UNSUPPORTED, "raster_cell_idx must be strictly increasing (pixels in raster cell order, as "
+                          "terra::cells() returns them); sort the tile's pixels by cell number");
+        }
+    }
     if (rc) return rc;
     pl->ds_nx = cfg->lifehistory.ds_temp_humid.nx; pl->ds_ny = cfg->lifehistory.ds_temp_humid.ny;
     pl->gx.assign(cfg->lifehistory.ds_temp_humid.x, cfg->lifehistory.ds_temp_humid.x + pl->ds_nx);
@@ -892,6 +971,9 @@ int mms_chain_create(const mms_chain_config *cfg, mms_chain_plan **out)
         s->cell0 = cell0;
         s->n_cells = n;
         s->c_stride = ((n + mms::kBlock - 1) / mms::kBlock) * mms::kBlock;
+        s->out_col0 = out_boundary(pl, cell0);
+        s->out_cols = out_boundary(pl, cell0 + n) - s->out_col0;
+        s->out_stride = pl->scatter ? std::max<int64_t>(32, ((s->out_cols + 31) / 32) * 32) : s->c_stride;
         plan_chunks(pl, s.get(), n_sm_guess);
         pl->shards.push_back(std::move(s));
     }

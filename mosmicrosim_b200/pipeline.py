@@ -256,7 +256,8 @@ def terraclimate_to_monthly_climate(pixel_terraclimate_data, *, pad_last=False, 
 
 def _run_vectors(run, n_cells, start, end, carried, lifehistory_functions, species, included_dates,
                  aggregate_by, dates_predict, habitats, model_water_temperature, water_shade_proportion,
-                 burnin_years_pop, extra_variables, math_mode, devices, water_temperature_options=None):
+                 burnin_years_pop, extra_variables, math_mode, devices, water_temperature_options=None,
+                 cell_idx=None, n_raster_cells=None):
     """interpolate_daily_climate() ... summarise_vectors() in one pipelined call (mms_chain_run[_terraclimate]);
     `run(plan, out)` hands the monthly knots (either form) and the output buffers to the plan."""
     species = _match_arg(species, SPECIES, "species")
@@ -291,7 +292,7 @@ def _run_vectors(run, n_cells, start, end, carried, lifehistory_functions, speci
             densmod=backend.make_densmod(lh.das_densmod.type, lh.das_densmod.dd_effect, lh.das_densmod.surface_area_cm2),
             tables=lh.tables(), period_of_day=period_of_day, n_periods=len(p_start), burnin_years_water=0,
             burnin_years_pop=burnin_years_pop, mean_vars=names, want_wet_hours=True, math_mode=math_mode,
-            devices=devices, water_temperature=wt) as plan:
+            devices=devices, water_temperature=wt, raster_cell_idx=cell_idx, n_raster_cells=n_raster_cells) as plan:
         out = run(plan, plan.allocate_outputs())
     res = {"longitude": carried.get("longitude"), "latitude": carried.get("latitude"),
            "species": species, "start": p_start, "end": p_end, "wet_hours": out["wet_hours"]}
@@ -306,7 +307,7 @@ def monthly_climate_to_vectors(pixel_monthly_climate, lifehistory_functions, spe
                                included_dates=None, aggregate_by="month", dates_predict=None, *,
                                habitats=None, model_water_temperature=False, water_shade_proportion=1,
                                burnin_years_pop=1, extra_variables=(), math_mode="fast", devices=None,
-                               water_temperature_options=None):
+                               water_temperature_options=None, cell_idx=None, n_raster_cells=None):
     """tc_to_vectors() (R/pipeline_functions.R:1099-1130) from
     interpolate_daily_climate() to summarise_vectors(), for a whole tile in one
     fused kernel launch per device.
@@ -319,18 +320,24 @@ def monthly_climate_to_vectors(pixel_monthly_climate, lifehistory_functions, spe
       (the reference's sysdata object of the same name).
     Returns a dict: longitude, latitude, species, start[P], end[P] and one
     [P, C] array per vector variable -- the `pixel_vectors` tibbles side by side.
+    cell_idx / n_raster_cells: the pixels' 0-based raster cell numbers (strictly increasing) and the raster's size;
+      every row then comes back as a whole raster slice [P, n_raster_cells] with NaN where the raster has no pixel
+      of the tile -- the assignment raster[cell_idx] <- values of create_vector_raster_slice()
+      (R/pipeline_functions.R:1316-1322), done by the kernel's stores on the device.
     """
     start, end, monthly, altitude = _monthly_array(pixel_monthly_climate)
     return _run_vectors(lambda plan, out: plan.run(monthly, altitude, out), monthly.shape[2], start, end,
                         pixel_monthly_climate, lifehistory_functions, species, included_dates, aggregate_by,
                         dates_predict, habitats, model_water_temperature, water_shade_proportion,
-                        burnin_years_pop, extra_variables, math_mode, devices, water_temperature_options)
+                        burnin_years_pop, extra_variables, math_mode, devices, water_temperature_options,
+                        cell_idx, n_raster_cells)
 
 
 def tc_to_vectors(pixel_terraclimate_data, lifehistory_functions, species=SPECIES, included_dates=None, *,
                   aggregate_by="month", dates_predict=None, pad_last=False, habitats=None,
                   model_water_temperature=False, water_shade_proportion=1, burnin_years_pop=1,
-                  extra_variables=(), math_mode="fast", devices=None, water_temperature_options=None):
+                  extra_variables=(), math_mode="fast", devices=None, water_temperature_options=None,
+                  cell_idx=None, n_raster_cells=None):
     """tc_to_vectors(pixel_terraclimate_data, species, included_dates), R/pipeline_functions.R:1099-1130,
     whole: the six raw TerraClimate variables go to the device and process_terraclimate_pixel_vars()
     (R/terraclimate.R:581-643) runs there, in front of the fused chain (mms_chain_upload_terraclimate).
@@ -343,7 +350,7 @@ def tc_to_vectors(pixel_terraclimate_data, lifehistory_functions, species=SPECIE
                         tc.shape[2], start, end, pixel_terraclimate_data, lifehistory_functions, species,
                         included_dates, aggregate_by, dates_predict, habitats, model_water_temperature,
                         water_shade_proportion, burnin_years_pop, extra_variables, math_mode, devices,
-                        water_temperature_options)
+                        water_temperature_options, cell_idx, n_raster_cells)
 
 
 def raster_slice(vectors, variable, year, month):

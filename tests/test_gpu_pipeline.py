@@ -196,3 +196,36 @@ def test_das_spline_at_and_above_one(gpu, mode, species):
     assert (das_h > 1.0).any() and (das_h == 1.0).any()
     assert np.isnan(ref["hourly"][0, ORACLE_VAR["aquatic"]]).any()
     compare(case, out, ref, 1e-11 if mode == "strict" else REL_TOL_FAST)
+
+
+@pytest.mark.parametrize("devices,chunks,workers", [([0], "1", "1"), ([0], "4", "3"), ([0, 0, 0], "2", "2")])
+def test_outputs_scattered_into_raster_order(gpu, monkeypatch, devices, chunks, workers):
+    """N2: with raster_cell_idx the rows come back as whole raster slices -- pixel c in column cell_idx[c], NaN (0 in
+    the integer outputs) where the raster has no pixel of the tile -- exactly what the numpy scatter
+    raster[:, cell_idx] = values of the plain run gives (create_vector_raster_slice(), R/pipeline_functions.R:1316-1322);
+    summaries, hourly series and flags, pageable and pinned buffers, several chunks / workers / shards."""
+    monkeypatch.setenv("MMS_CHAIN_CHUNKS", chunks)
+    monkeypatch.setenv("MMS_HOST_WORKERS", workers)
+    case = Case(n_cells=700 + 19, habitats=[syn.habitat_cone(), syn.habitat_cylinder(leak_per_hour=0.002)])
+    rng = np.random.default_rng(9)
+    R = 2600
+    cell_idx = np.sort(rng.choice(np.arange(5, R - 40), size=case.C, replace=False))     # gaps in front, inside, behind
+    kw = case.gpu_kwargs(mean_vars=list(backend.VAR_NAMES[:8]), hourly_vars=["aquatic", "mdr"], want_wet_hours=True,
+                         want_wet_flags=True, devices=devices)
+    plain = backend.run_chain(case.monthly, case.altitude, **kw)
+    with backend.ChainPlan(case.C, raster_cell_idx=cell_idx, n_raster_cells=R, **kw) as plan:
+        got = plan.run(case.monthly, case.altitude)
+        pinned = plan.run(case.monthly, case.altitude, plan.allocate_outputs(pinned=True))
+        plan.upload(case.monthly, case.altitude)
+        plan.launch()
+        resident = plan.download(plan.allocate_outputs())
+    for k in KEYS:
+        fill = np.nan if plain[k].dtype == np.float64 else 0
+        want = np.full(plain[k].shape[:-1] + (R,), fill, dtype=plain[k].dtype)
+        want[..., cell_idx] = plain[k]
+        for out in (got, pinned, resident):
+            assert out[k].shape == want.shape
+            assert np.array_equal(out[k], want, equal_nan=True), k
+    with pytest.raises(backend.MmsError) as e:          # not in raster order
+        backend.ChainPlan(case.C, raster_cell_idx=cell_idx[::-1].copy(), n_raster_cells=R, **kw)
+    assert e.value.code == "MMS_ERR_UNSUPPORTED"
