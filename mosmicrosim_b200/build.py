@@ -30,6 +30,7 @@ UNITS = [
     ("mmsgpu_api.cu", "mmsgpu_api.o", []),
     ("api_common.cu", "api_common.o", []),
     ("api_twins.cu", "api_twins.o", []),
+    ("host_pipeline.cu", "host_pipeline.o", []),
     ("host_copy.cpp", "host_copy.o", []),       # g++ only (AVX2 streaming stores behind a run-time check)
     ("measure.cu", "measure.o", []),
 ]

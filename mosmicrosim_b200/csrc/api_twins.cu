@@ -1,9 +1,124 @@
 // api_twins.cu -- host side of the stage-level twins (R matrices in, R matrices out) and of the state-free
 // verbs of include/mmsgpu.h.  Validates the call, moves the data, launches the sm_100a kernels; no model
 // arithmetic happens here and there is no CPU fallback.  Citations are relative to the reference root.
-#include "api_common.h"
+#include "host_pipeline.h"
 
 using namespace mms_api;
+
+namespace {
+
+// One stage-level twin call: n_pixels series of n_times steps per matrix, R's column-major layout (each pixel's
+// series contiguous).  The pixels are processed in chunks of about one round of the persistent stage kernel through
+// a Pipe (host_pipeline.h): the upload of chunk k+1, the kernel of chunk k and the download of chunk k-1 overlap,
+// pageable matrices (R's) go through the workers' pinned bounce buffers.  Matrices that do not fit in the device's
+// free memory are walked in several passes of as many pixels as do fit.
+struct TwinArrays {
+    std::vector<const double *> in;                  // H-by-C inputs
+    const double *per_pixel = nullptr;               // [C] (altitude) or nullptr
+    std::vector<std::pair<void *, size_t>> out;      // H-by-C outputs: pointer, bytes per value (8, or 1 for the flags)
+};
+using TwinLaunch = std::function<cudaError_t(int64_t n_pixels, const std::vector<char *> &d_in, const double *d_per_pixel,
+                                             const std::vector<char *> &d_out, cudaStream_t)>;
+
+int run_twin(int device, int64_t H, int64_t C, const TwinArrays &a, int round_pixels, const TwinLaunch &launch)
+{
+    int rc = pick_device(device);
+    if (rc) return rc;
+    // pixels per pass: what fits in 80 % of the free device memory (MMS_TWIN_PASS_PIXELS: tests)
+    size_t bytes_per_pixel = a.per_pixel ? 8 : 0;
+    for (size_t k = 0; k < a.in.size(); ++k) bytes_per_pixel += (size_t)H * 8;
+    for (auto &o : a.out) bytes_per_pixel += (size_t)H * o.second;
+    size_t free_b = 0, total_b = 0;
+    MMS_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    int64_t pass_pixels = (int64_t)std::min<size_t>((size_t)C, (size_t)(0.8 * (double)free_b) / bytes_per_pixel);
+    if (const char *e = std::getenv("MMS_TWIN_PASS_PIXELS")) pass_pixels = std::min<int64_t>(C, std::max<int64_t>(1, std::atoll(e)));
+    if (pass_pixels < 1) return fail(MMS_ERR_ALLOC, "one pixel's series (%zu bytes) do not fit in the device's free memory", bytes_per_pixel);
+    if (pass_pixels < C) pass_pixels = std::max<int64_t>(32, pass_pixels / 32 * 32);
+
+    std::vector<DevBuf> d_in(a.in.size()), d_out(a.out.size());
+    DevBuf d_pp;
+    for (auto &b : d_in) if ((rc = b.alloc((size_t)pass_pixels * H * 8))) return rc;
+    for (size_t k = 0; k < a.out.size(); ++k) if ((rc = d_out[k].alloc((size_t)pass_pixels * H * a.out[k].second))) return rc;
+    if (a.per_pixel && (rc = d_pp.alloc((size_t)pass_pixels * 8))) return rc;
+
+    float kernel_ms = 0.f;
+    for (int64_t p0 = 0; p0 < C; p0 += pass_pixels) {
+        const int64_t np = std::min(pass_pixels, C - p0);
+        Pipe pipe;
+        pipe.device = device;
+        pipe.window_unit = 1;
+        // the twins move 40-56 bytes per pixel-step for a few flops: what matters is that the copies of the next and the
+        // previous chunk overlap the kernel and that the first upload / last download (not overlapped) are short --
+        // chunks of about half a GB (all arrays together), at least one per round of the persistent kernel
+        int64_t n_chunks = std::max<int64_t>((np + round_pixels - 1) / round_pixels,
+                                             (int64_t)(((size_t)np * bytes_per_pixel) >> 29));
+        if (const char *e = std::getenv("MMS_TWIN_CHUNKS")) n_chunks = std::max<int64_t>(1, std::atoll(e));
+        n_chunks = std::max<int64_t>(1, std::min<int64_t>(n_chunks, std::min<int64_t>(64, (np + 31) / 32)));
+        const int64_t blocks = (np + 31) / 32;
+        for (int64_t k = 0; k < n_chunks; ++k) {
+            PipeChunk c;
+            c.c0 = blocks * k / n_chunks * 32;
+            c.n_cols = c.n_cells = std::min(np, blocks * (k + 1) / n_chunks * 32) - c.c0;
+            pipe.chunks.push_back(c);
+        }
+        PipeJob job;
+        job.kind = PIPE_RUN;
+        auto mat = [&](const void *host, void *dev, size_t elem) {
+            Mat m;
+            m.host = (char *)const_cast<void *>(host) + (size_t)p0 * elem;
+            m.dev = (char *)dev;
+            m.host_pitch = m.dev_pitch = 0;
+            m.rows = 1;
+            m.elem = elem;
+            return m;
+        };
+        for (size_t k = 0; k < a.in.size(); ++k) job.in.push_back(mat(a.in[k], d_in[k].p, (size_t)H * 8));
+        if (a.per_pixel) job.in.push_back(mat(a.per_pixel, d_pp.p, 8));
+        for (size_t k = 0; k < a.out.size(); ++k) job.out.push_back(mat(a.out[k].first, d_out[k].p, (size_t)H * a.out[k].second));
+        const bool pinned = classify_mats(job.in) & classify_mats(job.out);
+        // small calls (tests, single pixels) are not worth a team of workers
+        const size_t pass_bytes = (size_t)np * bytes_per_pixel;
+        const int n_workers = pinned ? 1 : (int)std::max<size_t>(1, std::min<size_t>((size_t)default_workers(1), pass_bytes / ((size_t)64 << 20)));
+        job.workers = n_workers;
+        job.run_chunk = [&](int k) {
+            const PipeChunk &c = pipe.chunks[k];
+            std::vector<char *> di, dd;
+            for (size_t j = 0; j < a.in.size(); ++j) di.push_back((char *)d_in[j].p + (size_t)c.c0 * H * 8);
+            for (size_t j = 0; j < a.out.size(); ++j) dd.push_back((char *)d_out[j].p + (size_t)c.c0 * H * a.out[j].second);
+            const cudaError_t e = launch(c.n_cells, di, a.per_pixel ? (const double *)d_pp.p + c.c0 : nullptr, dd, pipe.s_compute);
+            if (e != cudaSuccess) { pipe.set_error(MMS_ERR_CUDA, std::string("stage kernel launch failed: ") + cudaGetErrorString(e)); return false; }
+            return true;
+        };
+        pipe.start(n_workers);
+        PipeJob setup;
+        setup.kind = PIPE_CALL;
+        setup.call = [&] { return pipe.create_device_objects(); };
+        std::string msg;
+        int r = pipe.run(&setup, &msg);
+        if (!r) r = pipe.run(&job, &msg);
+        if (!r) {
+            for (PipeChunk &c : pipe.chunks) {
+                float t = 0.f;
+                if (c.kernel_recorded && cudaEventSynchronize(c.ev_t1) == cudaSuccess && cudaEventElapsedTime(&t, c.ev_t0, c.ev_t1) == cudaSuccess) kernel_ms += t;
+            }
+        }
+        pipe.stop();
+        pipe.destroy_device_objects();
+        if (r) return fail_str(r, msg);
+    }
+    stage_kernel_ms() = kernel_ms;
+    return MMS_OK;
+}
+
+// pixels one round of the persistent stage kernels holds on this device (chain_tu.cu, stage_plan)
+int twin_round_pixels(int device, int math_mode)
+{
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+    return n_sm * (math_mode ? 12 : 16) * 32;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -23,36 +138,29 @@ static int water_twin(const double *rainfall, const double *air_temperature, con
                     "(R: subscript out of bounds, R/sim_water.R:240)", mms::kHoursPerYear, (long long)n_times);
     int rc = pick_device(device);
     if (rc) return rc;
-    mms::WaterStageParams p{};
-    if ((rc = derive_habitat(*habitat, p.hab))) return rc;
-    const size_t bytes = sizeof(double) * (size_t)n_times * (size_t)n_pixels;
-    DevBuf in[4], alt, area, vol, wetb;
-    const double *src[4] = {rainfall, air_temperature, humidity, windspeed};
-    Stream st;
-    MMS_CUDA(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
-    for (int k = 0; k < 4; ++k) {
-        if ((rc = in[k].alloc(bytes))) return rc;
-        MMS_CUDA(cudaMemcpyAsync(in[k].p, src[k], bytes, cudaMemcpyHostToDevice, st));
-    }
-    if ((rc = alt.alloc(sizeof(double) * n_pixels)) || (rc = area.alloc(bytes)) ||
-        (water_volume && (rc = vol.alloc(bytes))) || (wet && (rc = wetb.alloc((size_t)n_times * n_pixels))))
-        return rc;
-    MMS_CUDA(cudaMemcpyAsync(alt.p, altitude, sizeof(double) * n_pixels, cudaMemcpyHostToDevice, st));
-    p.rainfall = (const double *)in[0].p; p.air_temperature = (const double *)in[1].p;
-    p.humidity = (const double *)in[2].p; p.windspeed = (const double *)in[3].p;
-    p.altitude = (const double *)alt.p;
-    p.water_surface_area = (double *)area.p; p.water_volume = (double *)vol.p; p.wet = (uint8_t *)wetb.p;
-    p.H = n_times; p.C = n_pixels; p.burnin_years = burnin_years;
-    p.burnin_steps = whole_series ? n_times : (int64_t)mms::kHoursPerYear;
-    EventTimer timer(st);
-    MMS_CUDA(math_mode ? mms::launch_water_stage_strict(p, st) : mms::launch_water_stage_fast(p, st));
-    timer.stop();
-    MMS_CUDA(cudaMemcpyAsync(water_surface_area, area.p, bytes, cudaMemcpyDeviceToHost, st));
-    if (water_volume) MMS_CUDA(cudaMemcpyAsync(water_volume, vol.p, bytes, cudaMemcpyDeviceToHost, st));
-    if (wet) MMS_CUDA(cudaMemcpyAsync(wet, wetb.p, (size_t)n_times * n_pixels, cudaMemcpyDeviceToHost, st));
-    MMS_CUDA(cudaStreamSynchronize(st));
-    stage_kernel_ms() = timer.ms();
-    return MMS_OK;
+    mms::WaterStageParams base{};
+    if ((rc = derive_habitat(*habitat, base.hab))) return rc;
+    base.H = n_times; base.burnin_years = burnin_years;
+    base.burnin_steps = whole_series ? n_times : (int64_t)mms::kHoursPerYear;
+    TwinArrays a;
+    a.in = {rainfall, air_temperature, humidity, windspeed};
+    a.per_pixel = altitude;
+    a.out.push_back({water_surface_area, 8});
+    if (water_volume) a.out.push_back({water_volume, 8});
+    if (wet) a.out.push_back({wet, 1});
+    const bool has_vol = water_volume != nullptr, has_wet = wet != nullptr;
+    return run_twin(device, n_times, n_pixels, a, twin_round_pixels(device, math_mode),
+                    [&](int64_t n, const std::vector<char *> &di, const double *d_alt, const std::vector<char *> &dd, cudaStream_t st) {
+                        mms::WaterStageParams p = base;
+                        p.rainfall = (const double *)di[0]; p.air_temperature = (const double *)di[1];
+                        p.humidity = (const double *)di[2]; p.windspeed = (const double *)di[3];
+                        p.altitude = d_alt;
+                        p.water_surface_area = (double *)dd[0];
+                        p.water_volume = has_vol ? (double *)dd[1] : nullptr;
+                        p.wet = has_wet ? (uint8_t *)dd[has_vol ? 2 : 1] : nullptr;
+                        p.C = n;
+                        return math_mode ? mms::launch_water_stage_strict(p, st) : mms::launch_water_stage_fast(p, st);
+                    });
 }
 
 int mms_water_vectorised(const double *rainfall, const double *air_temperature, const double *humidity,
@@ -87,34 +195,23 @@ static int population_twin(const double *larval_habitat_area, const double *mdr,
     if (!whole_series && burnin_years > 0 && n_times < mms::kHoursPerYear)
         return fail(MMS_ERR_BURNIN, "burn-in repeats the first %d rows but the matrices have %lld "
                     "(R: subscript out of bounds, R/sim_pop_dynamics.R:233)", mms::kHoursPerYear, (long long)n_times);
-    int rc = pick_device(device);
-    if (rc) return rc;
-    const size_t bytes = sizeof(double) * (size_t)n_times * (size_t)n_pixels;
-    DevBuf in[5], aq, ad;
-    const double *src[5] = {larval_habitat_area, mdr, efd, das_zerodensity, ds};
-    Stream st;
-    MMS_CUDA(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
-    for (int k = 0; k < 5; ++k) {
-        if ((rc = in[k].alloc(bytes))) return rc;
-        MMS_CUDA(cudaMemcpyAsync(in[k].p, src[k], bytes, cudaMemcpyHostToDevice, st));
-    }
-    if ((rc = aq.alloc(bytes)) || (rc = ad.alloc(bytes))) return rc;
-    mms::PopStageParams p{};
-    p.larval_habitat_area = (const double *)in[0].p; p.mdr = (const double *)in[1].p; p.efd = (const double *)in[2].p;
-    p.das_zerodensity = (const double *)in[3].p; p.ds = (const double *)in[4].p;
-    p.aquatic = (double *)aq.p; p.adult = (double *)ad.p;
-    p.H = n_times; p.C = n_pixels; p.burnin_years = burnin_years;
-    p.burnin_steps = whole_series ? n_times : (int64_t)mms::kHoursPerYear;
-    p.densmod_type = densmod->type; p.dd_effect = densmod->dd_effect; p.surface_area_cm2 = densmod->surface_area_cm2;
-    p.initial_adult = initial_adult; p.initial_aquatic = initial_aquatic;
-    EventTimer timer(st);
-    MMS_CUDA(math_mode ? mms::launch_pop_stage_strict(p, st) : mms::launch_pop_stage_fast(p, st));
-    timer.stop();
-    MMS_CUDA(cudaMemcpyAsync(aquatic, aq.p, bytes, cudaMemcpyDeviceToHost, st));
-    MMS_CUDA(cudaMemcpyAsync(adult, ad.p, bytes, cudaMemcpyDeviceToHost, st));
-    MMS_CUDA(cudaStreamSynchronize(st));
-    stage_kernel_ms() = timer.ms();
-    return MMS_OK;
+    mms::PopStageParams base{};
+    base.H = n_times; base.burnin_years = burnin_years;
+    base.burnin_steps = whole_series ? n_times : (int64_t)mms::kHoursPerYear;
+    base.densmod_type = densmod->type; base.dd_effect = densmod->dd_effect; base.surface_area_cm2 = densmod->surface_area_cm2;
+    base.initial_adult = initial_adult; base.initial_aquatic = initial_aquatic;
+    TwinArrays a;
+    a.in = {larval_habitat_area, mdr, efd, das_zerodensity, ds};
+    a.out = {{aquatic, 8}, {adult, 8}};
+    return run_twin(device, n_times, n_pixels, a, twin_round_pixels(device, math_mode),
+                    [&](int64_t n, const std::vector<char *> &di, const double *, const std::vector<char *> &dd, cudaStream_t st) {
+                        mms::PopStageParams p = base;
+                        p.larval_habitat_area = (const double *)di[0]; p.mdr = (const double *)di[1]; p.efd = (const double *)di[2];
+                        p.das_zerodensity = (const double *)di[3]; p.ds = (const double *)di[4];
+                        p.aquatic = (double *)dd[0]; p.adult = (double *)dd[1];
+                        p.C = n;
+                        return math_mode ? mms::launch_pop_stage_strict(p, st) : mms::launch_pop_stage_fast(p, st);
+                    });
 }
 
 int mms_population_vectorised(const double *larval_habitat_area, const double *mdr, const double *efd,

@@ -19,84 +19,22 @@
 //
 // No model arithmetic per cell-hour happens here, and there is no CPU fallback.
 // Citations are relative to the reference root.
-#include <atomic>
-#include <condition_variable>
-#include <deque>
-#include <memory>
-#include <mutex>
-#include <thread>
-
-#include "api_common.h"
+#include "host_pipeline.h"
 
 using namespace mms_api;
 
-namespace mms_api {
-// host_copy.cpp: streaming-store row copy between caller memory and the pinned bounce buffers
-void copy_rows(char *dst, size_t dpitch, const char *src, size_t spitch, size_t width, size_t rows);
-}
-
 namespace {
 
-constexpr size_t kSlotBytes = (size_t)16 << 20;   // one pinned bounce buffer
-constexpr int kSlots = 2;                         // bounce buffers per worker and direction
-constexpr int kMaxWorkers = 8;                    // host threads per device
 constexpr int kMaxChunks = 64;                    // chunks per shard
-
-// a host <-> device array with the cell index fastest: `rows` rows of cells, this shard's part
-struct Mat {
-    char *host = nullptr;       // the shard's first cell of row 0 on the host
-    size_t host_pitch = 0;      // bytes between rows on the host
-    char *dev = nullptr;        // the same on the device
-    size_t dev_pitch = 0;
-    size_t rows = 0;
-    int elem = 8;               // bytes per cell
-    bool pinned = false;        // the driver can DMA the host side directly
-};
-
-enum JobKind { JOB_NONE = 0, JOB_SETUP, JOB_UPLOAD, JOB_RUN, JOB_DOWNLOAD, JOB_EXIT };
-
-struct Job {
-    JobKind kind = JOB_NONE;
-    bool terraclimate = false;          // inputs are the raw TerraClimate variables (N1 front end)
-    std::vector<Mat> in, out;
-    const double *n_days = nullptr;     // [M] terraclimate only
-    const int32_t *month_id = nullptr;  // [M]
-    int workers = 1;                    // workers that move data in this job (1 when everything is pinned)
-};
-
-struct Chunk {
-    int64_t c0 = 0;       // first column within the shard
-    int64_t n_cols = 0;   // columns (whole 32-cell units)
-    int64_t n_cells = 0;  // real cells among them
-    cudaEvent_t ev_kernel = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
-    std::vector<cudaEvent_t> ev_in;   // [workers]
-    bool kernel_recorded = false;
-};
-
-struct Shard;
-
-struct Worker {
-    Shard *shard = nullptr;
-    int id = 0;
-    std::thread th;
-    cudaStream_t s_in = nullptr, s_out = nullptr;
-    PinBuf pin_in[kSlots], pin_out[kSlots];
-    cudaEvent_t ev_slot_in[kSlots] = {nullptr, nullptr}, ev_slot_out[kSlots] = {nullptr, nullptr};
-    bool slot_in_used[kSlots] = {false, false};
-    int next_in = 0, next_out = 0;
-    struct Pending { int slot; char *dst; size_t pitch, width, rows; };
-    std::deque<Pending> pending;
-};
 
 struct Shard {
     mms_chain_plan *plan = nullptr;
     int device = 0;
-    int64_t cell0 = 0, n_cells = 0, c_stride = 0;
+    int64_t cell0 = 0, n_cells = 0, c_stride = 0;   // the shard's cells [cell0, cell0 + n_cells) of the caller's arrays
     // output geometry: rows of out_stride columns; the shard's first column is column out_col0 of the caller's rows.
     // Without a scatter that is the cell geometry again (out_col0 = cell0, out_stride = c_stride).
     int64_t out_col0 = 0, out_cols = 0, out_stride = 0;
     int64_t *d_out_col = nullptr;     // [c_stride] column of every cell relative to out_col0 (scatter only)
-    cudaStream_t s_compute = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // whole-shard launch (mms_chain_launch)
     bool timing_chunks = false;                 // kernel time = sum over chunks (mms_chain_run) or ev0..ev1
     double *d_monthly = nullptr, *d_altitude = nullptr;
@@ -114,27 +52,7 @@ struct Shard {
     double *d_sin_lat = nullptr, *d_cos_lat = nullptr, *d_clear_sky = nullptr;
     int n_sm = 0;
     bool launched = false;
-    std::vector<Chunk> chunks;
-    std::vector<std::unique_ptr<Worker>> workers;
-
-    // job control
-    std::mutex mu;
-    std::condition_variable cv;
-    uint64_t job_seq = 0;
-    const Job *job = nullptr;
-    int pending = 0;                         // workers still busy with the current job
-    std::unique_ptr<std::atomic<int>[]> arrived;   // [chunk] workers that delivered their inputs
-    std::vector<char> enqueued;              // [chunk] kernels of the chunk are on the compute stream (guarded by mu)
-    std::atomic<bool> failed{false};
-    int err_status = MMS_OK;
-    std::string err_msg;
-
-    void set_error(int status, const std::string &msg)
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        if (!failed.load()) { err_status = status; err_msg = msg; failed.store(true); }
-        cv.notify_all();
-    }
+    Pipe pipe;                     // the device's compute stream, chunks and host workers (host_pipeline.h)
 };
 
 }  // namespace
@@ -186,18 +104,7 @@ int64_t out_boundary(const mms_chain_plan *pl, int64_t b)
     return pl->cell_idx[(size_t)b];
 }
 
-// CUDA call inside a worker / the pipeline: record the failure in the shard and leave
-#define MMS_CUDA_W(shard, call)                                                                   \
-    do {                                                                                          \
-        cudaError_t e_ = (call);                                                                  \
-        if (e_ != cudaSuccess) {                                                                  \
-            char b_[512];                                                                         \
-            snprintf(b_, sizeof b_, "CUDA error %s at %s:%d (%s) on device %d", cudaGetErrorName(e_), __FILE__, \
-                     __LINE__, cudaGetErrorString(e_), (shard)->device);                          \
-            (shard)->set_error(e_ == cudaErrorMemoryAllocation ? MMS_ERR_ALLOC : MMS_ERR_CUDA, b_); \
-            return false;                                                                         \
-        }                                                                                         \
-    } while (0)
+#define MMS_CUDA_W(shard, call) MMS_CUDA_P(&(shard)->pipe, call)
 
 template <typename T>
 bool dev_alloc(Shard *s, T **p, size_t count)
@@ -220,12 +127,12 @@ bool dev_upload(Shard *s, T **p, const std::vector<T> &v, cudaStream_t st)
 bool setup_shard(Shard *s)
 {
     mms_chain_plan *pl = s->plan;
-    MMS_CUDA_W(s, cudaStreamCreateWithFlags(&s->s_compute, cudaStreamNonBlocking));
+    if (!s->pipe.create_device_objects()) return false;
     MMS_CUDA_W(s, cudaEventCreate(&s->ev0));
     MMS_CUDA_W(s, cudaEventCreate(&s->ev1));
     const size_t cs = (size_t)s->c_stride, os = (size_t)s->out_stride;
     const size_t H = (size_t)24 * pl->D;
-    cudaStream_t st = s->s_compute;
+    cudaStream_t st = s->pipe.s_compute;
     if (pl->scatter) {
         std::vector<int64_t> col((size_t)s->c_stride, 0);
         for (int64_t c = 0; c < s->n_cells; ++c) col[(size_t)c] = pl->cell_idx[(size_t)(s->cell0 + c)] - s->out_col0;
@@ -257,16 +164,9 @@ bool setup_shard(Shard *s)
         MMS_CUDA_W(s, cudaMemsetAsync(s->d_cos_lat, 0, sizeof(double) * cs, st));
         MMS_CUDA_W(s, cudaMemsetAsync(s->d_clear_sky, 0, sizeof(double) * 12 * cs, st));
     }
-    if (!dev_alloc(s, &s->d_error, 2 * s->chunks.size())) return false;
-    MMS_CUDA_W(s, cudaMemsetAsync(s->d_error, 0, 2 * s->chunks.size() * sizeof(int32_t), st));
+    if (!dev_alloc(s, &s->d_error, 2 * s->pipe.chunks.size())) return false;
+    MMS_CUDA_W(s, cudaMemsetAsync(s->d_error, 0, 2 * s->pipe.chunks.size() * sizeof(int32_t), st));
     MMS_CUDA_W(s, cudaDeviceGetAttribute(&s->n_sm, cudaDevAttrMultiProcessorCount, s->device));
-    for (Chunk &c : s->chunks) {
-        MMS_CUDA_W(s, cudaEventCreateWithFlags(&c.ev_kernel, cudaEventDisableTiming));
-        MMS_CUDA_W(s, cudaEventCreate(&c.ev_t0));
-        MMS_CUDA_W(s, cudaEventCreate(&c.ev_t1));
-        c.ev_in.assign(s->workers.size(), nullptr);
-        for (cudaEvent_t &e : c.ev_in) MMS_CUDA_W(s, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    }
     MMS_CUDA_W(s, cudaStreamSynchronize(st));
     return true;
 }
@@ -279,25 +179,19 @@ void free_shard_device(Shard *s)
                     s->d_wet_flags, s->d_error, s->d_terra, s->d_out_col, s->d_sun_day, s->d_month_of_day, s->d_sin_lat, s->d_cos_lat,
                     s->d_clear_sky};
     for (void *q : ptrs) if (q) cudaFree(q);
-    for (Chunk &c : s->chunks) {
-        if (c.ev_kernel) cudaEventDestroy(c.ev_kernel);
-        if (c.ev_t0) cudaEventDestroy(c.ev_t0);
-        if (c.ev_t1) cudaEventDestroy(c.ev_t1);
-        for (cudaEvent_t e : c.ev_in) if (e) cudaEventDestroy(e);
-    }
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
-    if (s->s_compute) cudaStreamDestroy(s->s_compute);
+    s->pipe.destroy_device_objects();
 }
 
 // ---- kernels of one column window [c0, c0 + n_cols) of a shard ------------------------------------------
 
 // the forcing rows of the window are on the device: derive what the fused kernel reads
-bool enqueue_transform(Shard *s, const Job &job, int64_t c0, int64_t n_cols, int64_t n_cells)
+bool enqueue_transform(Shard *s, bool terraclimate, int64_t c0, int64_t n_cols, int64_t n_cells)
 {
     mms_chain_plan *pl = s->plan;
     if (n_cols <= 0) return true;
-    if (job.terraclimate) {
+    if (terraclimate) {
         // process_terraclimate_pixel_vars() on the device (R/terraclimate.R:581-643), rainfall stored as log1p
         const size_t cs = (size_t)s->c_stride;
         double *d_tc = s->d_terra, *d_cs = d_tc + (size_t)MMS_NTERRACLIMATE * pl->M * cs;
@@ -308,12 +202,12 @@ bool enqueue_transform(Shard *s, const Job &job, int64_t c0, int64_t n_cols, int
         p.monthly = s->d_monthly + c0;
         p.c_stride = s->c_stride; p.n_cells = n_cells; p.n_cols = n_cols; p.M = pl->M; p.log1p_rainfall = 1;
         p.wind_factor = terraclimate_wind_factor();
-        MMS_CUDA_W(s, pl->math_mode ? mms::launch_terraclimate_strict(p, s->s_compute) : mms::launch_terraclimate_fast(p, s->s_compute));
+        MMS_CUDA_W(s, pl->math_mode ? mms::launch_terraclimate_strict(p, s->pipe.s_compute) : mms::launch_terraclimate_fast(p, s->pipe.s_compute));
     } else {
         // rainfall_daily = log1p(rainfall_daily) before interpolation, R/sim_microclimate.R:33
         double *rain = s->d_monthly + (size_t)MMS_F_RAINFALL_DAILY * pl->M * s->c_stride + c0;
-        MMS_CUDA_W(s, pl->math_mode ? mms::launch_log1p_rows_strict(rain, pl->M, n_cols, s->c_stride, s->s_compute)
-                                    : mms::launch_log1p_rows_fast(rain, pl->M, n_cols, s->c_stride, s->s_compute));
+        MMS_CUDA_W(s, pl->math_mode ? mms::launch_log1p_rows_strict(rain, pl->M, n_cols, s->c_stride, s->pipe.s_compute)
+                                    : mms::launch_log1p_rows_fast(rain, pl->M, n_cols, s->c_stride, s->pipe.s_compute));
     }
     pl->launches += 1;
     return true;
@@ -324,7 +218,7 @@ bool enqueue_chain(Shard *s, int64_t c0, int64_t n_cols, int64_t n_cells, int er
 {
     mms_chain_plan *pl = s->plan;
     if (n_cols <= 0) return true;
-    cudaStream_t st = s->s_compute;
+    cudaStream_t st = s->pipe.s_compute;
     const size_t os = (size_t)s->out_stride;
     const size_t H = (size_t)24 * pl->D;
     // output columns of this window, relative to the shard's first output column
@@ -395,19 +289,6 @@ bool enqueue_chain(Shard *s, int64_t c0, int64_t n_cols, int64_t n_cells, int er
     return true;
 }
 
-// ---- workers ------------------------------------------------------------------------------------------
-
-// columns [w0, w0 + wn) of chunk c that worker `w` of `workers` moves (real cells only, whole 32-cell units)
-void worker_window(const Chunk &c, int w, int workers, int64_t &w0, int64_t &wn)
-{
-    const int64_t units = (c.n_cells + 31) / 32;
-    const int64_t per = (units + workers - 1) / workers;
-    const int64_t a = std::min<int64_t>((int64_t)w * per * 32, c.n_cells);
-    const int64_t b = std::min<int64_t>((int64_t)(w + 1) * per * 32, c.n_cells);
-    w0 = c.c0 + a;
-    wn = b - a;
-}
-
 // the output columns (relative to the shard's first output column) that go with the cell window [w0, w0 + wn)
 void out_window(const Shard *s, int64_t w0, int64_t wn, int64_t &o0, int64_t &on)
 {
@@ -417,260 +298,20 @@ void out_window(const Shard *s, int64_t w0, int64_t wn, int64_t &o0, int64_t &on
     on = wn > 0 ? b - a : 0;
 }
 
-bool ensure_slots(Worker *wk, bool in)
+// hand one job per shard to the shards' workers and wait for all of them; returns the first failure
+int dispatch(mms_chain_plan *pl, std::vector<PipeJob> &jobs)
 {
-    Shard *s = wk->shard;
-    PinBuf *bufs = in ? wk->pin_in : wk->pin_out;
-    cudaEvent_t *evs = in ? wk->ev_slot_in : wk->ev_slot_out;
-    for (int k = 0; k < kSlots; ++k) {
-        if (!bufs[k].p) MMS_CUDA_W(s, cudaHostAlloc(&bufs[k].p, kSlotBytes, cudaHostAllocPortable));
-        bufs[k].bytes = kSlotBytes;
-        if (!evs[k]) MMS_CUDA_W(s, cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming));
-    }
-    return true;
-}
-
-// host -> device: the worker's columns of one array
-bool stage_in(Worker *wk, const Mat &m, int64_t w0, int64_t wn)
-{
-    Shard *s = wk->shard;
-    if (wn <= 0 || m.rows == 0) return true;
-    const size_t off = (size_t)w0 * m.elem, width = (size_t)wn * m.elem;
-    if (m.pinned) {
-        MMS_CUDA_W(s, cudaMemcpy2DAsync(m.dev + off, m.dev_pitch, m.host + off, m.host_pitch, width, m.rows,
-                                        cudaMemcpyHostToDevice, wk->s_in));
-        return true;
-    }
-    if (!ensure_slots(wk, true)) return false;
-    const size_t col_step = std::min(width, kSlotBytes);
-    for (size_t col = 0; col < width; col += col_step) {
-        const size_t wd = std::min(col_step, width - col);
-        const size_t rows_per = std::max<size_t>(1, kSlotBytes / wd);
-        for (size_t r0 = 0; r0 < m.rows; r0 += rows_per) {
-            const size_t nr = std::min(rows_per, m.rows - r0);
-            const int slot = wk->next_in;
-            wk->next_in = (slot + 1) % kSlots;
-            if (wk->slot_in_used[slot]) MMS_CUDA_W(s, cudaEventSynchronize(wk->ev_slot_in[slot]));
-            char *buf = (char *)wk->pin_in[slot].p;
-            copy_rows(buf, wd, m.host + r0 * m.host_pitch + off + col, m.host_pitch, wd, nr);
-            MMS_CUDA_W(s, cudaMemcpy2DAsync(m.dev + r0 * m.dev_pitch + off + col, m.dev_pitch, buf, wd, wd, nr,
-                                            cudaMemcpyHostToDevice, wk->s_in));
-            MMS_CUDA_W(s, cudaEventRecord(wk->ev_slot_in[slot], wk->s_in));
-            wk->slot_in_used[slot] = true;
-        }
-    }
-    return true;
-}
-
-bool drain_one(Worker *wk)
-{
-    Shard *s = wk->shard;
-    const Worker::Pending q = wk->pending.front();
-    wk->pending.pop_front();
-    MMS_CUDA_W(s, cudaEventSynchronize(wk->ev_slot_out[q.slot]));
-    copy_rows(q.dst, q.pitch, (const char *)wk->pin_out[q.slot].p, q.width, q.width, q.rows);
-    return true;
-}
-
-// device -> host: the worker's columns of one array (the stream already waits for the producing kernel)
-bool stage_out(Worker *wk, const Mat &m, int64_t w0, int64_t wn)
-{
-    Shard *s = wk->shard;
-    if (wn <= 0 || m.rows == 0) return true;
-    const size_t off = (size_t)w0 * m.elem, width = (size_t)wn * m.elem;
-    if (m.pinned) {
-        MMS_CUDA_W(s, cudaMemcpy2DAsync(m.host + off, m.host_pitch, m.dev + off, m.dev_pitch, width, m.rows,
-                                        cudaMemcpyDeviceToHost, wk->s_out));
-        return true;
-    }
-    if (!ensure_slots(wk, false)) return false;
-    const size_t col_step = std::min(width, kSlotBytes);
-    for (size_t col = 0; col < width; col += col_step) {
-        const size_t wd = std::min(col_step, width - col);
-        const size_t rows_per = std::max<size_t>(1, kSlotBytes / wd);
-        for (size_t r0 = 0; r0 < m.rows; r0 += rows_per) {
-            const size_t nr = std::min(rows_per, m.rows - r0);
-            if ((int)wk->pending.size() == kSlots && !drain_one(wk)) return false;
-            const int slot = wk->next_out;
-            wk->next_out = (slot + 1) % kSlots;
-            MMS_CUDA_W(s, cudaMemcpy2DAsync(wk->pin_out[slot].p, wd, m.dev + r0 * m.dev_pitch + off + col, m.dev_pitch, wd, nr,
-                                            cudaMemcpyDeviceToHost, wk->s_out));
-            MMS_CUDA_W(s, cudaEventRecord(wk->ev_slot_out[slot], wk->s_out));
-            wk->pending.push_back({slot, m.host + r0 * m.host_pitch + off + col, m.host_pitch, wd, nr});
-        }
-    }
-    return true;
-}
-
-// this worker's inputs of chunk k are on their way: the last worker to say so enqueues the chunk's kernels
-void arrive(Worker *wk, const Job &job, int k)
-{
-    Shard *s = wk->shard;
-    Chunk &c = s->chunks[k];
-    const int total = (int)s->workers.size();
-    if (!s->failed.load()) {
-        if (cudaEventRecord(c.ev_in[wk->id], wk->s_in) != cudaSuccess) s->set_error(MMS_ERR_CUDA, "cudaEventRecord failed");
-    }
-    if (s->arrived[k].fetch_add(1, std::memory_order_acq_rel) + 1 != total) return;
-    bool ok = !s->failed.load();
-    if (ok) {
-        for (int w = 0; w < total && ok; ++w)
-            if (cudaStreamWaitEvent(s->s_compute, c.ev_in[w], 0) != cudaSuccess) { s->set_error(MMS_ERR_CUDA, "cudaStreamWaitEvent failed"); ok = false; }
-    }
-    if (ok) ok = enqueue_transform(s, job, c.c0, c.n_cols, c.n_cells);
-    if (ok && job.kind == JOB_RUN) {
-        ok = cudaEventRecord(c.ev_t0, s->s_compute) == cudaSuccess;
-        if (ok) ok = enqueue_chain(s, c.c0, c.n_cols, c.n_cells, k);
-        if (ok) ok = cudaEventRecord(c.ev_t1, s->s_compute) == cudaSuccess && cudaEventRecord(c.ev_kernel, s->s_compute) == cudaSuccess;
-        if (!ok) s->set_error(MMS_ERR_CUDA, "launching the fused chain failed");
-    }
-    {
-        std::lock_guard<std::mutex> lk(s->mu);
-        s->enqueued[k] = 1;
-        if (ok && job.kind == JOB_RUN) c.kernel_recorded = true;
-    }
-    s->cv.notify_all();
-}
-
-bool do_in(Worker *wk, const Job &job, int k)
-{
-    Shard *s = wk->shard;
-    const Chunk &c = s->chunks[k];
-    int64_t w0 = 0, wn = 0;
-    if (wk->id < job.workers) worker_window(c, wk->id, job.workers, w0, wn);
-    if (job.terraclimate && wk->id == 0 && k == 0) {
-        // the two small per-month vectors ride in front of worker 0's first copy (every chunk's kernels wait
-        // for worker 0's event of that chunk, recorded later on the same stream)
-        mms_chain_plan *pl = s->plan;
-        double *d_nd = s->d_terra + (size_t)(MMS_NTERRACLIMATE * pl->M + 12) * s->c_stride;
-        int32_t *d_mid = reinterpret_cast<int32_t *>(d_nd + pl->M);
-        MMS_CUDA_W(s, cudaMemcpyAsync(d_nd, job.n_days, sizeof(double) * pl->M, cudaMemcpyHostToDevice, wk->s_in));
-        MMS_CUDA_W(s, cudaMemcpyAsync(d_mid, job.month_id, sizeof(int32_t) * pl->M, cudaMemcpyHostToDevice, wk->s_in));
-    }
-    for (const Mat &m : job.in)
-        if (!stage_in(wk, m, w0, wn)) return false;
-    return true;
-}
-
-bool do_out(Worker *wk, const Job &job, int k)
-{
-    Shard *s = wk->shard;
-    Chunk &c = s->chunks[k];
-    if (job.kind == JOB_RUN) {
-        std::unique_lock<std::mutex> lk(s->mu);
-        s->cv.wait(lk, [&] { return s->enqueued[k] || s->failed.load(); });
-    }
-    if (s->failed.load()) return false;
-    if (c.kernel_recorded) MMS_CUDA_W(s, cudaStreamWaitEvent(wk->s_out, c.ev_kernel, 0));
-    int64_t w0 = 0, wn = 0, o0 = 0, on = 0;
-    if (wk->id < job.workers) worker_window(c, wk->id, job.workers, w0, wn);
-    out_window(s, w0, wn, o0, on);
-    for (const Mat &m : job.out)
-        if (!stage_out(wk, m, o0, on)) return false;
-    while (!wk->pending.empty())
-        if (!drain_one(wk)) return false;
-    return true;
-}
-
-void run_job(Worker *wk, const Job &job)
-{
-    Shard *s = wk->shard;
-    const int n = (int)s->chunks.size();
-    switch (job.kind) {
-    case JOB_SETUP:
-        if (wk->id == 0) setup_shard(s);
-        break;
-    case JOB_UPLOAD:
-    case JOB_RUN: {
-        bool ok = true;
-        for (int k = 0; k <= n; ++k) {
-            if (k < n) {
-                if (ok && !s->failed.load()) ok = do_in(wk, job, k);
-                arrive(wk, job, k);              // always, so that nobody waits for a worker that gave up
-            }
-            if (job.kind == JOB_RUN && k >= 1 && ok && !s->failed.load()) ok = do_out(wk, job, k - 1);
-        }
-        // the host buffers may be reused as soon as the call returns
-        if (cudaStreamSynchronize(wk->s_in) != cudaSuccess) s->set_error(MMS_ERR_CUDA, "cudaStreamSynchronize failed");
-        if (job.kind == JOB_RUN && cudaStreamSynchronize(wk->s_out) != cudaSuccess) s->set_error(MMS_ERR_CUDA, "cudaStreamSynchronize failed");
-        break;
-    }
-    case JOB_DOWNLOAD: {
-        bool ok = true;
-        for (int k = 0; k < n && ok && !s->failed.load(); ++k) ok = do_out(wk, job, k);
-        if (cudaStreamSynchronize(wk->s_out) != cudaSuccess) s->set_error(MMS_ERR_CUDA, "cudaStreamSynchronize failed");
-        break;
-    }
-    default:
-        break;
-    }
-    wk->pending.clear();
-}
-
-void worker_main(Worker *wk)
-{
-    Shard *s = wk->shard;
-    bool ok = cudaSetDevice(s->device) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithFlags(&wk->s_in, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithFlags(&wk->s_out, cudaStreamNonBlocking) == cudaSuccess;
-    if (!ok) s->set_error(MMS_ERR_CUDA, "a host worker could not create its streams");
-    uint64_t seen = 0;
-    for (;;) {
-        const Job *job = nullptr;
-        {
-            std::unique_lock<std::mutex> lk(s->mu);
-            s->cv.wait(lk, [&] { return s->job_seq != seen; });
-            seen = s->job_seq;
-            job = s->job;
-        }
-        if (job->kind == JOB_EXIT) break;
-        if (ok) run_job(wk, *job);
-        {
-            std::lock_guard<std::mutex> lk(s->mu);
-            s->pending -= 1;
-        }
-        s->cv.notify_all();
-    }
-    for (int k = 0; k < kSlots; ++k) {
-        wk->pin_in[k].release();
-        wk->pin_out[k].release();
-        if (wk->ev_slot_in[k]) cudaEventDestroy(wk->ev_slot_in[k]);
-        if (wk->ev_slot_out[k]) cudaEventDestroy(wk->ev_slot_out[k]);
-    }
-    if (wk->s_in) cudaStreamDestroy(wk->s_in);
-    if (wk->s_out) cudaStreamDestroy(wk->s_out);
-}
-
-// hand one job per shard to the workers and wait for all of them; returns the first failure
-int dispatch(mms_chain_plan *pl, std::vector<Job> &jobs)
-{
-    for (size_t g = 0; g < pl->shards.size(); ++g) {
-        Shard *s = pl->shards[g].get();
-        std::lock_guard<std::mutex> lk(s->mu);
-        for (size_t k = 0; k < s->chunks.size(); ++k) {
-            s->arrived[k].store(0);
-            s->enqueued[k] = 0;
-            if (jobs[g].kind == JOB_RUN || jobs[g].kind == JOB_UPLOAD) s->chunks[k].kernel_recorded = false;
-        }
-        s->failed.store(false);
-        s->err_status = MMS_OK;
-        s->err_msg.clear();
-        s->job = &jobs[g];
-        s->pending = (int)s->workers.size();
-        s->job_seq += 1;
-    }
-    for (auto &sp : pl->shards) sp->cv.notify_all();
+    for (size_t g = 0; g < pl->shards.size(); ++g) pl->shards[g]->pipe.post(&jobs[g]);
     int rc = MMS_OK;
     for (auto &sp : pl->shards) {
-        Shard *s = sp.get();
-        std::unique_lock<std::mutex> lk(s->mu);
-        s->cv.wait(lk, [&] { return s->pending == 0; });
-        if (s->failed.load() && rc == MMS_OK) rc = fail_str(s->err_status, s->err_msg);
+        std::string msg;
+        const int r = sp->pipe.wait(&msg);
+        if (r != MMS_OK && rc == MMS_OK) rc = fail_str(r, msg);
     }
     return rc;
 }
 
-Mat make_mat(const void *host, size_t host_cells, void *dev, const Shard *s, size_t rows, int elem)
+Mat make_mat(const void *host, size_t host_cells, void *dev, const Shard *s, size_t rows, size_t elem)
 {
     Mat m;
     m.host = (char *)const_cast<void *>(host) + (size_t)s->cell0 * elem;
@@ -683,7 +324,7 @@ Mat make_mat(const void *host, size_t host_cells, void *dev, const Shard *s, siz
 }
 
 // an output array: rows of R columns on the host (R = C without a scatter), of out_stride on the device
-Mat make_out_mat(const mms_chain_plan *pl, void *host, void *dev, const Shard *s, size_t rows, int elem)
+Mat make_out_mat(const mms_chain_plan *pl, void *host, void *dev, const Shard *s, size_t rows, size_t elem)
 {
     Mat m;
     m.host = (char *)host + (size_t)s->out_col0 * elem;
@@ -695,7 +336,7 @@ Mat make_out_mat(const mms_chain_plan *pl, void *host, void *dev, const Shard *s
     return m;
 }
 
-void add_outputs(mms_chain_plan *pl, const Shard *s, const mms_chain_outputs *out, Job &job)
+void add_outputs(mms_chain_plan *pl, Shard *s, const mms_chain_outputs *out, PipeJob &job)
 {
     const size_t H = (size_t)24 * pl->D;
     if (out->mean_state && s->d_mean_state)
@@ -710,17 +351,18 @@ void add_outputs(mms_chain_plan *pl, const Shard *s, const mms_chain_outputs *ou
         job.out.push_back(make_out_mat(pl, out->wet_hours, s->d_wet_hours, s, (size_t)pl->S * pl->P, 4));
     if (out->wet_flags && s->d_wet_flags)
         job.out.push_back(make_out_mat(pl, out->wet_flags, s->d_wet_flags, s, (size_t)pl->S * H, 1));
+    job.out_window = [s](int64_t w0, int64_t wn, int64_t &o0, int64_t &on) { out_window(s, w0, wn, o0, on); };
 }
 
-// pinned or pageable?  One driver query per host array; a job whose arrays are all pinned needs one worker
-void classify(mms_chain_plan *pl, std::vector<Job> &jobs)
+// pinned or pageable?  One driver query per host array; a call whose arrays are all pinned needs one worker per device
+void classify(mms_chain_plan *pl, std::vector<PipeJob> &jobs)
 {
     bool all_pinned = true;
-    for (Job &j : jobs) {
-        for (Mat &m : j.in) { m.pinned = host_pointer_is_pinned(m.host); all_pinned = all_pinned && m.pinned; }
-        for (Mat &m : j.out) { m.pinned = host_pointer_is_pinned(m.host); all_pinned = all_pinned && m.pinned; }
+    for (PipeJob &j : jobs) {
+        all_pinned = classify_mats(j.in) && all_pinned;
+        all_pinned = classify_mats(j.out) && all_pinned;
     }
-    for (Job &j : jobs) j.workers = all_pinned ? 1 : pl->n_workers;
+    for (PipeJob &j : jobs) j.workers = all_pinned ? 1 : pl->n_workers;
 }
 
 // non-finite forcing seen by the kernels of the last launches (flags are zeroed at every launch)
@@ -730,9 +372,9 @@ int check_error_flags(mms_chain_plan *pl)
         Shard *s = sp.get();
         if (!s->launched) continue;
         MMS_CUDA(cudaSetDevice(s->device));
-        std::vector<int32_t> flags(2 * s->chunks.size(), 0);
+        std::vector<int32_t> flags(2 * s->pipe.chunks.size(), 0);
         MMS_CUDA(cudaMemcpy(flags.data(), s->d_error, flags.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-        for (size_t k = 0; k < s->chunks.size(); ++k)
+        for (size_t k = 0; k < s->pipe.chunks.size(); ++k)
             if (flags[2 * k])
                 return fail(MMS_ERR_NONFINITE, "non-finite (NA/NaN/Inf) monthly forcing in cells %lld..%lld; R's approx() "
                             "would drop those knots (na.rm = TRUE), the GPU backend refuses them",
@@ -755,39 +397,45 @@ int ensure_terra_staging(mms_chain_plan *pl)
     return MMS_OK;
 }
 
-void fill_inputs(mms_chain_plan *pl, std::vector<Job> &jobs, JobKind kind, const double *monthly,
+void fill_inputs(mms_chain_plan *pl, std::vector<PipeJob> &jobs, PipeKind kind, const double *monthly,
                  const double *terraclimate, const double *clear_sky, const int32_t *month_id, const double *n_days,
                  const double *altitude)
 {
-    jobs.assign(pl->shards.size(), Job());
+    jobs.assign(pl->shards.size(), PipeJob());
     const size_t C = (size_t)pl->C;
     for (size_t g = 0; g < pl->shards.size(); ++g) {
         Shard *s = pl->shards[g].get();
-        Job &j = jobs[g];
+        PipeJob &j = jobs[g];
         j.kind = kind;
-        if (terraclimate) {
-            j.terraclimate = true;
-            j.n_days = n_days;
-            j.month_id = month_id;
+        const bool tc = terraclimate != nullptr;
+        if (tc) {
             double *d_cs = s->d_terra + (size_t)MMS_NTERRACLIMATE * pl->M * s->c_stride;
             j.in.push_back(make_mat(terraclimate, C, s->d_terra, s, (size_t)MMS_NTERRACLIMATE * pl->M, 8));
             j.in.push_back(make_mat(clear_sky, C, d_cs, s, 12, 8));
+            // the two small per-month vectors ride in front of worker 0's first copy (every chunk's kernels wait
+            // for worker 0's event of that chunk, recorded later on the same stream)
+            j.before_first_copy = [s, pl, n_days, month_id](cudaStream_t st) {
+                double *d_nd = s->d_terra + (size_t)(MMS_NTERRACLIMATE * pl->M + 12) * s->c_stride;
+                int32_t *d_mid = reinterpret_cast<int32_t *>(d_nd + pl->M);
+                MMS_CUDA_W(s, cudaMemcpyAsync(d_nd, n_days, sizeof(double) * pl->M, cudaMemcpyHostToDevice, st));
+                MMS_CUDA_W(s, cudaMemcpyAsync(d_mid, month_id, sizeof(int32_t) * pl->M, cudaMemcpyHostToDevice, st));
+                return true;
+            };
         } else {
             j.in.push_back(make_mat(monthly, C, s->d_monthly, s, (size_t)MMS_NFORCING * pl->M, 8));
         }
         j.in.push_back(make_mat(altitude, C, s->d_altitude, s, 1, 8));
+        // what the fused kernel reads is derived from the rows of the chunk as soon as they are on the device ...
+        j.inputs_ready = [s, tc](int k) {
+            const PipeChunk &c = s->pipe.chunks[k];
+            return enqueue_transform(s, tc, c.c0, c.n_cols, c.n_cells);
+        };
+        // ... and, in a pipelined run, the chunk's fused kernel follows
+        j.run_chunk = [s](int k) {
+            const PipeChunk &c = s->pipe.chunks[k];
+            return enqueue_chain(s, c.c0, c.n_cols, c.n_cells, k);
+        };
     }
-}
-
-int plan_workers(int n_shards)
-{
-    if (const char *e = std::getenv("MMS_HOST_WORKERS")) {
-        const int w = std::atoi(e);
-        if (w >= 1) return std::min(w, 16);
-    }
-    const unsigned hw = std::thread::hardware_concurrency();
-    const int per = hw ? (int)hw / std::max(1, n_shards) : 2;
-    return std::max(1, std::min(kMaxWorkers, per));
 }
 
 // chunks of one shard: at most one round of the persistent kernel each (every warp slot of the device gets one
@@ -806,33 +454,15 @@ void plan_chunks(mms_chain_plan *pl, Shard *s, int n_sm_guess)
         if (f >= 1) n = f;
     }
     n = std::max<int64_t>(1, std::min<int64_t>(n, std::min<int64_t>(kMaxChunks, blocks)));
-    s->chunks.clear();
+    s->pipe.chunks.clear();
     for (int64_t k = 0; k < n; ++k) {
         const int64_t b0 = blocks * k / n, b1 = blocks * (k + 1) / n;
-        Chunk c;
+        PipeChunk c;
         c.c0 = b0 * 32;
         c.n_cols = (b1 - b0) * 32;
         c.n_cells = std::max<int64_t>(0, std::min<int64_t>(s->n_cells - c.c0, c.n_cols));
-        s->chunks.push_back(c);
+        s->pipe.chunks.push_back(c);
     }
-    s->arrived.reset(new std::atomic<int>[s->chunks.size()]);
-    s->enqueued.assign(s->chunks.size(), 0);
-}
-
-void stop_workers(Shard *s)
-{
-    if (s->workers.empty()) return;
-    Job bye;
-    bye.kind = JOB_EXIT;
-    {
-        std::lock_guard<std::mutex> lk(s->mu);
-        s->job = &bye;
-        s->job_seq += 1;
-    }
-    s->cv.notify_all();
-    for (auto &w : s->workers)
-        if (w->th.joinable()) w->th.join();
-    s->workers.clear();
 }
 
 }  // namespace
@@ -843,7 +473,7 @@ void mms_chain_destroy(mms_chain_plan *plan)
 {
     if (!plan) return;
     for (auto &sp : plan->shards) {
-        stop_workers(sp.get());
+        sp->pipe.stop();
         free_shard_device(sp.get());
     }
     delete plan;
@@ -968,6 +598,7 @@ int mms_chain_create(const mms_chain_config *cfg, mms_chain_plan **out)
         std::unique_ptr<Shard> s(new Shard());
         s->plan = pl;
         s->device = devs[g];
+        s->pipe.device = devs[g];
         s->cell0 = cell0;
         s->n_cells = n;
         s->c_stride = ((n + mms::kBlock - 1) / mms::kBlock) * mms::kBlock;
@@ -977,19 +608,15 @@ int mms_chain_create(const mms_chain_config *cfg, mms_chain_plan **out)
         plan_chunks(pl, s.get(), n_sm_guess);
         pl->shards.push_back(std::move(s));
     }
-    pl->n_workers = plan_workers((int)pl->shards.size());
-    for (auto &sp : pl->shards) {
-        for (int w = 0; w < pl->n_workers; ++w) {
-            std::unique_ptr<Worker> wk(new Worker());
-            wk->shard = sp.get();
-            wk->id = w;
-            sp->workers.push_back(std::move(wk));
-        }
-        for (auto &wk : sp->workers) wk->th = std::thread(worker_main, wk.get());
-    }
+    pl->n_workers = default_workers((int)pl->shards.size());
+    for (auto &sp : pl->shards) sp->pipe.start(pl->n_workers);
     // device memory, tables and events of every shard, in parallel (one CUDA context each)
-    std::vector<Job> jobs(pl->shards.size());
-    for (Job &j : jobs) j.kind = JOB_SETUP;
+    std::vector<PipeJob> jobs(pl->shards.size());
+    for (size_t g = 0; g < jobs.size(); ++g) {
+        Shard *s = pl->shards[g].get();
+        jobs[g].kind = PIPE_CALL;
+        jobs[g].call = [s] { return setup_shard(s); };
+    }
     rc = dispatch(pl, jobs);
     if (rc) { mms_chain_destroy(plu.release()); return rc; }
     *out = plu.release();
@@ -999,8 +626,8 @@ int mms_chain_create(const mms_chain_config *cfg, mms_chain_plan **out)
 int mms_chain_upload(mms_chain_plan *pl, const double *monthly, const double *altitude)
 {
     if (!pl || !monthly || !altitude) return fail(MMS_ERR_INVALID_ARG, "NULL plan, monthly or altitude");
-    std::vector<Job> jobs;
-    fill_inputs(pl, jobs, JOB_UPLOAD, monthly, nullptr, nullptr, nullptr, nullptr, altitude);
+    std::vector<PipeJob> jobs;
+    fill_inputs(pl, jobs, PIPE_UPLOAD, monthly, nullptr, nullptr, nullptr, nullptr, altitude);
     classify(pl, jobs);
     const int rc = dispatch(pl, jobs);
     if (rc) return rc;
@@ -1018,8 +645,8 @@ int mms_chain_upload_terraclimate(mms_chain_plan *pl, const double *terraclimate
     int rc = check_month_ids(month_id, n_days, pl->M);
     if (rc) return rc;
     if ((rc = ensure_terra_staging(pl))) return rc;
-    std::vector<Job> jobs;
-    fill_inputs(pl, jobs, JOB_UPLOAD, nullptr, terraclimate, clear_sky, month_id, n_days, altitude);
+    std::vector<PipeJob> jobs;
+    fill_inputs(pl, jobs, PIPE_UPLOAD, nullptr, terraclimate, clear_sky, month_id, n_days, altitude);
     classify(pl, jobs);
     if ((rc = dispatch(pl, jobs))) return rc;
     pl->uploaded = true;
@@ -1060,13 +687,17 @@ int mms_chain_launch(mms_chain_plan *pl)
     for (auto &sp : pl->shards) {
         Shard *s = sp.get();
         MMS_CUDA(cudaSetDevice(s->device));
-        s->failed.store(false);
-        MMS_CUDA(cudaEventRecord(s->ev0, s->s_compute));
+        s->pipe.clear_error();
+        MMS_CUDA(cudaEventRecord(s->ev0, s->pipe.s_compute));
         // resident data: one launch over the whole shard
-        if (!enqueue_chain(s, 0, s->c_stride, s->n_cells, 0)) return fail_str(s->err_status, s->err_msg);
-        MMS_CUDA(cudaEventRecord(s->ev1, s->s_compute));
-        for (Chunk &c : s->chunks) {
-            MMS_CUDA(cudaEventRecord(c.ev_kernel, s->s_compute));
+        if (!enqueue_chain(s, 0, s->c_stride, s->n_cells, 0)) {
+            std::string msg;
+            const int r = s->pipe.wait(&msg);
+            return fail_str(r ? r : MMS_ERR_CUDA, msg);
+        }
+        MMS_CUDA(cudaEventRecord(s->ev1, s->pipe.s_compute));
+        for (PipeChunk &c : s->pipe.chunks) {
+            MMS_CUDA(cudaEventRecord(c.ev_kernel, s->pipe.s_compute));
             c.kernel_recorded = true;
         }
         s->timing_chunks = false;
@@ -1080,7 +711,7 @@ int mms_chain_sync(mms_chain_plan *pl)
     if (!pl) return fail(MMS_ERR_INVALID_ARG, "NULL plan");
     for (auto &sp : pl->shards) {
         MMS_CUDA(cudaSetDevice(sp->device));
-        MMS_CUDA(cudaStreamSynchronize(sp->s_compute));
+        MMS_CUDA(cudaStreamSynchronize(sp->pipe.s_compute));
     }
     return check_error_flags(pl);
 }
@@ -1088,9 +719,9 @@ int mms_chain_sync(mms_chain_plan *pl)
 int mms_chain_download(mms_chain_plan *pl, const mms_chain_outputs *out)
 {
     if (!pl || !out) return fail(MMS_ERR_INVALID_ARG, "NULL plan or outputs");
-    std::vector<Job> jobs(pl->shards.size());
+    std::vector<PipeJob> jobs(pl->shards.size());
     for (size_t g = 0; g < pl->shards.size(); ++g) {
-        jobs[g].kind = JOB_DOWNLOAD;
+        jobs[g].kind = PIPE_DOWNLOAD;
         add_outputs(pl, pl->shards[g].get(), out, jobs[g]);
     }
     classify(pl, jobs);
@@ -1099,7 +730,7 @@ int mms_chain_download(mms_chain_plan *pl, const mms_chain_outputs *out)
     return mms_chain_sync(pl);
 }
 
-static int run_pipelined(mms_chain_plan *pl, std::vector<Job> &jobs, const mms_chain_outputs *out)
+static int run_pipelined(mms_chain_plan *pl, std::vector<PipeJob> &jobs, const mms_chain_outputs *out)
 {
     if (pl->wt.enabled && !pl->location_set) return fail(MMS_ERR_INVALID_ARG, "the water-temperature model needs mms_chain_set_location() first");
     for (size_t g = 0; g < pl->shards.size(); ++g) add_outputs(pl, pl->shards[g].get(), out, jobs[g]);
@@ -1114,8 +745,8 @@ static int run_pipelined(mms_chain_plan *pl, std::vector<Job> &jobs, const mms_c
 int mms_chain_run(mms_chain_plan *pl, const double *monthly, const double *altitude, const mms_chain_outputs *out)
 {
     if (!pl || !monthly || !altitude || !out) return fail(MMS_ERR_INVALID_ARG, "NULL plan, monthly, altitude or outputs");
-    std::vector<Job> jobs;
-    fill_inputs(pl, jobs, JOB_RUN, monthly, nullptr, nullptr, nullptr, nullptr, altitude);
+    std::vector<PipeJob> jobs;
+    fill_inputs(pl, jobs, PIPE_RUN, monthly, nullptr, nullptr, nullptr, nullptr, altitude);
     return run_pipelined(pl, jobs, out);
 }
 
@@ -1128,8 +759,8 @@ int mms_chain_run_terraclimate(mms_chain_plan *pl, const double *terraclimate, c
     int rc = check_month_ids(month_id, n_days, pl->M);
     if (rc) return rc;
     if ((rc = ensure_terra_staging(pl))) return rc;
-    std::vector<Job> jobs;
-    fill_inputs(pl, jobs, JOB_RUN, nullptr, terraclimate, clear_sky, month_id, n_days, altitude);
+    std::vector<PipeJob> jobs;
+    fill_inputs(pl, jobs, PIPE_RUN, nullptr, terraclimate, clear_sky, month_id, n_days, altitude);
     return run_pipelined(pl, jobs, out);
 }
 
@@ -1143,7 +774,7 @@ int mms_chain_kernel_ms(mms_chain_plan *pl, float *ms)
         MMS_CUDA(cudaSetDevice(s->device));
         float t = 0.f;
         if (s->timing_chunks) {
-            for (Chunk &c : s->chunks) {
+            for (PipeChunk &c : s->pipe.chunks) {
                 if (c.n_cols <= 0 || !c.kernel_recorded) continue;
                 float tc = 0.f;
                 MMS_CUDA(cudaEventSynchronize(c.ev_t1));
@@ -1171,7 +802,7 @@ int mms_chain_plan_info(mms_chain_plan *pl, int32_t *n_shards, int32_t *n_chunks
 {
     if (!pl) return fail(MMS_ERR_INVALID_ARG, "NULL plan");
     if (n_shards) *n_shards = (int32_t)pl->shards.size();
-    if (n_chunks_per_shard) *n_chunks_per_shard = pl->shards.empty() ? 0 : (int32_t)pl->shards[0]->chunks.size();
+    if (n_chunks_per_shard) *n_chunks_per_shard = pl->shards.empty() ? 0 : (int32_t)pl->shards[0]->pipe.chunks.size();
     if (n_workers_per_shard) *n_workers_per_shard = pl->n_workers;
     return MMS_OK;
 }

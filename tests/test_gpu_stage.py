@@ -221,3 +221,41 @@ def test_twins_ragged_shapes_with_burnin_and_cylinder(gpu, mode, tol):
         gotp = pipeline.simulate_population_vectorised(*cols, dmh, burnin_years=burn, math_mode=mode)
         assert rel_err(gotp["aquatic"], refp["aquatic"]) <= tol, (H, C)
         assert rel_err(gotp["adult"], refp["adult"]) <= tol, (H, C)
+
+
+@pytest.mark.parametrize("chunks,pass_pixels,workers", [("3", "0", "2"), ("2", "64", "1"), ("5", "96", "3")])
+def test_twins_chunked_pipeline_and_passes(gpu, monkeypatch, chunks, pass_pixels, workers):
+    """The twins' host pipeline: pixels in several chunks (upload / kernel / download overlapped), several host workers,
+    and several passes when the matrices do not fit in device memory (forced here) -- the same bits as one chunk in
+    one pass, from pageable and from pinned matrices."""
+    case, m = hourly_inputs(n_cells=211)
+    hab = syn.habitat_cylinder(leak_per_hour=0.003)
+    dmh = syn.synthetic_lifehistory("An. gambiae").das_densmod
+    names = ("larval_habitat_area", "mdr", "efd", "das_zerodensity", "ds")
+
+    def both():
+        w = backend.water_vectorised(m["rainfall"], m["air_temperature"], m["humidity"], m["windspeed"], case.altitude, hab,
+                                     burnin_years=1, want_volume=True, want_wet=True)
+        p = pipeline.simulate_population_vectorised(*[m[k] for k in names], dmh, burnin_years=1)
+        return w, p
+
+    monkeypatch.setenv("MMS_TWIN_CHUNKS", "1")
+    w0, p0 = both()
+    assert backend.stage_kernel_ms() > 0
+    monkeypatch.setenv("MMS_TWIN_CHUNKS", chunks)
+    monkeypatch.setenv("MMS_HOST_WORKERS", workers)
+    if pass_pixels != "0":
+        monkeypatch.setenv("MMS_TWIN_PASS_PIXELS", pass_pixels)
+    w1, p1 = both()
+    for k in ("water_surface_area", "water_volume", "wet"):
+        assert np.array_equal(w0[k], w1[k], equal_nan=True), k
+    for k in ("aquatic", "adult"):
+        assert np.array_equal(p0[k], p1[k], equal_nan=True), k
+    # pinned matrices: the DMA runs on them in place
+    pins = [backend.PinnedArray((case.C, case.H)) for _ in range(5)]             # [pixel][time] = R's column-major H x C
+    for pa, k in zip(pins, ("rainfall", "air_temperature", "humidity", "windspeed")):
+        pa.array[...] = m[k].T
+    w2 = backend.water_vectorised(*[pa.array.T for pa in pins[:4]], case.altitude, hab, burnin_years=1, want_volume=True,
+                                  want_wet=True)
+    for k in ("water_surface_area", "water_volume", "wet"):
+        assert np.array_equal(w0[k], w2[k], equal_nan=True), k
