@@ -73,7 +73,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O3", "-fPIC", "-fvisibility=hidden", "-c",
                    os.path.join(CSRC, src), "-o", o]
         if verbose:
-            cmd.insert(1, "-Xptxas=-v")
+            if not src.endswith(".cpp"):
+                cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:

@@ -49,9 +49,9 @@ int run_twin(int device, int64_t H, int64_t C, const TwinArrays &a, int round_pi
         pipe.window_unit = 1;
         // the twins move 40-56 bytes per pixel-step for a few flops: what matters is that the copies of the next and the
         // previous chunk overlap the kernel and that the first upload / last download (not overlapped) are short --
-        // chunks of about half a GB (all arrays together), at least one per round of the persistent kernel
+        // chunks of about one GB (all arrays together), at least one per round of the persistent kernel
         int64_t n_chunks = std::max<int64_t>((np + round_pixels - 1) / round_pixels,
-                                             (int64_t)(((size_t)np * bytes_per_pixel) >> 29));
+                                             (int64_t)(((size_t)np * bytes_per_pixel) >> 30));
         if (const char *e = std::getenv("MMS_TWIN_CHUNKS")) n_chunks = std::max<int64_t>(1, std::atoll(e));
         n_chunks = std::max<int64_t>(1, std::min<int64_t>(n_chunks, std::min<int64_t>(64, (np + 31) / 32)));
         const int64_t blocks = (np + 31) / 32;
@@ -78,7 +78,9 @@ int run_twin(int device, int64_t H, int64_t C, const TwinArrays &a, int round_pi
         const bool pinned = classify_mats(job.in) & classify_mats(job.out);
         // small calls (tests, single pixels) are not worth a team of workers
         const size_t pass_bytes = (size_t)np * bytes_per_pixel;
-        const int n_workers = pinned ? 1 : (int)std::max<size_t>(1, std::min<size_t>((size_t)default_workers(1), pass_bytes / ((size_t)64 << 20)));
+        // (pinned matrices need no staging, but several copy streams fill the PCIe link better than one: measured)
+        const size_t want = pass_bytes / ((size_t)64 << 20);
+        const int n_workers = (int)std::max<size_t>(1, std::min<size_t>(pinned ? 4 : (size_t)default_workers(1), want));
         job.workers = n_workers;
         job.run_chunk = [&](int k) {
             const PipeChunk &c = pipe.chunks[k];

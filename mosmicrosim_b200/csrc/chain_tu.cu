@@ -60,6 +60,22 @@ cudaError_t launch_one(ChainParams &p, int n_sm, cudaStream_t stream)
     p.n_cell_blocks = (int32_t)(p.n_cols / 32);
     p.n_units = p.n_cell_blocks * (p.S / kNS);
 #if !MMS_STRICT
+    // Habitat ensembles: the fan-out form shares the forcing half among all settings of a cell (chain_ws.cuh).
+    // MMS_CHAIN_FAN = 0 / 1 forces it off / on (tests, measurements).
+    {
+        int groups = kNS == 4 ? chain_fan_groups(p.S, false) : 0;
+        if (p.wt.enabled || ((p.mean_mask | p.hourly_mask) & (1u << MMS_V_WATER_TEMPERATURE)) || p.warp_specialised == 0) groups = 0;
+        if (const char *e = getenv("MMS_CHAIN_FAN")) { if (atoi(e) == 0) groups = 0; }
+        if (groups > 0) {
+            const int teams_max = chain_fan_teams_max(groups);
+            const int64_t per_round = (int64_t)n_sm * teams_max;
+            const int64_t rounds = (p.n_cell_blocks + per_round - 1) / per_round;
+            int teams = (int)((p.n_cell_blocks + (int64_t)n_sm * rounds - 1) / ((int64_t)n_sm * rounds));
+            teams = teams < 1 ? 1 : (teams > teams_max ? teams_max : teams);
+            const int64_t ctas = (p.n_cell_blocks + teams - 1) / teams;
+            return launch_chain_fan_fast(p, kFull, kHourly, (int)(ctas < n_sm ? ctas : n_sm), teams, groups, stream);
+        }
+    }
     // Which form?  Measured on B200 (profiles/r01_*): the pair form wins when the launch is
     // short of warps -- several settings per cell and at most two rounds of units per SM (the
     // 100k-cell tile of BASELINE configs[1]: 58.5 vs 67.4 ms) -- and loses a little when the

@@ -82,9 +82,9 @@ __device__ __forceinline__ void ds_prefetch_l1(const SurfaceDev &g, double tempe
     asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
 }
 
-__device__ __forceinline__ void pair_barrier(int pair)
+__device__ __forceinline__ void pair_barrier(int pair, int threads = 64)
 {
-    asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");   // barrier 0 is __syncthreads()
+    asm volatile("bar.sync %0, %1;" ::"r"(pair + 1), "r"(threads) : "memory");   // barrier 0 is __syncthreads()
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -120,7 +120,8 @@ struct RingEnd {
     double *slots;          // [kWsSlots][kWsFields][32], this lane's column
     uint32_t full, empty;   // shared-memory addresses of full[0], empty[0]
     uint32_t it;            // hand-offs so far
-    int pair;
+    int pair;               // named barrier of the team (pair + 1)
+    int bar_threads;        // threads that meet at it: 64 for a pair, 32 (1 + state warps) for a fan-out team
 };
 
 __device__ __forceinline__ RingEnd ring_end(double *ring, int pair, int lane)
@@ -132,6 +133,7 @@ __device__ __forceinline__ RingEnd ring_end(double *ring, int pair, int lane)
     r.empty = smem_u32(bars + kWsSlots);
     r.it = 0;
     r.pair = pair;
+    r.bar_threads = 64;
     return r;
 }
 
@@ -148,7 +150,7 @@ __device__ __forceinline__ double *ring_acquire_empty(RingEnd &r)
 __device__ __forceinline__ void ring_publish(RingEnd &r)
 {
     if (kWsRing > 0) mbar_arrive(r.full + 8 * (r.it & (kWsSlots - 1)));
-    else pair_barrier(r.pair);                       // the state warp may now read this buffer
+    else pair_barrier(r.pair, r.bar_threads);        // the state warp(s) may now read this buffer
     r.it += 1;
 }
 // state warp: the slot to read next (waits until the forcing warp has filled it)
@@ -159,7 +161,7 @@ __device__ __forceinline__ const double *ring_acquire_full(RingEnd &r)
         mbar_wait(r.full + 8 * slot, (r.it / kWsSlots) & 1);
         return r.slots + (size_t)slot * (kWsFields * 32);
     }
-    pair_barrier(r.pair);                            // the forcing warp has filled this buffer
+    pair_barrier(r.pair, r.bar_threads);             // the forcing warp has filled this buffer
     return r.slots + (size_t)(r.it & 1) * (kWsK * kWsFields * 32);
 }
 __device__ __forceinline__ void ring_release(RingEnd &r)
@@ -473,6 +475,49 @@ __device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &
     if (kRecord && pc.cur_period >= 0) flush(pc.cur_period);
 }
 
+// one work unit in one role: water burn-in years (R/sim_water.R:228-233), population burn-in years
+// (R/sim_pop_dynamics.R:221-226), then the full series -- identical loop structure in both roles, so the warps of
+// a team meet at every barrier
+template <int kNS, bool kFull, bool kHourly, int kDens>
+__device__ __forceinline__ void role_unit(const ChainParams &p, const SmemTables &tb, UnitCtx &u, RingEnd &ring,
+                                          bool forcing_role)
+{
+    if (forcing_role) {
+        u.p_a = air_pressure_kpa(__ldg(p.altitude + u.cell));
+        int bad = 0;
+        for (int y = 0; y < p.burnin_years_water; ++y)
+            forcing_pass<kFull, kHourly, true, false, kDens>(p, tb, u, ring, kDaysPerYear, bad);
+        for (int y = 0; y < p.burnin_years_pop; ++y)
+            forcing_pass<kFull, kHourly, false, false, kDens>(p, tb, u, ring, kDaysPerYear, bad);
+        forcing_pass<kFull, kHourly, false, true, kDens>(p, tb, u, ring, p.D, bad);
+        if (bad && u.live) atomicOr(p.error_flag, 1);
+    } else {
+        u.p_a = 0.0;
+        UnitState<kNS> st;
+#pragma unroll
+        for (int s = 0; s < kNS; ++s) {
+            st.aquatic[s] = p.initial_aquatic;               // R/sim_pop_dynamics.R:249-252
+            st.adult[s] = p.initial_adult;
+            st.volume[s] = p.hab[u.set0 + s].initial_volume; // R/sim_water.R:277
+            st.surface[s] = habitat_surface(p.hab[u.set0 + s], st.volume[s]);
+        }
+        for (int y = 0; y < p.burnin_years_water; ++y)
+            state_pass<kNS, kFull, kHourly, true, false, kDens>(p, u, st, ring, kDaysPerYear);
+        double vol0[kNS];
+#pragma unroll
+        for (int s = 0; s < kNS; ++s) vol0[s] = st.volume[s];
+        for (int y = 0; y < p.burnin_years_pop; ++y) {
+            state_pass<kNS, kFull, kHourly, false, false, kDens>(p, u, st, ring, kDaysPerYear);
+#pragma unroll
+            for (int s = 0; s < kNS; ++s) {
+                st.volume[s] = vol0[s];
+                st.surface[s] = habitat_surface(p.hab[u.set0 + s], vol0[s]);
+            }
+        }
+        state_pass<kNS, kFull, kHourly, false, true, kDens>(p, u, st, ring, p.D);
+    }
+}
+
 // ---- the kernel: warp 2i = forcing role, warp 2i + 1 = state role of pair i ---------------------
 // kDens: what the launcher knows at compile time, or -1 (read the parameters): bit 0 the density-dependence form
 // (0 logit, 1 cox_ph), then two bits per setting of a unit with its water-body shape + 1 (0 = read hab[].shape).
@@ -526,43 +571,62 @@ chain_kernel_ws(const __grid_constant__ ChainParams p)
         u.ocell = (p.out_col && u.live) ? __ldg(p.out_col + u.cell) : u.cell;
         u.n_mean_state = __popc(p.mean_mask & MMS_STATE_VAR_MASK);
         u.n_hourly_state = __popc(p.hourly_mask & MMS_STATE_VAR_MASK);
-        // passes: water burn-in years (R/sim_water.R:228-233), population burn-in years
-        // (R/sim_pop_dynamics.R:221-226), then the full series -- identical loop structure in
-        // both roles, so the two warps meet at every barrier
-        if (forcing_role) {
-            u.p_a = air_pressure_kpa(__ldg(p.altitude + u.cell));
-            int bad = 0;
-            for (int y = 0; y < p.burnin_years_water; ++y)
-                forcing_pass<kFull, kHourly, true, false, kDens>(p, tb, u, ring, kDaysPerYear, bad);
-            for (int y = 0; y < p.burnin_years_pop; ++y)
-                forcing_pass<kFull, kHourly, false, false, kDens>(p, tb, u, ring, kDaysPerYear, bad);
-            forcing_pass<kFull, kHourly, false, true, kDens>(p, tb, u, ring, p.D, bad);
-            if (bad && u.live) atomicOr(p.error_flag, 1);
-        } else {
-            u.p_a = 0.0;
-            UnitState<kNS> st;
-#pragma unroll
-            for (int s = 0; s < kNS; ++s) {
-                st.aquatic[s] = p.initial_aquatic;               // R/sim_pop_dynamics.R:249-252
-                st.adult[s] = p.initial_adult;
-                st.volume[s] = p.hab[u.set0 + s].initial_volume; // R/sim_water.R:277
-                st.surface[s] = habitat_surface(p.hab[u.set0 + s], st.volume[s]);
-            }
-            for (int y = 0; y < p.burnin_years_water; ++y)
-                state_pass<kNS, kFull, kHourly, true, false, kDens>(p, u, st, ring, kDaysPerYear);
-            double vol0[kNS];
-#pragma unroll
-            for (int s = 0; s < kNS; ++s) vol0[s] = st.volume[s];
-            for (int y = 0; y < p.burnin_years_pop; ++y) {
-                state_pass<kNS, kFull, kHourly, false, false, kDens>(p, u, st, ring, kDaysPerYear);
-#pragma unroll
-                for (int s = 0; s < kNS; ++s) {
-                    st.volume[s] = vol0[s];
-                    st.surface[s] = habitat_surface(p.hab[u.set0 + s], vol0[s]);
-                }
-            }
-            state_pass<kNS, kFull, kHourly, false, true, kDens>(p, u, st, ring, p.D);
-        }
+        role_unit<kNS, kFull, kHourly, kDens>(p, tb, u, ring, forcing_role);
+    }
+}
+
+
+// ---- fan-out form: ONE forcing warp feeds the state warps of ALL settings of its 32 cells -------------------------
+// For habitat ensembles (BASELINE configs[4]: 64 settings per cell): everything the forcing warp computes --
+// microclimate, evaporation rate, life-history tables, ds^(1/24), emergence, the density-free link -- does not depend
+// on the setting, yet the other two forms recompute it for every group of kNS settings (16 times
+// per cell-hour for 64 settings).  Here a team = 1 forcing warp + `groups` state warps (kNS settings each) works on
+// one cell block; every hour all state warps read the SAME ring slot (a lane reads its own cell's six values: the
+// same addresses in every warp, no bank conflict) behind one named barrier of (1 + groups) * 32 threads.
+// A CTA holds `teams` teams (one for 64 settings: 17 warps, <= 112 registers per thread).
+constexpr int kFanMaxWarps = kChainFanWarps;
+template <int kNS, bool kFull, bool kHourly, int kDens>
+__global__ void __launch_bounds__(kFanMaxWarps * 32, 1)
+chain_kernel_fan(const __grid_constant__ ChainParams p, int groups)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_coef = reinterpret_cast<double *>(smem_raw);              // [n][3][4]
+    double *s_x = s_coef + (size_t)p.spline.n * 12;                     // [n]
+    double *s_gx = s_x + p.spline.n;                                    // [nx]
+    double *s_gy = s_gx + p.ds.nx;                                      // [ny]
+    double *s_ring = s_gy + p.ds.ny;                                    // [teams][kWsRingDoubles]
+    const int team_warps = groups + 1;
+    const int n_teams = (blockDim.x >> 5) / team_warps;
+    int *s_unit = reinterpret_cast<int *>(s_ring + (size_t)n_teams * kWsRingDoubles);   // [teams]
+    for (int k = threadIdx.x; k < p.spline.n * 12; k += blockDim.x) s_coef[k] = p.spline.coef[k];
+    for (int k = threadIdx.x; k < p.spline.n; k += blockDim.x) s_x[k] = p.spline.x[k];
+    for (int k = threadIdx.x; k < p.ds.nx; k += blockDim.x) s_gx[k] = p.ds.x[k];
+    for (int k = threadIdx.x; k < p.ds.ny; k += blockDim.x) s_gy[k] = p.ds.y[k];
+    ::mms::fm::math_tables_init();
+    __syncthreads();
+    SmemTables tb{s_x, s_coef, s_gx, s_gy};
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int team = warp / team_warps, role = warp % team_warps;      // role 0 = forcing, role g + 1 = settings of group g
+    if (team >= n_teams) return;
+    const bool forcing_role = role == 0;
+    RingEnd ring = ring_end(s_ring + (size_t)team * kWsRingDoubles, team, lane);
+    ring.bar_threads = team_warps * 32;
+
+    for (;;) {
+        if (forcing_role && lane == 0) s_unit[team] = atomicAdd(p.unit_counter, 1);
+        pair_barrier(team, ring.bar_threads);
+        const int cb = s_unit[team];                 // a unit of this form = one cell block, all settings
+        pair_barrier(team, ring.bar_threads);        // everybody has read it before it is overwritten
+        if (cb >= p.n_cell_blocks) break;
+        UnitCtx u;
+        u.cell = (int64_t)cb * 32 + lane; u.cs = p.c_stride; u.set0 = forcing_role ? 0 : (role - 1) * kNS; u.H = 24 * p.D;
+        u.live = u.cell < p.n_cells; u.write_forcing = true;
+        u.os = p.out_stride;
+        u.ocell = (p.out_col && u.live) ? __ldg(p.out_col + u.cell) : u.cell;
+        u.n_mean_state = __popc(p.mean_mask & MMS_STATE_VAR_MASK);
+        u.n_hourly_state = __popc(p.hourly_mask & MMS_STATE_VAR_MASK);
+        role_unit<kNS, kFull, kHourly, kDens>(p, tb, u, ring, forcing_role);
     }
 }
 

@@ -60,7 +60,30 @@ cudaError_t launch_pairs_ns(const ChainParams &p, bool full, bool hourly, int gr
     return hourly ? launch_pairs<kNS, false, true>(p, grid, pairs, stream) : launch_pairs<kNS, false, false>(p, grid, pairs, stream);
 }
 
+template <bool kFull, bool kHourly>
+cudaError_t launch_fan(const ChainParams &p, int grid, int teams, int groups, cudaStream_t stream)
+{
+    // summaries only: the density-dependence form compiled in (the shapes differ between the groups: run time)
+    constexpr bool kSpecialise = !kFull && !kHourly;
+    auto kern = chain_kernel_fan<4, kFull, kHourly, -1>;
+    if (kSpecialise) kern = p.densmod_type == 1 ? chain_kernel_fan<4, kFull, kHourly, kSpecialise ? 1 : -1>
+                                                : chain_kernel_fan<4, kFull, kHourly, kSpecialise ? 0 : -1>;
+    const size_t smem = sizeof(double) * ((size_t)p.spline.n * 13 + p.ds.nx + p.ds.ny + (size_t)teams * kWsRingDoubles) +
+                        sizeof(int) * (size_t)teams;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    kern<<<grid, teams * (groups + 1) * 32, smem, stream>>>(p, groups);
+    return cudaGetLastError();
+}
+
 }  // namespace
+
+cudaError_t launch_chain_fan_fast(const ChainParams &p, bool full, bool hourly, int grid, int teams, int groups,
+                                  cudaStream_t stream)
+{
+    if (full) return hourly ? launch_fan<true, true>(p, grid, teams, groups, stream) : launch_fan<true, false>(p, grid, teams, groups, stream);
+    return hourly ? launch_fan<false, true>(p, grid, teams, groups, stream) : launch_fan<false, false>(p, grid, teams, groups, stream);
+}
 
 // settings_per_thread: 1, 2 or 4 (what launch_chain chose); grid / pairs: the persistent-CTA shape chosen by launch_one
 cudaError_t launch_chain_ws_fast(const ChainParams &p, int settings_per_thread, bool full, bool hourly, int grid,

@@ -14,6 +14,7 @@ constexpr int kChainMaxWarps = 16;   // largest persistent CTA of the fused kern
 constexpr int kChainFewWarps = 12;   // second instantiation: <= 384 threads, <= 168 registers / thread
 constexpr int kChainMaxPairs = 11;   // warp-specialised kernel: 11 forcing + 11 state warps, <= 88 registers / thread
 constexpr int kChainFewPairs = 10;   // second instantiation: 640 threads, <= 96 registers / thread
+constexpr int kChainFanWarps = 17;   // fan-out form: 1 forcing + up to 16 state warps per team, <= 112 registers / thread
 constexpr int kHoursPerYear = 8760;  // n_times_year <- 365 * 24, R/sim_water.R:229, R/sim_pop_dynamics.R:222
 constexpr int kDaysPerYear = 365;
 
@@ -126,6 +127,9 @@ cudaError_t launch_chain_strict(ChainParams &p, int n_sm, cudaStream_t stream);
 // the warp-pair form (chain_ws_tu.cu), called by launch_chain_fast when it picks that form
 cudaError_t launch_chain_ws_fast(const ChainParams &p, int settings_per_thread, bool full, bool hourly, int grid,
                                  int pairs, cudaStream_t stream);
+// the fan-out form (chain_ws_tu.cu): `teams` teams of 1 forcing + `groups` state warps (4 settings each) per CTA
+cudaError_t launch_chain_fan_fast(const ChainParams &p, bool full, bool hourly, int grid, int teams, int groups,
+                                  cudaStream_t stream);
 // monthly rainfall -> log1p(rainfall) in place (R/sim_microclimate.R:33): n_rows rows of `width` doubles, `pitch` apart
 cudaError_t launch_log1p_rows_fast(double *rows, int64_t n_rows, int64_t width, int64_t pitch, cudaStream_t stream);
 cudaError_t launch_log1p_rows_strict(double *rows, int64_t n_rows, int64_t width, int64_t pitch, cudaStream_t stream);
@@ -134,8 +138,13 @@ cudaError_t launch_log1p_rows_strict(double *rows, int64_t n_rows, int64_t width
 // n_sm SMs, and the settings a thread integrates -- what the host pipeline sizes its chunks with (chain_tu.cu
 // launch_one picks the same forms)
 inline int chain_settings_per_thread(int S) { return S % 4 == 0 ? 4 : (S % 2 == 0 ? 2 : 1); }
+// fan-out form (chain_ws.cuh chain_kernel_fan): fast mode, four settings per state warp, at least two state warps
+inline int chain_fan_groups(int S, bool strict) { return (!strict && S % 4 == 0 && S >= 8) ? S / 4 : 0; }
+inline int chain_fan_teams_max(int groups) { return groups > 0 ? (kChainFanWarps / (groups + 1) < 15 ? kChainFanWarps / (groups + 1) : 15) : 0; }
 inline int chain_round_units(int S, bool strict, int n_sm)
 {
+    const int groups = chain_fan_groups(S, strict);
+    if (groups > 0) return n_sm * chain_fan_teams_max(groups) * groups;    // units are (cell block, group of 4 settings)
     const bool pairs = !strict && chain_settings_per_thread(S) == 2;
     return n_sm * (pairs ? kChainMaxPairs : kChainMaxWarps);
 }

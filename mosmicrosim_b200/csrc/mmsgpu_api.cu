@@ -362,7 +362,18 @@ void classify(mms_chain_plan *pl, std::vector<PipeJob> &jobs)
         all_pinned = classify_mats(j.in) && all_pinned;
         all_pinned = classify_mats(j.out) && all_pinned;
     }
-    for (PipeJob &j : jobs) j.workers = all_pinned ? 1 : pl->n_workers;
+    // pageable memory: every worker stages its share.  Pinned memory needs no staging, but a few copy streams fill
+    // the PCIe link better than one when the chunks are large
+    for (size_t g = 0; g < jobs.size(); ++g) {
+        PipeJob &j = jobs[g];
+        if (!all_pinned) { j.workers = pl->n_workers; continue; }
+        const Shard *s = pl->shards[g].get();
+        size_t bytes = 0;
+        for (const Mat &m : j.in) bytes += m.rows * m.elem;
+        for (const Mat &m : j.out) bytes += m.rows * m.elem;
+        bytes = bytes * (size_t)s->n_cells / std::max<size_t>(1, s->pipe.chunks.size());      // per chunk
+        j.workers = (int)std::max<size_t>(1, std::min<size_t>(std::min(4, pl->n_workers), bytes / ((size_t)16 << 20)));
+    }
 }
 
 // non-finite forcing seen by the kernels of the last launches (flags are zeroed at every launch)

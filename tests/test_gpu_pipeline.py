@@ -229,3 +229,25 @@ def test_outputs_scattered_into_raster_order(gpu, monkeypatch, devices, chunks, 
     with pytest.raises(backend.MmsError) as e:          # not in raster order
         backend.ChainPlan(case.C, raster_cell_idx=cell_idx[::-1].copy(), n_raster_cells=R, **kw)
     assert e.value.code == "MMS_ERR_UNSUPPORTED"
+
+
+@pytest.mark.parametrize("n_settings", [8, 12, 64])
+@pytest.mark.parametrize("fan", ["0", "1"])
+def test_ensemble_forms(gpu, monkeypatch, n_settings, fan):
+    """Habitat ensembles: the fan-out form (one forcing warp feeding the state warps of all settings of its cells,
+    chosen automatically for 8, 12, ... settings) and the form it replaces (every group of four settings recomputes the
+    forcing), both against the oracle: hourly series, flags, summaries over included dates, NA cells, ragged cells."""
+    monkeypatch.setenv("MMS_CHAIN_FAN", fan)
+    included = syn.year_dates(2001, 1)[15:250]
+    case = Case(n_cells=45, habitats=syn.habitat_ensemble(64)[5:5 + n_settings] if n_settings < 64 else syn.habitat_ensemble(64),
+                included=included, out_of_range_fraction=0.1)
+    ref = case.oracle()
+    names = ["adult", "aquatic", "mdr", "ds", "larval_habitat_area", "water_volume", "air_temperature"]
+    out = backend.run_chain(case.monthly, case.altitude, **case.gpu_kwargs(
+        mean_vars=names, hourly_vars=["adult", "larval_habitat_area", "efd"], want_wet_hours=True, want_wet_flags=True))
+    compare(case, out, ref, REL_TOL_FAST)
+    for species in ("An. gambiae", "An. stephensi"):          # summaries only: density dependence compiled in
+        c2 = Case(n_cells=45, species=species, habitats=case.habitats, out_of_range_fraction=0.1)
+        out2 = backend.run_chain(c2.monthly, c2.altitude, **c2.gpu_kwargs(mean_vars=["adult", "aquatic"], want_wet_hours=True,
+                                                                          burnin_years_water=1))
+        compare(c2, out2, c2.oracle(want_hourly=False, burnin_years_water=1), REL_TOL_FAST, what=("mean",))
