@@ -225,6 +225,8 @@ def big_configs(n_dev: int, which=("cfg3", "cfg5", "cfg4")):
                      agg="month", names=["adult", "aquatic"], wet=True),
     }
     results = {}
+    # the other ranks of a torchrun launch are idle by now: this process may use every host core
+    os.environ["MMS_HOST_WORKERS"] = str(max(1, min(12, host_threads() // max(1, n_dev))))
     for name in which:
         sp = specs[name]
         try:
@@ -255,6 +257,24 @@ def big_configs(n_dev: int, which=("cfg3", "cfg5", "cfg4")):
                 secs.append(time.perf_counter() - t0)
                 kms.append(plan.kernel_ms() * n_tiles)
             sec = float(np.mean(secs))
+            # the same call on buffers from mms_host_alloc (page-locked: the DMA runs on them in place, no bounce copy)
+            pinned = None
+            if os.environ.get("MMS_BENCH_PINNED_CONFIGS", "1") != "0":
+                try:
+                    t0 = time.perf_counter()
+                    pm, pa = backend.PinnedArray(monthly.shape), backend.PinnedArray(altitude.shape)
+                    pm.array[...] = monthly
+                    pa.array[...] = altitude
+                    pout = plan.allocate_outputs(pinned=True)
+                    t_alloc = time.perf_counter() - t0
+                    plan.run(pm.array, pa.array, pout)
+                    t0 = time.perf_counter()
+                    for _t in range(n_tiles):
+                        plan.run(pm.array, pa.array, pout)
+                    pinned = {"seconds_e2e": time.perf_counter() - t0, "allocation_and_fill_s": t_alloc}
+                    del pm, pa, pout
+                except Exception as e:
+                    pinned = {"error": f"{type(e).__name__}: {e}"}
             S = len(sp["habitats"])
             H = 24 * len(dp)
             info = plan.info()
@@ -270,6 +290,8 @@ def big_configs(n_dev: int, which=("cfg3", "cfg5", "cfg4")):
                 "setting_cell_years_per_s_e2e": sp["cells"] * S * (H / 8760.0) / sec,
                 "h2d_bytes": int(h2d * n_tiles), "d2h_bytes": int(d2h * n_tiles),
                 "host_memory": "pageable (numpy) in and out, staged through the plan's pinned bounce buffers",
+                "pinned_host_memory": pinned,
+                "host_workers_per_device": int(os.environ["MMS_HOST_WORKERS"]),
                 "plan": info, "plan_create_s": create_s, "input_generation_s": t_gen,
                 "adult_mean_finite_fraction": finite,
                 "path": "one mms_chain_create(devices = 0..N-1) plan, mms_chain_run per tile, one host output buffer",
@@ -328,6 +350,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (libmmsgpu has no CPU fallback)")
     w = workload(rank)
     dev = local_rank
+    # host threads of this rank's plan: the box's cores are shared by the ranks (the library reads LOCAL_WORLD_SIZE
+    # too; stated here so that the line records it)
+    host_workers = max(1, min(12, host_threads() // max(1, world)))
+    os.environ["MMS_HOST_WORKERS"] = str(host_workers)
     peak_fp64 = backend.measure_fp64_peak(dev)          # TFLOP/s, DFMA loop, this GPU, now
     hbm_copy = backend.measure_hbm_copy(dev)
     dinfo = backend.device_info(dev)
@@ -436,6 +462,7 @@ def main():
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "value_per_core", "kind", "sample")}
     plan.close()
     del pin_m, pin_a, out, out_pageable
+    os.environ.pop("MMS_HOST_WORKERS", None)      # the multi-device plans below size their own teams
 
     # ---- the north-star configurations at full size, one multi-device plan over the N GPUs (rank 0) ----
     want_configs = not args.no_configs and os.environ.get("MMS_BENCH_CONFIGS", "1") != "0"

@@ -61,8 +61,13 @@ int default_workers(int n_devices)
         const int w = std::atoi(e);
         if (w >= 1) return std::min(w, 16);
     }
+    // the hardware threads are shared among the devices of the call -- and, in a one-process-per-GPU launch
+    // (torchrun / mpirun export the number of local processes), among those processes
+    int procs = 1;
+    for (const char *name : {"LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE", "MPI_LOCALNRANKS"})
+        if (const char *e = std::getenv(name)) { const int v = std::atoi(e); if (v > 1) { procs = v; break; } }
     const unsigned hw = std::thread::hardware_concurrency();
-    const int per = hw ? (int)hw / std::max(1, n_devices) : 2;
+    const int per = hw ? (int)hw / std::max(1, n_devices * procs) : 2;
     return std::max(1, std::min(kMaxWorkers, per));
 }
 
@@ -274,7 +279,7 @@ bool Pipe::stage_out(Worker *wk, const Mat &m, int64_t w0, int64_t wn)
 void Pipe::arrive(Worker *wk, const PipeJob &job, int k)
 {
     PipeChunk &c = chunks[k];
-    const int total = (int)workers_.size();
+    const int total = std::max(1, std::min(job.workers, (int)workers_.size()));   // the workers that take part in this job
     if (!failed_.load()) {
         if (cudaEventRecord(c.ev_in[wk->id], wk->s_in) != cudaSuccess) set_error(MMS_ERR_CUDA, "cudaEventRecord failed");
     }
@@ -303,7 +308,7 @@ bool Pipe::do_in(Worker *wk, const PipeJob &job, int k)
 {
     const PipeChunk &c = chunks[k];
     int64_t w0 = 0, wn = 0;
-    if (wk->id < job.workers) worker_window(c, wk->id, job.workers, window_unit, w0, wn);
+    worker_window(c, wk->id, std::max(1, job.workers), window_unit, w0, wn);
     if (wk->id == 0 && k == 0 && job.before_first_copy && !job.before_first_copy(wk->s_in)) return false;
     for (const Mat &m : job.in)
         if (!stage_in(wk, m, w0, wn)) return false;
@@ -320,7 +325,7 @@ bool Pipe::do_out(Worker *wk, const PipeJob &job, int k)
     if (failed_.load()) return false;
     if (c.kernel_recorded) MMS_CUDA_P(this, cudaStreamWaitEvent(wk->s_out, c.ev_kernel, 0));
     int64_t w0 = 0, wn = 0, o0 = 0, on = 0;
-    if (wk->id < job.workers) worker_window(c, wk->id, job.workers, window_unit, w0, wn);
+    worker_window(c, wk->id, std::max(1, job.workers), window_unit, w0, wn);
     if (job.out_window) job.out_window(w0, wn, o0, on);
     else { o0 = w0; on = wn; }
     for (const Mat &m : job.out)
@@ -333,6 +338,8 @@ bool Pipe::do_out(Worker *wk, const PipeJob &job, int k)
 void Pipe::run_job(Worker *wk, const PipeJob &job)
 {
     const int n = (int)chunks.size();
+    // workers beyond the job's team (pinned buffers need few copy streams, small jobs few stagers) sit this one out
+    if (job.kind != PIPE_CALL && wk->id >= std::max(1, job.workers)) return;
     switch (job.kind) {
     case PIPE_CALL:
         if (wk->id == 0 && job.call && !job.call() && !failed_.load()) set_error(MMS_ERR_CUDA, "device set-up failed");

@@ -51,6 +51,19 @@ def needs_extrapolation(mid_day: np.ndarray, day_predict: np.ndarray) -> bool:
     return bool(np.any((day_predict > mid_day.max()) | (day_predict < mid_day.min())))
 
 
+def clip_dates_predict(start, end, dates_predict):
+    """Drop the prediction days that lie outside the monthly mid-dates.  The reference's default dates_predict
+    (midpoints rounded half to even) can overhang the knots (unrounded midpoints) by half a day -- a 30-day first
+    month, a non-leap February last month (R/sim_microclimate.R:14-24,31) -- and the reference then fits an
+    mgcv::gam for the whole series (R/spline_interpolation.R:30-112), which the GPU backend does not reproduce.
+    Returns (clipped dates, number of days dropped)."""
+    mid = month_mid_days(start, end)
+    dp = np.asarray(dates_predict, dtype="datetime64[D]")
+    x = _as_days(dp).astype(np.int64).astype(np.float64)
+    keep = (x >= mid.min()) & (x <= mid.max())
+    return dp[keep], int((~keep).sum())
+
+
 def period_index(dates_predict, aggregate_by="month", included_dates=None):
     """Map every simulated day to a summary period, as aggregate_vectors() does
     (R/pipeline_functions.R:1030-1091): filter(date %in% included_dates), then

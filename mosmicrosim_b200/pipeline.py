@@ -124,8 +124,16 @@ def interpolate_daily_climate(pixel_monthly_climate, dates_predict=None, *, math
     pixel of the tile.  Returns the tile's `daily_climate` tibbles side by side: a dict with
     `date` [D], the pixel columns carried through, and one [D, C] array per daily variable."""
     start, end, monthly, altitude = _monthly_array(pixel_monthly_climate)
+    on_extrapolation = _match_arg(on_extrapolation, ("error", "clip"), "on_extrapolation")
     if dates_predict is None:
         dates_predict = dates.default_dates_predict(start, end)
+    if on_extrapolation == "clip":
+        # a half-day overhang of the default dates over the knots (30-day first month, non-leap February last month)
+        # would send the reference into its mgcv::gam branch, which the library refuses (MMS_ERR_EXTRAPOLATION)
+        dates_predict, dropped = dates.clip_dates_predict(start, end, dates_predict)
+        if dropped:
+            warnings.warn(f"{dropped} prediction day(s) outside the monthly mid-dates dropped "
+                          "(the reference would extrapolate them with an mgcv::gam)")
     mid_day, day_predict = dates.datenums(start, end, dates_predict)
     daily = backend.daily_from_monthly(monthly, mid_day, day_predict, math_mode=math_mode, device=device)
     out = {"date": np.asarray(dates_predict, "datetime64[D]"), "altitude": altitude,
@@ -257,7 +265,7 @@ def terraclimate_to_monthly_climate(pixel_terraclimate_data, *, pad_last=False, 
 def _run_vectors(run, n_cells, start, end, carried, lifehistory_functions, species, included_dates,
                  aggregate_by, dates_predict, habitats, model_water_temperature, water_shade_proportion,
                  burnin_years_pop, extra_variables, math_mode, devices, water_temperature_options=None,
-                 cell_idx=None, n_raster_cells=None):
+                 cell_idx=None, n_raster_cells=None, on_extrapolation="error"):
     """interpolate_daily_climate() ... summarise_vectors() in one pipelined call (mms_chain_run[_terraclimate]);
     `run(plan, out)` hands the monthly knots (either form) and the output buffers to the plan."""
     species = _match_arg(species, SPECIES, "species")
@@ -266,8 +274,16 @@ def _run_vectors(run, n_cells, start, end, carried, lifehistory_functions, speci
     if water_shade_proportion != 1 and not model_water_temperature:
         warnings.warn("water temperature is not being modelled, so water_shade_proportion argument is ignored")
     lh: Lifehistory = lifehistory_functions[{"An. gambiae": "An_gambiae", "An. stephensi": "An_stephensi"}[species]]
+    on_extrapolation = _match_arg(on_extrapolation, ("error", "clip"), "on_extrapolation")
     if dates_predict is None:
         dates_predict = dates.default_dates_predict(start, end)
+    if on_extrapolation == "clip":
+        # a half-day overhang of the default dates over the knots (30-day first month, non-leap February last month)
+        # would send the reference into its mgcv::gam branch, which the library refuses (MMS_ERR_EXTRAPOLATION)
+        dates_predict, dropped = dates.clip_dates_predict(start, end, dates_predict)
+        if dropped:
+            warnings.warn(f"{dropped} prediction day(s) outside the monthly mid-dates dropped "
+                          "(the reference would extrapolate them with an mgcv::gam)")
     mid_day, day_predict = dates.datenums(start, end, dates_predict)
     period_of_day, p_start, p_end = dates.period_index(dates_predict, aggregate_by, included_dates)
     if habitats is None:      # R/pipeline_functions.R:431-441
@@ -307,7 +323,8 @@ def monthly_climate_to_vectors(pixel_monthly_climate, lifehistory_functions, spe
                                included_dates=None, aggregate_by="month", dates_predict=None, *,
                                habitats=None, model_water_temperature=False, water_shade_proportion=1,
                                burnin_years_pop=1, extra_variables=(), math_mode="fast", devices=None,
-                               water_temperature_options=None, cell_idx=None, n_raster_cells=None):
+                               water_temperature_options=None, cell_idx=None, n_raster_cells=None,
+                               on_extrapolation="error"):
     """tc_to_vectors() (R/pipeline_functions.R:1099-1130) from
     interpolate_daily_climate() to summarise_vectors(), for a whole tile in one
     fused kernel launch per device.
@@ -320,6 +337,9 @@ def monthly_climate_to_vectors(pixel_monthly_climate, lifehistory_functions, spe
       (the reference's sysdata object of the same name).
     Returns a dict: longitude, latitude, species, start[P], end[P] and one
     [P, C] array per vector variable -- the `pixel_vectors` tibbles side by side.
+    on_extrapolation: "error" (default) or "clip": what to do when prediction days lie outside the monthly
+      mid-dates -- the reference's default dates overhang them by half a day when the series starts in a 30-day
+      month or ends in a non-leap February (dates.clip_dates_predict) -- where the reference fits an mgcv::gam.
     cell_idx / n_raster_cells: the pixels' 0-based raster cell numbers (strictly increasing) and the raster's size;
       every row then comes back as a whole raster slice [P, n_raster_cells] with NaN where the raster has no pixel
       of the tile -- the assignment raster[cell_idx] <- values of create_vector_raster_slice()
@@ -330,14 +350,14 @@ def monthly_climate_to_vectors(pixel_monthly_climate, lifehistory_functions, spe
                         pixel_monthly_climate, lifehistory_functions, species, included_dates, aggregate_by,
                         dates_predict, habitats, model_water_temperature, water_shade_proportion,
                         burnin_years_pop, extra_variables, math_mode, devices, water_temperature_options,
-                        cell_idx, n_raster_cells)
+                        cell_idx, n_raster_cells, on_extrapolation)
 
 
 def tc_to_vectors(pixel_terraclimate_data, lifehistory_functions, species=SPECIES, included_dates=None, *,
                   aggregate_by="month", dates_predict=None, pad_last=False, habitats=None,
                   model_water_temperature=False, water_shade_proportion=1, burnin_years_pop=1,
                   extra_variables=(), math_mode="fast", devices=None, water_temperature_options=None,
-                  cell_idx=None, n_raster_cells=None):
+                  cell_idx=None, n_raster_cells=None, on_extrapolation="error"):
     """tc_to_vectors(pixel_terraclimate_data, species, included_dates), R/pipeline_functions.R:1099-1130,
     whole: the six raw TerraClimate variables go to the device and process_terraclimate_pixel_vars()
     (R/terraclimate.R:581-643) runs there, in front of the fused chain (mms_chain_upload_terraclimate).
@@ -350,7 +370,7 @@ def tc_to_vectors(pixel_terraclimate_data, lifehistory_functions, species=SPECIE
                         tc.shape[2], start, end, pixel_terraclimate_data, lifehistory_functions, species,
                         included_dates, aggregate_by, dates_predict, habitats, model_water_temperature,
                         water_shade_proportion, burnin_years_pop, extra_variables, math_mode, devices,
-                        water_temperature_options, cell_idx, n_raster_cells)
+                        water_temperature_options, cell_idx, n_raster_cells, on_extrapolation)
 
 
 def raster_slice(vectors, variable, year, month):

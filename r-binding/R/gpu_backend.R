@@ -6,9 +6,10 @@
 # does in R, and no CPU fallback: with the GPU backend selected and no CUDA
 # device the .Call errors.
 #
-# NOT EXECUTED in the development image of the B200 backend (no R there); the
-# Python package mosmicrosim_b200/ mirrors these wrappers on the same C ABI and
-# is what the test-suite drives.
+# NOT EXECUTED in the development image of the B200 backend (no R there), and
+# src/mmsgpu_shim.c has only been compiled against a stub of R's C API
+# (tests/r_stub/): UNTESTED UNDER R.  The Python package mosmicrosim_b200/
+# mirrors these wrappers on the same C ABI and is what the test-suite drives.
 
 mms_backend <- function() {
   getOption("mosmicrosim.backend", "r")
@@ -93,6 +94,17 @@ simulate_population_vectorised_gpu <- function(
     larval_habitat_area_matrix, mdr_matrix, efd_matrix, das_zerodensity_matrix,
     ds_matrix, das_densmod_function, initial_adult = 100, initial_aquatic = 100,
     burnin_years = 1) {
+  # the shim insists on double matrices of identical dimensions (an integer or mis-sized matrix
+  # would be an out-of-bounds read in the host-to-device copy)
+  storage.mode(larval_habitat_area_matrix) <- "double"
+  storage.mode(mdr_matrix) <- "double"
+  storage.mode(efd_matrix) <- "double"
+  storage.mode(das_zerodensity_matrix) <- "double"
+  storage.mode(ds_matrix) <- "double"
+  stopifnot(identical(dim(mdr_matrix), dim(larval_habitat_area_matrix)),
+            identical(dim(efd_matrix), dim(larval_habitat_area_matrix)),
+            identical(dim(das_zerodensity_matrix), dim(larval_habitat_area_matrix)),
+            identical(dim(ds_matrix), dim(larval_habitat_area_matrix)))
   .Call("mms_R_population_vectorised", larval_habitat_area_matrix, mdr_matrix,
         efd_matrix, das_zerodensity_matrix, ds_matrix,
         mms_densmod(das_densmod_function), as.numeric(initial_adult),
@@ -179,47 +191,103 @@ summarise_vectors_gpu <- function(hourly, dates_predict, aggregate_by = c("month
 }
 
 # ---- the fused pipeline --------------------------------------------------------
+
+# [pixels, months, variables] array (the pixel index fastest, as the kernel wants it) from a list column of
+# per-pixel monthly tibbles: ONE bind_rows() and one reshape -- not an interpreted loop over the pixels, which
+# at the 1.5 M pixels of the Africa grid would be the run time
+mms_pack_pixels <- function(list_col, vars) {
+  n_pixels <- length(list_col)
+  n_months <- nrow(list_col[[1]])
+  all <- dplyr::bind_rows(list_col)
+  if (nrow(all) != n_pixels * n_months) stop("all pixels of a tile must have the same months", call. = FALSE)
+  a <- array(as.numeric(unlist(all[vars], use.names = FALSE)), dim = c(n_months, n_pixels, length(vars)))
+  aperm(a, c(2, 1, 3))
+}
+
+# options list of the shim's extensions (NULL = the reference's behaviour)
+mms_chain_options <- function(chain, pixels, model_water_temperature, water_shade_proportion, clear_sky,
+                              cell_idx, n_raster_cells, water_temperature_options = list()) {
+  # simulate_hourly_conditions() argument handling, R/pipeline_functions.R:324-338
+  if (water_shade_proportion != 1 & !model_water_temperature) {
+    warning("water temperature is not being modelled, ",
+            "so water_shade_proportion argument is ignored", call. = FALSE)
+  }
+  opts <- list()
+  if (model_water_temperature) {
+    # EXTENSION: the reference stop()s here; the GPU backend models the water temperature (DESIGN.md section 5)
+    if (is.null(clear_sky)) stop("model_water_temperature = TRUE needs the pixels' clear-sky radiation", call. = FALSE)
+    wt <- utils::modifyList(list(albedo = 0, emissivity = 0.97, convection_w_m2_k = 0), water_temperature_options)
+    opts$water_temperature <- c(wt, list(
+      shade_proportion = as.numeric(water_shade_proportion),
+      day_of_year = as.integer(format(chain$dates_predict, "%j")),          # doy(), R/utils.R:46-48
+      month_of_day = as.integer(lubridate::month(chain$dates_predict)),
+      latitude = as.numeric(pixels$latitude),
+      clear_sky = clear_sky))                                               # [pixels, 12]
+  }
+  if (!is.null(cell_idx)) {
+    # rows come back as whole raster slices: raster[cell_idx] <- values of create_vector_raster_slice()
+    # (R/pipeline_functions.R:1316-1322) done by the kernel's stores; terra cell numbers are 1-based
+    opts$cell_idx <- as.numeric(cell_idx) - 1
+    opts$n_raster_cells <- as.numeric(n_raster_cells)
+  }
+  if (length(opts)) opts else NULL
+}
+
 # tc_to_vectors() (R/pipeline_functions.R:1099-1130) from interpolate_daily_climate()
 # on, for the whole tile in one call.  pixel_monthly_climate is the tibble that
 # terraclimate_to_monthly_climate() returns; the result has the schema of
 # summarise_vectors(): longitude, latitude, species, pixel_vectors = list(tibble(
 # start, end, adult, aquatic, mdr, efd, das_zerodensity, ds)).
+#   on_extrapolation: the reference's default dates_predict can overhang the monthly mid-dates by half a day (a
+#     30-day first month, a non-leap February last month: R/sim_microclimate.R:14-24,31), where the reference fits an
+#     mgcv::gam (R/spline_interpolation.R:30-112) that the GPU backend does not reproduce: "error" (default) stops,
+#     "clip" drops the overhanging prediction days with a warning.
+#   cell_idx, n_raster_cells: return whole raster slices instead of tile rows (simplify = TRUE implied).
 monthly_climate_to_vectors_gpu <- function(pixel_monthly_climate,
                                            species = c("An. gambiae", "An. stephensi"),
                                            included_dates = NULL,
-                                           aggregate_by = c("month", "day")) {
+                                           aggregate_by = c("month", "day"),
+                                           model_water_temperature = FALSE,
+                                           water_shade_proportion = 1,
+                                           clear_sky = NULL,
+                                           on_extrapolation = c("error", "clip"),
+                                           cell_idx = NULL, n_raster_cells = NULL,
+                                           simplify = !is.null(cell_idx)) {
   species <- match.arg(species)
   aggregate_by <- match.arg(aggregate_by)
   lifehistory <- switch(species,
                         "An. gambiae" = lifehistory_functions$An_gambiae,
                         "An. stephensi" = lifehistory_functions$An_stephensi)
   first <- pixel_monthly_climate$monthly_climate[[1]]
-  n_pixels <- nrow(pixel_monthly_climate)
   vars <- c("tmin", "tmax", "rhmin", "rhmax", "wsmin", "wsmax", "ccmin", "ccmax",
             "rainfall_daily")
-  # [cells, months, 9]: the cell index is the fastest one, as the kernel wants it
-  monthly <- array(NA_real_, dim = c(n_pixels, nrow(first), length(vars)))
-  for (i in seq_len(n_pixels)) {
-    monthly[i, , ] <- as.matrix(pixel_monthly_climate$monthly_climate[[i]][, vars])
-  }
-  chain <- mms_chain_setup(first, included_dates, aggregate_by)
+  monthly <- mms_pack_pixels(pixel_monthly_climate$monthly_climate, vars)
+  chain <- mms_chain_setup(first, included_dates, aggregate_by, match.arg(on_extrapolation))
+  opts <- mms_chain_options(chain, pixel_monthly_climate, model_water_temperature, water_shade_proportion,
+                            clear_sky, cell_idx, n_raster_cells)
   res <- .Call("mms_R_run_chain", monthly, as.numeric(pixel_monthly_climate$altitude),
                chain$mid_day, chain$day_predict, chain$period_of_day,
                list(mms_habitat()),                # R/pipeline_functions.R:431-441
                mms_densmod(lifehistory$das_densmod), mms_lifehistory_tables(lifehistory),
                63L,                                # the six vector_variables
-               length(chain$periods), 1L, mms_math_mode(), mms_devices(),
+               length(chain$periods), 1L, mms_math_mode(), mms_devices(), opts,
                PACKAGE = "mosmicrosim")
-  mms_vectors_tibble(res, pixel_monthly_climate, species, chain$periods, aggregate_by)
+  mms_vectors_result(res, pixel_monthly_climate, species, chain$periods, aggregate_by, simplify)
 }
 
 # dates exactly as daily_from_monthly_climate() derives them (R/sim_microclimate.R:12-31) and periods
 # exactly as aggregate_vectors() groups them (R/pipeline_functions.R:1050-1088); `first` is any pixel's
 # monthly tibble (all pixels of a tile share start / end)
-mms_chain_setup <- function(first, included_dates, aggregate_by) {
+mms_chain_setup <- function(first, included_dates, aggregate_by, on_extrapolation = "error") {
   midpoint <- first$start + round((first$end - first$start) / 2)
   dates_predict <- seq(from = min(midpoint), to = max(midpoint), by = 1)
   mid_date <- first$start + (first$end - first$start) / 2
+  outside <- dates_predict < min(mid_date) | dates_predict > max(mid_date)     # R/spline_interpolation.R:30-31
+  if (any(outside) && on_extrapolation == "clip") {
+    warning(sum(outside), " prediction day(s) outside the monthly mid-dates dropped ",
+            "(the reference would extrapolate them with an mgcv::gam)", call. = FALSE)
+    dates_predict <- dates_predict[!outside]
+  }
   if (is.null(included_dates)) included_dates <- dates_predict
   keep <- dates_predict %in% included_dates
   key <- if (aggregate_by == "month") lubridate::floor_date(dates_predict, "month") else dates_predict
@@ -227,16 +295,24 @@ mms_chain_setup <- function(first, included_dates, aggregate_by) {
   list(mid_day = as.numeric(mid_date - min(mid_date)),
        day_predict = as.numeric(dates_predict - min(mid_date)),
        period_of_day = as.integer(ifelse(keep, match(key, periods) - 1L, -1L)),
-       periods = periods)
+       periods = periods, dates_predict = dates_predict)
 }
 
-# the summarise_vectors() schema from the library's [cell, period, variable] arrays
-mms_vectors_tibble <- function(res, pixels, species, periods, aggregate_by) {
-  n_pixels <- nrow(pixels)
+# the summarise_vectors() schema from the library's [column, period, variable] arrays; simplify = TRUE returns the
+# arrays themselves (list(start, end, adult = [columns, periods], ...)) -- at a million pixels building a tibble per
+# pixel is slower than the simulation
+mms_vectors_result <- function(res, pixels, species, periods, aggregate_by, simplify = FALSE) {
   n_periods <- length(periods)
-  state <- array(res$mean_state, dim = c(n_pixels, n_periods, 2))      # adult, aquatic
-  forcing <- array(res$mean_forcing, dim = c(n_pixels, n_periods, 4))  # mdr, efd, das_zerodensity, ds
+  n_cols <- length(res$mean_state) / (n_periods * 2)                     # pixels, or raster cells
+  state <- array(res$mean_state, dim = c(n_cols, n_periods, 2))          # adult, aquatic
+  forcing <- array(res$mean_forcing, dim = c(n_cols, n_periods, 4))      # mdr, efd, das_zerodensity, ds
   end <- if (aggregate_by == "month") lubridate::ceiling_date(periods + 1, "month") - 1 else periods
+  if (simplify) {
+    return(list(start = periods, end = end, species = species,
+                adult = state[, , 1], aquatic = state[, , 2], mdr = forcing[, , 1], efd = forcing[, , 2],
+                das_zerodensity = forcing[, , 3], ds = forcing[, , 4]))
+  }
+  n_pixels <- nrow(pixels)
   dplyr::tibble(
     longitude = pixels$longitude,
     latitude = pixels$latitude,
@@ -257,7 +333,12 @@ mms_vectors_tibble <- function(res, pixels, species, periods, aggregate_by) {
 tc_to_vectors_gpu <- function(pixel_terraclimate_data,
                               species = c("An. gambiae", "An. stephensi"),
                               included_dates = NULL,
-                              aggregate_by = c("month", "day")) {
+                              aggregate_by = c("month", "day"),
+                              model_water_temperature = FALSE,
+                              water_shade_proportion = 1,
+                              on_extrapolation = c("error", "clip"),
+                              cell_idx = NULL, n_raster_cells = NULL,
+                              simplify = !is.null(cell_idx)) {
   species <- match.arg(species)
   aggregate_by <- match.arg(aggregate_by)
   lifehistory <- switch(species,
@@ -269,26 +350,27 @@ tc_to_vectors_gpu <- function(pixel_terraclimate_data,
   altitude <- altitude_m(longitude = coords$longitude, latitude = coords$latitude,
                          altitude_raster = tc_elev)
   cell_id <- terra::extract(tc_gads, coords, ID = FALSE)[, 1]
-  clear_sky <- t(vapply(match(cell_id, clear_sky_lookup$cell_id),
-                        function(k) as.numeric(clear_sky_lookup$clear_sky_SOLR[[k]]), numeric(12)))
+  # [pixels, 12]: one lookup per DISTINCT GADS cell, not per pixel
+  lookup_rows <- match(cell_id, clear_sky_lookup$cell_id)
+  solr <- do.call(rbind, lapply(clear_sky_lookup$clear_sky_SOLR, as.numeric))
+  clear_sky <- solr[lookup_rows, , drop = FALSE]
+  storage.mode(clear_sky) <- "double"
   first <- pixel_terraclimate_data$monthly_terraclimate[[1]]
-  n_pixels <- nrow(pixel_terraclimate_data)
   vars <- c("tmax", "tmin", "ppt", "ws", "vpd", "srad")
-  values <- array(NA_real_, dim = c(n_pixels, nrow(first), length(vars)))
-  for (i in seq_len(n_pixels)) {
-    values[i, , ] <- as.matrix(pixel_terraclimate_data$monthly_terraclimate[[i]][, vars])
-  }
+  values <- mms_pack_pixels(pixel_terraclimate_data$monthly_terraclimate, vars)
   terraclimate <- list(
     values = values, clear_sky = clear_sky,
     month_id = as.integer(lubridate::month(first$start + (first$end - first$start) / 2)),  # R/terraclimate.R:591
     n_days = as.numeric(first$end - first$start))                                          # :592
-  chain <- mms_chain_setup(first, included_dates, aggregate_by)
+  chain <- mms_chain_setup(first, included_dates, aggregate_by, match.arg(on_extrapolation))
+  opts <- mms_chain_options(chain, pixel_terraclimate_data, model_water_temperature, water_shade_proportion,
+                            clear_sky, cell_idx, n_raster_cells)
   res <- .Call("mms_R_run_chain_terraclimate", terraclimate, as.numeric(altitude),
                chain$mid_day, chain$day_predict, chain$period_of_day,
                list(mms_habitat()), mms_densmod(lifehistory$das_densmod),
                mms_lifehistory_tables(lifehistory), 63L, length(chain$periods), 1L,
-               mms_math_mode(), mms_devices(), PACKAGE = "mosmicrosim")
-  mms_vectors_tibble(res, pixel_terraclimate_data, species, chain$periods, aggregate_by)
+               mms_math_mode(), mms_devices(), opts, PACKAGE = "mosmicrosim")
+  mms_vectors_result(res, pixel_terraclimate_data, species, chain$periods, aggregate_by, simplify)
 }
 
 # ---- the switch: one line each in the reference's own functions ------------------

@@ -32,6 +32,53 @@ static void check(int status)
     if (status != MMS_OK) Rf_error("%s", mms_last_error());
 }
 
+/* REAL() of an argument that must be a double vector / matrix / array (REAL() of an integer matrix would read
+ * past its end): the R wrappers coerce with storage.mode<- / as.numeric, this is the backstop */
+static double *real_arg(SEXP x, const char *name)
+{
+    if (TYPEOF(x) != REALSXP) Rf_error("mmsgpu: '%s' must be of type double", name);
+    return REAL(x);
+}
+
+static int *int_arg(SEXP x, const char *name)
+{
+    if (TYPEOF(x) != INTSXP) Rf_error("mmsgpu: '%s' must be of type integer", name);
+    return INTEGER(x);
+}
+
+/* an n_times x n_pixels double matrix of the expected dimensions */
+static double *matrix_arg(SEXP m, int64_t H, int64_t C, const char *name)
+{
+    if (TYPEOF(m) != REALSXP || !Rf_isMatrix(m)) Rf_error("mmsgpu: '%s' must be a double matrix", name);
+    if (Rf_nrows(m) != H || Rf_ncols(m) != C)
+        Rf_error("mmsgpu: '%s' is %d x %d, expected %lld x %lld", name, Rf_nrows(m), Rf_ncols(m), (long long)H, (long long)C);
+    return REAL(m);
+}
+
+/* an H x C double matrix; H * C may exceed 2^31 - 1 (a long vector), each dimension may not (R's dim is integer) */
+static SEXP alloc_matrix(int64_t H, int64_t C)
+{
+    if (H > INT32_MAX || C > INT32_MAX) Rf_error("mmsgpu: matrix dimensions beyond R's integer dim");
+    SEXP m = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)H * (R_xlen_t)C));
+    SEXP dim = PROTECT(Rf_allocVector(INTSXP, 2));
+    INTEGER(dim)[0] = (int)H;
+    INTEGER(dim)[1] = (int)C;
+    Rf_setAttrib(m, R_DimSymbol, dim);
+    UNPROTECT(2);
+    return m;
+}
+
+/* list element by name, or R_NilValue */
+static SEXP list_get_opt(SEXP list, const char *name)
+{
+    if (list == R_NilValue) return R_NilValue;
+    SEXP names = Rf_getAttrib(list, R_NamesSymbol);
+    if (names == R_NilValue) return R_NilValue;
+    for (R_xlen_t i = 0; i < Rf_xlength(list); ++i)
+        if (strcmp(CHAR(STRING_ELT(names, i)), name) == 0) return VECTOR_ELT(list, i);
+    return R_NilValue;
+}
+
 /* list element by name (R-exts idiom) */
 static SEXP list_get(SEXP list, const char *name)
 {
@@ -89,15 +136,17 @@ SEXP mms_R_device_count(void)
 SEXP mms_R_water_vectorised(SEXP rainfall, SEXP air_temperature, SEXP humidity, SEXP windspeed,
                             SEXP altitude, SEXP habitat, SEXP burnin_years, SEXP math_mode, SEXP device)
 {
+    if (!Rf_isMatrix(rainfall)) Rf_error("mmsgpu: 'rainfall_matrix' must be a matrix");
     const int64_t H = Rf_nrows(rainfall), C = Rf_ncols(rainfall);
-    if (Rf_nrows(air_temperature) != H || Rf_ncols(air_temperature) != C || Rf_nrows(humidity) != H ||
-        Rf_ncols(humidity) != C || Rf_nrows(windspeed) != H || Rf_ncols(windspeed) != C)
-        Rf_error("all microclimate matrices must have the same dimensions");
+    const double *rn = matrix_arg(rainfall, H, C, "rainfall_matrix");
+    const double *ta = matrix_arg(air_temperature, H, C, "air_temperature_matrix");
+    const double *rh = matrix_arg(humidity, H, C, "humidity_matrix");
+    const double *ws = matrix_arg(windspeed, H, C, "windspeed_matrix");
     if (Rf_xlength(altitude) != C) Rf_error("altitude_vector must have one element per pixel");
     mms_habitat hb = habitat_from(habitat);
-    SEXP area = PROTECT(Rf_allocMatrix(REALSXP, (int)H, (int)C));
-    check(mms_water_vectorised(REAL(rainfall), REAL(air_temperature), REAL(humidity), REAL(windspeed),
-                               REAL(altitude), H, C, &hb, Rf_asInteger(burnin_years), Rf_asInteger(math_mode),
+    SEXP area = PROTECT(alloc_matrix(H, C));
+    check(mms_water_vectorised(rn, ta, rh, ws, real_arg(altitude, "altitude_vector"), H, C, &hb,
+                               Rf_asInteger(burnin_years), Rf_asInteger(math_mode),
                                Rf_asInteger(device), REAL(area), NULL, NULL));
     SEXP out = PROTECT(Rf_allocVector(VECSXP, 1));
     SEXP names = PROTECT(Rf_allocVector(STRSXP, 1));
@@ -113,11 +162,18 @@ SEXP mms_R_population_vectorised(SEXP larval_habitat_area, SEXP mdr, SEXP efd, S
                                  SEXP densmod, SEXP initial_adult, SEXP initial_aquatic, SEXP burnin_years,
                                  SEXP math_mode, SEXP device)
 {
+    if (!Rf_isMatrix(larval_habitat_area)) Rf_error("mmsgpu: 'larval_habitat_area_matrix' must be a matrix");
     const int64_t H = Rf_nrows(larval_habitat_area), C = Rf_ncols(larval_habitat_area);
+    /* every matrix: double, and of the dimensions of the first (a mismatch would be an out-of-bounds host read) */
+    const double *area_in = matrix_arg(larval_habitat_area, H, C, "larval_habitat_area_matrix");
+    const double *mdr_in = matrix_arg(mdr, H, C, "mdr_matrix");
+    const double *efd_in = matrix_arg(efd, H, C, "efd_matrix");
+    const double *das_in = matrix_arg(das_zerodensity, H, C, "das_zerodensity_matrix");
+    const double *ds_in = matrix_arg(ds, H, C, "ds_matrix");
     mms_densmod dm = densmod_from(densmod);
-    SEXP aquatic = PROTECT(Rf_allocMatrix(REALSXP, (int)H, (int)C));
-    SEXP adult = PROTECT(Rf_allocMatrix(REALSXP, (int)H, (int)C));
-    check(mms_population_vectorised(REAL(larval_habitat_area), REAL(mdr), REAL(efd), REAL(das_zerodensity), REAL(ds),
+    SEXP aquatic = PROTECT(alloc_matrix(H, C));
+    SEXP adult = PROTECT(alloc_matrix(H, C));
+    check(mms_population_vectorised(area_in, mdr_in, efd_in, das_in, ds_in,
                                     H, C, &dm, Rf_asReal(initial_adult), Rf_asReal(initial_aquatic),
                                     Rf_asInteger(burnin_years), Rf_asInteger(math_mode), Rf_asInteger(device),
                                     REAL(aquatic), REAL(adult)));
@@ -185,10 +241,16 @@ SEXP mms_R_population_series(SEXP larval_habitat_area, SEXP mdr, SEXP efd, SEXP 
  *   habitats       list of habitat lists;  densmod list;  tables list(mdr=z, efd=z, das=z, ds=list(x,y,z))
  *   mean_var_mask  integer;  n_periods integer;  burnin_years_pop integer;  math_mode integer
  *   devices        integer vector of CUDA ordinals (length 0 = all)
- * Returns list(mean_state = [C, P, ns, S], mean_forcing = [C, P, nf], wet_hours = [C, P, S]). */
+ *   options        NULL, or a named list with the extensions:
+ *                    water_temperature = list(shade_proportion, albedo, emissivity, convection_w_m2_k,
+ *                                             day_of_year = integer [D], month_of_day = integer [D],
+ *                                             latitude = double [C], clear_sky = double [C, 12])
+ *                    cell_idx = double [C] 0-based raster cell numbers (strictly increasing), n_raster_cells = double
+ * Returns list(mean_state = [R, P, ns, S], mean_forcing = [R, P, nf], wet_hours = [R, P, S]) with R = C, or
+ * n_raster_cells when cell_idx is given (every [ , p, v, s] column is then a whole raster slice). */
 static SEXP run_chain_impl(SEXP monthly, SEXP terraclimate, SEXP altitude, SEXP mid_day, SEXP day_predict,
                            SEXP period_of_day, SEXP habitats, SEXP densmod, SEXP tables, SEXP mean_var_mask,
-                           SEXP n_periods, SEXP burnin_years_pop, SEXP math_mode, SEXP devices)
+                           SEXP n_periods, SEXP burnin_years_pop, SEXP math_mode, SEXP devices, SEXP options)
 {
     mms_chain_config cfg;
     memset(&cfg, 0, sizeof cfg);
@@ -200,9 +262,10 @@ static SEXP run_chain_impl(SEXP monthly, SEXP terraclimate, SEXP altitude, SEXP 
     if (terraclimate == R_NilValue && Rf_xlength(monthly) != (R_xlen_t)cfg.n_cells * cfg.n_months * MMS_NFORCING)
         Rf_error("monthly must be a [cells, months, 9] array");
     if (cfg.n_settings < 1 || cfg.n_settings > MMS_MAX_SETTINGS) Rf_error("1 to %d habitat settings", MMS_MAX_SETTINGS);
-    cfg.mid_day = REAL(mid_day);
-    cfg.day_predict = REAL(day_predict);
-    cfg.period_of_day = (const int32_t *)INTEGER(period_of_day);
+    cfg.mid_day = real_arg(mid_day, "mid_day");
+    cfg.day_predict = real_arg(day_predict, "day_predict");
+    if (Rf_xlength(period_of_day) != cfg.n_days) Rf_error("period_of_day must have one entry per simulated day");
+    cfg.period_of_day = (const int32_t *)int_arg(period_of_day, "period_of_day");
     mms_habitat hab[MMS_MAX_SETTINGS];
     for (int s = 0; s < cfg.n_settings; ++s) hab[s] = habitat_from(VECTOR_ELT(habitats, s));
     cfg.habitats = hab;
@@ -224,12 +287,45 @@ static SEXP run_chain_impl(SEXP monthly, SEXP terraclimate, SEXP altitude, SEXP 
     cfg.want_wet_hours = 1;
     cfg.math_mode = Rf_asInteger(math_mode);
     cfg.n_devices = (int32_t)Rf_xlength(devices);
-    cfg.devices = cfg.n_devices ? (const int32_t *)INTEGER(devices) : NULL;
+    cfg.devices = cfg.n_devices ? (const int32_t *)int_arg(devices, "devices") : NULL;
+
+    /* extensions: the water-temperature model, rows scattered into raster cell order */
+    SEXP wt = list_get_opt(options, "water_temperature");
+    const double *latitude = NULL, *wt_clear_sky = NULL;
+    if (wt != R_NilValue) {
+        cfg.water_temperature.enabled = 1;
+        cfg.water_temperature.shade_proportion = Rf_asReal(list_get(wt, "shade_proportion"));
+        cfg.water_temperature.albedo = Rf_asReal(list_get(wt, "albedo"));
+        cfg.water_temperature.emissivity = Rf_asReal(list_get(wt, "emissivity"));
+        cfg.water_temperature.convection_w_m2_k = Rf_asReal(list_get(wt, "convection_w_m2_k"));
+        SEXP doy = list_get(wt, "day_of_year"), mon = list_get(wt, "month_of_day");
+        if (Rf_xlength(doy) != cfg.n_days || Rf_xlength(mon) != cfg.n_days)
+            Rf_error("day_of_year and month_of_day must have one entry per simulated day");
+        cfg.water_temperature.day_of_year = (const int32_t *)int_arg(doy, "day_of_year");
+        cfg.water_temperature.month_of_day = (const int32_t *)int_arg(mon, "month_of_day");
+        if (Rf_xlength(list_get(wt, "latitude")) != (R_xlen_t)cfg.n_cells ||
+            Rf_xlength(list_get(wt, "clear_sky")) != (R_xlen_t)cfg.n_cells * 12)
+            Rf_error("latitude must have one entry per pixel and clear_sky be a [cells, 12] matrix");
+        latitude = real_arg(list_get(wt, "latitude"), "latitude");
+        wt_clear_sky = real_arg(list_get(wt, "clear_sky"), "clear_sky");
+    }
+    SEXP cell_idx = list_get_opt(options, "cell_idx");
+    R_xlen_t n_out = (R_xlen_t)cfg.n_cells;
+    if (cell_idx != R_NilValue) {
+        if (Rf_xlength(cell_idx) != (R_xlen_t)cfg.n_cells) Rf_error("cell_idx must have one entry per pixel");
+        const double *ci = real_arg(cell_idx, "cell_idx");
+        int64_t *idx = (int64_t *)R_alloc((size_t)cfg.n_cells, sizeof(int64_t));      /* freed by R at the end of .Call */
+        for (int64_t c = 0; c < cfg.n_cells; ++c) idx[c] = (int64_t)ci[c];
+        cfg.raster_cell_idx = idx;
+        cfg.n_raster_cells = (int64_t)Rf_asReal(list_get(options, "n_raster_cells"));
+        if (cfg.n_raster_cells < cfg.n_cells) Rf_error("n_raster_cells is smaller than the number of pixels");
+        n_out = (R_xlen_t)cfg.n_raster_cells;
+    }
 
     int ns = 0, nf = 0;
     for (int v = 0; v < MMS_NVARS; ++v)
         if (cfg.mean_var_mask >> v & 1u) { if (MMS_STATE_VAR_MASK >> v & 1u) ++ns; else ++nf; }
-    const R_xlen_t C = (R_xlen_t)cfg.n_cells, P = cfg.n_periods, S = cfg.n_settings;
+    const R_xlen_t C = n_out, P = cfg.n_periods, S = cfg.n_settings;
     SEXP mean_state = PROTECT(Rf_allocVector(REALSXP, C * P * ns * S));
     SEXP mean_forcing = PROTECT(Rf_allocVector(REALSXP, C * P * nf));
     SEXP wet_hours = PROTECT(Rf_allocVector(INTSXP, C * P * S));
@@ -238,20 +334,32 @@ static SEXP run_chain_impl(SEXP monthly, SEXP terraclimate, SEXP altitude, SEXP 
     out.mean_state = REAL(mean_state);
     out.mean_forcing = REAL(mean_forcing);
     out.wet_hours = (int32_t *)INTEGER(wet_hours);
-    if (terraclimate == R_NilValue) {
-        check(mms_run_chain(&cfg, REAL(monthly), REAL(altitude), &out));
+    /* create, [set_location,] run (upload, kernels and download pipelined in chunks), destroy -- the plan is
+     * destroyed before an error is raised (Rf_error does not return) */
+    mms_chain_plan *plan = NULL;
+    check(mms_chain_create(&cfg, &plan));
+    int rc = MMS_OK;
+    if (wt != R_NilValue) rc = mms_chain_set_location(plan, latitude, wt_clear_sky);
+    if (rc != MMS_OK) {
+    } else if (terraclimate == R_NilValue) {
+        rc = mms_chain_run(plan, real_arg(monthly, "monthly"), real_arg(altitude, "altitude"), &out);
     } else {
         /* list(values = [cells, months, 6], clear_sky = [cells, 12], month_id = integer [months], n_days = double [months]) */
         SEXP values = list_get(terraclimate, "values"), clear_sky = list_get(terraclimate, "clear_sky");
         SEXP month_id = list_get(terraclimate, "month_id"), n_days = list_get(terraclimate, "n_days");
-        if (Rf_xlength(values) != (R_xlen_t)cfg.n_cells * cfg.n_months * MMS_NTERRACLIMATE)
-            Rf_error("terraclimate values must be a [cells, months, 6] array");
-        if (Rf_xlength(clear_sky) != (R_xlen_t)cfg.n_cells * 12) Rf_error("clear_sky must be a [cells, 12] matrix");
-        if (Rf_xlength(month_id) != cfg.n_months || Rf_xlength(n_days) != cfg.n_months)
-            Rf_error("month_id and n_days must have one entry per month");
-        check(mms_run_chain_terraclimate(&cfg, REAL(values), REAL(clear_sky), (const int32_t *)INTEGER(month_id),
-                                         REAL(n_days), REAL(altitude), &out));
+        if (Rf_xlength(values) != (R_xlen_t)cfg.n_cells * cfg.n_months * MMS_NTERRACLIMATE ||
+            Rf_xlength(clear_sky) != (R_xlen_t)cfg.n_cells * 12 || Rf_xlength(month_id) != cfg.n_months ||
+            Rf_xlength(n_days) != cfg.n_months || TYPEOF(values) != REALSXP || TYPEOF(clear_sky) != REALSXP ||
+            TYPEOF(month_id) != INTSXP || TYPEOF(n_days) != REALSXP || TYPEOF(altitude) != REALSXP) {
+            mms_chain_destroy(plan);
+            Rf_error("terraclimate must be list(values = double [cells, months, 6], clear_sky = double [cells, 12], "
+                     "month_id = integer [months], n_days = double [months])");
+        }
+        rc = mms_chain_run_terraclimate(plan, REAL(values), REAL(clear_sky), (const int32_t *)INTEGER(month_id),
+                                        REAL(n_days), REAL(altitude), &out);
     }
+    mms_chain_destroy(plan);
+    check(rc);
 
     SEXP res = PROTECT(Rf_allocVector(VECSXP, 3));
     SEXP names = PROTECT(Rf_allocVector(STRSXP, 3));
@@ -268,10 +376,10 @@ static SEXP run_chain_impl(SEXP monthly, SEXP terraclimate, SEXP altitude, SEXP 
 
 SEXP mms_R_run_chain(SEXP monthly, SEXP altitude, SEXP mid_day, SEXP day_predict, SEXP period_of_day,
                      SEXP habitats, SEXP densmod, SEXP tables, SEXP mean_var_mask, SEXP n_periods,
-                     SEXP burnin_years_pop, SEXP math_mode, SEXP devices)
+                     SEXP burnin_years_pop, SEXP math_mode, SEXP devices, SEXP options)
 {
     return run_chain_impl(monthly, R_NilValue, altitude, mid_day, day_predict, period_of_day, habitats, densmod,
-                          tables, mean_var_mask, n_periods, burnin_years_pop, math_mode, devices);
+                          tables, mean_var_mask, n_periods, burnin_years_pop, math_mode, devices, options);
 }
 
 /* The same from the raw TerraClimate variables (tc_to_vectors() whole, R/pipeline_functions.R:1099-1130):
@@ -279,10 +387,10 @@ SEXP mms_R_run_chain(SEXP monthly, SEXP altitude, SEXP mid_day, SEXP day_predict
 SEXP mms_R_run_chain_terraclimate(SEXP terraclimate, SEXP altitude, SEXP mid_day, SEXP day_predict,
                                   SEXP period_of_day, SEXP habitats, SEXP densmod, SEXP tables,
                                   SEXP mean_var_mask, SEXP n_periods, SEXP burnin_years_pop, SEXP math_mode,
-                                  SEXP devices)
+                                  SEXP devices, SEXP options)
 {
     return run_chain_impl(R_NilValue, terraclimate, altitude, mid_day, day_predict, period_of_day, habitats,
-                          densmod, tables, mean_var_mask, n_periods, burnin_years_pop, math_mode, devices);
+                          densmod, tables, mean_var_mask, n_periods, burnin_years_pop, math_mode, devices, options);
 }
 
 /* process_terraclimate_pixel_vars() for a tile: values [C, M, 6], clear_sky [C, 12] -> monthly [C, M, 9] */
@@ -383,8 +491,8 @@ static const R_CallMethodDef call_methods[] = {
     {"mms_R_population_vectorised", (DL_FUNC)&mms_R_population_vectorised, 11},
     {"mms_R_water_series", (DL_FUNC)&mms_R_water_series, 9},
     {"mms_R_population_series", (DL_FUNC)&mms_R_population_series, 11},
-    {"mms_R_run_chain", (DL_FUNC)&mms_R_run_chain, 13},
-    {"mms_R_run_chain_terraclimate", (DL_FUNC)&mms_R_run_chain_terraclimate, 13},
+    {"mms_R_run_chain", (DL_FUNC)&mms_R_run_chain, 14},
+    {"mms_R_run_chain_terraclimate", (DL_FUNC)&mms_R_run_chain_terraclimate, 14},
     {"mms_R_terraclimate_to_monthly", (DL_FUNC)&mms_R_terraclimate_to_monthly, 7},
     {"mms_R_summarise_vectors", (DL_FUNC)&mms_R_summarise_vectors, 6},
     {NULL, NULL, 0}};

@@ -6,7 +6,10 @@
 #define INTSXP 13
 #define STRSXP 16
 #define VECSXP 19
-extern SEXP R_NilValue, R_NamesSymbol;
+extern SEXP R_NilValue, R_NamesSymbol, R_DimSymbol;
+int TYPEOF(SEXP);
+int Rf_isMatrix(SEXP);            /* Rboolean in R */
+char *R_alloc(size_t, int);       /* R_ext/Memory.h */
 double *REAL(SEXP);
 int *INTEGER(SEXP);
 SEXP Rf_allocVector(unsigned int, R_xlen_t);

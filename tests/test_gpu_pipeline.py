@@ -8,7 +8,7 @@ import pytest
 
 import oracle
 from helpers import ORACLE_VAR, REL_TOL_FAST, Case, rel_err
-from mosmicrosim_b200 import backend, dates, lifehistory as lh, synthetic as syn
+from mosmicrosim_b200 import backend, dates, lifehistory as lh, pipeline, synthetic as syn
 from test_gpu_chain import compare
 
 pytestmark = pytest.mark.gpu
@@ -251,3 +251,33 @@ def test_ensemble_forms(gpu, monkeypatch, n_settings, fan):
         out2 = backend.run_chain(c2.monthly, c2.altitude, **c2.gpu_kwargs(mean_vars=["adult", "aquatic"], want_wet_hours=True,
                                                                           burnin_years_water=1))
         compare(c2, out2, c2.oracle(want_hourly=False, burnin_years_water=1), REL_TOL_FAST, what=("mean",))
+
+
+def test_april_start_series_errors_by_default_and_runs_clipped(gpu):
+    """The default dates of a series that starts in a 30-day month overhang the knots by half a day (the reference's
+    GAM branch): MMS_ERR_EXTRAPOLATION by default, the clipped run equals the oracle on the clipped dates."""
+    months = np.datetime64("2001-04", "M") + np.arange(23)                 # April 2001 .. February 2003
+    start = months.astype("datetime64[D]")
+    end = (months + 1).astype("datetime64[D]") - np.timedelta64(1, "D")
+    C = 25
+    monthly, altitude = syn.synthetic_forcing(C, start, out_of_range_fraction=0.0)
+    case = Case(n_cells=C)
+    pmc = {"start": start, "end": end, "altitude": altitude, "longitude": np.arange(C * 1.0), "latitude": np.arange(C * 1.0)}
+    for v, name in enumerate(pipeline.FORCING_VARS):
+        pmc[name] = monthly[v]
+    lhf = {"An_gambiae": case.lh, "An_stephensi": syn.synthetic_lifehistory("An. stephensi")}
+    with pytest.raises(backend.MmsError) as e:
+        pipeline.monthly_climate_to_vectors(pmc, lhf)
+    assert e.value.code == "MMS_ERR_EXTRAPOLATION"
+    with pytest.warns(UserWarning, match="dropped"):
+        res = pipeline.monthly_climate_to_vectors(pmc, lhf, on_extrapolation="clip")
+    dp, dropped = dates.clip_dates_predict(start, end, dates.default_dates_predict(start, end))
+    assert dropped == 2
+    mid_day, day_predict = dates.datenums(start, end, dp)
+    pod, ps, _ = dates.period_index(dp, "month")
+    dm = case.densmod
+    ref = oracle.run_chain(monthly, mid_day, day_predict, altitude, [oracle.habitat()],
+                           oracle.densmod(dm["type_"], dm["dd_effect"], dm["surface_area_cm2"]), case.tables, pod, len(ps),
+                           want_hourly=False)
+    for name in pipeline.VECTOR_VARIABLES:
+        assert rel_err(res[name], ref["mean"][0, ORACLE_VAR[name]]) <= REL_TOL_FAST, name

@@ -171,6 +171,26 @@ def test_pipeline_argument_handling_mirrors_the_reference():
             assert any("water_shade_proportion" in str(x.message) for x in wlist)
 
 
+def test_half_day_overhang_of_the_default_dates_is_detected_and_clipped():
+    """A series that starts in a 30-day month (April) and ends in a non-leap February: the reference's default
+    dates_predict (midpoint rounded half to even, R/sim_microclimate.R:14-24) starts half a day BEFORE the first knot
+    (unrounded midpoint, :31) and ends half a day AFTER the last one -> its GAM branch.  The library refuses
+    (MMS_ERR_EXTRAPOLATION); the mirrors can clip those days with a warning."""
+    months = np.datetime64("2001-04", "M") + np.arange(11)                 # April 2001 .. February 2002
+    start = months.astype("datetime64[D]")
+    end = (months + 1).astype("datetime64[D]") - np.timedelta64(1, "D")
+    dp = dates.default_dates_predict(start, end)
+    mid_day, day_predict = dates.datenums(start, end, dp)
+    assert mid_day[0] == 0.0 and day_predict[0] == -0.5 and day_predict[-1] == mid_day[-1] + 0.5
+    assert dates.needs_extrapolation(mid_day, day_predict)
+    clipped, dropped = dates.clip_dates_predict(start, end, dp)
+    assert dropped == 2 and len(clipped) == len(dp) - 2
+    assert not dates.needs_extrapolation(*dates.datenums(start, end, clipped))
+    # a December .. January series (what monthly_summary_days() produces, R/terraclimate.R:91-98) needs no clipping
+    s2, e2 = syn.month_table(2001, 1)
+    assert dates.clip_dates_predict(s2, e2, dates.default_dates_predict(s2, e2))[1] == 0
+
+
 # ---- one process per GPU: shards == whole (gloo, world size 2, CPU) --------------------------
 
 WORKER = r"""
