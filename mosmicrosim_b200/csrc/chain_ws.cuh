@@ -71,6 +71,53 @@ constexpr int kWsRingDoubles = kWsSlots * kWsK * kWsFields * 32 + 2 * kWsSlots; 
 #define MMS_WS_DSPREFETCH 0
 #endif
 
+// Which role evaluates the last, transcendental step of the three per-cell-hour products that do not depend on the
+// setting: bit 0 the density-free link of das0 (division + log), bit 1 exp(-mdr / 24), bit 2 ds^(1/24) (log + exp).
+// A set bit moves that step from the forcing warp (which then hands over the raw rate) to the state warp.  The
+// forcing warp is the critical role of the pair: ncu (profiles/r02_ncu_chain_ws.txt) has the state warps waiting
+// at the hand-off barrier for a quarter of their time.
+// MEASURED (BASELINE configs[1], ms per launch; 52.8 with everything in the forcing warp): bit 0 alone 51.4, bit 1 alone
+// 52.1, bits 0+1 55.0, bit 2 alone 53.0, bits 0+2 56.9, all three 61.1 -- the two roles are within a few per cent of
+// each other, whatever the barrier-stall samples suggest.  Default: the link moves (the pair kernel only; in the
+// fan-out kernel sixteen state warps would each repeat it).
+#ifndef MMS_WS_SPLIT
+#define MMS_WS_SPLIT 1
+#endif
+constexpr int kWsSplit = MMS_WS_SPLIT;
+
+// hour_forcing() (chain_kernel.cuh) without the steps that MMS_WS_SPLIT leaves to the state warp
+template <bool kFull, bool kWaterOnly, int kSplit>
+__device__ __forceinline__ HourF hour_forcing_ws(const ChainParams &p, const SmemTables &tb, const DayCtx &dc,
+                                                 double p_a, int h, int dens_type)
+{
+    if (kSplit == 0) return hour_forcing<kFull, kWaterOnly>(p, tb, dc, p_a, h, dens_type);
+    HourF f;
+    hour_microclimate<kFull>(p.hr, dc, h, f);
+    f.mdr = f.efd = f.das0 = f.ds = 0.0;
+    double dx = 0.0;
+    double4 c0 = make_double4(0, 0, 0, 0), c1 = c0, c2 = c0;
+    DsFetch dsf;
+    if (!kWaterOnly) {
+        dsf = ds_fetch(p.ds, f.air_t, f.rh);
+        const int i = spline_interval(p.spline, tb.sx, f.air_t);
+        dx = f.air_t - tb.sx[i];
+        const double4 *cf = reinterpret_cast<const double4 *>(tb.coef + (size_t)i * 12);
+        c0 = cf[0]; c1 = cf[1]; c2 = cf[2];
+    }
+    f.evap = evaporation_rate(f.air_t, f.rh, p_a, f.wind);
+    if (!kWaterOnly) {
+        f.ds = ds_blend(dsf);
+        f.mdr = ensure_positive(c0.x + dx * (c0.y + dx * (c0.z + dx * c0.w)));
+        f.efd = ensure_positive(c1.x + dx * (c1.y + dx * (c1.z + dx * c1.w)));
+        f.das0 = ensure_positive(c2.x + dx * (c2.y + dx * (c2.z + dx * c2.w)));
+        f.ph.egg = f.efd * kLitC[3];
+        f.ph.surv_ad = (kSplit & 4) ? f.ds : r_pow_pos(f.ds, kLitC[3]);
+        f.ph.one_m_emf = (kSplit & 2) ? f.mdr : pop_emergence_complement(f.mdr);
+        f.ph.link0 = (kSplit & 1) ? f.das0 : pop_link0(dens_type, f.das0);
+    }
+    return f;
+}
+
 // prefetch.global.L1 of the quad record the ds look-up of (temperature, humidity) will read
 __device__ __forceinline__ void ds_prefetch_l1(const SurfaceDev &g, double temperature, double humidity)
 {
@@ -239,7 +286,7 @@ struct PeriodCursor {
 };
 
 // ---- forcing warp ---------------------------------------------------------------------------
-template <bool kFull, bool kHourly, bool kWaterOnly, bool kRecord, int kDens>
+template <bool kFull, bool kHourly, bool kWaterOnly, bool kRecord, int kDens, int kSplit>
 __device__ __forceinline__ void forcing_pass(const ChainParams &p, const SmemTables &tb, const UnitCtx &u,
                                              RingEnd &ring, int n_days, int &bad)
 {
@@ -313,7 +360,7 @@ __device__ __forceinline__ void forcing_pass(const ChainParams &p, const SmemTab
 #if MMS_WS_DSPREFETCH == 1
                 const HourF f = hour_forcing_from<kFull, kWaterOnly>(p, tb, now, u.p_a, kDens >= 0 ? (kDens & 1) : p.densmod_type);
 #else
-                const HourF f = hour_forcing<kFull, kWaterOnly>(p, tb, dc, u.p_a, h, kDens >= 0 ? (kDens & 1) : p.densmod_type);
+                const HourF f = hour_forcing_ws<kFull, kWaterOnly, kSplit>(p, tb, dc, u.p_a, h, kDens >= 0 ? (kDens & 1) : p.densmod_type);
 #endif
                 double *rec = slot + (size_t)k * (kWsFields * 32);
                 rec[0 * 32] = f.evap;
@@ -362,7 +409,7 @@ __device__ __forceinline__ void forcing_pass(const ChainParams &p, const SmemTab
 }
 
 // ---- state warp ------------------------------------------------------------------------------
-template <int kNS, bool kFull, bool kHourly, bool kWaterOnly, bool kRecord, int kDens>
+template <int kNS, bool kFull, bool kHourly, bool kWaterOnly, bool kRecord, int kDens, int kSplit>
 __device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &u, UnitState<kNS> &st,
                                            RingEnd &ring, int n_days)
 {
@@ -422,11 +469,17 @@ __device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &
                 PopHour ph;
                 ph.surv_ad = rec[1 * 32];
                 ph.one_m_emf = rec[2 * 32];
-                ph.emf = 1.0 - ph.one_m_emf;
                 ph.egg = rec[3 * 32];
                 ph.link0 = rec[4 * 32];
                 const double gain_m_h = rec[5 * 32];
                 if (k == kWsK - 1) ring_release(ring);   // the values are in registers: the forcing warp may refill the slot
+                if (!kWaterOnly) {
+                    // the steps MMS_WS_SPLIT moved here: same device functions on the same values, same results
+                    if (kSplit & 4) ph.surv_ad = r_pow_pos(ph.surv_ad, kLitC[3]);
+                    if (kSplit & 2) ph.one_m_emf = pop_emergence_complement(ph.one_m_emf);
+                    if (kSplit & 1) ph.link0 = pop_link0(kDens >= 0 ? (kDens & 1) : p.densmod_type, ph.link0);
+                }
+                ph.emf = 1.0 - ph.one_m_emf;
 #pragma unroll
                 for (int s = 0; s < kNS; ++s) {
                     const HabitatDev &hb = p.hab[u.set0 + s];
@@ -478,7 +531,7 @@ __device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &
 // one work unit in one role: water burn-in years (R/sim_water.R:228-233), population burn-in years
 // (R/sim_pop_dynamics.R:221-226), then the full series -- identical loop structure in both roles, so the warps of
 // a team meet at every barrier
-template <int kNS, bool kFull, bool kHourly, int kDens>
+template <int kNS, bool kFull, bool kHourly, int kDens, int kSplit>
 __device__ __forceinline__ void role_unit(const ChainParams &p, const SmemTables &tb, UnitCtx &u, RingEnd &ring,
                                           bool forcing_role)
 {
@@ -486,10 +539,10 @@ __device__ __forceinline__ void role_unit(const ChainParams &p, const SmemTables
         u.p_a = air_pressure_kpa(__ldg(p.altitude + u.cell));
         int bad = 0;
         for (int y = 0; y < p.burnin_years_water; ++y)
-            forcing_pass<kFull, kHourly, true, false, kDens>(p, tb, u, ring, kDaysPerYear, bad);
+            forcing_pass<kFull, kHourly, true, false, kDens, kSplit>(p, tb, u, ring, kDaysPerYear, bad);
         for (int y = 0; y < p.burnin_years_pop; ++y)
-            forcing_pass<kFull, kHourly, false, false, kDens>(p, tb, u, ring, kDaysPerYear, bad);
-        forcing_pass<kFull, kHourly, false, true, kDens>(p, tb, u, ring, p.D, bad);
+            forcing_pass<kFull, kHourly, false, false, kDens, kSplit>(p, tb, u, ring, kDaysPerYear, bad);
+        forcing_pass<kFull, kHourly, false, true, kDens, kSplit>(p, tb, u, ring, p.D, bad);
         if (bad && u.live) atomicOr(p.error_flag, 1);
     } else {
         u.p_a = 0.0;
@@ -502,19 +555,19 @@ __device__ __forceinline__ void role_unit(const ChainParams &p, const SmemTables
             st.surface[s] = habitat_surface(p.hab[u.set0 + s], st.volume[s]);
         }
         for (int y = 0; y < p.burnin_years_water; ++y)
-            state_pass<kNS, kFull, kHourly, true, false, kDens>(p, u, st, ring, kDaysPerYear);
+            state_pass<kNS, kFull, kHourly, true, false, kDens, kSplit>(p, u, st, ring, kDaysPerYear);
         double vol0[kNS];
 #pragma unroll
         for (int s = 0; s < kNS; ++s) vol0[s] = st.volume[s];
         for (int y = 0; y < p.burnin_years_pop; ++y) {
-            state_pass<kNS, kFull, kHourly, false, false, kDens>(p, u, st, ring, kDaysPerYear);
+            state_pass<kNS, kFull, kHourly, false, false, kDens, kSplit>(p, u, st, ring, kDaysPerYear);
 #pragma unroll
             for (int s = 0; s < kNS; ++s) {
                 st.volume[s] = vol0[s];
                 st.surface[s] = habitat_surface(p.hab[u.set0 + s], vol0[s]);
             }
         }
-        state_pass<kNS, kFull, kHourly, false, true, kDens>(p, u, st, ring, p.D);
+        state_pass<kNS, kFull, kHourly, false, true, kDens, kSplit>(p, u, st, ring, p.D);
     }
 }
 
@@ -571,7 +624,7 @@ chain_kernel_ws(const __grid_constant__ ChainParams p)
         u.ocell = (p.out_col && u.live) ? __ldg(p.out_col + u.cell) : u.cell;
         u.n_mean_state = __popc(p.mean_mask & MMS_STATE_VAR_MASK);
         u.n_hourly_state = __popc(p.hourly_mask & MMS_STATE_VAR_MASK);
-        role_unit<kNS, kFull, kHourly, kDens>(p, tb, u, ring, forcing_role);
+        role_unit<kNS, kFull, kHourly, kDens, kWsSplit>(p, tb, u, ring, forcing_role);
     }
 }
 
@@ -626,7 +679,7 @@ chain_kernel_fan(const __grid_constant__ ChainParams p, int groups)
         u.ocell = (p.out_col && u.live) ? __ldg(p.out_col + u.cell) : u.cell;
         u.n_mean_state = __popc(p.mean_mask & MMS_STATE_VAR_MASK);
         u.n_hourly_state = __popc(p.hourly_mask & MMS_STATE_VAR_MASK);
-        role_unit<kNS, kFull, kHourly, kDens>(p, tb, u, ring, forcing_role);
+        role_unit<kNS, kFull, kHourly, kDens, 0>(p, tb, u, ring, forcing_role);
     }
 }
 

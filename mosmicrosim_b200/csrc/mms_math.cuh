@@ -157,25 +157,24 @@ __device__ __forceinline__ void pop_hour_air(PopHour &ph, double efd, double ds)
     ph.egg = efd * MMS_LIT(3, kTimestep);
 }
 
-// the part that takes the WATER temperature rates (R/sim_pop_dynamics.R:108,114): emergence, density-free link
-__device__ __forceinline__ void pop_hour_water(PopHour &ph, int densmod_type, double mdr, double das0)
+// exp(-timestep * mdr): 1 - emergence_fraction, R/sim_pop_dynamics.R:58-59,74
+__device__ __forceinline__ double pop_emergence_complement(double mdr)
 {
 #if MMS_STRICT
-    const double e = exp(-(kTimestep * mdr));
+    return exp(-(kTimestep * mdr));
 #else
-    const double e = ::mms::fm::exp_core(kLitC[4] * mdr);   // mdr is a clamped spline value: 0 <= mdr << 708 * 24
+    return ::mms::fm::exp_core(kLitC[4] * mdr);   // mdr is a clamped spline value: 0 <= mdr << 708 * 24
 #endif
-    ph.emf = 1.0 - e;
-#if MMS_STRICT
-    ph.one_m_emf = 1.0 - ph.emf;
-#else
-    ph.one_m_emf = e;
-#endif
+}
+
+// the density-free part of the density dependence: logit(das0), or the cox_ph link of das0
+// (R/lifehistory_estimation_functions.R:551-553 / :533,:571)
+__device__ __forceinline__ double pop_link0(int densmod_type, double das0)
+{
     if (densmod_type == 1) {
-        // cox_ph, R/lifehistory_estimation_functions.R:551-553
         const double daily_mortality_zero_density = 1.0 - das0;
 #if MMS_STRICT
-        ph.link0 = log(-log(1.0 - daily_mortality_zero_density));
+        return log(-log(1.0 - daily_mortality_zero_density));
 #else
         // log p'; exp(loghaz) = -log p' * exp(dd*D).  A spline that overshoots 1 (positive_spline clamps at 0 only):
         // p' > 1 -> the reference takes log(-log p') of a negative number: NaN; p' == 1 -> log(-0) = -Inf, das_t = 1:
@@ -183,18 +182,30 @@ __device__ __forceinline__ void pop_hour_water(PopHour &ph, int densmod_type, do
         const double pp = 1.0 - daily_mortality_zero_density;
         double lp = ::mms::fm::log_nonneg(pp);
         lp = ::mms::fm::sel(pp == 1.0, 0.0, lp);
-        ph.link0 = ::mms::fm::sel(pp > 1.0, ::mms::fm::make_nan(), lp);
-#endif
-    } else {
-#if MMS_STRICT
-        ph.link0 = log(das0 / (1.0 - das0));                         // logit(), :533,:571
-#else
-        const double om = 1.0 - das0;                                // das0 == 1 -> p / 0 = +Inf like R
-        const double odds = ::mms::fm::sel(om == 0.0, ::mms::fm::make_inf(),
-                                           ::mms::fm::div_fast(das0, ::mms::fm::sel(om == 0.0, 1.0, om)));
-        ph.link0 = ::mms::fm::log_nonneg(odds);
+        return ::mms::fm::sel(pp > 1.0, ::mms::fm::make_nan(), lp);
 #endif
     }
+#if MMS_STRICT
+    return log(das0 / (1.0 - das0));                             // logit(), :533,:571
+#else
+    const double om = 1.0 - das0;                                // das0 == 1 -> p / 0 = +Inf like R
+    const double odds = ::mms::fm::sel(om == 0.0, ::mms::fm::make_inf(),
+                                       ::mms::fm::div_fast(das0, ::mms::fm::sel(om == 0.0, 1.0, om)));
+    return ::mms::fm::log_nonneg(odds);
+#endif
+}
+
+// the part that takes the WATER temperature rates (R/sim_pop_dynamics.R:108,114): emergence, density-free link
+__device__ __forceinline__ void pop_hour_water(PopHour &ph, int densmod_type, double mdr, double das0)
+{
+    const double e = pop_emergence_complement(mdr);
+    ph.emf = 1.0 - e;
+#if MMS_STRICT
+    ph.one_m_emf = 1.0 - ph.emf;
+#else
+    ph.one_m_emf = e;
+#endif
+    ph.link0 = pop_link0(densmod_type, das0);
 }
 
 __device__ __forceinline__ PopHour pop_hour(int densmod_type, double mdr, double efd, double das0, double ds)

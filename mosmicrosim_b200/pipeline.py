@@ -119,7 +119,8 @@ def _monthly_array(pixel_monthly_climate):
     return start, end, monthly, altitude
 
 
-def interpolate_daily_climate(pixel_monthly_climate, dates_predict=None, *, math_mode="fast", device=0):
+def interpolate_daily_climate(pixel_monthly_climate, dates_predict=None, *, on_extrapolation="error", math_mode="fast",
+                              device=0):
     """interpolate_daily_climate() (R/pipeline_functions.R:258-275): monthly -> daily for every
     pixel of the tile.  Returns the tile's `daily_climate` tibbles side by side: a dict with
     `date` [D], the pixel columns carried through, and one [D, C] array per daily variable."""
