@@ -65,11 +65,12 @@ def main(raw_csv, src_csv, warp_hours):
         ops = [data[k][idx["Source"]].split()[0 if not data[k][idx["Source"]].strip().startswith("@") else 1] for k in range(a, b)]
         n_fp = sum(1 for o in ops if o.startswith(fp64))
         smp = sum(int(data[k][idx["# Samples"]]) for k in range(a, b))
-        role = "forcing (writes the ring: STS)" if any(o.startswith("STS") for o in ops) else \
-               ("state (reads the ring: LDS after the barrier)" if any(o.startswith("BAR") for o in ops[:4]) or True else "")
+        has_bar = any(o.startswith("BAR") for o in ops)
+        role = "forcing warp (writes the ring: STS)" if has_bar and any(o.startswith("STS") for o in ops) else \
+               ("state warp (reads the ring after the barrier)" if has_bar else "hour loop (one role: monolithic form)")
         st = {s: sum(int(data[k][idx[s]]) for k in range(a, b)) for s in STALLS if s in idx}
         st = {k: v for k, v in st.items() if v}
-        print(f"  instr {a:5d}..{b:5d}: {b - a:4d} instructions / warp-hour, {n_fp:3d} FP64, {smp:8d} samples, role guess: {role}")
+        print(f"  instr {a:5d}..{b:5d}: {b - a:4d} instructions / warp-hour, {n_fp:3d} FP64, {smp:8d} samples, {role}")
         print("      stalls: " + ", ".join(f"{k[6:]} {v} ({100.0 * v / max(smp, 1):.0f} %)" for k, v in sorted(st.items(), key=lambda kv: -kv[1])))
     # opcode mix over everything
     mix = {}
