@@ -265,7 +265,7 @@ __device__ __forceinline__ HourF hour_forcing(const ChainParams &p, const SmemTa
 #endif
         const int i = spline_interval(p.spline, tb.sx, f.air_t);
         dx = f.air_t - tb.sx[i];
-        const double4 *cf = reinterpret_cast<const double4 *>(tb.coef + (size_t)i * 12);
+        const double4 *cf = reinterpret_cast<const double4 *>(tb.coef + (size_t)i * kSplineRow);
         c0 = cf[0]; c1 = cf[1]; c2 = cf[2];
     }
     // ---- evaporation rate per unit area, R/sim_water.R:264-270 (air temperature)
@@ -436,7 +436,7 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
                     if (!kWaterOnly) {
                         const int i = spline_interval(p.spline, tb.sx, tw);        // R/sim_pop_dynamics.R:108,114
                         const double dx = tw - tb.sx[i];
-                        const double4 *cf = reinterpret_cast<const double4 *>(tb.coef + (size_t)i * 12);
+                        const double4 *cf = reinterpret_cast<const double4 *>(tb.coef + (size_t)i * kSplineRow);
                         const double4 c0 = cf[0], c2 = cf[2];
                         fx.mdr = ensure_positive(c0.x + dx * (c0.y + dx * (c0.z + dx * c0.w)));
                         fx.das0 = ensure_positive(c2.x + dx * (c2.y + dx * (c2.z + dx * c2.w)));
@@ -600,10 +600,10 @@ chain_kernel(const __grid_constant__ ChainParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_coef = reinterpret_cast<double *>(smem_raw);              // [n][3][4]
-    double *s_x = s_coef + (size_t)p.spline.n * 12;                     // [n]
+    double *s_x = s_coef + (size_t)p.spline.n * kSplineRow;                     // [n]
     double *s_gx = s_x + p.spline.n;                                    // [nx]
     double *s_gy = s_gx + p.ds.nx;                                      // [ny]
-    for (int k = threadIdx.x; k < p.spline.n * 12; k += blockDim.x) s_coef[k] = p.spline.coef[k];
+    for (int k = threadIdx.x; k < p.spline.n * 12; k += blockDim.x) s_coef[(k / 12) * kSplineRow + k % 12] = p.spline.coef[k];
     for (int k = threadIdx.x; k < p.spline.n; k += blockDim.x) s_x[k] = p.spline.x[k];
     for (int k = threadIdx.x; k < p.ds.nx; k += blockDim.x) s_gx[k] = p.ds.x[k];
     for (int k = threadIdx.x; k < p.ds.ny; k += blockDim.x) s_gy[k] = p.ds.y[k];

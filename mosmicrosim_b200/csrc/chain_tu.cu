@@ -43,7 +43,7 @@ cudaError_t launch_kernel(const ChainParams &p, int grid, int warps, cudaStream_
             kern = dens ? chain_kernel<kNS, kFull, kHourly, kMaxWarps, kShapeToo ? 5 : -1>
                         : chain_kernel<kNS, kFull, kHourly, kMaxWarps, kShapeToo ? 4 : -1>;
     }
-    const size_t smem = sizeof(double) * ((size_t)p.spline.n * 13 + p.ds.nx + p.ds.ny);
+    const size_t smem = sizeof(double) * ((size_t)p.spline.n * (kSplineRow + 1) + p.ds.nx + p.ds.ny);
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     kern<<<grid, warps * 32, smem, stream>>>(p);
@@ -163,7 +163,7 @@ cudaError_t MMS_LAUNCH(launch_lifehistory)(const ChainParams &p, int64_t n, cons
                                            const double *humidity, double *mdr, double *efd, double *das0, double *ds,
                                            int n_sm, cudaStream_t stream)
 {
-    const size_t smem = sizeof(double) * ((size_t)p.spline.n * 13 + p.ds.nx + p.ds.ny);
+    const size_t smem = sizeof(double) * ((size_t)p.spline.n * (kSplineRow + 1) + p.ds.nx + p.ds.ny);
     cudaError_t err = cudaFuncSetAttribute(lifehistory_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     const int64_t want = (n + 511) / 512;

@@ -101,7 +101,7 @@ __device__ __forceinline__ HourF hour_forcing_ws(const ChainParams &p, const Sme
         dsf = ds_fetch(p.ds, f.air_t, f.rh);
         const int i = spline_interval(p.spline, tb.sx, f.air_t);
         dx = f.air_t - tb.sx[i];
-        const double4 *cf = reinterpret_cast<const double4 *>(tb.coef + (size_t)i * 12);
+        const double4 *cf = reinterpret_cast<const double4 *>(tb.coef + (size_t)i * kSplineRow);
         c0 = cf[0]; c1 = cf[1]; c2 = cf[2];
     }
     f.evap = evaporation_rate(f.air_t, f.rh, p_a, f.wind);
@@ -248,7 +248,7 @@ __device__ __forceinline__ HourF hour_forcing_from(const ChainParams &p, const S
     if (!kWaterOnly) {
         const int i = spline_interval(p.spline, tb.sx, f.air_t);
         dx = f.air_t - tb.sx[i];
-        const double4 *cf = reinterpret_cast<const double4 *>(tb.coef + (size_t)i * 12);
+        const double4 *cf = reinterpret_cast<const double4 *>(tb.coef + (size_t)i * kSplineRow);
         c0 = cf[0]; c1 = cf[1]; c2 = cf[2];
     }
     f.evap = evaporation_rate(f.air_t, f.rh, p_a, f.wind);      // R/sim_water.R:264-270 (air temperature)
@@ -581,13 +581,13 @@ chain_kernel_ws(const __grid_constant__ ChainParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_coef = reinterpret_cast<double *>(smem_raw);              // [n][3][4]
-    double *s_x = s_coef + (size_t)p.spline.n * 12;                     // [n]
+    double *s_x = s_coef + (size_t)p.spline.n * kSplineRow;                     // [n]
     double *s_gx = s_x + p.spline.n;                                    // [nx]
     double *s_gy = s_gx + p.ds.nx;                                      // [ny]
     double *s_ring = s_gy + p.ds.ny;                                    // [pairs][kWsRingDoubles]
     const int n_pairs = blockDim.x >> 6;
     int *s_unit = reinterpret_cast<int *>(s_ring + (size_t)n_pairs * kWsRingDoubles);   // [pairs]
-    for (int k = threadIdx.x; k < p.spline.n * 12; k += blockDim.x) s_coef[k] = p.spline.coef[k];
+    for (int k = threadIdx.x; k < p.spline.n * 12; k += blockDim.x) s_coef[(k / 12) * kSplineRow + k % 12] = p.spline.coef[k];
     for (int k = threadIdx.x; k < p.spline.n; k += blockDim.x) s_x[k] = p.spline.x[k];
     for (int k = threadIdx.x; k < p.ds.nx; k += blockDim.x) s_gx[k] = p.ds.x[k];
     for (int k = threadIdx.x; k < p.ds.ny; k += blockDim.x) s_gy[k] = p.ds.y[k];
@@ -644,14 +644,14 @@ chain_kernel_fan(const __grid_constant__ ChainParams p, int groups)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_coef = reinterpret_cast<double *>(smem_raw);              // [n][3][4]
-    double *s_x = s_coef + (size_t)p.spline.n * 12;                     // [n]
+    double *s_x = s_coef + (size_t)p.spline.n * kSplineRow;                     // [n]
     double *s_gx = s_x + p.spline.n;                                    // [nx]
     double *s_gy = s_gx + p.ds.nx;                                      // [ny]
     double *s_ring = s_gy + p.ds.ny;                                    // [teams][kWsRingDoubles]
     const int team_warps = groups + 1;
     const int n_teams = (blockDim.x >> 5) / team_warps;
     int *s_unit = reinterpret_cast<int *>(s_ring + (size_t)n_teams * kWsRingDoubles);   // [teams]
-    for (int k = threadIdx.x; k < p.spline.n * 12; k += blockDim.x) s_coef[k] = p.spline.coef[k];
+    for (int k = threadIdx.x; k < p.spline.n * 12; k += blockDim.x) s_coef[(k / 12) * kSplineRow + k % 12] = p.spline.coef[k];
     for (int k = threadIdx.x; k < p.spline.n; k += blockDim.x) s_x[k] = p.spline.x[k];
     for (int k = threadIdx.x; k < p.ds.nx; k += blockDim.x) s_gx[k] = p.ds.x[k];
     for (int k = threadIdx.x; k < p.ds.ny; k += blockDim.x) s_gy[k] = p.ds.y[k];

@@ -15,6 +15,14 @@ constexpr int kChainFewWarps = 12;   // second instantiation: <= 384 threads, <=
 constexpr int kChainMaxPairs = 11;   // warp-specialised kernel: 11 forcing + 11 state warps, <= 88 registers / thread
 constexpr int kChainFewPairs = 10;   // second instantiation: 640 threads, <= 96 registers / thread
 constexpr int kChainFanWarps = 17;   // fan-out form: 1 forcing + up to 16 state warps per team, <= 112 registers / thread
+// doubles per knot of the shared-memory copy of the spline table: [mdr, efd, das][y, b, c, d] = 12, padded so that
+// the rows of 32 lanes with unrelated temperatures spread over all eight 16-byte bank groups (a 96-byte stride reaches
+// only four of them; 112 bytes = 7 groups, coprime with 8).  MEASURED, one B200: 12 -> 14 takes the pair kernel on
+// BASELINE configs[1] from 51.39 to 50.51 ms and the life-history verb (100k cells x 8760 h) from 18.46 to 14.91 ms.
+#ifndef MMS_SPLINE_ROW
+#define MMS_SPLINE_ROW 14
+#endif
+constexpr int kSplineRow = MMS_SPLINE_ROW;
 constexpr int kHoursPerYear = 8760;  // n_times_year <- 365 * 24, R/sim_water.R:229, R/sim_pop_dynamics.R:222
 constexpr int kDaysPerYear = 365;
 

@@ -202,10 +202,10 @@ __global__ void __launch_bounds__(512, 2) lifehistory_kernel(const __grid_consta
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_coef = reinterpret_cast<double *>(smem_raw);              // [n][3][4]
-    double *s_x = s_coef + (size_t)p.spline.n * 12;
+    double *s_x = s_coef + (size_t)p.spline.n * kSplineRow;
     double *s_gx = s_x + p.spline.n;
     double *s_gy = s_gx + p.ds.nx;
-    for (int k = threadIdx.x; k < p.spline.n * 12; k += blockDim.x) s_coef[k] = p.spline.coef[k];
+    for (int k = threadIdx.x; k < p.spline.n * 12; k += blockDim.x) s_coef[(k / 12) * kSplineRow + k % 12] = p.spline.coef[k];
     for (int k = threadIdx.x; k < p.spline.n; k += blockDim.x) s_x[k] = p.spline.x[k];
     for (int k = threadIdx.x; k < p.ds.nx; k += blockDim.x) s_gx[k] = p.ds.x[k];
     for (int k = threadIdx.x; k < p.ds.ny; k += blockDim.x) s_gy[k] = p.ds.y[k];
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(512, 2) lifehistory_kernel(const __grid_consta
         // mdr and das take the water temperature, efd the air temperature (R/sim_pop_dynamics.R:108-114)
         const int iw = spline_interval(p.spline, tb.sx, tw), ia = spline_interval(p.spline, tb.sx, ta);
         const double dw = tw - tb.sx[iw], da = ta - tb.sx[ia];
-        const double *cw = tb.coef + (size_t)iw * 12, *ca = tb.coef + (size_t)ia * 12;
+        const double *cw = tb.coef + (size_t)iw * kSplineRow, *ca = tb.coef + (size_t)ia * kSplineRow;
         mdr[i] = ensure_positive(cw[0] + dw * (cw[1] + dw * (cw[2] + dw * cw[3])));
         efd[i] = ensure_positive(ca[4] + da * (ca[5] + da * (ca[6] + da * ca[7])));
         das0[i] = ensure_positive(cw[8] + dw * (cw[9] + dw * (cw[10] + dw * cw[11])));

@@ -55,6 +55,54 @@ def test_r_shim_compiles_against_the_abi_header():
     assert r.returncode == 0, r.stderr
 
 
+def _r_call_sites(text):
+    """(.Call name, number of positional arguments after the name) for every .Call in an R source."""
+    out, k = [], 0
+    while True:
+        k = text.find(".Call(", k)
+        if k < 0:
+            return out
+        i, depth, args, cur, quote = k + 6, 1, [], "", None
+        while depth:
+            ch = text[i]
+            if quote:
+                quote = None if ch == quote else quote
+            elif ch in "\"'":
+                quote = ch
+            elif ch in "([{":
+                depth += 1
+            elif ch in ")]}":
+                depth -= 1
+                if depth == 0:
+                    break
+            elif ch == "," and depth == 1:
+                args.append(cur.strip())
+                cur, ch = "", ""
+            cur += ch
+            i += 1
+        args.append(cur.strip())
+        positional = [a for a in args[1:] if not a.startswith("PACKAGE")]
+        out.append((args[0].strip("\"'"), len(positional)))
+        k = i
+
+
+def test_r_calls_match_the_registration_table():
+    """Every .Call in r-binding/R/gpu_backend.R names an entry point the shim registers, with the registered number
+    of arguments (R checks this only at call time; R is not installed here)."""
+    import re
+    shim = open(os.path.join(ROOT, "r-binding", "src", "mmsgpu_shim.c")).read()
+    registered = {m.group(1): int(m.group(2)) for m in
+                  re.finditer(r'\{"(mms_R_\w+)",\s*\(DL_FUNC\)&\1,\s*(\d+)\}', shim)}
+    defined = {m.group(1): m.group(2).count("SEXP") for m in
+               re.finditer(r"^SEXP (mms_R_\w+)\(([^)]*)\)", shim, re.M)}
+    assert registered and registered == defined, (registered, defined)
+    sites = _r_call_sites(open(os.path.join(ROOT, "r-binding", "R", "gpu_backend.R")).read())
+    assert sites
+    for name, n_args in sites:
+        assert registered.get(name) == n_args, (name, n_args, registered.get(name))
+    assert {n for n, _ in sites} | {"mms_R_device_count", "mms_R_terraclimate_to_monthly"} >= set(registered)
+
+
 def test_no_cpu_fallback_without_a_device():
     if backend.device_count() > 0:
         pytest.skip("a GPU is visible")
