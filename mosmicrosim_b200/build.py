@@ -26,6 +26,7 @@ UNITS = [
     # (source, object, extra flags)
     ("chain_tu.cu", "chain_fast.o", ["-DMMS_STRICT=0"]),
     ("chain_ws_tu.cu", "chain_ws_fast.o", ["-DMMS_STRICT=0"]),
+    ("chain_team_tu.cu", "chain_team_fast.o", ["-DMMS_STRICT=0"]),
     ("chain_tu.cu", "chain_strict.o", ["-DMMS_STRICT=1", "-fmad=false"]),
     ("mmsgpu_api.cu", "mmsgpu_api.o", []),
     ("api_common.cu", "api_common.o", []),

@@ -76,6 +76,21 @@ cudaError_t launch_one(ChainParams &p, int n_sm, cudaStream_t stream)
             return launch_chain_fan_fast(p, kFull, kHourly, (int)(ctas < n_sm ? ctas : n_sm), teams, groups, stream);
         }
     }
+    // Team form (chain_team.cuh): climate / rates / state warps at <= 64 registers, 30-32 warps per SM.
+    // MMS_CHAIN_TEAM = 1 selects it (one or two settings per unit, no water-temperature model).
+    if ((kNS == 1 || kNS == 2) && !p.wt.enabled && !((p.mean_mask | p.hourly_mask) & (1u << MMS_V_WATER_TEMPERATURE))) {
+        const char *e = getenv("MMS_CHAIN_TEAM");
+        if (e && atoi(e) != 0) {
+            const int teams_cap = kNS == 1 ? kChainTeams1 : kChainTeams2;
+            const int teams_max = p.force_warps > 0 && p.force_warps < teams_cap ? p.force_warps : teams_cap;
+            const int64_t per_round = (int64_t)n_sm * teams_max;
+            const int64_t rounds = (p.n_units + per_round - 1) / per_round;
+            int teams = (int)((p.n_units + (int64_t)n_sm * rounds - 1) / ((int64_t)n_sm * rounds));
+            teams = teams < 1 ? 1 : (teams > teams_max ? teams_max : teams);
+            const int64_t ctas = (p.n_units + teams - 1) / teams;
+            return launch_chain_team_fast(p, kNS, kFull, kHourly, (int)(ctas < n_sm ? ctas : n_sm), teams, stream);
+        }
+    }
     // Which form?  Measured on B200 (profiles/r01_*): the pair form wins when the launch is
     // short of warps -- several settings per cell and at most two rounds of units per SM (the
     // 100k-cell tile of BASELINE configs[1]: 58.5 vs 67.4 ms) -- and loses a little when the

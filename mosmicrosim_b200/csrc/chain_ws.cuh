@@ -409,9 +409,32 @@ __device__ __forceinline__ void forcing_pass(const ChainParams &p, const SmemTab
 }
 
 // ---- state warp ------------------------------------------------------------------------------
-template <int kNS, bool kFull, bool kHourly, bool kWaterOnly, bool kRecord, int kDens, int kSplit>
+// How a state warp receives an hour's state-independent values: from the forcing warp of its pair / fan-out team
+// through the ring (PairLink), or from the two forcing roles of a team (TeamLink, chain_team.cuh)
+struct PairLink {
+    RingEnd &ring;
+    const double *slot;
+    __device__ __forceinline__ void begin_pass() {}
+    __device__ __forceinline__ void end_pass() {}
+    // hour h0 + k of a hand-off of kWsK hours
+    __device__ __forceinline__ void fetch(int h, int k, double &evap, PopHour &ph, double &gain_m_h)
+    {
+        (void)h;
+        if (k == 0) slot = ring_acquire_full(ring);
+        const double *rec = slot + (size_t)k * (kWsFields * 32);
+        evap = rec[0 * 32];
+        ph.surv_ad = rec[1 * 32];
+        ph.one_m_emf = rec[2 * 32];
+        ph.egg = rec[3 * 32];
+        ph.link0 = rec[4 * 32];
+        gain_m_h = rec[5 * 32];
+        if (k == kWsK - 1) ring_release(ring);   // the values are in registers: the forcing warp may refill the slot
+    }
+};
+
+template <int kNS, bool kFull, bool kHourly, bool kWaterOnly, bool kRecord, int kDens, int kSplit, class Link>
 __device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &u, UnitState<kNS> &st,
-                                           RingEnd &ring, int n_days)
+                                           Link &link, int n_days)
 {
     constexpr uint32_t kState = MMS_STATE_VAR_MASK;
     const int lane = threadIdx.x & 31;
@@ -449,6 +472,7 @@ __device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &
     };
 
     (void)lane;
+    link.begin_pass();
     for (int day = 0; day < n_days; ++day) {
         if (kRecord) {
             bool fresh;
@@ -461,18 +485,11 @@ __device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &
         }
 #pragma unroll 1
         for (int h0 = 0; h0 < 24; h0 += kWsK) {
-            const double *slot = ring_acquire_full(ring);
 #pragma unroll kWsUnrollS
             for (int k = 0; k < kWsK; ++k) {
-                const double *rec = slot + (size_t)k * (kWsFields * 32);
-                const double evap = rec[0 * 32];
+                double evap, gain_m_h;
                 PopHour ph;
-                ph.surv_ad = rec[1 * 32];
-                ph.one_m_emf = rec[2 * 32];
-                ph.egg = rec[3 * 32];
-                ph.link0 = rec[4 * 32];
-                const double gain_m_h = rec[5 * 32];
-                if (k == kWsK - 1) ring_release(ring);   // the values are in registers: the forcing warp may refill the slot
+                link.fetch(h0 + k, k, evap, ph, gain_m_h);
                 if (!kWaterOnly) {
                     // the steps MMS_WS_SPLIT moved here: same device functions on the same values, same results
                     if (kSplit & 4) ph.surv_ad = r_pow_pos(ph.surv_ad, kLitC[3]);
@@ -525,12 +542,41 @@ __device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &
             }
         }
     }
+    link.end_pass();
     if (kRecord && pc.cur_period >= 0) flush(pc.cur_period);
 }
 
-// one work unit in one role: water burn-in years (R/sim_water.R:228-233), population burn-in years
-// (R/sim_pop_dynamics.R:221-226), then the full series -- identical loop structure in both roles, so the warps of
-// a team meet at every barrier
+// one work unit in the state role: water burn-in years (R/sim_water.R:228-233), population burn-in years
+// (R/sim_pop_dynamics.R:221-226), then the full series
+template <int kNS, bool kFull, bool kHourly, int kDens, int kSplit, class Link>
+__device__ __forceinline__ void state_unit(const ChainParams &p, const UnitCtx &u, Link &link)
+{
+    UnitState<kNS> st;
+#pragma unroll
+    for (int s = 0; s < kNS; ++s) {
+        st.aquatic[s] = p.initial_aquatic;               // R/sim_pop_dynamics.R:249-252
+        st.adult[s] = p.initial_adult;
+        st.volume[s] = p.hab[u.set0 + s].initial_volume; // R/sim_water.R:277
+        st.surface[s] = habitat_surface(p.hab[u.set0 + s], st.volume[s]);
+    }
+    for (int y = 0; y < p.burnin_years_water; ++y)
+        state_pass<kNS, kFull, kHourly, true, false, kDens, kSplit>(p, u, st, link, kDaysPerYear);
+    double vol0[kNS];
+#pragma unroll
+    for (int s = 0; s < kNS; ++s) vol0[s] = st.volume[s];
+    for (int y = 0; y < p.burnin_years_pop; ++y) {
+        state_pass<kNS, kFull, kHourly, false, false, kDens, kSplit>(p, u, st, link, kDaysPerYear);
+#pragma unroll
+        for (int s = 0; s < kNS; ++s) {
+            st.volume[s] = vol0[s];
+            st.surface[s] = habitat_surface(p.hab[u.set0 + s], vol0[s]);
+        }
+    }
+    state_pass<kNS, kFull, kHourly, false, true, kDens, kSplit>(p, u, st, link, p.D);
+}
+
+// one work unit in one role -- identical loop structure in both roles (burn-in passes, then the full series), so
+// the warps of a team meet at every barrier
 template <int kNS, bool kFull, bool kHourly, int kDens, int kSplit>
 __device__ __forceinline__ void role_unit(const ChainParams &p, const SmemTables &tb, UnitCtx &u, RingEnd &ring,
                                           bool forcing_role)
@@ -546,28 +592,8 @@ __device__ __forceinline__ void role_unit(const ChainParams &p, const SmemTables
         if (bad && u.live) atomicOr(p.error_flag, 1);
     } else {
         u.p_a = 0.0;
-        UnitState<kNS> st;
-#pragma unroll
-        for (int s = 0; s < kNS; ++s) {
-            st.aquatic[s] = p.initial_aquatic;               // R/sim_pop_dynamics.R:249-252
-            st.adult[s] = p.initial_adult;
-            st.volume[s] = p.hab[u.set0 + s].initial_volume; // R/sim_water.R:277
-            st.surface[s] = habitat_surface(p.hab[u.set0 + s], st.volume[s]);
-        }
-        for (int y = 0; y < p.burnin_years_water; ++y)
-            state_pass<kNS, kFull, kHourly, true, false, kDens, kSplit>(p, u, st, ring, kDaysPerYear);
-        double vol0[kNS];
-#pragma unroll
-        for (int s = 0; s < kNS; ++s) vol0[s] = st.volume[s];
-        for (int y = 0; y < p.burnin_years_pop; ++y) {
-            state_pass<kNS, kFull, kHourly, false, false, kDens, kSplit>(p, u, st, ring, kDaysPerYear);
-#pragma unroll
-            for (int s = 0; s < kNS; ++s) {
-                st.volume[s] = vol0[s];
-                st.surface[s] = habitat_surface(p.hab[u.set0 + s], vol0[s]);
-            }
-        }
-        state_pass<kNS, kFull, kHourly, false, true, kDens, kSplit>(p, u, st, ring, p.D);
+        PairLink link{ring, nullptr};
+        state_unit<kNS, kFull, kHourly, kDens, kSplit>(p, u, link);
     }
 }
 

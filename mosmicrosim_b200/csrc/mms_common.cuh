@@ -10,10 +10,18 @@
 namespace mms {
 
 constexpr int kBlock = 128;          // cell padding granule of a shard (keeps [period][cell] rows 1 KB aligned)
-constexpr int kChainMaxWarps = 16;   // largest persistent CTA of the fused kernel: 512 threads, <= 128 registers / thread
+#ifndef MMS_CHAIN_MAX_WARPS
+#define MMS_CHAIN_MAX_WARPS 16
+#endif
+constexpr int kChainMaxWarps = MMS_CHAIN_MAX_WARPS;   // largest persistent CTA of the fused kernel: 512 threads, <= 128 registers / thread
 constexpr int kChainFewWarps = 12;   // second instantiation: <= 384 threads, <= 168 registers / thread
-constexpr int kChainMaxPairs = 11;   // warp-specialised kernel: 11 forcing + 11 state warps, <= 88 registers / thread
+#ifndef MMS_CHAIN_MAX_PAIRS
+#define MMS_CHAIN_MAX_PAIRS 11
+#endif
+constexpr int kChainMaxPairs = MMS_CHAIN_MAX_PAIRS;   // warp-specialised kernel: 11 forcing + 11 state warps, <= 88 registers / thread
 constexpr int kChainFewPairs = 10;   // second instantiation: 640 threads, <= 96 registers / thread
+constexpr int kChainTeams1 = 10;     // team form, one setting: 10 teams of climate + rates + state warp = 960 threads, <= 64 registers
+constexpr int kChainTeams2 = 8;      // team form, two settings: 8 teams of climate + rates + 2 state warps = 1024 threads, <= 64 registers
 constexpr int kChainFanWarps = 17;   // fan-out form: 1 forcing + up to 16 state warps per team, <= 112 registers / thread
 // doubles per knot of the shared-memory copy of the spline table: [mdr, efd, das][y, b, c, d] = 12, padded so that
 // the rows of 32 lanes with unrelated temperatures spread over all eight 16-byte bank groups (a 96-byte stride reaches
@@ -135,6 +143,9 @@ cudaError_t launch_chain_strict(ChainParams &p, int n_sm, cudaStream_t stream);
 // the warp-pair form (chain_ws_tu.cu), called by launch_chain_fast when it picks that form
 cudaError_t launch_chain_ws_fast(const ChainParams &p, int settings_per_thread, bool full, bool hourly, int grid,
                                  int pairs, cudaStream_t stream);
+// the team form (chain_team_tu.cu): `teams` teams of a climate, a rates and settings_per_unit (1 or 2) state warps per CTA
+cudaError_t launch_chain_team_fast(const ChainParams &p, int settings_per_unit, bool full, bool hourly, int grid,
+                                   int teams, cudaStream_t stream);
 // the fan-out form (chain_ws_tu.cu): `teams` teams of 1 forcing + `groups` state warps (4 settings each) per CTA
 cudaError_t launch_chain_fan_fast(const ChainParams &p, bool full, bool hourly, int grid, int teams, int groups,
                                   cudaStream_t stream);

@@ -123,6 +123,30 @@ def test_both_kernel_forms(gpu, monkeypatch, form, n_settings):
     compare(case, out2, ref2, REL_TOL_FAST, what=("mean",))
 
 
+@pytest.mark.parametrize("n_settings", [1, 2, 6])
+def test_team_form(gpu, monkeypatch, n_settings):
+    """The team form (MMS_CHAIN_TEAM=1: climate / rates / state warps, chain_team.cuh; an experiment kept behind its
+    switch, profiles/r02_pair_kernel_binder.md): against the oracle like the other forms, and -- same device functions on
+    the same values -- bit for bit what the pair form gives."""
+    included = syn.year_dates(2001, 1)[20:200]
+    case = Case(n_cells=77, habitats=syn.habitat_ensemble(8)[2:2 + n_settings], included=included,
+                out_of_range_fraction=0.2)
+    kw = case.gpu_kwargs(mean_vars=ALL_VARS, hourly_vars=ALL_VARS, want_wet_hours=True, want_wet_flags=True,
+                         math_mode="fast")
+    kw2 = case.gpu_kwargs(mean_vars=list(backend.VAR_NAMES[:6]), want_wet_hours=True, math_mode="fast",
+                          burnin_years_water=1)
+    monkeypatch.setenv("MMS_CHAIN_WS", "1")
+    pair, pair2 = backend.run_chain(case.monthly, case.altitude, **kw), backend.run_chain(case.monthly, case.altitude, **kw2)
+    monkeypatch.setenv("MMS_CHAIN_TEAM", "1")
+    team, team2 = backend.run_chain(case.monthly, case.altitude, **kw), backend.run_chain(case.monthly, case.altitude, **kw2)
+    compare(case, team, case.oracle(), REL_TOL_FAST)
+    compare(case, team2, case.oracle(want_hourly=False, burnin_years_water=1), REL_TOL_FAST, what=("mean",))
+    for a, b in ((pair, team), (pair2, team2)):
+        for k in a:
+            if isinstance(a[k], np.ndarray):
+                assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
 @pytest.mark.parametrize("mode,tol", [("strict", REL_TOL_STRICT), ("fast", REL_TOL_FAST)])
 def test_chain_two_years_with_leap_day(gpu, mode, tol):
     """2004-2005: 731 days, M = 26 knots; the burn-in still repeats the first 8760 steps
