@@ -43,11 +43,23 @@ static __constant__ double kExpC[8] = {
 };
 static __constant__ double kLogC[4] = {1.0 / 3.0, 0.2, -1.0 / 6.0, 0.0};
 
-// The two tables (2.3 KB) live in shared memory; every kernel that uses the fast math calls
-// math_tables_init() once per block before its first __syncthreads().
+// The two tables (2.3 KB) live in shared memory; every kernel that uses the fast math calls math_tables_init() once
+// per block before its first __syncthreads().  The lanes of a warp look up unrelated entries, and entries that share
+// a bank serialise: ncu on the pair form of the fused kernel (profiles/r02_ncu_chain_ws.txt) counts 10.2 G shared-
+// memory wavefronts where 4.7 G would do, the shared-memory pipe 68 % busy.  MMS_MATH_TABLE_COPIES=1 REPLICATES the
+// tables across the banks -- lane l reads copy l % 16 of the exp table (an 8-byte load is served per half-warp: 16
+// lanes, 16 distinct bank pairs, whatever the entries) and copy l % 8 of the log table (a 16-byte load is served per
+// quarter-warp) -- 20 KB, conflict free.  MEASURED (one B200, ms per launch, one copy -> replicated): pair form on
+// BASELINE configs[1] 50.53 -> 50.79, monolithic form 100k cells x 1 setting 41.03 -> 40.87, fan-out form 9472 cells x 64
+// settings 104.5 -> 101.9: the conflicts are not what the kernels wait for (the look-ups sit inside FP64 dependency
+// chains that are longer than the replays).  Off by default (the shared memory is better spent elsewhere).
+#ifndef MMS_MATH_TABLE_COPIES
+#define MMS_MATH_TABLE_COPIES 0    // 1: replicated, conflict-free tables
+#endif
+constexpr int kExpCopies = MMS_MATH_TABLE_COPIES ? 16 : 1, kLogCopies = MMS_MATH_TABLE_COPIES ? 8 : 1;
 struct MathTables {
-    double2 logt[128];     // (c_k, -log c_k)
-    double expt[32];       // 2^(j/32)
+    double2 logt[128 * kLogCopies];    // [k][copy]: (c_k, -log c_k)
+    double expt[32 * kExpCopies];      // [j][copy]: 2^(j/32)
 };
 
 __device__ __forceinline__ MathTables &math_tables()
@@ -59,11 +71,21 @@ __device__ __forceinline__ MathTables &math_tables()
 __device__ __forceinline__ void math_tables_init()
 {
     MathTables &t = math_tables();
-    for (int k = threadIdx.x; k < 128; k += blockDim.x) {
+    for (int i = threadIdx.x; i < 128 * kLogCopies; i += blockDim.x) {
+        const int k = i / kLogCopies;
         const double c = 1.0 / (1.0 + (k + 0.5) / 128.0);
-        t.logt[k] = make_double2(c, -log(c));
+        t.logt[i] = make_double2(c, -log(c));
     }
-    for (int j = threadIdx.x; j < 32; j += blockDim.x) t.expt[j] = exp2(j / 32.0);
+    for (int i = threadIdx.x; i < 32 * kExpCopies; i += blockDim.x) t.expt[i] = exp2((i / kExpCopies) / 32.0);
+}
+
+__device__ __forceinline__ double exp_table(int j)
+{
+    return math_tables().expt[j * kExpCopies + (int)(threadIdx.x & (kExpCopies - 1))];
+}
+__device__ __forceinline__ double2 log_table(int k)
+{
+    return math_tables().logt[k * kLogCopies + (int)(threadIdx.x & (kLogCopies - 1))];
 }
 
 __device__ __forceinline__ double rcp_approx(double a)
@@ -120,7 +142,7 @@ __device__ __forceinline__ double exp_core(double x)
     const double nf = t - magic;
     double r = fma(nf, kExpC[1], x);
     r = fma(nf, kExpC[2], r);
-    const double tj = math_tables().expt[n & 31];
+    const double tj = exp_table(n & 31);
     const double r2 = r * r;
     // exp(r) - 1 = r + r^2 (1/2 + r/6 + r^2 (1/24 + r/120 + r^2/720)): two short chains
     const double pa = fma(r, kExpC[3], 0.5);
@@ -145,7 +167,7 @@ __device__ __forceinline__ double log_core(double x)
 {
     const int hi = __double2hiint(x);
     const double ef = (double)((hi >> 20) - 1023);
-    const double2 ct = math_tables().logt[(hi >> 13) & 127];
+    const double2 ct = log_table((hi >> 13) & 127);
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));   // [1, 2)
     const double r = fma(m, ct.x, -1.0);                      // |r| <= 2^-8
     const double r2 = r * r;

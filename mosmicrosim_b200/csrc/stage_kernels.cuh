@@ -39,7 +39,7 @@ constexpr int kStageMaxWarps = 16;               // 128 registers
 constexpr int kStageFewWarps = 12;               // second instantiation: 168 registers (more hoisting, no spills)
 constexpr int kWaterInputs = 4, kPopInputs = 5;
 constexpr int kPopChunk = 2;                     // steps whose state-independent half is evaluated together (4: 38.3 vs 31.6 ms)
-constexpr size_t kStageSmemBudget = 220 * 1024;  // dynamic shared memory of a CTA (227 KB minus static tables, reserve)
+constexpr size_t kStageSmemBudget = 200 * 1024;  // dynamic shared memory of a CTA (227 KB minus the static math tables -- 20.5 KB when replicated -- and a reserve)
 constexpr size_t stage_smem_bytes(int n_inputs, int warps)
 {
     return sizeof(double) * 2 * (size_t)n_inputs * kStageTile * (size_t)warps;
