@@ -78,6 +78,12 @@ bool classify_mats(std::vector<Mat> &mats)
     return all;
 }
 
+// the workers that take part in a job: the first job.workers of the started ones (at least one)
+int Pipe::team_size(const PipeJob &job) const
+{
+    return std::max(1, std::min(job.workers, (int)workers_.size()));
+}
+
 void Pipe::set_error(int status, const std::string &msg)
 {
     std::lock_guard<std::mutex> lk(mu_);
@@ -279,7 +285,7 @@ bool Pipe::stage_out(Worker *wk, const Mat &m, int64_t w0, int64_t wn)
 void Pipe::arrive(Worker *wk, const PipeJob &job, int k)
 {
     PipeChunk &c = chunks[k];
-    const int total = std::max(1, std::min(job.workers, (int)workers_.size()));   // the workers that take part in this job
+    const int total = team_size(job);
     if (!failed_.load()) {
         if (cudaEventRecord(c.ev_in[wk->id], wk->s_in) != cudaSuccess) set_error(MMS_ERR_CUDA, "cudaEventRecord failed");
     }
@@ -308,7 +314,7 @@ bool Pipe::do_in(Worker *wk, const PipeJob &job, int k)
 {
     const PipeChunk &c = chunks[k];
     int64_t w0 = 0, wn = 0;
-    worker_window(c, wk->id, std::max(1, job.workers), window_unit, w0, wn);
+    worker_window(c, wk->id, team_size(job), window_unit, w0, wn);
     if (wk->id == 0 && k == 0 && job.before_first_copy && !job.before_first_copy(wk->s_in)) return false;
     for (const Mat &m : job.in)
         if (!stage_in(wk, m, w0, wn)) return false;
@@ -325,7 +331,7 @@ bool Pipe::do_out(Worker *wk, const PipeJob &job, int k)
     if (failed_.load()) return false;
     if (c.kernel_recorded) MMS_CUDA_P(this, cudaStreamWaitEvent(wk->s_out, c.ev_kernel, 0));
     int64_t w0 = 0, wn = 0, o0 = 0, on = 0;
-    worker_window(c, wk->id, std::max(1, job.workers), window_unit, w0, wn);
+    worker_window(c, wk->id, team_size(job), window_unit, w0, wn);
     if (job.out_window) job.out_window(w0, wn, o0, on);
     else { o0 = w0; on = wn; }
     for (const Mat &m : job.out)
@@ -339,7 +345,7 @@ void Pipe::run_job(Worker *wk, const PipeJob &job)
 {
     const int n = (int)chunks.size();
     // workers beyond the job's team (pinned buffers need few copy streams, small jobs few stagers) sit this one out
-    if (job.kind != PIPE_CALL && wk->id >= std::max(1, job.workers)) return;
+    if (job.kind != PIPE_CALL && wk->id >= team_size(job)) return;
     switch (job.kind) {
     case PIPE_CALL:
         if (wk->id == 0 && job.call && !job.call() && !failed_.load()) set_error(MMS_ERR_CUDA, "device set-up failed");

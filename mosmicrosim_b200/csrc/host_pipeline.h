@@ -104,6 +104,7 @@ private:
     struct Worker;
     void worker_main(Worker *wk);
     void run_job(Worker *wk, const PipeJob &job);
+    int team_size(const PipeJob &job) const;
     void arrive(Worker *wk, const PipeJob &job, int k);
     bool do_in(Worker *wk, const PipeJob &job, int k);
     bool do_out(Worker *wk, const PipeJob &job, int k);
