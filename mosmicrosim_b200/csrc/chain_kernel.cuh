@@ -271,20 +271,57 @@ __device__ __forceinline__ HourF hour_forcing(const ChainParams &p, const SmemTa
     // ---- evaporation rate per unit area, R/sim_water.R:264-270 (air temperature)
     f.evap = evaporation_rate(f.air_t, f.rh, p_a, f.wind);
     if (!kWaterOnly) {
+        // what does not need the ds quad first: its first use comes as late as the hour allows
+        f.efd = ensure_positive(c1.x + dx * (c1.y + dx * (c1.z + dx * c1.w)));
+        if (!kWT) {
+            f.mdr = ensure_positive(c0.x + dx * (c0.y + dx * (c0.z + dx * c0.w)));
+            f.das0 = ensure_positive(c2.x + dx * (c2.y + dx * (c2.z + dx * c2.w)));
+            pop_hour_water(f.ph, dens_type, f.mdr, f.das0);
+        }
 #if !MMS_STRICT
         f.ds = ds_blend(dsf);
 #endif
-        f.efd = ensure_positive(c1.x + dx * (c1.y + dx * (c1.z + dx * c1.w)));
-        if (kWT) {
-            pop_hour_air(f.ph, f.efd, f.ds);
-        } else {
-            f.mdr = ensure_positive(c0.x + dx * (c0.y + dx * (c0.z + dx * c0.w)));
-            f.das0 = ensure_positive(c2.x + dx * (c2.y + dx * (c2.z + dx * c2.w)));
-            f.ph = pop_hour(dens_type, f.mdr, f.efd, f.das0, f.ds);
-        }
+        pop_hour_air(f.ph, f.efd, f.ds);
     }
     return f;
 }
+
+#if !MMS_STRICT
+// hour_forcing() in two phases, so that the monolithic hour loop can put the population update of the previous hour
+// and the water step between the request of the ds quad (an L2 access: ncu had 10-18 % of the loop's stall samples
+// on its first use, profiles/r02_ncu_chain_mono.txt) and that first use.  MEASURED (one B200, ms per launch,
+// MMS_MONO_LATE_DS 0 -> 1): 100k cells x 1 setting 41.02 -> 37.87, x 4 settings 105.5 -> 97.3, 151 552 cells x 1 setting
+// x 2 years 84.98 -> 80.34.  Same operations on the same values: the results do not change.
+#ifndef MMS_MONO_LATE_DS
+#define MMS_MONO_LATE_DS 1
+#endif
+template <bool kFull, bool kWaterOnly>
+__device__ __forceinline__ HourF hour_forcing_early(const ChainParams &p, const DayCtx &dc, double p_a, int h, DsFetch &dsf)
+{
+    HourF f;
+    hour_microclimate<kFull>(p.hr, dc, h, f);
+    f.mdr = f.efd = f.das0 = f.ds = 0.0;
+    if (!kWaterOnly) dsf = ds_fetch(p.ds, f.air_t, f.rh);
+    f.evap = evaporation_rate(f.air_t, f.rh, p_a, f.wind);
+    return f;
+}
+template <bool kWaterOnly>
+__device__ __forceinline__ void hour_forcing_late(const ChainParams &p, const SmemTables &tb, HourF &f, const DsFetch &dsf,
+                                                  int dens_type)
+{
+    if (kWaterOnly) return;
+    const int i = spline_interval(p.spline, tb.sx, f.air_t);
+    const double dx = f.air_t - tb.sx[i];
+    const double4 *cf = reinterpret_cast<const double4 *>(tb.coef + (size_t)i * kSplineRow);
+    const double4 c0 = cf[0], c1 = cf[1], c2 = cf[2];
+    f.efd = ensure_positive(c1.x + dx * (c1.y + dx * (c1.z + dx * c1.w)));
+    f.mdr = ensure_positive(c0.x + dx * (c0.y + dx * (c0.z + dx * c0.w)));
+    f.das0 = ensure_positive(c2.x + dx * (c2.y + dx * (c2.z + dx * c2.w)));
+    pop_hour_water(f.ph, dens_type, f.mdr, f.das0);
+    f.ds = ds_blend(dsf);
+    pop_hour_air(f.ph, f.efd, f.ds);
+}
+#endif
 
 // ---- per-unit state carried across passes ---------------------------------------
 template <int kNS>
@@ -519,6 +556,17 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
         water_step(f, 0);
 #pragma unroll 1
         for (int h = 0; h < 23; ++h) {
+#if !MMS_STRICT && MMS_MONO_LATE_DS
+            if (!kWT) {
+                DsFetch dsf;
+                HourF fn = hour_forcing_early<kFull, kWaterOnly>(p, dc, u.p_a, h + 1, dsf);   // requests the ds quad
+                pop_and_record(f, h);
+                water_step(fn, h + 1);
+                hour_forcing_late<kWaterOnly>(p, tb, fn, dsf, dens_type);                     // first use of the quad
+                f = fn;
+                continue;
+            }
+#endif
             HourF fn = hour_forcing<kFull, kWaterOnly, kWT>(p, tb, dc, u.p_a, h + 1, dens_type);
             pop_and_record(f, h);
             water_step(fn, h + 1);

@@ -106,14 +106,15 @@ __device__ __forceinline__ HourF hour_forcing_ws(const ChainParams &p, const Sme
     }
     f.evap = evaporation_rate(f.air_t, f.rh, p_a, f.wind);
     if (!kWaterOnly) {
-        f.ds = ds_blend(dsf);
+        // the ds quad (an L2 access) is used as late as the hour allows
         f.mdr = ensure_positive(c0.x + dx * (c0.y + dx * (c0.z + dx * c0.w)));
         f.efd = ensure_positive(c1.x + dx * (c1.y + dx * (c1.z + dx * c1.w)));
         f.das0 = ensure_positive(c2.x + dx * (c2.y + dx * (c2.z + dx * c2.w)));
         f.ph.egg = f.efd * kLitC[3];
-        f.ph.surv_ad = (kSplit & 4) ? f.ds : r_pow_pos(f.ds, kLitC[3]);
         f.ph.one_m_emf = (kSplit & 2) ? f.mdr : pop_emergence_complement(f.mdr);
         f.ph.link0 = (kSplit & 1) ? f.das0 : pop_link0(dens_type, f.das0);
+        f.ds = ds_blend(dsf);
+        f.ph.surv_ad = (kSplit & 4) ? f.ds : r_pow_pos(f.ds, kLitC[3]);
     }
     return f;
 }
