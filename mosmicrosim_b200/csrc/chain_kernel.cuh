@@ -458,6 +458,16 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
 
         // the water recursion of one hour: volume, surface <- hour h (needs that hour's evaporation rate only)
         auto water_step = [&](HourF &fx, int h) {
+#if !MMS_STRICT
+            if (!kWT) {
+                // all settings of the thread stage by stage (mms_fastmath.cuh: why)
+                int shape[kNS];
+                MMS_EACH(s, kNS) shape[s] = kShapeAll >= 0 ? kShapeAll : p.hab[set0 + s].shape;
+                water_step_n<kNS>(p.hab + set0, st.volume, st.surface, fx.evap, gain, shape);   // R/sim_water.R:279-294
+                if (kFull) MMS_EACH(s, kNS) st.water_t[s] = fx.air_t;   // water_temperature = air_temperature, R/sim_microclimate.R:163
+                return;
+            }
+#endif
 #pragma unroll
             for (int s = 0; s < kNS; ++s) {
                 const HabitatDev &hb = p.hab[set0 + s];
@@ -489,10 +499,15 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
         // the population update of hour h (volume, surface are already at hour h) + the outputs of hour h
         auto pop_and_record = [&](const HourF &f, int h) {
             if (!kWaterOnly) {
+#if !MMS_STRICT
+                // larval_habitat_area = water_surface_area, R/sim_pop_dynamics.R:123; all settings stage by stage
+                iterate_state_n<kNS>(st.aquatic, st.adult, f.ph, dens_type, p.dd_effect, p.surface_area_cm2, st.surface);
+#else
 #pragma unroll
                 for (int s = 0; s < kNS; ++s)   // larval_habitat_area = water_surface_area, R/sim_pop_dynamics.R:123
                     iterate_state(st.aquatic[s], st.adult[s], f.ph, dens_type, p.dd_effect,
                                   p.surface_area_cm2, st.surface[s]);
+#endif
             }
             if (kRecord) {
                 // branch free: days outside included_dates add 0 (their sums are never written)

@@ -498,17 +498,21 @@ __device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &
                     if (kSplit & 1) ph.link0 = pop_link0(kDens >= 0 ? (kDens & 1) : p.densmod_type, ph.link0);
                 }
                 ph.emf = 1.0 - ph.one_m_emf;
-#pragma unroll
-                for (int s = 0; s < kNS; ++s) {
-                    const HabitatDev &hb = p.hab[u.set0 + s];
-                    st.volume[s] = iterate_volume(hb, st.volume[s], st.surface[s], evap,
-                                                  hb.catchment_area * gain_m_h);             // R/sim_water.R:279-287
-                    // shape of setting s: compiled in when the launcher knew it (two bits per setting, 0 = run time)
-                    const int shape_bits = kDens >= 0 ? (kDens >> (1 + 2 * s)) & 3 : 0;
-                    st.surface[s] = habitat_surface(hb, st.volume[s], shape_bits ? shape_bits - 1 : hb.shape);   // :294
+                {
+                    // all settings of the thread stage by stage (mms_fastmath.cuh: why); the shape of setting s is
+                    // compiled in when the launcher knew it (two bits per setting of kDens, 0 = run time)
+                    double gain[kNS];
+                    int shape[kNS];
+                    MMS_EACH(s, kNS) {
+                        const HabitatDev &hb = p.hab[u.set0 + s];
+                        gain[s] = hb.catchment_area * gain_m_h;                                    // R/sim_water.R:122-123
+                        const int shape_bits = kDens >= 0 ? (kDens >> (1 + 2 * s)) & 3 : 0;
+                        shape[s] = shape_bits ? shape_bits - 1 : hb.shape;
+                    }
+                    water_step_n<kNS>(p.hab + u.set0, st.volume, st.surface, evap, gain, shape);   // :279-294
                     if (!kWaterOnly)
-                        iterate_state(st.aquatic[s], st.adult[s], ph, kDens >= 0 ? (kDens & 1) : p.densmod_type, p.dd_effect,
-                                      p.surface_area_cm2, st.surface[s]);
+                        iterate_state_n<kNS>(st.aquatic, st.adult, ph, kDens >= 0 ? (kDens & 1) : p.densmod_type, p.dd_effect,
+                                             p.surface_area_cm2, st.surface);
                 }
                 if (kRecord) {
 #pragma unroll

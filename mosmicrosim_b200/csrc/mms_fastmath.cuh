@@ -95,14 +95,34 @@ __device__ __forceinline__ double rcp_approx(double a)
     return r;
 }
 
+// Every function below comes as an N-wide form over small arrays, written STAGE BY STAGE (operation k of all N
+// elements, then operation k + 1 of all N ...), and the scalar form is its N = 1 case.  Why: a thread that integrates
+// several habitat settings owns that many independent dependency chains, but ptxas leaves code written setting by
+// setting almost serial (tools/sass_deps.py on the fan-out kernel's state loop: 46 % of the FP64 operations sat
+// directly behind their producer, 30 % one instruction later) -- and every back-to-back pair waits out the 8-cycle
+// FP64 latency.  Stage-major source order puts N - 1 independent operations between producer and consumer.  Same
+// operations on the same values: the results do not depend on N.
+#define MMS_EACH(i, n) _Pragma("unroll") for (int i = 0; i < (n); ++i)
+
 // a / b, normal finite operands, ~1.5 ulp: MUFU + 5 DFMA, no branch (CUDA's IEEE division
 // carries a slow-path branch into the hour loop)
+template <int N>
+__device__ __forceinline__ void div_fast_n(const double (&a)[N], const double (&b)[N], double (&q)[N])
+{
+    double r[N], e[N];
+    MMS_EACH(i, N) r[i] = rcp_approx(b[i]);
+    MMS_EACH(i, N) e[i] = fma(-b[i], r[i], 1.0);
+    MMS_EACH(i, N) r[i] = fma(e[i], r[i], r[i]);
+    MMS_EACH(i, N) e[i] = fma(-b[i], r[i], 1.0);
+    MMS_EACH(i, N) r[i] = fma(e[i], r[i], r[i]);
+    MMS_EACH(i, N) q[i] = a[i] * r[i];
+}
 __device__ __forceinline__ double div_fast(double a, double b)
 {
-    double r = rcp_approx(b);
-    r = fma(fma(-b, r, 1.0), r, r);
-    r = fma(fma(-b, r, 1.0), r, r);
-    return a * r;
+    const double av[1] = {a}, bv[1] = {b};
+    double q[1];
+    div_fast_n<1>(av, bv, q);
+    return q[0];
 }
 
 // c ? a : b as a real SELP: written in PTX so that the compiler cannot turn the select back
@@ -134,64 +154,123 @@ __device__ __forceinline__ bool is_nan_bits(double x)
 }
 
 // exp(x) for |x| <= 708 (caller guarantees it)
-__device__ __forceinline__ double exp_core(double x)
+template <int N>
+__device__ __forceinline__ void exp_core_n(const double (&x)[N], double (&out)[N])
 {
     const double magic = 6755399441055744.0;                  // 1.5 * 2^52
-    const double t = fma(x, kExpC[0], magic);
-    const int n = __double2loint(t);                          // rint(x * 32 / ln2) = 32 m + j
-    const double nf = t - magic;
-    double r = fma(nf, kExpC[1], x);
-    r = fma(nf, kExpC[2], r);
-    const double tj = exp_table(n & 31);
-    const double r2 = r * r;
+    double t[N], nf[N], r[N], tj[N], r2[N], pa[N], pb[N], p[N], res[N];
+    int n[N];
+    MMS_EACH(i, N) t[i] = fma(x[i], kExpC[0], magic);
+    MMS_EACH(i, N) { n[i] = __double2loint(t[i]); nf[i] = t[i] - magic; }   // rint(x * 32 / ln2) = 32 m + j
+    MMS_EACH(i, N) r[i] = fma(nf[i], kExpC[1], x[i]);
+    MMS_EACH(i, N) r[i] = fma(nf[i], kExpC[2], r[i]);
+    MMS_EACH(i, N) tj[i] = exp_table(n[i] & 31);
+    MMS_EACH(i, N) r2[i] = r[i] * r[i];
     // exp(r) - 1 = r + r^2 (1/2 + r/6 + r^2 (1/24 + r/120 + r^2/720)): two short chains
-    const double pa = fma(r, kExpC[3], 0.5);
-    const double pb = fma(r2, kExpC[6], fma(r, kExpC[5], kExpC[4]));
-    const double p = fma(r2, fma(r2, pb, pa), r);
-    const double res = fma(tj, p, tj);
-    return __hiloint2double(__double2hiint(res) + ((n >> 5) << 20), __double2loint(res));
+    MMS_EACH(i, N) pa[i] = fma(r[i], kExpC[3], 0.5);
+    MMS_EACH(i, N) pb[i] = fma(r[i], kExpC[5], kExpC[4]);
+    MMS_EACH(i, N) pb[i] = fma(r2[i], kExpC[6], pb[i]);
+    MMS_EACH(i, N) p[i] = fma(r2[i], pb[i], pa[i]);
+    MMS_EACH(i, N) p[i] = fma(r2[i], p[i], r[i]);
+    MMS_EACH(i, N) res[i] = fma(tj[i], p[i], tj[i]);
+    MMS_EACH(i, N) out[i] = __hiloint2double(__double2hiint(res[i]) + ((n[i] >> 5) << 20), __double2loint(res[i]));
+}
+__device__ __forceinline__ double exp_core(double x)
+{
+    const double xv[1] = {x};
+    double r[1];
+    exp_core_n<1>(xv, r);
+    return r[0];
 }
 
 // exp(x), any x: |x| >= 708 saturates to 0 / +Inf, NaN -> NaN
+template <int N>
+__device__ __forceinline__ void exp_sat_n(const double (&x)[N], double (&out)[N])
+{
+    double xs[N], r[N];
+    bool big[N];
+    MMS_EACH(i, N) {
+        big[i] = ((unsigned)__double2hiint(x[i]) & 0x7fffffffu) >= 0x40862000u;   // |x| >= 708, Inf, NaN
+        xs[i] = sel(big[i], 0.0, x[i]);
+    }
+    exp_core_n<N>(xs, r);
+    MMS_EACH(i, N) {
+        const double special = is_nan_bits(x[i]) ? make_nan() : ((__double2hiint(x[i]) < 0) ? 0.0 : make_inf());
+        out[i] = sel(big[i], special, r[i]);
+    }
+}
 __device__ __forceinline__ double exp_sat(double x)
 {
-    const int hi = __double2hiint(x);
-    const bool big = ((unsigned)hi & 0x7fffffffu) >= 0x40862000u;   // |x| >= 708, Inf, NaN
-    const double r = exp_core(sel(big, 0.0, x));
-    const double special = is_nan_bits(x) ? make_nan() : ((hi < 0) ? 0.0 : make_inf());
-    return sel(big, special, r);
+    const double xv[1] = {x};
+    double r[1];
+    exp_sat_n<1>(xv, r);
+    return r[0];
 }
 
 // log(x) for normal, positive, finite x (caller guarantees it)
+template <int N>
+__device__ __forceinline__ void log_core_n(const double (&x)[N], double (&out)[N])
+{
+    double ef[N], m[N], r[N], r2[N], pa[N], pb[N], l1p[N];
+    double2 ct[N];
+    MMS_EACH(i, N) {
+        const int hi = __double2hiint(x[i]);
+        ef[i] = (double)((hi >> 20) - 1023);
+        ct[i] = log_table((hi >> 13) & 127);
+        m[i] = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x[i]));   // [1, 2)
+    }
+    MMS_EACH(i, N) r[i] = fma(m[i], ct[i].x, -1.0);           // |r| <= 2^-8
+    MMS_EACH(i, N) r2[i] = r[i] * r[i];
+    // log1p(r) = r + r^2 (-1/2 + r/3 + r^2 (-1/4 + r/5 - r^2/6)): two short chains
+    MMS_EACH(i, N) pa[i] = fma(r[i], kLogC[0], -0.5);
+    MMS_EACH(i, N) pb[i] = fma(r[i], kLogC[1], -0.25);
+    MMS_EACH(i, N) pb[i] = fma(r2[i], kLogC[2], pb[i]);
+    MMS_EACH(i, N) l1p[i] = fma(r2[i], pb[i], pa[i]);
+    MMS_EACH(i, N) l1p[i] = fma(r2[i], l1p[i], r[i]);
+    MMS_EACH(i, N) out[i] = fma(ef[i], kLn2Hi, ct[i].y) + fma(ef[i], kLn2Lo, l1p[i]);
+}
 __device__ __forceinline__ double log_core(double x)
 {
-    const int hi = __double2hiint(x);
-    const double ef = (double)((hi >> 20) - 1023);
-    const double2 ct = log_table((hi >> 13) & 127);
-    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));   // [1, 2)
-    const double r = fma(m, ct.x, -1.0);                      // |r| <= 2^-8
-    const double r2 = r * r;
-    // log1p(r) = r + r^2 (-1/2 + r/3 + r^2 (-1/4 + r/5 - r^2/6)): two short chains
-    const double pa = fma(r, kLogC[0], -0.5);
-    const double pb = fma(r2, kLogC[2], fma(r, kLogC[1], -0.25));
-    const double l1p = fma(r2, fma(r2, pb, pa), r);
-    return fma(ef, kLn2Hi, ct.y) + fma(ef, kLn2Lo, l1p);
+    const double xv[1] = {x};
+    double r[1];
+    log_core_n<1>(xv, r);
+    return r[0];
 }
 
 // log(x), any x: +-0 -> -Inf, x < 0 or NaN -> NaN, +Inf -> +Inf, positive denormal -> log(DBL_MIN)
+template <int N>
+__device__ __forceinline__ void log_sat_n(const double (&x)[N], double (&out)[N])
+{
+    double xs[N], r[N];
+    MMS_EACH(i, N) xs[i] = sel_pos_normal(x[i], x[i], 1.0);
+    log_core_n<N>(xs, r);
+    MMS_EACH(i, N) {
+        const int hi = __double2hiint(x[i]);
+        const bool zero = (((unsigned)hi & 0x7fffffffu) | (unsigned)__double2loint(x[i])) == 0u;
+        const bool pinf = hi == 0x7ff00000 && __double2loint(x[i]) == 0;
+        double special = (hi < 0 || is_nan_bits(x[i])) ? make_nan() : -708.3964185322641;   // negative / NaN, else denormal
+        special = pinf ? make_inf() : special;
+        special = zero ? -make_inf() : special;
+        out[i] = sel_pos_normal(x[i], r[i], special);
+    }
+}
 __device__ __forceinline__ double log_sat(double x)
 {
-    const int hi = __double2hiint(x);
-    const double r = log_core(sel_pos_normal(x, x, 1.0));
-    const bool zero = (((unsigned)hi & 0x7fffffffu) | (unsigned)__double2loint(x)) == 0u;
-    const bool pinf = hi == 0x7ff00000 && __double2loint(x) == 0;
-    double special = (hi < 0 || is_nan_bits(x)) ? make_nan() : -708.3964185322641;   // negative / NaN, else denormal
-    special = pinf ? make_inf() : special;
-    special = zero ? -make_inf() : special;
-    return sel_pos_normal(x, r, special);
+    const double xv[1] = {x};
+    double r[1];
+    log_sat_n<1>(xv, r);
+    return r[0];
 }
 
 // R's x ^ y for a positive, non-integer literal y, any x < Inf: 0 -> 0, x < 0 / NaN -> NaN
+template <int N>
+__device__ __forceinline__ void pow_pos_n(const double (&x)[N], double y, double (&out)[N])
+{
+    double l[N];
+    log_sat_n<N>(x, l);
+    MMS_EACH(i, N) l[i] = y * l[i];
+    exp_sat_n<N>(l, out);
+}
 __device__ __forceinline__ double pow_pos(double x, double y)
 {
     return exp_sat(y * log_sat(x));
@@ -203,13 +282,26 @@ __device__ __forceinline__ double pow_pos(double x, double y)
 
 // x ^ y for x in [0, 1e300] or NaN and a literal 0 < y < 1 (water volume, survival probabilities):
 // 0 and positive denormals -> 0 (R: 0 resp. ~1e-200), NaN -> NaN
+template <int N>
+__device__ __forceinline__ void pow_unit_n(const double (&x)[N], double y, double (&out)[N])
+{
+    double xs[N], l[N], r[N];
+    MMS_EACH(i, N) xs[i] = sel_pos_normal(x[i], x[i], 1.0);
+    log_core_n<N>(xs, l);
+    MMS_EACH(i, N) l[i] = y * l[i];
+    exp_core_n<N>(l, r);
+    MMS_EACH(i, N) {
+        // not positive-normal: keep sign/exponent/quiet bit only -> 0 stays 0, NaN stays NaN
+        const double special = __hiloint2double(__double2hiint(x[i]) & 0xfff80000, 0);
+        out[i] = sel_pos_normal(x[i], r[i], special);
+    }
+}
 __device__ __forceinline__ double pow_unit(double x, double y)
 {
-    const double xs = sel_pos_normal(x, x, 1.0);
-    const double r = exp_core(y * log_core(xs));
-    // not positive-normal: keep sign/exponent/quiet bit only -> 0 stays 0, NaN stays NaN
-    const double special = __hiloint2double(__double2hiint(x) & 0xfff80000, 0);
-    return sel_pos_normal(x, r, special);
+    const double xv[1] = {x};
+    double r[1];
+    pow_unit_n<1>(xv, y, r);
+    return r[0];
 }
 
 // log(x) for x in [0, +Inf] or NaN (odds, probabilities): 0 / denormal -> -Inf, +Inf -> +Inf,

@@ -141,6 +141,31 @@ __device__ __forceinline__ double iterate_volume(const HabitatDev &hb, double vo
     return y;
 }
 
+#if !MMS_STRICT
+// The water step of the N settings a thread integrates, stage by stage (mms_fastmath.cuh: why).  hab = the first of
+// the N consecutive settings; shape[i]: 0 cone, 1 cylinder.  Same operations as iterate_volume() / habitat_surface().
+template <int N>
+__device__ __forceinline__ void water_step_n(const HabitatDev *hab, double (&volume)[N], double (&surface)[N],
+                                             double evap_rate, const double (&gain)[N], const int (&shape)[N])
+{
+    double x[N], y[N];
+    MMS_EACH(i, N) x[i] = volume[i] - (evap_rate * surface[i]) * kLitC[2];         // R/sim_water.R:107-116
+    MMS_EACH(i, N) x[i] = x[i] - hab[i].leak_per_hour * volume[i];                 // EXTENSION (leak = 0: x - 0 == x)
+    MMS_EACH(i, N) x[i] = ensure_positive(x[i]);                                   // R/utils.R:159-161
+    MMS_EACH(i, N) y[i] = x[i] + gain[i];                                          // :126
+    MMS_EACH(i, N) volume[i] = (y[i] > hab[i].max_volume) ? hab[i].max_volume : y[i];   // enforce_max(), R/utils.R:164-168
+    bool all_cones = true;
+    MMS_EACH(i, N) all_cones = all_cones && shape[i] == 0;
+    if (all_cones) {                                                               // cone_volume_to_surface(), :24-31
+        double pw[N];
+        ::mms::fm::pow_unit_n<N>(volume, kLitC[1], pw);
+        MMS_EACH(i, N) surface[i] = kLitC[0] * pw[i];
+    } else {
+        MMS_EACH(i, N) surface[i] = habitat_surface(hab[i], volume[i], shape[i]);
+    }
+}
+#endif
+
 // State-independent part of iterate_state() for one hour.
 struct PopHour {
     double surv_ad;     // ds ^ timestep                          R/sim_pop_dynamics.R:50
@@ -259,20 +284,16 @@ __device__ __forceinline__ double iterate_volume_temperature(const HabitatDev &h
 }
 
 // iterate_state(), R/sim_pop_dynamics.R:14-96 (state dependent part)
+#if MMS_STRICT
 __device__ __forceinline__ void iterate_state(double &aquatic, double &adult, const PopHour &ph,
                                               int densmod_type, double dd_effect, double area_cm2,
                                               double larval_habitat_area)
 {
     const double aq = (aquatic != aquatic) ? 0.0 : aquatic;     // :33
     const double ad = (adult != adult) ? 0.0 : adult;           // :34
-#if MMS_STRICT
     const double density = aq / (larval_habitat_area + kEps);   // :42
-#else
-    const double density = ::mms::fm::div_fast(aq, larval_habitat_area + kEps);
-#endif
     const double density_dish = density * area_cm2;             // densmod :549 / :569
     double surv_aq;
-#if MMS_STRICT
     double das_t;
     if (densmod_type == 1) {
         const double loghaz = ph.link0 + dd_effect * density_dish;          // :556-557
@@ -283,39 +304,6 @@ __device__ __forceinline__ void iterate_state(double &aquatic, double &adult, co
         das_t = 1.0 / (1.0 + exp(-lg));                                     // :537,:578
     }
     surv_aq = r_pow_pos(das_t, kTimestep);                                  // :49
-#else
-    if (densmod_type == 1) {
-        // exp(-exp(log(-log p') + dd*D)) = exp(log p' * exp(dd*D)); the reference's
-        // 1 - (1 - z) rounding (z < 1.1e-16 -> 0) is kept literally.  dd*D is clamped to
-        // +-700 before exp (beyond that z is 0 or 1 either way) so that 0 * Inf cannot arise.
-        const double u = dd_effect * density_dish;
-        const int uhi = __double2hiint(u);
-        const bool ubig = ((unsigned)uhi & 0x7fffffffu) >= 0x4085e000u;      // |u| >= 700, Inf, NaN
-        const double e1 = ::mms::fm::exp_core(::mms::fm::sel(ubig, (uhi < 0) ? -700.0 : 700.0, u));
-        double z = ::mms::fm::exp_sat(ph.link0 * e1);
-        z = ::mms::fm::sel(::mms::fm::is_nan_bits(u), u, z);
-        const double das_t = 1.0 - (1.0 - z);
-        surv_aq = ::mms::fm::pow_pos(das_t, kLitC[3]);
-    } else {
-        // das_t = 1 / (1 + e), e = exp(a), a = -lg;  das_t ^ (1/24) = exp(-log(1 + e) / 24).
-        // a is clamped to [-50, 40] for e: below, 1 + e == 1 exactly; above, log(1 + e) == a
-        // to double precision, and e = Inf (a > 709.78...) makes the reference's das_t 0.
-        const double a = -(ph.link0 + dd_effect * density_dish);
-        const int ahi = __double2hiint(a);
-        const unsigned aabs = (unsigned)ahi & 0x7fffffffu;
-        const bool hi_side = ahi >= 0x40440000;                               // a >= 40 (or +Inf, +NaN)
-        const bool lo_side = ahi < 0 && aabs >= 0x40490000u;                  // a <= -50 (or -Inf, -NaN)
-        const double ac = ::mms::fm::sel(hi_side || lo_side, hi_side ? 40.0 : -50.0, a);
-        double L = ::mms::fm::log_core(1.0 + ::mms::fm::exp_core(ac));
-        L = ::mms::fm::sel(hi_side, a, L);
-        // -L / 24 is within [-29.6, 0] whenever the result is used: beyond a = 709.78 the select
-        // below wins (exp(a) = Inf -> das_t = 0); a NaN a propagates through exp_core
-        const bool overflow = ahi > 0x40862e42 || (ahi == 0x40862e42 && (unsigned)__double2loint(a) > 0xfefa39efu);
-        surv_aq = ::mms::fm::exp_core(kLitC[4] * ::mms::fm::sel(overflow, 0.0, L));
-        surv_aq = ::mms::fm::sel(overflow, 0.0, surv_aq);
-        surv_aq = ::mms::fm::sel(::mms::fm::is_nan_bits(a), a, surv_aq);
-    }
-#endif
     const double surviving_adult = ad * ph.surv_ad;             // :67
     const double surviving_aquatic = aq * surv_aq;              // :68
     const double new_aquatic = surviving_adult * ph.egg;        // :71
@@ -324,6 +312,93 @@ __device__ __forceinline__ void iterate_state(double &aquatic, double &adult, co
     aquatic = remaining_aquatic + new_aquatic;                  // :92
     adult = surviving_adult + new_adult + kEps;                 // :93
 }
+#else
+// N settings of one cell at once, stage by stage (mms_fastmath.cuh: why); the scalar form is N = 1
+template <int N>
+__device__ __forceinline__ void iterate_state_n(double (&aquatic)[N], double (&adult)[N], const PopHour &ph,
+                                                int densmod_type, double dd_effect, double area_cm2,
+                                                const double (&larval_habitat_area)[N])
+{
+    double aq[N], ad[N], den[N], density[N], surv_aq[N];
+    MMS_EACH(i, N) aq[i] = (aquatic[i] != aquatic[i]) ? 0.0 : aquatic[i];     // :33
+    MMS_EACH(i, N) ad[i] = (adult[i] != adult[i]) ? 0.0 : adult[i];           // :34
+    MMS_EACH(i, N) den[i] = larval_habitat_area[i] + kEps;
+    ::mms::fm::div_fast_n<N>(aq, den, density);                                // :42
+    if (densmod_type == 1) {
+        // exp(-exp(log(-log p') + dd*D)) = exp(log p' * exp(dd*D)); the reference's
+        // 1 - (1 - z) rounding (z < 1.1e-16 -> 0) is kept literally.  dd*D is clamped to
+        // +-700 before exp (beyond that z is 0 or 1 either way) so that 0 * Inf cannot arise.
+        double u[N], uc[N], e1[N], z[N], das_t[N];
+        MMS_EACH(i, N) {
+            const double density_dish = density[i] * area_cm2;                 // densmod :549
+            u[i] = dd_effect * density_dish;
+            const int uhi = __double2hiint(u[i]);
+            const bool ubig = ((unsigned)uhi & 0x7fffffffu) >= 0x4085e000u;     // |u| >= 700, Inf, NaN
+            uc[i] = ::mms::fm::sel(ubig, (uhi < 0) ? -700.0 : 700.0, u[i]);
+        }
+        ::mms::fm::exp_core_n<N>(uc, e1);
+        MMS_EACH(i, N) e1[i] = ph.link0 * e1[i];
+        ::mms::fm::exp_sat_n<N>(e1, z);
+        MMS_EACH(i, N) {
+            z[i] = ::mms::fm::sel(::mms::fm::is_nan_bits(u[i]), u[i], z[i]);
+            das_t[i] = 1.0 - (1.0 - z[i]);
+        }
+        ::mms::fm::pow_pos_n<N>(das_t, kLitC[3], surv_aq);
+    } else {
+        // das_t = 1 / (1 + e), e = exp(a), a = -lg;  das_t ^ (1/24) = exp(-log(1 + e) / 24).
+        // a is clamped to [-50, 40] for e: below, 1 + e == 1 exactly; above, log(1 + e) == a
+        // to double precision, and e = Inf (a > 709.78...) makes the reference's das_t 0.
+        double a[N], ac[N], e[N], L[N], arg[N];
+        bool hi_side[N], overflow[N];
+        MMS_EACH(i, N) {
+            const double density_dish = density[i] * area_cm2;                 // densmod :569
+            a[i] = -(ph.link0 + dd_effect * density_dish);
+        }
+        MMS_EACH(i, N) {
+            const int ahi = __double2hiint(a[i]);
+            const unsigned aabs = (unsigned)ahi & 0x7fffffffu;
+            hi_side[i] = ahi >= 0x40440000;                                     // a >= 40 (or +Inf, +NaN)
+            const bool lo_side = ahi < 0 && aabs >= 0x40490000u;                // a <= -50 (or -Inf, -NaN)
+            ac[i] = ::mms::fm::sel(hi_side[i] || lo_side, hi_side[i] ? 40.0 : -50.0, a[i]);
+        }
+        ::mms::fm::exp_core_n<N>(ac, e);
+        MMS_EACH(i, N) e[i] = 1.0 + e[i];
+        ::mms::fm::log_core_n<N>(e, L);
+        MMS_EACH(i, N) {
+            L[i] = ::mms::fm::sel(hi_side[i], a[i], L[i]);
+            // -L / 24 is within [-29.6, 0] whenever the result is used: beyond a = 709.78 the select
+            // below wins (exp(a) = Inf -> das_t = 0); a NaN a propagates through exp_core
+            const int ahi = __double2hiint(a[i]);
+            overflow[i] = ahi > 0x40862e42 || (ahi == 0x40862e42 && (unsigned)__double2loint(a[i]) > 0xfefa39efu);
+            arg[i] = kLitC[4] * ::mms::fm::sel(overflow[i], 0.0, L[i]);
+        }
+        ::mms::fm::exp_core_n<N>(arg, surv_aq);
+        MMS_EACH(i, N) {
+            surv_aq[i] = ::mms::fm::sel(overflow[i], 0.0, surv_aq[i]);
+            surv_aq[i] = ::mms::fm::sel(::mms::fm::is_nan_bits(a[i]), a[i], surv_aq[i]);
+        }
+    }
+    MMS_EACH(i, N) {
+        const double surviving_adult = ad[i] * ph.surv_ad;             // :67
+        const double surviving_aquatic = aq[i] * surv_aq[i];           // :68
+        const double new_aquatic = surviving_adult * ph.egg;           // :71
+        const double remaining_aquatic = surviving_aquatic * ph.one_m_emf;   // :74
+        const double new_adult = surviving_aquatic * ph.emf;           // :77
+        aquatic[i] = remaining_aquatic + new_aquatic;                  // :92
+        adult[i] = surviving_adult + new_adult + kEps;                 // :93
+    }
+}
+__device__ __forceinline__ void iterate_state(double &aquatic, double &adult, const PopHour &ph,
+                                              int densmod_type, double dd_effect, double area_cm2,
+                                              double larval_habitat_area)
+{
+    double aqv[1] = {aquatic}, adv[1] = {adult};
+    const double area[1] = {larval_habitat_area};
+    iterate_state_n<1>(aqv, adv, ph, densmod_type, dd_effect, area_cm2, area);
+    aquatic = aqv[0];
+    adult = adv[0];
+}
+#endif
 
 }  // namespace MMS_MODE
 }  // namespace mms
