@@ -61,6 +61,11 @@ struct TeamEnd {
 // what the state warps see of a team
 struct TeamLink {
     const TeamEnd &t;
+    template <int kNS, bool kFull, bool kHourly, bool kRecord, int kDens, int kSplit>
+    __device__ __forceinline__ void pop_pass(const ChainParams &p, const UnitCtx &u, UnitState<kNS> &st, int n_days)
+    {
+        state_pass<kNS, kFull, kHourly, false, kRecord, kDens, kSplit>(p, u, st, *this, n_days);
+    }
     __device__ __forceinline__ void begin_pass() { t.step(); }
     __device__ __forceinline__ void end_pass() { t.step(); }
     __device__ __forceinline__ void fetch(int h, int, double &evap, PopHour &ph, double &gain_m_h)

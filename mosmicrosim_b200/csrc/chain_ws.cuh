@@ -54,7 +54,13 @@ constexpr int kWsFields = 6;         // evap, surv_ad, exp(-mdr/24), egg, link0,
 #define MMS_WS_RING 0
 #endif
 constexpr int kWsRing = MMS_WS_RING;             // slots (a power of two), or 0
-constexpr int kWsSlots = kWsRing > 0 ? kWsRing : 2;
+// MMS_WS_PIPE: the state warp of a pair runs the water step of hour h next to the population update of hour h - 1
+// (state_pass_pipe below); it then reads two consecutive slots while the forcing warp fills a third: four slots
+#ifndef MMS_WS_PIPE
+#define MMS_WS_PIPE 1
+#endif
+constexpr int kWsBarSlots = MMS_WS_PIPE ? 4 : 2;
+constexpr int kWsSlots = kWsRing > 0 ? kWsRing : kWsBarSlots;
 static_assert(kWsRing == 0 || (kWsRing & (kWsRing - 1)) == 0, "the ring needs a power-of-two number of slots");
 static_assert(kWsRing == 0 || MMS_WS_K == 1, "the mbarrier ring hands over one hour at a time");
 constexpr int kWsRingDoubles = kWsSlots * kWsK * kWsFields * 32 + 2 * kWsSlots;   // per pair: slots, then full[] / empty[] mbarriers
@@ -193,7 +199,7 @@ __device__ __forceinline__ double *ring_acquire_empty(RingEnd &r)
         mbar_wait(r.empty + 8 * slot, ((r.it / kWsSlots) & 1) ^ 1);
         return r.slots + (size_t)slot * (kWsFields * 32);
     }
-    return r.slots + (size_t)(r.it & 1) * (kWsK * kWsFields * 32);
+    return r.slots + (size_t)(r.it & (kWsBarSlots - 1)) * (kWsK * kWsFields * 32);
 }
 __device__ __forceinline__ void ring_publish(RingEnd &r)
 {
@@ -210,7 +216,7 @@ __device__ __forceinline__ const double *ring_acquire_full(RingEnd &r)
         return r.slots + (size_t)slot * (kWsFields * 32);
     }
     pair_barrier(r.pair, r.bar_threads);             // the forcing warp has filled this buffer
-    return r.slots + (size_t)(r.it & 1) * (kWsK * kWsFields * 32);
+    return r.slots + (size_t)(r.it & (kWsBarSlots - 1)) * (kWsK * kWsFields * 32);
 }
 __device__ __forceinline__ void ring_release(RingEnd &r)
 {
@@ -412,9 +418,24 @@ __device__ __forceinline__ void forcing_pass(const ChainParams &p, const SmemTab
 // ---- state warp ------------------------------------------------------------------------------
 // How a state warp receives an hour's state-independent values: from the forcing warp of its pair / fan-out team
 // through the ring (PairLink), or from the two forcing roles of a team (TeamLink, chain_team.cuh)
+template <int kNS, bool kFull, bool kHourly, bool kRecord, int kDens, int kSplit>
+__device__ __forceinline__ void state_pass_pipe(const ChainParams &p, const UnitCtx &u, UnitState<kNS> &st,
+                                                RingEnd &ring, int n_days);
+template <int kNS, bool kFull, bool kHourly, bool kWaterOnly, bool kRecord, int kDens, int kSplit, class Link>
+__device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &u, UnitState<kNS> &st,
+                                           Link &link, int n_days);
+
 struct PairLink {
     RingEnd &ring;
     const double *slot;
+    bool pipelined;         // a pair (two settings per state warp at most): the software-pipelined hour loop
+    // a pass with the population (burn-in year or the recorded series)
+    template <int kNS, bool kFull, bool kHourly, bool kRecord, int kDens, int kSplit>
+    __device__ __forceinline__ void pop_pass(const ChainParams &p, const UnitCtx &u, UnitState<kNS> &st, int n_days)
+    {
+        if (MMS_WS_PIPE && kNS <= 2 && pipelined) state_pass_pipe<kNS, kFull, kHourly, kRecord, kDens, kSplit>(p, u, st, ring, n_days);
+        else state_pass<kNS, kFull, kHourly, false, kRecord, kDens, kSplit>(p, u, st, *this, n_days);
+    }
     __device__ __forceinline__ void begin_pass() {}
     __device__ __forceinline__ void end_pass() {}
     // hour h0 + k of a hand-off of kWsK hours
@@ -551,6 +572,147 @@ __device__ __forceinline__ void state_pass(const ChainParams &p, const UnitCtx &
     if (kRecord && pc.cur_period >= 0) flush(pc.cur_period);
 }
 
+// The state pass of a PAIR with the hour loop software-pipelined: in one loop body the water step of hour h (it needs
+// that hour's evaporation rate and rain only) and the population update of hour h - 1 (it needs the surface of hour
+// h - 1, kept) -- the population does not feed back into the water, so a thread with kNS settings has 2 kNS independent
+// chains in the body instead of kNS.  The pending hour's rates are re-read from the previous ring slot (four slots:
+// the forcing warp is filling a third).  Day and period bookkeeping of a day runs at the END of the iteration that
+// recorded the last hour of the day before.  Same operations on the same values as state_pass().
+template <int kNS, bool kFull, bool kHourly, bool kRecord, int kDens, int kSplit>
+__device__ __forceinline__ void state_pass_pipe(const ChainParams &p, const UnitCtx &u, UnitState<kNS> &st,
+                                                RingEnd &ring, int n_days)
+{
+    static_assert(kWsK == 1 && kWsRing == 0 && kWsBarSlots == 4, "one hour per hand-off through the four-slot barrier ring");
+    constexpr uint32_t kState = MMS_STATE_VAR_MASK;
+    const int dens_type = kDens >= 0 ? (kDens & 1) : p.densmod_type;
+    double acc[kNS][4];
+    int acc_wet[kNS];
+    auto reset = [&]() {
+        MMS_EACH(s, kNS) {
+            acc_wet[s] = 0;
+            MMS_EACH(k, 4) acc[s][k] = 0.0;
+        }
+    };
+    reset();
+    PeriodCursor pc;
+    pc.init();
+
+    auto flush = [&](int period) {
+        if (!u.live) return;
+        const int64_t at = (int64_t)period * u.os + u.ocell;
+        const double n = (double)pc.acc_n;
+        MMS_EACH(s, kNS) {
+            const int vid[4] = {MMS_V_ADULT, MMS_V_AQUATIC, MMS_V_LARVAL_HABITAT_AREA, MMS_V_WATER_VOLUME};
+            MMS_EACH(k, 4) {
+                if (!kFull && k >= 2) continue;
+                if (p.mean_mask & (1u << vid[k])) {
+                    const int64_t row = (int64_t)(u.set0 + s) * u.n_mean_state + out_slot(p.mean_mask, kState, vid[k]);
+                    p.mean_state[row * p.P * u.os + at] = acc[s][k] / n;
+                }
+            }
+            if (p.wet_hours) p.wet_hours[(int64_t)(u.set0 + s) * p.P * u.os + at] = acc_wet[s];
+        }
+    };
+    auto begin_day = [&](int day) {
+        if (!kRecord) return;
+        bool fresh;
+        const int to_flush = pc.begin_day(p, day, fresh);
+        if (fresh) {
+            if (to_flush >= 0) flush(to_flush);
+            reset();
+            pc.acc_n = 0;
+        }
+    };
+    // the next slot the forcing warp has filled, and the one before it
+    auto next_slot = [&](const double *&cur, const double *&prev) {
+        pair_barrier(ring.pair, ring.bar_threads);
+        cur = ring.slots + (size_t)(ring.it & 3) * (kWsFields * 32);
+        prev = ring.slots + (size_t)((ring.it - 1) & 3) * (kWsFields * 32);
+        ring.it += 1;
+    };
+    auto water = [&](const double *rec) {
+        const double evap = rec[0 * 32], gain_m_h = rec[5 * 32];
+        double gain[kNS];
+        int shape[kNS];
+        MMS_EACH(s, kNS) {
+            const HabitatDev &hb = p.hab[u.set0 + s];
+            gain[s] = hb.catchment_area * gain_m_h;                                    // R/sim_water.R:122-123
+            const int shape_bits = kDens >= 0 ? (kDens >> (1 + 2 * s)) & 3 : 0;
+            shape[s] = shape_bits ? shape_bits - 1 : hb.shape;
+        }
+        water_step_n<kNS>(p.hab + u.set0, st.volume, st.surface, evap, gain, shape);   // :279-294
+    };
+    auto rates = [&](const double *rec) {
+        PopHour ph;
+        ph.surv_ad = rec[1 * 32];
+        ph.one_m_emf = rec[2 * 32];
+        ph.egg = rec[3 * 32];
+        ph.link0 = rec[4 * 32];
+        if (kSplit & 4) ph.surv_ad = r_pow_pos(ph.surv_ad, kLitC[3]);
+        if (kSplit & 2) ph.one_m_emf = pop_emergence_complement(ph.one_m_emf);
+        if (kSplit & 1) ph.link0 = pop_link0(dens_type, ph.link0);
+        ph.emf = 1.0 - ph.one_m_emf;
+        return ph;
+    };
+    // the outputs of hour (day, h): population now, water body as it was at that hour
+    auto record = [&](int day, int h, const double (&surface)[kNS], const double (&volume)[kNS]) {
+        if (!kRecord) return;
+        MMS_EACH(s, kNS) {
+            acc[s][0] += (pc.acc_on ? st.adult[s] : 0.0);
+            acc[s][1] += (pc.acc_on ? st.aquatic[s] : 0.0);
+            if (kFull) {
+                acc[s][2] += (pc.acc_on ? surface[s] : 0.0);
+                acc[s][3] += (pc.acc_on ? volume[s] : 0.0);
+            }
+            acc_wet[s] += (volume[s] > 0.0) ? pc.acc_inc : 0;
+        }
+        pc.acc_n += pc.acc_inc;
+        if (kHourly && u.live) {
+            const int64_t tc = (int64_t)(day * 24 + h) * u.os + u.ocell;
+            MMS_EACH(s, kNS) {
+                const double val[4] = {st.adult[s], st.aquatic[s], surface[s], volume[s]};
+                const int vid[4] = {MMS_V_ADULT, MMS_V_AQUATIC, MMS_V_LARVAL_HABITAT_AREA, MMS_V_WATER_VOLUME};
+                MMS_EACH(q, 4) {
+                    if (!kFull && q >= 2) continue;
+                    if (p.hourly_mask & (1u << vid[q])) {
+                        const int64_t row = (int64_t)(u.set0 + s) * u.n_hourly_state + out_slot(p.hourly_mask, kState, vid[q]);
+                        p.hourly_state[row * u.H * u.os + tc] = val[q];
+                    }
+                }
+                if (p.wet_flags) p.wet_flags[(int64_t)(u.set0 + s) * u.H * u.os + tc] = (volume[s] > 0.0) ? 1 : 0;
+            }
+        }
+    };
+
+    const double *cur, *prev;
+    begin_day(0);
+    next_slot(cur, prev);
+    water(cur);                                      // hour 0 of day 0; its population update is pending
+    int pday = 0, phour = 0;
+    for (int day = 0; day < n_days; ++day) {
+#pragma unroll 1
+        for (int h = (day == 0) ? 1 : 0; h < 24; ++h) {
+            next_slot(cur, prev);
+            const PopHour ph = rates(prev);
+            double surface_prev[kNS], volume_prev[kNS];
+            MMS_EACH(s, kNS) { surface_prev[s] = st.surface[s]; volume_prev[s] = st.volume[s]; }
+            water(cur);                                                                                   // hour (day, h)
+            iterate_state_n<kNS>(st.aquatic, st.adult, ph, dens_type, p.dd_effect, p.surface_area_cm2, surface_prev);   // hour (pday, phour)
+            record(pday, phour, surface_prev, volume_prev);
+            if (h == 0) begin_day(day);              // the day before is complete: its period may end here
+            pday = day;
+            phour = h;
+        }
+    }
+    {   // the last hour's population update
+        const double *last = ring.slots + (size_t)((ring.it - 1) & 3) * (kWsFields * 32);
+        const PopHour ph = rates(last);
+        iterate_state_n<kNS>(st.aquatic, st.adult, ph, dens_type, p.dd_effect, p.surface_area_cm2, st.surface);
+        record(pday, phour, st.surface, st.volume);
+    }
+    if (kRecord && pc.cur_period >= 0) flush(pc.cur_period);
+}
+
 // one work unit in the state role: water burn-in years (R/sim_water.R:228-233), population burn-in years
 // (R/sim_pop_dynamics.R:221-226), then the full series
 template <int kNS, bool kFull, bool kHourly, int kDens, int kSplit, class Link>
@@ -570,14 +732,14 @@ __device__ __forceinline__ void state_unit(const ChainParams &p, const UnitCtx &
 #pragma unroll
     for (int s = 0; s < kNS; ++s) vol0[s] = st.volume[s];
     for (int y = 0; y < p.burnin_years_pop; ++y) {
-        state_pass<kNS, kFull, kHourly, false, false, kDens, kSplit>(p, u, st, link, kDaysPerYear);
+        link.template pop_pass<kNS, kFull, kHourly, false, kDens, kSplit>(p, u, st, kDaysPerYear);
 #pragma unroll
         for (int s = 0; s < kNS; ++s) {
             st.volume[s] = vol0[s];
             st.surface[s] = habitat_surface(p.hab[u.set0 + s], vol0[s]);
         }
     }
-    state_pass<kNS, kFull, kHourly, false, true, kDens, kSplit>(p, u, st, link, p.D);
+    link.template pop_pass<kNS, kFull, kHourly, true, kDens, kSplit>(p, u, st, p.D);
 }
 
 // one work unit in one role -- identical loop structure in both roles (burn-in passes, then the full series), so
@@ -597,7 +759,7 @@ __device__ __forceinline__ void role_unit(const ChainParams &p, const SmemTables
         if (bad && u.live) atomicOr(p.error_flag, 1);
     } else {
         u.p_a = 0.0;
-        PairLink link{ring, nullptr};
+        PairLink link{ring, nullptr, ring.bar_threads == 64};
         state_unit<kNS, kFull, kHourly, kDens, kSplit>(p, u, link);
     }
 }
