@@ -17,6 +17,8 @@
 // Arithmetic is exactly that of the monolithic fast kernel (same device functions).
 #pragma once
 
+#include <cuda_pipeline.h>
+
 #include "chain_kernel.cuh"
 
 #if !MMS_STRICT
@@ -63,7 +65,21 @@ constexpr int kWsBarSlots = MMS_WS_PIPE ? 4 : 2;
 constexpr int kWsSlots = kWsRing > 0 ? kWsRing : kWsBarSlots;
 static_assert(kWsRing == 0 || (kWsRing & (kWsRing - 1)) == 0, "the ring needs a power-of-two number of slots");
 static_assert(kWsRing == 0 || MMS_WS_K == 1, "the mbarrier ring hands over one hour at a time");
-constexpr int kWsRingDoubles = kWsSlots * kWsK * kWsFields * 32 + 2 * kWsSlots;   // per pair: slots, then full[] / empty[] mbarriers
+// MMS_WS_QUAD_ASYNC: the forcing warp requests the ds(T, RH) quad of hour h + 1 -- an L2 access, 20-25 % of its stall
+// samples at the first use (profiles/r02_ncu_chain_ws.txt) -- while it works on hour h, with cp.async into a
+// double-buffered shared-memory record: an asynchronous copy holds no registers (carrying the requested quad in
+// registers spilled: MMS_WS_DSPREFETCH above).  The microclimate of hour h + 1 that locates the quad is parked in the
+// ring slot of hour h + 1, which nobody reads yet (the state warp is at slots h - 1 and h - 2 at most).
+// MEASURED (BASELINE configs[1], one B200): 54.6 ms against 49.6 ms without -- the forcing warp's hour grows from 261 to
+// 331 instructions (parking and re-reading six values, the copy's address, commit / wait, one more uniform branch),
+// which costs more than the stall it removes.  Parity-tested, off by default.
+#ifndef MMS_WS_QUAD_ASYNC
+#define MMS_WS_QUAD_ASYNC 0
+#endif
+constexpr int kWsQuadDoubles = MMS_WS_QUAD_ASYNC ? 2 * 4 * 32 : 0;               // [buffer][half][lane][2]
+constexpr int kWsRingDoubles = kWsSlots * kWsK * kWsFields * 32 + 2 * kWsSlots + kWsQuadDoubles;   // per pair: slots, full[] / empty[] mbarriers, quad buffers
+static_assert(!MMS_WS_QUAD_ASYNC || (kWsRing == 0 && kWsBarSlots == 4 && MMS_WS_K == 1),
+              "the asynchronous quad parks the next hour's microclimate in the fourth ring slot");
 
 // The ds(T, RH) quad table (2 MB) lives in L2: its look-up is the one long-latency load of the forcing warp's hour
 // (19 % of the forcing warps' stall samples sit on the first use of the quad).  Round 2 tried to request the quad of
@@ -75,6 +91,9 @@ constexpr int kWsRingDoubles = kWsSlots * kWsK * kWsFields * 32 + 2 * kWsSlots; 
 // (1 = carry the requested quad in registers; 2 = only a prefetch.global.L1 of its two sectors, nothing carried.)
 #ifndef MMS_WS_DSPREFETCH
 #define MMS_WS_DSPREFETCH 0
+#endif
+#if MMS_WS_QUAD_ASYNC && MMS_WS_DSPREFETCH
+#error "MMS_WS_DSPREFETCH and MMS_WS_QUAD_ASYNC are alternatives"
 #endif
 
 // Which role evaluates the last, transcendental step of the three per-cell-hour products that do not depend on the
@@ -174,6 +193,7 @@ struct RingEnd {
     double *slots;          // [kWsSlots][kWsFields][32], this lane's column
     uint32_t full, empty;   // shared-memory addresses of full[0], empty[0]
     uint32_t it;            // hand-offs so far
+    double *quad;           // [2 buffers][2 halves][32][2], this lane's first half
     int pair;               // named barrier of the team (pair + 1)
     int bar_threads;        // threads that meet at it: 64 for a pair, 32 (1 + state warps) for a fan-out team
 };
@@ -183,6 +203,7 @@ __device__ __forceinline__ RingEnd ring_end(double *ring, int pair, int lane)
     RingEnd r;
     r.slots = ring + lane;
     uint64_t *bars = reinterpret_cast<uint64_t *>(ring + kWsSlots * kWsK * kWsFields * 32);
+    r.quad = ring + kWsSlots * kWsK * kWsFields * 32 + 2 * kWsSlots + 2 * lane;
     r.full = smem_u32(bars);
     r.empty = smem_u32(bars + kWsSlots);
     r.it = 0;
@@ -292,6 +313,35 @@ struct PeriodCursor {
     }
 };
 
+#if MMS_WS_QUAD_ASYNC
+// ds_fetch() (chain_kernel.cuh) in two steps: where the quad is, and -- an hour later -- the look-up from the copy
+__device__ __forceinline__ void ds_request(const SurfaceDev &g, double temperature, double humidity, double *buf,
+                                           double &ex, double &ey)
+{
+    const double fx = (temperature - g.x0) * g.inv_dx, fy = (humidity - g.y0) * g.inv_dy;
+    int i = __double2int_rd(fx), j = __double2int_rd(fy);     // NaN -> 0
+    i = min(max(i, 0), g.nx - 2);
+    j = min(max(j, 0), g.ny - 2);
+    ex = fx - (double)i;
+    ey = fy - (double)j;                                      // == 1 on the last grid line
+    const double2 *q = reinterpret_cast<const double2 *>(g.quad) + (i + (g.nx - 1) * j) * 2;
+    __pipeline_memcpy_async(buf, q, 16);                      // (z00, z10)
+    __pipeline_memcpy_async(buf + 2 * 32, q + 1, 16);         // (z01, z11)
+    __pipeline_commit();
+}
+__device__ __forceinline__ DsFetch ds_arrived(const SurfaceDev &g, double temperature, double humidity, const double *buf,
+                                              double ex, double ey)
+{
+    DsFetch d;
+    d.inside = temperature >= g.x0 && temperature <= g.x1 && humidity >= g.y0 && humidity <= g.y1;
+    d.ex = ex;
+    d.ey = ey;
+    d.a = *reinterpret_cast<const double2 *>(buf);
+    d.b = *reinterpret_cast<const double2 *>(buf + 2 * 32);
+    return d;
+}
+#endif
+
 // ---- forcing warp ---------------------------------------------------------------------------
 template <bool kFull, bool kHourly, bool kWaterOnly, bool kRecord, int kDens, int kSplit>
 __device__ __forceinline__ void forcing_pass(const ChainParams &p, const SmemTables &tb, const UnitCtx &u,
@@ -347,6 +397,22 @@ __device__ __forceinline__ void forcing_pass(const ChainParams &p, const SmemTab
 #if MMS_WS_DSPREFETCH == 1
         HourAhead ahead = hour_ahead<kFull, kWaterOnly>(p, dc, 0);
 #endif
+#if MMS_WS_QUAD_ASYNC
+        constexpr bool kAsync = !kWaterOnly;
+        // the microclimate of hour hn into the ring slot `park` (its own hour's slot, not yet in use), its quad requested
+        auto look_ahead = [&](int hn, double *park) {
+            HourF fa;
+            hour_microclimate<kFull>(p.hr, dc, hn, fa);
+            double ex, ey;
+            ds_request(p.ds, fa.air_t, fa.rh, ring.quad + (hn & 1) * (4 * 32), ex, ey);
+            park[0 * 32] = fa.air_t; park[1 * 32] = fa.rh; park[2 * 32] = fa.wind;
+            if (kFull) park[3 * 32] = fa.cloud;
+            park[4 * 32] = ex; park[5 * 32] = ey;
+        };
+        if (kAsync) look_ahead(0, ring.slots + (size_t)(ring.it & 3) * (kWsFields * 32));
+#else
+        constexpr bool kAsync = false;
+#endif
 #pragma unroll 1
         for (int h0 = 0; h0 < 24; h0 += kWsK) {
 #if MMS_WS_DSPREFETCH == 1
@@ -366,6 +432,32 @@ __device__ __forceinline__ void forcing_pass(const ChainParams &p, const SmemTab
                 const int h = h0 + k;
 #if MMS_WS_DSPREFETCH == 1
                 const HourF f = hour_forcing_from<kFull, kWaterOnly>(p, tb, now, u.p_a, kDens >= 0 ? (kDens & 1) : p.densmod_type);
+#elif MMS_WS_QUAD_ASYNC
+                HourF f;
+                if (kAsync) {
+                    if (h < 23) look_ahead(h + 1, ring.slots + (size_t)((ring.it + 1) & 3) * (kWsFields * 32));
+                    const int dens_type = kDens >= 0 ? (kDens & 1) : p.densmod_type;
+                    f.air_t = slot[0 * 32]; f.rh = slot[1 * 32]; f.wind = slot[2 * 32];
+                    f.cloud = kFull ? slot[3 * 32] : 0.0;
+                    const double ex = slot[4 * 32], ey = slot[5 * 32];
+                    const int i = spline_interval(p.spline, tb.sx, f.air_t);
+                    const double dx = f.air_t - tb.sx[i];
+                    const double4 *cf = reinterpret_cast<const double4 *>(tb.coef + (size_t)i * kSplineRow);
+                    const double4 c0 = cf[0], c1 = cf[1], c2 = cf[2];
+                    f.evap = evaporation_rate(f.air_t, f.rh, u.p_a, f.wind);
+                    f.mdr = ensure_positive(c0.x + dx * (c0.y + dx * (c0.z + dx * c0.w)));
+                    f.efd = ensure_positive(c1.x + dx * (c1.y + dx * (c1.z + dx * c1.w)));
+                    f.das0 = ensure_positive(c2.x + dx * (c2.y + dx * (c2.z + dx * c2.w)));
+                    f.ph.egg = f.efd * kLitC[3];
+                    f.ph.one_m_emf = (kSplit & 2) ? f.mdr : pop_emergence_complement(f.mdr);
+                    f.ph.link0 = (kSplit & 1) ? f.das0 : pop_link0(dens_type, f.das0);
+                    if (h < 23) __pipeline_wait_prior(1);     // this hour's quad has landed (the next one's may be in flight)
+                    else __pipeline_wait_prior(0);
+                    f.ds = ds_blend(ds_arrived(p.ds, f.air_t, f.rh, ring.quad + (h & 1) * (4 * 32), ex, ey));
+                    f.ph.surv_ad = (kSplit & 4) ? f.ds : r_pow_pos(f.ds, kLitC[3]);
+                } else {
+                    f = hour_forcing_ws<kFull, kWaterOnly, kSplit>(p, tb, dc, u.p_a, h, kDens >= 0 ? (kDens & 1) : p.densmod_type);
+                }
 #else
                 const HourF f = hour_forcing_ws<kFull, kWaterOnly, kSplit>(p, tb, dc, u.p_a, h, kDens >= 0 ? (kDens & 1) : p.densmod_type);
 #endif
@@ -777,7 +869,8 @@ chain_kernel_ws(const __grid_constant__ ChainParams p)
     double *s_x = s_coef + (size_t)p.spline.n * kSplineRow;                     // [n]
     double *s_gx = s_x + p.spline.n;                                    // [nx]
     double *s_gy = s_gx + p.ds.nx;                                      // [ny]
-    double *s_ring = s_gy + p.ds.ny;                                    // [pairs][kWsRingDoubles]
+    double *s_ring = s_gy + p.ds.ny;
+    s_ring += (reinterpret_cast<uintptr_t>(s_ring) >> 3) & 1;           // 16-byte aligned (cp.async records)                                    // [pairs][kWsRingDoubles]
     const int n_pairs = blockDim.x >> 6;
     int *s_unit = reinterpret_cast<int *>(s_ring + (size_t)n_pairs * kWsRingDoubles);   // [pairs]
     for (int k = threadIdx.x; k < p.spline.n * 12; k += blockDim.x) s_coef[(k / 12) * kSplineRow + k % 12] = p.spline.coef[k];
@@ -840,7 +933,8 @@ chain_kernel_fan(const __grid_constant__ ChainParams p, int groups)
     double *s_x = s_coef + (size_t)p.spline.n * kSplineRow;                     // [n]
     double *s_gx = s_x + p.spline.n;                                    // [nx]
     double *s_gy = s_gx + p.ds.nx;                                      // [ny]
-    double *s_ring = s_gy + p.ds.ny;                                    // [teams][kWsRingDoubles]
+    double *s_ring = s_gy + p.ds.ny;
+    s_ring += (reinterpret_cast<uintptr_t>(s_ring) >> 3) & 1;           // 16-byte aligned (cp.async records)                                    // [teams][kWsRingDoubles]
     const int team_warps = groups + 1;
     const int n_teams = (blockDim.x >> 5) / team_warps;
     int *s_unit = reinterpret_cast<int *>(s_ring + (size_t)n_teams * kWsRingDoubles);   // [teams]

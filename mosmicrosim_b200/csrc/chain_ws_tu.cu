@@ -37,7 +37,7 @@ template <int kNS, bool kFull, bool kHourly, int kMaxPairs>
 cudaError_t launch_kernel_ws(const ChainParams &p, int grid, int pairs, cudaStream_t stream)
 {
     auto kern = pick_kernel_ws<kNS, kFull, kHourly, kMaxPairs>(p);
-    const size_t smem = sizeof(double) * ((size_t)p.spline.n * (kSplineRow + 1) + p.ds.nx + p.ds.ny + (size_t)pairs * kWsRingDoubles) +
+    const size_t smem = sizeof(double) * ((size_t)p.spline.n * (kSplineRow + 1) + p.ds.nx + p.ds.ny + 1 + (size_t)pairs * kWsRingDoubles) +
                         sizeof(int) * (size_t)pairs;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
@@ -68,7 +68,7 @@ cudaError_t launch_fan(const ChainParams &p, int grid, int teams, int groups, cu
     auto kern = chain_kernel_fan<4, kFull, kHourly, -1>;
     if (kSpecialise) kern = p.densmod_type == 1 ? chain_kernel_fan<4, kFull, kHourly, kSpecialise ? 1 : -1>
                                                 : chain_kernel_fan<4, kFull, kHourly, kSpecialise ? 0 : -1>;
-    const size_t smem = sizeof(double) * ((size_t)p.spline.n * (kSplineRow + 1) + p.ds.nx + p.ds.ny + (size_t)teams * kWsRingDoubles) +
+    const size_t smem = sizeof(double) * ((size_t)p.spline.n * (kSplineRow + 1) + p.ds.nx + p.ds.ny + 1 + (size_t)teams * kWsRingDoubles) +
                         sizeof(int) * (size_t)teams;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
