@@ -574,6 +574,8 @@ __device__ __forceinline__ void run_pass(const ChainParams &p, const SmemTables 
 #if !MMS_STRICT && MMS_MONO_LATE_DS
             if (!kWT) {
                 DsFetch dsf;
+                // (measured, 100k cells x 1 setting, ms: this order 37.7; evaporation rate after the population update
+                // 39.5; late part before the water step 37.7; both 38.8)
                 HourF fn = hour_forcing_early<kFull, kWaterOnly>(p, dc, u.p_a, h + 1, dsf);   // requests the ds quad
                 pop_and_record(f, h);
                 water_step(fn, h + 1);

@@ -61,6 +61,10 @@ constexpr int kWsRing = MMS_WS_RING;             // slots (a power of two), or 0
 #ifndef MMS_WS_PIPE
 #define MMS_WS_PIPE 1
 #endif
+#ifndef MMS_WS_PIPE_MAX_NS
+#define MMS_WS_PIPE_MAX_NS 2       // 4: the fan-out form's state warps (four settings each) as well -- measured
+                                   // slower (9472 cells x 64 settings: 102.6 against 90.0 ms: eight chains at 96 registers)
+#endif
 constexpr int kWsBarSlots = MMS_WS_PIPE ? 4 : 2;
 constexpr int kWsSlots = kWsRing > 0 ? kWsRing : kWsBarSlots;
 static_assert(kWsRing == 0 || (kWsRing & (kWsRing - 1)) == 0, "the ring needs a power-of-two number of slots");
@@ -525,7 +529,7 @@ struct PairLink {
     template <int kNS, bool kFull, bool kHourly, bool kRecord, int kDens, int kSplit>
     __device__ __forceinline__ void pop_pass(const ChainParams &p, const UnitCtx &u, UnitState<kNS> &st, int n_days)
     {
-        if (MMS_WS_PIPE && kNS <= 2 && pipelined) state_pass_pipe<kNS, kFull, kHourly, kRecord, kDens, kSplit>(p, u, st, ring, n_days);
+        if (MMS_WS_PIPE && kNS <= MMS_WS_PIPE_MAX_NS && pipelined) state_pass_pipe<kNS, kFull, kHourly, kRecord, kDens, kSplit>(p, u, st, ring, n_days);
         else state_pass<kNS, kFull, kHourly, false, kRecord, kDens, kSplit>(p, u, st, *this, n_days);
     }
     __device__ __forceinline__ void begin_pass() {}
@@ -851,7 +855,7 @@ __device__ __forceinline__ void role_unit(const ChainParams &p, const SmemTables
         if (bad && u.live) atomicOr(p.error_flag, 1);
     } else {
         u.p_a = 0.0;
-        PairLink link{ring, nullptr, ring.bar_threads == 64};
+        PairLink link{ring, nullptr, ring.bar_threads == 64 || MMS_WS_PIPE_MAX_NS >= 4};
         state_unit<kNS, kFull, kHourly, kDens, kSplit>(p, u, link);
     }
 }
