@@ -14,6 +14,10 @@
 // role needs about half the registers, so twice as many warps -- twice as many independent
 // instruction streams -- fit per SM for the same number of cells in flight.
 //
+// Round 2: the state warp's hour loop is itself software-pipelined (state_pass_pipe: the water step of hour h next to
+// the population update of hour h - 1, through a four-slot ring), and the settings of a thread go through the
+// stage-major N-wide forms of the arithmetic (mms_fastmath.cuh).
+//
 // Arithmetic is exactly that of the monolithic fast kernel (same device functions).
 #pragma once
 

@@ -127,7 +127,8 @@ def test_both_kernel_forms(gpu, monkeypatch, form, n_settings):
 def test_team_form(gpu, monkeypatch, n_settings):
     """The team form (MMS_CHAIN_TEAM=1: climate / rates / state warps, chain_team.cuh; an experiment kept behind its
     switch, profiles/r02_pair_kernel_binder.md): against the oracle like the other forms, and -- same device functions on
-    the same values -- bit for bit what the pair form gives."""
+    the same values -- bit for bit what the pair form gives.  The pair form's state warp runs the software-pipelined
+    hour loop (state_pass_pipe), the team form's state warps the plain one: the comparison covers that too."""
     included = syn.year_dates(2001, 1)[20:200]
     case = Case(n_cells=77, habitats=syn.habitat_ensemble(8)[2:2 + n_settings], included=included,
                 out_of_range_fraction=0.2)
