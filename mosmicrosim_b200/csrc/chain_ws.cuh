@@ -69,6 +69,9 @@ constexpr int kWsRing = MMS_WS_RING;             // slots (a power of two), or 0
 #define MMS_WS_PIPE_MAX_NS 2       // 4: the fan-out form's state warps (four settings each) as well -- measured
                                    // slower (9472 cells x 64 settings: 102.6 against 90.0 ms: eight chains at 96 registers)
 #endif
+#if MMS_WS_RING > 0 && MMS_WS_PIPE
+#error "the mbarrier ring experiment (MMS_WS_RING) needs -DMMS_WS_PIPE=0: the pipelined state pass uses the barrier ring"
+#endif
 constexpr int kWsBarSlots = MMS_WS_PIPE ? 4 : 2;
 constexpr int kWsSlots = kWsRing > 0 ? kWsRing : kWsBarSlots;
 static_assert(kWsRing == 0 || (kWsRing & (kWsRing - 1)) == 0, "the ring needs a power-of-two number of slots");
