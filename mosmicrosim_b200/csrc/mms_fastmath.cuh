@@ -52,7 +52,9 @@ static __constant__ double kLogC[4] = {1.0 / 3.0, 0.2, -1.0 / 6.0, 0.0};
 // quarter-warp) -- 20 KB, conflict free.  MEASURED (one B200, ms per launch, one copy -> replicated): pair form on
 // BASELINE configs[1] 50.53 -> 50.79, monolithic form 100k cells x 1 setting 41.03 -> 40.87, fan-out form 9472 cells x 64
 // settings 104.5 -> 101.9: the conflicts are not what the kernels wait for (the look-ups sit inside FP64 dependency
-// chains that are longer than the replays).  Off by default (the shared memory is better spent elsewhere).
+// chains that are longer than the replays).  Re-measured on the round's final kernels: pair form 49.6 -> 49.8, fan-out
+// form 89.8 -> 91.7, monolithic form 37.6 -> 36.4 -- so build.py turns it on for the translation unit of the
+// monolithic form (chain_tu.cu) only; off by default.
 #ifndef MMS_MATH_TABLE_COPIES
 #define MMS_MATH_TABLE_COPIES 0    // 1: replicated, conflict-free tables
 #endif
