@@ -1,5 +1,6 @@
 // host_copy.cpp -- the row copies between caller (pageable) memory and the host pipeline's pinned bounce buffers
-// (mmsgpu_api.cu).  Compiled by g++ alone (build.py) so that it can use the AVX2 streaming stores: a bounce copy
+// (host_pipeline.cu), and the split of a chunk's columns among the workers: the CUDA-free pieces of the pipeline, so
+// that tests/c_driver/host_copy_test.cpp can check them on a CPU.  Compiled by g++ alone (build.py) so that it can use the AVX2 streaming stores: a bounce copy
 // is written once and next read by the DMA engine (upload) or never again by this thread (download), so the
 // destination lines should not be read for ownership nor stay in the cache -- about twice the bandwidth of a
 // cached memcpy per thread on the hosts measured.  Falls back to memcpy on CPUs without AVX2.
@@ -51,6 +52,17 @@ static bool have_avx2()
     return yes;
 }
 #endif
+
+// which columns of a chunk a worker moves (host_pipeline.h)
+void window_of_worker(int64_t c0, int64_t n_cells, int w, int workers, int64_t unit, int64_t &w0, int64_t &wn)
+{
+    const int64_t units = (n_cells + unit - 1) / unit;
+    const int64_t per = (units + workers - 1) / workers;
+    const int64_t a = (int64_t)w * per * unit < n_cells ? (int64_t)w * per * unit : n_cells;
+    const int64_t b = (int64_t)(w + 1) * per * unit < n_cells ? (int64_t)(w + 1) * per * unit : n_cells;
+    w0 = c0 + a;
+    wn = b - a;
+}
 
 // rows x width bytes from src (pitch spitch) to dst (pitch dpitch)
 void copy_rows(char *dst, size_t dpitch, const char *src, size_t spitch, size_t width, size_t rows)

@@ -47,12 +47,7 @@ Pipe::~Pipe() { stop(); }
 
 void worker_window(const PipeChunk &c, int w, int workers, int64_t unit, int64_t &w0, int64_t &wn)
 {
-    const int64_t units = (c.n_cells + unit - 1) / unit;
-    const int64_t per = (units + workers - 1) / workers;
-    const int64_t a = std::min<int64_t>((int64_t)w * per * unit, c.n_cells);
-    const int64_t b = std::min<int64_t>((int64_t)(w + 1) * per * unit, c.n_cells);
-    w0 = c.c0 + a;
-    wn = b - a;
+    window_of_worker(c.c0, c.n_cells, w, workers, unit, w0, wn);      // host_copy.cpp (CPU-tested)
 }
 
 int default_workers(int n_devices)

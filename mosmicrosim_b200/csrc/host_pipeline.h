@@ -34,6 +34,9 @@ constexpr int kMaxWorkers = 12;                   // host threads per device
 
 // host_copy.cpp: streaming-store row copy between caller memory and the pinned bounce buffers
 void copy_rows(char *dst, size_t dpitch, const char *src, size_t spitch, size_t width, size_t rows);
+// columns [w0, w0 + wn) of a chunk (first column c0, n_cells columns) that worker w of `workers` moves: whole units of
+// `unit` columns except at the chunk's end; the windows of all workers tile the chunk (host_copy.cpp)
+void window_of_worker(int64_t c0, int64_t n_cells, int w, int workers, int64_t unit, int64_t &w0, int64_t &wn);
 
 // Process-wide pool of the pinned bounce buffers (kSlotBytes each): page-locking memory is slow (milliseconds per
 // buffer), and the stage-level twins build a pipe per call.  Buffers go back to the pool when a pipe stops and are

@@ -103,6 +103,17 @@ def test_r_calls_match_the_registration_table():
     assert {n for n, _ in sites} | {"mms_R_device_count", "mms_R_terraclimate_to_monthly"} >= set(registered)
 
 
+def test_host_copy_and_worker_windows(tmp_path):
+    """copy_rows() (AVX2 streaming stores, ragged heads / tails / pitches) against memcpy, and the tiling of a chunk by
+    its workers' windows: tests/c_driver/host_copy_test.cpp, g++ only."""
+    exe = str(tmp_path / "host_copy_test")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror",
+                    os.path.join(ROOT, "tests", "c_driver", "host_copy_test.cpp"),
+                    os.path.join(ROOT, "mosmicrosim_b200", "csrc", "host_copy.cpp"), "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
+
+
 def test_no_cpu_fallback_without_a_device():
     if backend.device_count() > 0:
         pytest.skip("a GPU is visible")
