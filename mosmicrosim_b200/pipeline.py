@@ -119,6 +119,40 @@ def _monthly_array(pixel_monthly_climate):
     return start, end, monthly, altitude
 
 
+def fill_na_knots(monthly, start, end):
+    """What stats::approx() does with NA knots, done to the knots: approx(x, y, xout) drops the (x, y) pairs with an NA
+    (na.rm = TRUE, R/spline_interpolation.R:25-27), i.e. it interpolates linearly between the neighbouring knots that
+    are left -- the same line as through an NA knot REPLACED by the linear interpolation of its two non-NA neighbours
+    (approx1()'s formula at the knot's own date; rainfall in the log1p space it is interpolated in,
+    R/sim_microclimate.R:33,61).  The device library refuses NA knots (MMS_ERR_NONFINITE: its kernels read the two
+    knots of a day without a search); this host-side pass makes such tiles acceptable with the reference's results
+    to rounding (<= 1e-12 relative; tests/test_host.py).  NA runs at the start or the end of a series cannot be filled
+    (the reference gives NA days there, not the GAM) and stay NA: the library still refuses those pixels.
+    monthly: [9][M][C] (FORCING_VARS order); returns (filled copy, number of knots filled)."""
+    a = np.array(monthly, dtype=np.float64, copy=True)
+    x = dates.month_mid_days(start, end).astype(np.float64)
+    M = a.shape[1]
+    rain = FORCING_VARS.index("rainfall_daily")
+    a[rain] = np.log1p(a[rain])
+    missing = np.isnan(a)
+    n_filled = 0
+    if missing.any():
+        idx = np.arange(M)[None, :, None]
+        prev = np.maximum.accumulate(np.where(missing, -1, idx), axis=1)                      # last non-NA knot at or before m
+        nxt = np.minimum.accumulate(np.where(missing, M, idx)[:, ::-1], axis=1)[:, ::-1]       # first non-NA knot at or after m
+        fill = missing & (prev >= 0) & (nxt < M)
+        pi, ni = np.clip(prev, 0, M - 1), np.clip(nxt, 0, M - 1)
+        yi, yj = np.take_along_axis(a, pi, axis=1), np.take_along_axis(a, ni, axis=1)
+        xi, xj = x[pi], x[ni]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            y = yi + (yj - yi) * ((x[None, :, None] - xi) / (xj - xi))                        # approx1()
+        a[fill] = y[fill]
+        n_filled = int(fill.sum())
+    back = np.expm1(a[rain])
+    a[rain] = np.where(np.isnan(np.asarray(monthly[rain], dtype=np.float64)), back, monthly[rain])   # untouched knots keep their bits
+    return a, n_filled
+
+
 def interpolate_daily_climate(pixel_monthly_climate, dates_predict=None, *, on_extrapolation="error", math_mode="fast",
                               device=0):
     """interpolate_daily_climate() (R/pipeline_functions.R:258-275): monthly -> daily for every
@@ -325,7 +359,7 @@ def monthly_climate_to_vectors(pixel_monthly_climate, lifehistory_functions, spe
                                habitats=None, model_water_temperature=False, water_shade_proportion=1,
                                burnin_years_pop=1, extra_variables=(), math_mode="fast", devices=None,
                                water_temperature_options=None, cell_idx=None, n_raster_cells=None,
-                               on_extrapolation="error"):
+                               on_extrapolation="error", na_knots="error"):
     """tc_to_vectors() (R/pipeline_functions.R:1099-1130) from
     interpolate_daily_climate() to summarise_vectors(), for a whole tile in one
     fused kernel launch per device.
@@ -345,8 +379,14 @@ def monthly_climate_to_vectors(pixel_monthly_climate, lifehistory_functions, spe
       every row then comes back as a whole raster slice [P, n_raster_cells] with NaN where the raster has no pixel
       of the tile -- the assignment raster[cell_idx] <- values of create_vector_raster_slice()
       (R/pipeline_functions.R:1316-1322), done by the kernel's stores on the device.
+    na_knots: "error" (default: the library refuses NA in the monthly forcing) or "interpolate": NA knots between two
+      non-NA ones are replaced by what stats::approx(), which drops them, interpolates there (fill_na_knots()).
     """
     start, end, monthly, altitude = _monthly_array(pixel_monthly_climate)
+    if na_knots == "interpolate":
+        monthly, _ = fill_na_knots(monthly, start, end)
+    elif na_knots != "error":
+        raise ValueError("na_knots must be 'error' or 'interpolate'")
     return _run_vectors(lambda plan, out: plan.run(monthly, altitude, out), monthly.shape[2], start, end,
                         pixel_monthly_climate, lifehistory_functions, species, included_dates, aggregate_by,
                         dates_predict, habitats, model_water_temperature, water_shade_proportion,

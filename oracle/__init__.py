@@ -150,6 +150,8 @@ def spline_seasonal(values, datenum, datenum_predict):
     values, datenum, dp = _d(values), _d(datenum), _d(datenum_predict)
     out = np.empty(len(dp))
     rc = lib().mmso_spline_seasonal(_p(values), _p(datenum), len(values), _p(dp), len(dp), _p(out))
+    if rc == -3:
+        raise ValueError("need at least two non-NA values to interpolate (stats::approx)")
     if rc:
         raise ValueError("extrapolation needed (GAM branch, R/spline_interpolation.R:30-112, not restated)")
     return out
@@ -161,6 +163,8 @@ def daily_from_monthly(monthly, mid_day, day_predict):
     M, D = monthly.shape[1], len(dp)
     daily = np.empty((NFORCING, D))
     rc = lib().mmso_daily_from_monthly(_p(monthly), _p(mid_day), M, _p(dp), D, _p(daily))
+    if rc == -3:
+        raise ValueError("need at least two non-NA values to interpolate (stats::approx)")
     if rc:
         raise ValueError("extrapolation needed (GAM branch not restated)")
     return daily
@@ -393,6 +397,8 @@ def run_chain(monthly, mid_day, day_predict, altitude, habitats, densmod_, table
     rc = lib().mmso_run_chain(ct.byref(ch))
     if rc == -1:
         raise ValueError("extrapolation needed or burn-in longer than the series")
+    if rc == -3:
+        raise ValueError("need at least two non-NA values to interpolate (stats::approx)")
     if rc:
         raise RuntimeError(f"oracle chain failed: {rc}")
     return out

@@ -55,8 +55,21 @@ int mmso_spline_seasonal(const double *values, const double *datenum, int M,
     }
     for (int d = 0; d < D; ++d)
         if (datenum_predict[d] > hi || datenum_predict[d] < lo) return -1;
+    /* stats::approx(x, y, xout) has na.rm = TRUE: regularize.values() drops the (x, y) pairs with an NA before
+     * approx1() sees them (R sources src/library/stats/R/approx.R; restated from the published source), and
+     * approx() stops with "need at least two non-NA values to interpolate" below two pairs (here: -3).  Prediction
+     * dates outside the knots that are left get NA (rule = 1) -- not the GAM: `extrapolation` above looks at the
+     * dates only. */
+    double *xk = (double *)malloc(sizeof(double) * (size_t)M), *yk = (double *)malloc(sizeof(double) * (size_t)M);
+    if (!xk || !yk) { free(xk); free(yk); return -2; }
+    long n = 0;
+    for (int m = 0; m < M; ++m)
+        if (!isnan(values[m]) && !isnan(datenum[m])) { xk[n] = datenum[m]; yk[n] = values[m]; ++n; }
+    if (n < 2) { free(xk); free(yk); return -3; }
     for (int d = 0; d < D; ++d)
-        out[d] = mmso_approx1(datenum_predict[d], datenum, values, M);
+        out[d] = mmso_approx1(datenum_predict[d], xk, yk, n);
+    free(xk);
+    free(yk);
     return 0;
 }
 

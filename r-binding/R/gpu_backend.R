@@ -243,6 +243,9 @@ mms_chain_options <- function(chain, pixels, model_water_temperature, water_shad
 #     mgcv::gam (R/spline_interpolation.R:30-112) that the GPU backend does not reproduce: "error" (default) stops,
 #     "clip" drops the overhanging prediction days with a warning.
 #   cell_idx, n_raster_cells: return whole raster slices instead of tile rows (simplify = TRUE implied).
+#   na_knots: the library refuses NA in the monthly forcing ("error", default); "interpolate" first replaces every NA
+#     knot that has non-NA neighbours on both sides by what stats::approx() -- which drops NA pairs,
+#     R/spline_interpolation.R:25-27 -- interpolates at that knot's date (mms_fill_na_knots()).
 monthly_climate_to_vectors_gpu <- function(pixel_monthly_climate,
                                            species = c("An. gambiae", "An. stephensi"),
                                            included_dates = NULL,
@@ -252,9 +255,11 @@ monthly_climate_to_vectors_gpu <- function(pixel_monthly_climate,
                                            clear_sky = NULL,
                                            on_extrapolation = c("error", "clip"),
                                            cell_idx = NULL, n_raster_cells = NULL,
-                                           simplify = !is.null(cell_idx)) {
+                                           simplify = !is.null(cell_idx),
+                                           na_knots = c("error", "interpolate")) {
   species <- match.arg(species)
   aggregate_by <- match.arg(aggregate_by)
+  na_knots <- match.arg(na_knots)
   lifehistory <- switch(species,
                         "An. gambiae" = lifehistory_functions$An_gambiae,
                         "An. stephensi" = lifehistory_functions$An_stephensi)
@@ -263,6 +268,7 @@ monthly_climate_to_vectors_gpu <- function(pixel_monthly_climate,
             "rainfall_daily")
   monthly <- mms_pack_pixels(pixel_monthly_climate$monthly_climate, vars)
   chain <- mms_chain_setup(first, included_dates, aggregate_by, match.arg(on_extrapolation))
+  if (na_knots == "interpolate" && anyNA(monthly)) monthly <- mms_fill_na_knots(monthly, chain$mid_day)
   opts <- mms_chain_options(chain, pixel_monthly_climate, model_water_temperature, water_shade_proportion,
                             clear_sky, cell_idx, n_raster_cells)
   res <- .Call("mms_R_run_chain", monthly, as.numeric(pixel_monthly_climate$altitude),
@@ -273,6 +279,27 @@ monthly_climate_to_vectors_gpu <- function(pixel_monthly_climate,
                length(chain$periods), 1L, mms_math_mode(), mms_devices(), opts,
                PACKAGE = "mosmicrosim")
   mms_vectors_result(res, pixel_monthly_climate, species, chain$periods, aggregate_by, simplify)
+}
+
+# NA knots of the packed forcing array [pixels, months, 9]: approx(x, y, xout) drops the (x, y) pairs with an NA, i.e.
+# it interpolates between the neighbouring knots that are left; replacing the NA knot by approx()'s own value at the
+# knot's date gives the same daily series (rainfall in the log1p space it is interpolated in,
+# R/sim_microclimate.R:33,61).  NA runs at either end of a series stay NA (the library then refuses the tile; the
+# reference has NA days there).  Only pixels with an NA are touched.
+mms_fill_na_knots <- function(monthly, mid_day) {
+  rain <- dim(monthly)[3]                          # rainfall_daily is the last of the nine variables
+  for (v in seq_len(dim(monthly)[3])) {
+    for (p in which(rowSums(is.na(monthly[, , v, drop = FALSE])) > 0)) {
+      y <- monthly[p, , v]
+      if (v == rain) y <- log1p(y)
+      if (sum(!is.na(y)) < 2) next
+      f <- stats::approx(mid_day, y, xout = mid_day)$y
+      if (v == rain) f <- expm1(f)
+      hole <- is.na(monthly[p, , v])
+      monthly[p, hole, v] <- f[hole]
+    }
+  }
+  monthly
 }
 
 # dates exactly as daily_from_monthly_climate() derives them (R/sim_microclimate.R:12-31) and periods

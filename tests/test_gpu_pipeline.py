@@ -281,3 +281,36 @@ def test_april_start_series_errors_by_default_and_runs_clipped(gpu):
                            want_hourly=False)
     for name in pipeline.VECTOR_VARIABLES:
         assert rel_err(res[name], ref["mean"][0, ORACLE_VAR[name]]) <= REL_TOL_FAST, name
+
+
+def test_na_knots_refused_by_default_and_interpolated_on_request(gpu):
+    """NA in the monthly forcing: MMS_ERR_NONFINITE by default; with na_knots="interpolate" the knots are filled on the
+    host the way stats::approx() -- which drops them -- interpolates there, and the run equals the oracle (whose
+    restatement of approx() drops them) on the tile WITH the holes."""
+    start, end = syn.month_table(2001, 1)
+    C = 25
+    monthly, altitude = syn.synthetic_forcing(C, start, out_of_range_fraction=0.0)
+    rng = np.random.default_rng(9)
+    holes = monthly.copy()
+    for c in range(0, C, 3):
+        v = int(rng.integers(0, 9))
+        m0 = int(rng.integers(2, holes.shape[1] - 4))
+        holes[v, m0:m0 + int(rng.integers(1, 3)), c] = np.nan
+    case = Case(n_cells=C)
+    pmc = {"start": start, "end": end, "altitude": altitude, "longitude": np.arange(C * 1.0), "latitude": np.arange(C * 1.0)}
+    for v, name in enumerate(pipeline.FORCING_VARS):
+        pmc[name] = holes[v]
+    lhf = {"An_gambiae": case.lh, "An_stephensi": syn.synthetic_lifehistory("An. stephensi")}
+    with pytest.raises(backend.MmsError) as e:
+        pipeline.monthly_climate_to_vectors(pmc, lhf)
+    assert e.value.code == "MMS_ERR_NONFINITE"
+    res = pipeline.monthly_climate_to_vectors(pmc, lhf, na_knots="interpolate")
+    dp = dates.default_dates_predict(start, end)
+    mid_day, day_predict = dates.datenums(start, end, dp)
+    pod, ps, _ = dates.period_index(dp, "month")
+    dm = case.densmod
+    ref = oracle.run_chain(holes, mid_day, day_predict, altitude, [oracle.habitat()],
+                           oracle.densmod(dm["type_"], dm["dd_effect"], dm["surface_area_cm2"]), case.tables, pod, len(ps),
+                           want_hourly=False)
+    for name in pipeline.VECTOR_VARIABLES:
+        assert rel_err(res[name], ref["mean"][0, ORACLE_VAR[name]]) <= REL_TOL_FAST, name

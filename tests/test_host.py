@@ -12,6 +12,7 @@ import warnings
 import numpy as np
 import pytest
 
+import oracle
 from helpers import Case
 from mosmicrosim_b200 import backend, dates, lifehistory as lh, pipeline, synthetic as syn
 
@@ -112,6 +113,42 @@ def test_host_copy_and_worker_windows(tmp_path):
                     os.path.join(ROOT, "mosmicrosim_b200", "csrc", "host_copy.cpp"), "-o", exe], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
+
+
+def test_na_knots_are_filled_like_approx_drops_them():
+    """stats::approx() drops NA knots (restated in the oracle's spline_seasonal); pipeline.fill_na_knots() replaces an
+    NA knot by the linear interpolation of its neighbours -- the same daily series to rounding.  Leading / trailing NA
+    knots cannot be filled: the reference has NA days there."""
+    start, end = syn.month_table(2001, 1)
+    dp = syn.year_dates(2001, 1)
+    mid_day, day_predict = dates.datenums(start, end, dp)
+    monthly, _ = syn.synthetic_forcing(8, start, seed=11)                  # [9][M][C]
+    rng = np.random.default_rng(5)
+    holes = monthly.copy()
+    M = holes.shape[1]
+    for c in range(6):                                                     # interior NA knots, single and in runs
+        for v in rng.choice(9, size=3, replace=False):
+            m0 = int(rng.integers(1, M - 3))
+            holes[v, m0:m0 + int(rng.integers(1, 3)), c] = np.nan
+    filled, n = pipeline.fill_na_knots(holes, start, end)
+    assert n == int(np.isnan(holes).sum()) and np.isfinite(filled).all()
+    assert np.array_equal(filled[~np.isnan(holes)], holes[~np.isnan(holes)])          # the other knots keep their bits
+    for c in range(8):
+        ref = oracle.daily_from_monthly(holes[:, :, c], mid_day, day_predict)          # drops the NA knots
+        got = oracle.daily_from_monthly(filled[:, :, c], mid_day, day_predict)
+        assert np.isfinite(ref).all()
+        assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)) < 1e-12
+    # a leading NA knot stays NA (the reference: NA days, not the GAM) ...
+    edge = monthly.copy()
+    edge[2, 0, 0] = np.nan
+    filled, n = pipeline.fill_na_knots(edge, start, end)
+    assert n == 0 and np.isnan(filled[2, 0, 0])
+    ref = oracle.daily_from_monthly(edge[:, :, 0], mid_day, day_predict)
+    assert np.isnan(ref[2, 0]) and np.isfinite(ref[2, -1])
+    # ... and approx() needs two knots
+    edge[2, 1:, 0] = np.nan
+    with pytest.raises(ValueError, match="two non-NA"):
+        oracle.daily_from_monthly(edge[:, :, 0], mid_day, day_predict)
 
 
 def test_no_cpu_fallback_without_a_device():
@@ -256,6 +293,7 @@ WORKER = r"""
 import os, sys
 sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
 import numpy as np, torch, torch.distributed as dist
+import oracle
 import oracle
 from helpers import Case
 from mosmicrosim_b200 import backend
